@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the all-vs-all intersection-cardinality path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c3|c1|custom --rows R --bits M] [--kernel auto|popc|csa|umma]
+
+Metric (BASELINE.json): 64-bit word-pair AND+popcounts per second,
+``wp/s = R(R-1)/2 * ceil(M/64) / seconds`` for the strict upper triangle of XX^T.
+
+A *step* is one full query over the resident matrix.  Default workload is C3
+(200,000 rows x 131,072 bits, genotype-like synthetic rows), the configuration
+the north-star target is quoted on; it fits one GPU (3.28 GB).
+
+  value   device-resident: rows already in HBM, CUDA events around K steps
+          (``STORM_b200_pairw_device``), max over ranks.
+  e2e     the same query through the reference-facing host-buffer call
+          (``STORM_wrapper_diag_blocked``, storm.h:121-125; sharded form
+          ``STORM_b200_wrapper_diag_shard`` for N>1) from PINNED HOST memory:
+          H2D of the whole matrix + kernels + D2H of the total inside the timed
+          region, every step.
+  N>1     strong scaling: every rank holds the full matrix and owns 1/N of the
+          tile raster; the only collective is an 8-byte all-reduce of the total.
+
+``--impl reference`` times the unmodified reference's own CPU kernel
+(oracle/_ref/libstorm_ref.so, built from /root/reference by oracle/Makefile) on a
+bounded row sample of the same workload, with all host cores (our row-block
+partition around the reference's per-pair kernel; the reference itself has no
+threading).  Nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (rows, bits, generator)
+    "c3": (200_000, 131_072, "geno"),
+    "c1": (10_000, 65_536, "uniform32768"),
+}
+SEED = 20260117
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- #
+# reference arm (CPU)
+# --------------------------------------------------------------------------- #
+def reference_optimal_bsize(W: int) -> int:
+    b = int(256e3 / (W * 8))                 # benchmark.cpp:823-824
+    return max(5, b)
+
+
+def run_reference_sample(ref, vals, bsize: int, threads: int) -> float:
+    """Upper-triangle total of `vals` with the reference's per-pair kernel, row-block
+    partitioned over `threads` host threads (ctypes releases the GIL).  Returns seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = vals.shape[0]
+    TB = max(bsize, (max(1, n // (4 * threads)) // bsize) * bsize) if threads > 1 else n
+    tasks = []
+    for i0 in range(0, n, TB):
+        i1 = min(i0 + TB, n)
+        tasks.append(("diag", i0, i1, 0, 0))
+        for j0 in range(i1, n, TB):
+            tasks.append(("rect", i0, i1, j0, min(j0 + TB, n)))
+
+    def work(t):
+        kind, i0, i1, j0, j1 = t
+        if kind == "diag":
+            return ref.wrapper_diag_blocked(vals[i0:i1], bsize)       # storm.c:222-279
+        return ref.rect_blocked(vals, i0, i1, j0, j1, bsize)           # squares of storm.c:1212-1220
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        total = sum(work(t) for t in tasks)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            total = sum(ex.map(work, tasks))
+    dt = time.perf_counter() - t0
+    run_reference_sample.last_total = total
+    return dt
+
+
+def gen_rows_cpu(orc, gen: str, rows: int, bits: int, threads: int):
+    """Sample rows [0, rows) of the workload with the oracle's generator (bit-identical to the device one)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    W = (bits + 63) // 64
+    out = np.zeros((rows, W), dtype=np.uint64)
+    step = max(1, rows // (threads * 4))
+
+    def fill(r0):
+        n = min(step, rows - r0)
+        if gen == "geno":
+            out[r0:r0 + n] = orc.gen_dense_geno(SEED, n, bits, row0=r0)
+        else:
+            out[r0:r0 + n] = orc.gen_dense_uniform(SEED, n, int(gen[len("uniform"):]), bits, row0=r0)
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(fill, range(0, rows, step)))
+    return out
+
+
+def cpu_baseline(rows_total: int, bits: int, gen: str, target_s: float, threads: int):
+    """Time the reference (or, if its prebuilt .so is absent, the oracle port) on a bounded row sample."""
+    from oracle import oracle as O
+    orc = O.Oracle()
+    W = (bits + 63) // 64
+    bsize = reference_optimal_bsize(W)
+    if O.have_reference():
+        ref, kind = O.Reference(), "reference"
+        simd = ref.kernel_name(W)
+    else:
+        ref, kind, simd = None, "port", "scalar-popcnt"
+    # calibrate on a small sample, then size the timed sample for ~target_s
+    n0 = min(rows_total, max(4 * bsize, 600))
+    vals = gen_rows_cpu(orc, gen, n0, bits, threads)
+    if ref is not None:
+        dt = run_reference_sample(ref, vals, bsize, threads)
+    else:
+        t0 = time.perf_counter(); orc.wrapper_diag(vals); dt = time.perf_counter() - t0
+    rate = n0 * (n0 - 1) / 2 * W / dt
+    n = int(min(rows_total, max(n0, (2 * target_s * rate / W) ** 0.5)))
+    n = max(bsize, n // bsize * bsize)
+    if n > n0:
+        vals = gen_rows_cpu(orc, gen, n, bits, threads)
+    return {"orc": orc, "ref": ref, "kind": kind, "simd": simd, "vals": vals, "bsize": bsize, "rows": n, "W": W}
+
+
+def time_cpu_step(ctx, threads: int) -> float:
+    if ctx["ref"] is not None:
+        return run_reference_sample(ctx["ref"], ctx["vals"], ctx["bsize"], threads)
+    t0 = time.perf_counter()
+    ctx["orc"].wrapper_diag(ctx["vals"])
+    return time.perf_counter() - t0
+
+
+def main_reference(args, rows, bits, gen):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0                                           # other ranks exit without work
+    threads = os.cpu_count() or 1
+    W = (bits + 63) // 64
+    per_step = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    ctx = cpu_baseline(rows, bits, gen, per_step, threads)
+    n = ctx["rows"]
+    for _ in range(args.warmup):
+        time_cpu_step(ctx, threads)
+    t = [time_cpu_step(ctx, threads) for _ in range(args.steps)]
+    wp = n * (n - 1) / 2 * W
+    value = wp * args.steps / sum(t)
+    sample = (f"rows [0,{n}) of the {rows}x{bits} workload ({wp:.3e} wp/step), blocked bsize={ctx['bsize']}, "
+              f"per-pair kernel={ctx['simd']}, {threads} host threads over row blocks")
+    line = {
+        "impl": "reference", "metric": "xxt_wordpair_and_popcnt_per_s", "value": value, "unit": "wp/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t) / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: dense {rows}x{bits} XX^T upper triangle", "rows": rows, "bits": bits,
+                   "generator": gen, "sample_rows": n},
+        "cpu_baseline": {"value": value, "unit": "wp/s", "cores": threads, "kind": ctx["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": "wp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- #
+# our arm (GPU)
+# --------------------------------------------------------------------------- #
+def colcount_total_torch(rows_t, W, chunk=16384):
+    """sum_k C(c_k,2) from column popcounts with torch ops only (independent checksum)."""
+    import torch
+    counts = torch.zeros((64, W), dtype=torch.int64, device=rows_t.device)
+    for r0 in range(0, rows_t.shape[0], chunk):
+        blk = rows_t[r0:r0 + chunk, :W]
+        for b in range(64):
+            counts[b] += ((blk >> b) & 1).sum(dim=0, dtype=torch.int64)
+    return int((counts * (counts - 1) // 2).sum().item())
+
+
+def main_ours(args, rows, bits, gen):
+    import torch
+    import torch.distributed as dist
+    import stormbitmaps_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sb.load()
+    dev = torch.device("cuda", local_rank)
+    W = (bits + 63) // 64
+    kernel = args.kernel
+
+    # ---- resident input: every rank generates the same matrix on its own GPU ----
+    rows_t, _ = sb.alloc_rows(rows, bits, device=dev)
+    if gen == "geno":
+        sb.synth_geno_device(rows_t, bits, SEED)
+    else:
+        sb.synth_uniform_device(rows_t, bits, int(gen[len("uniform"):]), SEED)
+    torch.cuda.synchronize()
+    wp = rows * (rows - 1) / 2 * W
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def step():
+        total.zero_()
+        sb.pairw_device(rows_t, n_words=W, shard=rank, n_shards=world, kernel=kernel, total=total)
+        if world > 1:
+            dist.all_reduce(total)                         # 8 bytes: the only collective on the path
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = sb.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    launches = sb.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    elapsed = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed.item())
+    got_total = int(total.item())
+
+    # ---- e2e: host buffers through the reference-facing call -------------------
+    host = torch.empty((rows, W), dtype=torch.int64, pin_memory=True)
+    host.copy_(rows_t[:, :W])
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        part = sb.wrapper_diag_shard_ptr(host.data_ptr(), rows, W, rank, world)   # H2D + kernels + D2H inside
+        if world > 1:
+            t = torch.tensor([part], dtype=torch.int64, device=dev)
+            dist.all_reduce(t)
+            part = int(t.item())
+        return part
+
+    e2e_total = e2e_step()                                   # warm-up (allocates the scratch arena)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_total = e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = wp * e2e_steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- verification (outside the timed regions) -------------------------------
+    closed = colcount_total_torch(rows_t, W)
+    ok = (got_total == closed) and (e2e_total == closed)
+
+    peaks, peak_src = load_peaks()
+    value = wp * args.steps / (elapsed_ms * 1e-3)
+    used_kernel = sb.resolved_kernel_name(kernel, W)
+    n_tiles, tm, tn = sb.tile_count(rows, used_kernel)
+    # dominant kernel: one launch per step per rank; its duration is the step time
+    # minus the 8-byte all-reduce (N>1), measured by the same CUDA events
+    launch_ms = elapsed_ms / args.steps
+    if used_kernel == "umma":
+        # algorithmic work: 64 int8 MACs = 128 ops per 64-bit word pair
+        ops_per_launch = wp / world * 128.0
+        achieved = ops_per_launch / (launch_ms * 1e-3) / 1e12
+        peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "dense_umma_kernel",
+                    "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peak_src}); kind::i8 issues at "
+                                   "twice the bf16 rate, 1 MAC = 2 ops",
+                    "algorithmic": "128 int8 ops per 64-bit word pair"}
+    else:
+        # CUDA-core kernels: bound by the POPC issue rate, measured on this device
+        popc_rate, mhz = sb.microbench(0)
+        per_wp = 2.0                                       # 2 POPC.32 per 64-bit word pair (direct form)
+        achieved = wp / world * per_wp / (launch_ms * 1e-3)
+        roofline = {"bound": "issue", "achieved": achieved / 1e12, "peak": popc_rate / 1e12, "unit": "T POPC.32/s",
+                    "frac": achieved / popc_rate, "traffic": None, "kernel": f"dense_{used_kernel}_kernel",
+                    "peak_source": f"STORM_b200_microbench(POPC) on this device at {mhz:.0f} MHz",
+                    "algorithmic": "2 LOP3.32 + 2 POPC.32 per 64-bit word pair (SURVEY.md 8(d))",
+                    "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
+
+    line = {
+        "metric": "xxt_wordpair_and_popcnt_per_s", "value": value, "unit": "wp/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: dense {rows}x{bits} XX^T upper triangle", "rows": rows, "bits": bits,
+                   "generator": gen, "seed": SEED, "kernel": used_kernel, "tile": [tm, tn], "tiles": n_tiles,
+                   "parallelism": f"tile-raster shards x{world}, rows replicated",
+                   "l2": "inputs larger than L2 (%.2f GB vs 126 MB)" % (rows * W * 8 / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "wp/s", "h2d_bytes_per_step": rows * W * 8, "d2h_bytes_per_step": 8,
+                "steps": e2e_steps, "call": "STORM_wrapper_diag_blocked (host buffer, pinned)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "verified": {"total": got_total, "closed_form_total": closed, "match": ok},
+        "step_ms": step_ms,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = 1                                         # the reference is single-threaded
+        ctx = cpu_baseline(rows, bits, gen, 12.0, threads)
+        dt = time_cpu_step(ctx, threads)
+        n = ctx["rows"]
+        cwp = n * (n - 1) / 2 * W
+        line["cpu_baseline"] = {"value": cwp / dt, "unit": "wp/s", "cores": threads, "kind": ctx["kind"],
+                                "sample": f"rows [0,{n}) of the workload, STORM_wrapper_diag_blocked(bsize={ctx['bsize']}), "
+                                          f"per-pair kernel={ctx['simd']}, {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    if not ok:
+        print(f"VERIFICATION FAILED: total {got_total} e2e {e2e_total} closed form {closed}", file=sys.stderr)
+        return 1
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "custom"])
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--bits", type=int, default=None)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "umma"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.workload == "custom":
+        rows, bits, gen = args.rows or 20000, args.bits or 131072, "geno"
+    else:
+        rows, bits, gen = WORKLOADS[args.workload]
+        rows, bits = args.rows or rows, args.bits or bits
+    if args.impl == "reference":
+        return main_reference(args, rows, bits, gen)
+    return main_ours(args, rows, bits, gen)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

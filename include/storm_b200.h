@@ -1,0 +1,141 @@
+/*
+ * storm_b200.h -- additive C-ABI of libstorm_b200.so (nothing here exists in
+ * the reference; everything the reference declares is in storm.h).
+ *
+ * Plain pointers and sizes only: no torch / CUDA types in any signature.  A
+ * `stream` argument is a CUDA stream handle passed as void* (0 / NULL = the
+ * legacy default stream); a `d_` pointer is a device pointer on the current
+ * CUDA device of the calling thread.
+ *
+ * Conventions: int functions return 0 on success and a negative STORM_B200_E*
+ * code on failure; STORM_b200_last_error() returns a thread-local message for
+ * the most recent failure on the calling thread.
+ */
+#ifndef STORM_B200_H_
+#define STORM_B200_H_
+
+#include "storm.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STORM_B200_OK          0
+#define STORM_B200_EINVAL     -1   /* bad argument                                  */
+#define STORM_B200_ECUDA      -2   /* CUDA runtime / driver error (see last_error)  */
+#define STORM_B200_ENODEV     -3   /* no usable sm_100 device                       */
+#define STORM_B200_ENOMEM     -4   /* host or device allocation failed              */
+
+/* Which dense tile kernel answers a query.  AUTO picks
+ * UMMA when the shape fills its tiles and POPC otherwise. */
+#define STORM_B200_KERNEL_AUTO 0
+#define STORM_B200_KERNEL_POPC 1   /* CUDA cores: LOP3 + POPC register tiles          */
+#define STORM_B200_KERNEL_UMMA 2   /* tcgen05.mma kind::i8 on bits unpacked on the fly */
+#define STORM_B200_KERNEL_CSA  3   /* CUDA cores: carry-save adders feeding POPC        */
+
+/* ---- library / device ---------------------------------------------------- */
+const char* STORM_b200_last_error(void);
+const char* STORM_b200_version(void);
+int  STORM_b200_device_count(void);
+/* Name, SM count, compute capability major*10+minor of device `dev`. */
+int  STORM_b200_device_info(int dev, char* name, size_t name_len, int* sm_count, int* cc);
+/* Process-wide default kernel for the storm.h entry points (they have no
+ * parameter for it).  Returns the previous value. */
+int  STORM_b200_set_default_kernel(int kernel);
+
+/* ---- dense path on device-resident rows ----------------------------------
+ *
+ * Rows are row-major 64-bit words, row r at d_rows + r*row_stride_words; bit v
+ * of a row is (word[v/64] >> (v%64)) & 1 (storm.c:1114).  d_rows must be 16-byte
+ * aligned and row_stride_words even.  Words [n_words, row_stride_words) of each
+ * row are never read.
+ *
+ * The strict upper triangle is cut into row-block tiles; tiles are numbered in a
+ * fixed raster and shard s of n_shards owns a contiguous, equally sized range of
+ * tile indices (multi-GPU: one shard per rank, no data-path collective; the
+ * caller adds the partial totals).  *d_total (device, 8 bytes) is ACCUMULATED
+ * into with one 64-bit atomic add per CTA: zero it first.
+ *
+ * Replaces the loop nest of storm.c:1149-1173 / 1175-1241 (and 132-150, 222-279). */
+int STORM_b200_pairw_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                            uint64_t row_stride_words, uint32_t shard, uint32_t n_shards,
+                            int kernel, uint64_t* d_total, void* stream);
+
+/* Per-pair counts of the rectangle rows [i0,i1) x [j0,j1): d_out[(i-i0)*ld + (j-j0)]
+ * = popcount(row_i & row_j); with strict_upper != 0 entries with j <= i are
+ * written as 0 and excluded from the total.  d_total may be NULL.  d_out may be
+ * NULL (total only).  The per-pair expression is storm.c:1167. */
+int STORM_b200_pairw_rect_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                 uint64_t row_stride_words,
+                                 uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1,
+                                 int strict_upper, int kernel,
+                                 uint32_t* d_out, uint64_t ld, uint64_t* d_total, void* stream);
+
+/* XY^T over two device matrices with the same n_words (all n1 x n2 pairs). */
+int STORM_b200_square_device(const uint64_t* d_rows1, uint64_t n1, uint64_t stride1,
+                             const uint64_t* d_rows2, uint64_t n2, uint64_t stride2,
+                             uint32_t n_words, int kernel,
+                             uint32_t* d_out, uint64_t ld, uint64_t* d_total, void* stream);
+
+/* Number of tiles the triangle raster of `kernel` has for n_rows (so callers can
+ * reason about shard balance), and the tile edge lengths it uses. */
+uint64_t STORM_b200_tile_count(uint64_t n_rows, int kernel, uint32_t* tile_rows, uint32_t* tile_cols);
+
+/* Which kernel id AUTO (or the process default) resolves to for rows of n_words. */
+int STORM_b200_resolve_kernel(int kernel, uint32_t n_words);
+
+/* Sharded form of STORM_wrapper_diag (storm.h:95-98): HOST buffer of n_vectors x
+ * n_ints words (row pitch n_ints) -> upload -> this shard's partial total.
+ * UINT64_MAX on error. */
+uint64_t STORM_b200_wrapper_diag_shard(uint64_t n_vectors, const uint64_t* vals, uint64_t n_ints,
+                                       uint32_t shard, uint32_t n_shards, int kernel);
+
+/* ---- container extensions ------------------------------------------------ */
+/* Partial total of shard `shard` of `n_shards` (see above); UINT64_MAX on error. */
+uint64_t STORM_b200_contig_pairw_shard(STORM_contiguous_t* bitmap, uint32_t shard, uint32_t n_shards, int kernel);
+/* Per-pair counts into a HOST buffer out[(i-i0)*(j1-j0) + (j-j0)], strict upper triangle. */
+int STORM_b200_contig_pairw_rect(STORM_contiguous_t* bitmap, uint64_t i0, uint64_t i1,
+                                 uint64_t j0, uint64_t j1, uint32_t* out);
+/* Device arena of a contiguous container after making it current (uploads dirty
+ * rows).  Returns the device pointer and the row stride in words. */
+const uint64_t* STORM_b200_contig_device_rows(STORM_contiguous_t* bitmap, uint64_t* row_stride_words);
+/* Drop the device copy so that the next query uploads again (used to time the
+ * host-buffer path end to end). */
+int STORM_b200_contig_invalidate_device(STORM_contiguous_t* bitmap);
+/* Bulk ingest: n_rows rows given as one concatenated sorted position array and
+ * an offsets array of n_rows+1 entries.  Positions are uploaded once and the
+ * bits are scattered on the device; same row semantics as STORM_contig_add
+ * (rows with zero positions are skipped, D7). */
+int STORM_b200_contig_add_bulk(STORM_contiguous_t* bitmap, const uint32_t* positions,
+                               const uint64_t* offsets, uint64_t n_rows);
+/* Seconds spent in the last query of this object: [0] upload (H2D), [1] kernels, [2] total. */
+int STORM_b200_contig_last_timing(STORM_contiguous_t* bitmap, double out_seconds[3]);
+
+uint64_t STORM_b200_storm_pairw_shard(STORM_t* bitmap, uint32_t shard, uint32_t n_shards);
+/* Per-pair counts of a STORM_t rectangle into a HOST buffer (strict upper). */
+int STORM_b200_storm_pairw_rect(STORM_t* bitmap, uint64_t i0, uint64_t i1,
+                                uint64_t j0, uint64_t j1, uint32_t* out);
+
+/* ---- synthetic inputs on the device (bit-identical to oracle/storm_oracle.c) */
+/* benchmark.cpp:749-797 recipe: n_draws uniform positions with replacement per row. */
+int STORM_b200_synth_uniform_device(uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                    uint64_t row_stride_words, uint32_t M, uint32_t n_draws,
+                                    uint64_t seed, uint64_t row0, void* stream);
+/* Genotype-like rows. */
+int STORM_b200_synth_geno_device(uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                 uint64_t row_stride_words, uint32_t M,
+                                 uint64_t seed, uint64_t row0, void* stream);
+
+/* ---- measurement helpers -------------------------------------------------- */
+/* Issue-rate micro-benchmarks used as roofline denominators for the CUDA-core
+ * kernels (MEASURED_PEAKS.json only has HBM and bf16).  kind: 0 POPC.32,
+ * 1 LOP3.32, 2 IADD3, 3 POPC+LOP3 mixed.  Returns thread-instructions per
+ * second over the whole device in *rate and the SM clock (MHz) it ran at. */
+int STORM_b200_microbench(int kind, double* rate, double* sm_mhz);
+/* Number of kernel launches issued by this library since load (for bench.py). */
+uint64_t STORM_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STORM_B200_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of libstorm_b200.so (the C-ABI declared in include/*.h).
+
+There is no fallback: if the shared object is missing the import fails with
+instructions to build it, and if it loads but no sm_100 device is usable every
+query raises :class:`StormError` carrying ``STORM_b200_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libstorm_b200.so")
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+UINT64_MAX = 2**64 - 1
+
+KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_CSA = 0, 1, 2, 3
+KERNEL_NAMES = {"auto": 0, "popc": 1, "umma": 2, "csa": 3}
+
+
+class StormError(RuntimeError):
+    pass
+
+
+# every symbol include/storm.h and include/storm_b200.h declare: (restype, argtypes)
+SIGNATURES = {
+    # ---- storm.h: dense model
+    "STORM_contig_new": (C.c_void_p, [C.c_size_t]),
+    "STORM_contig_free": (None, [C.c_void_p]),
+    "STORM_contig_add": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
+    "STORM_contig_clear": (C.c_int, [C.c_void_p]),
+    "STORM_contig_pairw_intersect_cardinality": (C.c_uint64, [C.c_void_p]),
+    "STORM_contig_pairw_intersect_cardinality_blocked": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    "STORM_contig_pairw_intersect_cardinality_list": (C.c_uint64, [C.c_void_p]),
+    "STORM_contig_pairw_intersect_cardinality_blocked_list": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    # ---- storm.h: sparse model
+    "STORM_new": (C.c_void_p, []),
+    "STORM_free": (None, [C.c_void_p]),
+    "STORM_add": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
+    "STORM_clear": (C.c_int, [C.c_void_p]),
+    "STORM_pairw_intersect_cardinality": (C.c_uint64, [C.c_void_p]),
+    "STORM_pairw_intersect_cardinality_blocked": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    "STORM_intersect_cardinality_square": (C.c_uint64, [C.c_void_p, C.c_void_p]),
+    "STORM_serialized_size": (C.c_uint64, [C.c_void_p]),
+    "STORM_bitmap_cont_new": (C.c_void_p, []),
+    "STORM_bitmap_cont_init": (None, [C.c_void_p]),
+    "STORM_bitmap_cont_free": (None, [C.c_void_p]),
+    "STORM_bitmap_cont_add": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
+    "STORM_bitmap_cont_clear": (C.c_int, [C.c_void_p]),
+    "STORM_bitmap_cont_serialized_size": (C.c_uint32, [C.c_void_p]),
+    "STORM_bitmap_new": (C.c_void_p, []),
+    "STORM_bitmap_init": (None, [C.c_void_p]),
+    "STORM_bitmap_free": (None, [C.c_void_p]),
+    "STORM_bitmap_add": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
+    "STORM_bitmap_add_scalar_only": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
+    "STORM_bitmap_clear": (C.c_int, [C.c_void_p]),
+    "STORM_bitmap_serialized_size": (C.c_uint32, [C.c_void_p]),
+    # ---- storm.h: raw-buffer wrappers
+    "STORM_wrapper_diag": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, C.c_void_p]),
+    "STORM_wrapper_diag_blocked": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, C.c_void_p, C.c_uint32]),
+    "STORM_wrapper_square": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, u64p, C.c_uint32, C.c_void_p]),
+    "STORM_wrapper_diag_list": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, u32p, u32p, u32p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "STORM_wrapper_diag_list_blocked": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, u32p, u32p, u32p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    # ---- storm_b200.h
+    "STORM_b200_last_error": (C.c_char_p, []),
+    "STORM_b200_version": (C.c_char_p, []),
+    "STORM_b200_device_count": (C.c_int, []),
+    "STORM_b200_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "STORM_b200_set_default_kernel": (C.c_int, [C.c_int]),
+    "STORM_b200_pairw_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
+    "STORM_b200_pairw_rect_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "STORM_b200_square_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "STORM_b200_resolve_kernel": (C.c_int, [C.c_int, C.c_uint32]),
+    "STORM_b200_wrapper_diag_shard": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),
+    "STORM_b200_tile_count": (C.c_uint64, [C.c_uint64, C.c_int, u32p, u32p]),
+    "STORM_b200_contig_pairw_shard": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
+    "STORM_b200_contig_pairw_rect": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u32p]),
+    "STORM_b200_contig_device_rows": (C.c_void_p, [C.c_void_p, u64p]),
+    "STORM_b200_contig_invalidate_device": (C.c_int, [C.c_void_p]),
+    "STORM_b200_contig_add_bulk": (C.c_int, [C.c_void_p, u32p, u64p, C.c_uint64]),
+    "STORM_b200_contig_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "STORM_b200_storm_pairw_shard": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "STORM_b200_storm_pairw_rect": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u32p]),
+    "STORM_b200_synth_uniform_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "STORM_b200_synth_geno_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "STORM_b200_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "STORM_b200_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libstorm_b200.so and bind every declared symbol (raises if any is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m stormbitmaps_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().STORM_b200_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise StormError(f"{what} failed (code {rc}): {last_error()}")

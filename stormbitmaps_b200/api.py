@@ -1,0 +1,335 @@
+"""Host-side mirror of the reference's C API for the pairwise path.
+
+The method names follow storm.h one to one (``STORM_contig_add`` ->
+``StormContiguous.add`` ...), with the same argument meaning and error
+behaviour, so the parity tests read like calls against the reference.  All work
+happens in libstorm_b200.so; this module only marshals numpy / torch buffers to
+plain pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import KERNEL_AUTO, KERNEL_NAMES, StormError, UINT64_MAX, u32p, u64p
+
+
+def _kernel_id(kernel) -> int:
+    return KERNEL_NAMES[kernel] if isinstance(kernel, str) else int(kernel)
+
+
+def _u32(values) -> np.ndarray:
+    return np.ascontiguousarray(values, dtype=np.uint32)
+
+
+def _query(value: int, what: str) -> int:
+    """Reference convention: (uint64)-1 / -2 / -3 are error sentinels (storm.c:1150,1245-1246)."""
+    if value >= UINT64_MAX - 2:
+        raise StormError(f"{what} returned the error sentinel {value - 2**64}: {_lib.last_error()}")
+    return int(value)
+
+
+class StormContiguous:
+    """``STORM_contiguous_t`` (storm.h:188-200): dense rows of ``vector_length`` bits."""
+
+    def __init__(self, vector_length: int):
+        self._L = _lib.load()
+        self.vector_length = int(vector_length)
+        self._h = self._L.STORM_contig_new(self.vector_length)            # STORM_contig_new
+        if not self._h:
+            raise MemoryError("STORM_contig_new returned NULL")
+
+    # -- construction ------------------------------------------------------
+    def add(self, values: Sequence[int]) -> int:
+        """``STORM_contig_add``: one row from a sorted position list; returns n_values (0 adds no row)."""
+        v = _u32(values)
+        rc = self._L.STORM_contig_add(self._h, v.ctypes.data_as(u32p), v.size)
+        if rc < 0:
+            raise StormError(f"STORM_contig_add failed ({rc}): {_lib.last_error()}")
+        return rc
+
+    def add_bulk(self, positions: np.ndarray, offsets: np.ndarray) -> None:
+        """``STORM_b200_contig_add_bulk``: many rows at once, bits scattered on the device."""
+        p = _u32(positions)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _lib.check(self._L.STORM_b200_contig_add_bulk(self._h, p.ctypes.data_as(u32p), o.ctypes.data_as(u64p),
+                                                      o.size - 1), "STORM_b200_contig_add_bulk")
+
+    def clear(self) -> int:
+        return self._L.STORM_contig_clear(self._h)                          # STORM_contig_clear
+
+    # -- queries -----------------------------------------------------------
+    def pairw_intersect_cardinality(self) -> int:
+        return _query(self._L.STORM_contig_pairw_intersect_cardinality(self._h), "STORM_contig_pairw_intersect_cardinality")
+
+    def pairw_intersect_cardinality_blocked(self, bsize: int = 0) -> int:
+        return _query(self._L.STORM_contig_pairw_intersect_cardinality_blocked(self._h, bsize),
+                      "STORM_contig_pairw_intersect_cardinality_blocked")
+
+    def pairw_intersect_cardinality_list(self) -> int:
+        return _query(self._L.STORM_contig_pairw_intersect_cardinality_list(self._h), "STORM_contig_pairw_intersect_cardinality_list")
+
+    def pairw_intersect_cardinality_blocked_list(self, bsize: int = 0) -> int:
+        return _query(self._L.STORM_contig_pairw_intersect_cardinality_blocked_list(self._h, bsize),
+                      "STORM_contig_pairw_intersect_cardinality_blocked_list")
+
+    def pairw_shard(self, shard: int, n_shards: int, kernel=KERNEL_AUTO) -> int:
+        """Partial total of one shard of the tile raster (multi-GPU: one shard per rank)."""
+        return _query(self._L.STORM_b200_contig_pairw_shard(self._h, shard, n_shards, _kernel_id(kernel)),
+                      "STORM_b200_contig_pairw_shard")
+
+    def pairw_rect(self, i0: int, i1: int, j0: int, j1: int) -> np.ndarray:
+        """Per-pair counts of rows [i0,i1) x [j0,j1), strict upper triangle (j <= i reads 0)."""
+        out = np.zeros((i1 - i0, j1 - j0), dtype=np.uint32)
+        _lib.check(self._L.STORM_b200_contig_pairw_rect(self._h, i0, i1, j0, j1, out.ctypes.data_as(u32p)),
+                   "STORM_b200_contig_pairw_rect")
+        return out
+
+    def invalidate_device(self) -> None:
+        _lib.check(self._L.STORM_b200_contig_invalidate_device(self._h), "STORM_b200_contig_invalidate_device")
+
+    def last_timing(self) -> dict:
+        t = (C.c_double * 3)()
+        _lib.check(self._L.STORM_b200_contig_last_timing(self._h, t), "STORM_b200_contig_last_timing")
+        return {"upload_s": t[0], "kernel_s": t[1], "total_s": t[2]}
+
+    # -- lifetime ----------------------------------------------------------
+    def free(self) -> None:
+        if self._h:
+            self._L.STORM_contig_free(self._h)                              # STORM_contig_free
+            self._h = None
+
+    close = free
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Storm:
+    """``STORM_t`` (storm.h:175-178): rows of 65536-bit blocks, bitmap or u16 list each."""
+
+    def __init__(self):
+        self._L = _lib.load()
+        self._h = self._L.STORM_new()                                      # STORM_new
+        if not self._h:
+            raise MemoryError("STORM_new returned NULL")
+
+    def add(self, values: Sequence[int]) -> int:
+        v = _u32(values)
+        rc = self._L.STORM_add(self._h, v.ctypes.data_as(u32p), v.size)    # STORM_add
+        if rc < 0:
+            raise StormError(f"STORM_add failed ({rc}): {_lib.last_error()}")
+        return rc
+
+    def clear(self) -> int:
+        return self._L.STORM_clear(self._h)
+
+    def pairw_intersect_cardinality(self) -> int:
+        return _query(self._L.STORM_pairw_intersect_cardinality(self._h), "STORM_pairw_intersect_cardinality")
+
+    def pairw_intersect_cardinality_blocked(self, bsize: int = 0) -> int:
+        return _query(self._L.STORM_pairw_intersect_cardinality_blocked(self._h, bsize),
+                      "STORM_pairw_intersect_cardinality_blocked")
+
+    def pairw_shard(self, shard: int, n_shards: int) -> int:
+        return _query(self._L.STORM_b200_storm_pairw_shard(self._h, shard, n_shards), "STORM_b200_storm_pairw_shard")
+
+    def pairw_rect(self, i0: int, i1: int, j0: int, j1: int) -> np.ndarray:
+        out = np.zeros((i1 - i0, j1 - j0), dtype=np.uint32)
+        _lib.check(self._L.STORM_b200_storm_pairw_rect(self._h, i0, i1, j0, j1, out.ctypes.data_as(u32p)),
+                   "STORM_b200_storm_pairw_rect")
+        return out
+
+    def intersect_cardinality_square(self, other: "Storm") -> int:
+        return _query(self._L.STORM_intersect_cardinality_square(self._h, other._h), "STORM_intersect_cardinality_square")
+
+    def serialized_size(self) -> int:
+        return int(self._L.STORM_serialized_size(self._h))
+
+    def free(self) -> None:
+        if self._h:
+            self._L.STORM_free(self._h)
+            self._h = None
+
+    close = free
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# raw host buffers (storm.h:95-148)
+# ---------------------------------------------------------------------------
+def wrapper_diag(vals: np.ndarray) -> int:
+    """``STORM_wrapper_diag``: caller-owned host matrix (n_vectors, n_ints) of uint64 -> total."""
+    L = _lib.load()
+    v = np.ascontiguousarray(vals, dtype=np.uint64)
+    return _query(L.STORM_wrapper_diag(v.shape[0], v.ctypes.data_as(u64p), v.shape[1], None), "STORM_wrapper_diag")
+
+
+def wrapper_diag_ptr(ptr: int, n_vectors: int, n_ints: int, bsize: int = 0) -> int:
+    """``STORM_wrapper_diag_blocked`` on a raw host pointer (e.g. a pinned torch tensor)."""
+    L = _lib.load()
+    return _query(L.STORM_wrapper_diag_blocked(n_vectors, C.cast(ptr, u64p), n_ints, None, bsize), "STORM_wrapper_diag_blocked")
+
+
+def wrapper_diag_shard_ptr(ptr: int, n_vectors: int, n_ints: int, shard: int = 0, n_shards: int = 1,
+                           kernel=KERNEL_AUTO) -> int:
+    """``STORM_b200_wrapper_diag_shard``: host buffer -> upload -> partial total of one shard."""
+    L = _lib.load()
+    return _query(L.STORM_b200_wrapper_diag_shard(n_vectors, C.cast(ptr, u64p), n_ints, shard, n_shards,
+                                                  _kernel_id(kernel)), "STORM_b200_wrapper_diag_shard")
+
+
+def resolved_kernel_name(kernel, n_words: int) -> str:
+    """Name of the kernel AUTO / the process default resolves to for rows of n_words."""
+    kid = _lib.load().STORM_b200_resolve_kernel(_kernel_id(kernel), n_words)
+    return {v: k for k, v in KERNEL_NAMES.items()}[kid]
+
+
+def wrapper_square(v1: np.ndarray, v2: np.ndarray) -> int:
+    L = _lib.load()
+    a = np.ascontiguousarray(v1, dtype=np.uint64)
+    b = np.ascontiguousarray(v2, dtype=np.uint64)
+    if a.shape[1] != b.shape[1]:
+        raise ValueError("row widths differ")
+    return _query(L.STORM_wrapper_square(a.shape[0], a.ctypes.data_as(u64p), b.shape[0], b.ctypes.data_as(u64p),
+                                         a.shape[1], None), "STORM_wrapper_square")
+
+
+# ---------------------------------------------------------------------------
+# device-resident rows (torch tensors are only pointer carriers here)
+# ---------------------------------------------------------------------------
+def _rows_args(rows):
+    """rows: 2-D torch int64/uint64 CUDA tensor, row-major.  Returns (ptr, n_rows, stride_words)."""
+    if rows.dim() != 2 or rows.element_size() != 8 or not rows.is_cuda or rows.stride(1) != 1:
+        raise ValueError("rows must be a 2-D CUDA tensor of 64-bit words, contiguous along dim 1")
+    return rows.data_ptr(), rows.shape[0], rows.stride(0)
+
+
+def _stream_handle(stream) -> Optional[int]:
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    return int(stream)
+
+
+def pairw_device(rows, n_words: Optional[int] = None, shard: int = 0, n_shards: int = 1, kernel=KERNEL_AUTO,
+                 total=None, stream=None):
+    """``STORM_b200_pairw_device``: accumulate this shard's partial total into ``total`` (1-elem int64 CUDA tensor).
+
+    Asynchronous on ``stream`` (default: torch's current stream).  Returns ``total``."""
+    import torch
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    if total is None:
+        total = torch.zeros(1, dtype=torch.int64, device=rows.device)
+    _lib.check(L.STORM_b200_pairw_device(ptr, n_rows, n_words or rows.shape[1], stride, shard, n_shards,
+                                         _kernel_id(kernel), total.data_ptr(), _stream_handle(stream)),
+               "STORM_b200_pairw_device")
+    return total
+
+
+def pairw_rect_device(rows, i0, i1, j0, j1, n_words: Optional[int] = None, strict_upper: bool = True,
+                      kernel=KERNEL_AUTO, want_counts: bool = True, stream=None):
+    """``STORM_b200_pairw_rect_device``: (counts[int32 view of uint32], total) of a rectangle of pairs."""
+    import torch
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    out = torch.zeros((i1 - i0, j1 - j0), dtype=torch.int32, device=rows.device) if want_counts else None
+    total = torch.zeros(1, dtype=torch.int64, device=rows.device)
+    _lib.check(L.STORM_b200_pairw_rect_device(ptr, n_rows, n_words or rows.shape[1], stride, i0, i1, j0, j1,
+                                              int(strict_upper), _kernel_id(kernel),
+                                              out.data_ptr() if want_counts else None, j1 - j0,
+                                              total.data_ptr(), _stream_handle(stream)),
+               "STORM_b200_pairw_rect_device")
+    return out, total
+
+
+def square_device(rows1, rows2, n_words: Optional[int] = None, kernel=KERNEL_AUTO, want_counts: bool = False, stream=None):
+    """``STORM_b200_square_device``: XY^T over two device matrices."""
+    import torch
+    L = _lib.load()
+    p1, n1, s1 = _rows_args(rows1)
+    p2, n2, s2 = _rows_args(rows2)
+    out = torch.zeros((n1, n2), dtype=torch.int32, device=rows1.device) if want_counts else None
+    total = torch.zeros(1, dtype=torch.int64, device=rows1.device)
+    _lib.check(L.STORM_b200_square_device(p1, n1, s1, p2, n2, s2, n_words or rows1.shape[1], _kernel_id(kernel),
+                                          out.data_ptr() if want_counts else None, n2, total.data_ptr(),
+                                          _stream_handle(stream)), "STORM_b200_square_device")
+    return out, total
+
+
+def alloc_rows(n_rows: int, M: int, device="cuda"):
+    """Zeroed device arena in the library's layout: row stride padded to 128 bytes."""
+    import torch
+    n_words = (M + 63) // 64
+    stride = (n_words + 15) // 16 * 16
+    return torch.zeros((n_rows, stride), dtype=torch.int64, device=device), n_words
+
+
+def synth_uniform_device(rows, M: int, n_draws: int, seed: int, row0: int = 0, stream=None):
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    _lib.check(L.STORM_b200_synth_uniform_device(ptr, n_rows, (M + 63) // 64, stride, M, n_draws, seed, row0,
+                                                 _stream_handle(stream)), "STORM_b200_synth_uniform_device")
+    return rows
+
+
+def synth_geno_device(rows, M: int, seed: int, row0: int = 0, stream=None):
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    _lib.check(L.STORM_b200_synth_geno_device(ptr, n_rows, (M + 63) // 64, stride, M, seed, row0,
+                                              _stream_handle(stream)), "STORM_b200_synth_geno_device")
+    return rows
+
+
+def tile_count(n_rows: int, kernel=KERNEL_AUTO):
+    L = _lib.load()
+    tm, tn = C.c_uint32(), C.c_uint32()
+    n = L.STORM_b200_tile_count(n_rows, _kernel_id(kernel), C.byref(tm), C.byref(tn))
+    return int(n), tm.value, tn.value
+
+
+def microbench(kind: int):
+    L = _lib.load()
+    rate, mhz = C.c_double(), C.c_double()
+    _lib.check(L.STORM_b200_microbench(kind, C.byref(rate), C.byref(mhz)), "STORM_b200_microbench")
+    return rate.value, mhz.value
+
+
+def launch_count() -> int:
+    return int(_lib.load().STORM_b200_launch_count())
+
+
+def set_default_kernel(kernel) -> int:
+    return _lib.load().STORM_b200_set_default_kernel(_kernel_id(kernel))
+
+
+def device_info(dev: int = 0) -> dict:
+    L = _lib.load()
+    name = C.create_string_buffer(128)
+    sms, cc = C.c_int(), C.c_int()
+    _lib.check(L.STORM_b200_device_info(dev, name, 128, C.byref(sms), C.byref(cc)), "STORM_b200_device_info")
+    return {"name": name.value.decode(), "sm_count": sms.value, "cc": cc.value}

@@ -1,0 +1,109 @@
+// common.cuh -- shared declarations for libstorm_b200.so (sm_100a only).
+//
+// The library computes the StormBitmaps pairwise intersection-cardinality path
+// (reference: storm.c:1149-1241 dense, storm.c:877-961 sparse) on the GPU.
+// Nothing in here falls back to the CPU: every launcher reports CUDA failures
+// through set_error() and a negative return code.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "storm_b200.h"
+
+namespace storm {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+void count_launch(uint64_t n = 1);
+
+#define STORM_CUDA_TRY(expr)                                                         \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            ::storm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                  \
+            return STORM_B200_ECUDA;                                                 \
+        }                                                                            \
+    } while (0)
+
+// ---- one dense job: a set of (row-block, column-block) tiles -----------------
+//
+// A and B are row-major bitmaps (64-bit words).  A tile (bi, bj) covers A rows
+// [bi*TM, bi*TM+TM) x B rows [bj*TN, bj*TN+TN) where TM/TN belong to the kernel.
+// Tiles are numbered row-block-major; in triangle mode only tiles that intersect
+// the strict upper triangle exist and `row_prefix[bi]` is the number of tiles in
+// row blocks < bi (n_bi + 1 entries, device memory).
+struct DenseJob {
+    const uint64_t* A;
+    const uint64_t* B;
+    uint64_t strideA, strideB;   // words
+    uint64_t nA, nB;             // valid rows
+    uint32_t n_words;            // words per row that carry data
+    uint64_t i_off, j_off;       // global row index of A row 0 / B row 0 (for the j>i mask)
+    int strict_upper;            // count / emit only pairs with global j > global i
+    int triangle;                // 1: tile list is the triangle raster (needs row_prefix)
+    const uint64_t* row_prefix;  // device, n_bi + 1 entries (triangle mode)
+    uint32_t n_bi, n_bj;         // tile grid extents
+    uint64_t tile_begin, tile_end;  // this launch handles tiles [begin, end)
+    uint32_t* out;               // optional per-pair counts, out[(i)*ld + j] relative to A/B row 0
+    uint64_t ld;
+    unsigned long long* total;   // optional, accumulated with atomicAdd
+};
+
+// First column block of row block bi that intersects the strict upper triangle
+// when A == B (square matrix, same origin).
+__host__ __device__ inline uint32_t tri_jstart(uint32_t bi, uint32_t TM, uint32_t TN) {
+    return (uint32_t)(((uint64_t)bi * TM + 1) / TN);
+}
+
+// Map a linear tile index to (bi, bj).
+__device__ inline void tile_coords(const DenseJob& job, uint64_t t, uint32_t TM, uint32_t TN,
+                                   uint32_t& bi, uint32_t& bj) {
+    if (!job.triangle) {
+        bi = (uint32_t)(t / job.n_bj);
+        bj = (uint32_t)(t % job.n_bj);
+        return;
+    }
+    uint32_t lo = 0, hi = job.n_bi;          // largest bi with prefix[bi] <= t
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (job.row_prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    bi = lo;
+    bj = tri_jstart(lo, TM, TN) + (uint32_t)(t - job.row_prefix[lo]);
+}
+
+// ---- launchers (one per kernel family) ---------------------------------------
+struct TileShape { uint32_t tm, tn; };
+
+TileShape popc_tile_shape();
+int launch_dense_popc(const DenseJob& job, cudaStream_t stream);
+TileShape csa_tile_shape();
+int launch_dense_csa(const DenseJob& job, cudaStream_t stream);
+TileShape umma_tile_shape();
+int launch_dense_umma(const DenseJob& job, cudaStream_t stream);
+// UMMA needs at least one full K step of 128 bits and 16-byte aligned rows.
+bool umma_supports(const DenseJob& job);
+
+int launch_synth_uniform(uint64_t* d_rows, uint64_t n_rows, uint64_t stride, uint32_t M,
+                         uint32_t n_draws, uint64_t seed, uint64_t row0, cudaStream_t stream);
+int launch_synth_geno(uint64_t* d_rows, uint64_t n_rows, uint64_t stride, uint32_t M,
+                      uint64_t seed, uint64_t row0, cudaStream_t stream);
+int launch_scatter_positions(uint64_t* d_rows, uint64_t stride, const uint32_t* d_pos,
+                             const uint64_t* d_off, uint64_t n_rows, cudaStream_t stream);
+
+// ---- small device helpers ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace storm

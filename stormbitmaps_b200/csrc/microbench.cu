@@ -1,0 +1,96 @@
+// microbench.cu -- issue-rate micro-benchmarks for the CUDA-core roofline.
+//
+// MEASURED_PEAKS.json carries only the HBM and bf16 peaks; the CUDA-core tile
+// kernels are bound by the POPC (and, for the carry-save variant, the ALU) pipe,
+// so their roofline denominators are measured here on the device itself
+// (SURVEY.md section 7.3 item 1).  Each kernel runs 8 independent dependency
+// chains per thread, 16 warps per SM, long enough to amortise the launch.
+#include "common.cuh"
+
+namespace storm {
+namespace {
+
+constexpr int MB_THREADS = 256;
+constexpr int MB_UNROLL = 16;
+
+template <int KIND>
+__global__ void __launch_bounds__(MB_THREADS) mb_kernel(uint32_t* out, int iters, uint32_t seed, long long* cycles) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = seed * 2654435761u + threadIdx.x * 97u + i * 7919u + blockIdx.x;
+    const uint32_t a = seed | 1u, b = ~seed;
+    const long long c0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < MB_UNROLL; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (KIND == 0) {
+                    asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));
+                } else if (KIND == 1) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+                } else if (KIND == 2) {
+                    asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
+                } else {   // 1 POPC : 2 LOP3, the direct AND+popcount mix
+                    if ((i & 3) == 0) asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));
+                    else if ((i & 3) != 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b));
+                }
+            }
+        }
+    }
+    const long long c1 = clock64();
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= x[i];
+    if (r == 0x12345678u) out[0] = r;                 // keep the chains alive
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = c1 - c0;
+}
+
+template <int KIND>
+int run_kind(double* rate, double* mhz, double ops_per_inner) {
+    int dev = 0, sms = 0;
+    STORM_CUDA_TRY(cudaGetDevice(&dev));
+    STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint32_t* d_out = nullptr; long long* d_cyc = nullptr;
+    STORM_CUDA_TRY(cudaMalloc(&d_out, 4));
+    STORM_CUDA_TRY(cudaMalloc(&d_cyc, 8));
+    cudaEvent_t e0, e1;
+    STORM_CUDA_TRY(cudaEventCreate(&e0));
+    STORM_CUDA_TRY(cudaEventCreate(&e1));
+    const int grid = sms * 2, iters = 4096;
+    double best = 0, best_mhz = 0;
+    for (int rep = 0; rep < 4; ++rep) {                // rep 0 is the warm-up
+        STORM_CUDA_TRY(cudaEventRecord(e0));
+        mb_kernel<KIND><<<grid, MB_THREADS>>>(d_out, iters, 12345u + rep, d_cyc);
+        STORM_CUDA_TRY(cudaEventRecord(e1));
+        STORM_CUDA_TRY(cudaEventSynchronize(e1));
+        count_launch();
+        float ms = 0;
+        STORM_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        long long cyc = 0;
+        STORM_CUDA_TRY(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+        const double ops = (double)grid * MB_THREADS * iters * MB_UNROLL * ops_per_inner;
+        const double r = ops / (ms * 1e-3);
+        if (rep > 0 && r > best) { best = r; best_mhz = (double)cyc / (ms * 1e-3) / 1e6; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out); cudaFree(d_cyc);
+    *rate = best;
+    if (mhz) *mhz = best_mhz;
+    return STORM_B200_OK;
+}
+
+}  // namespace
+}  // namespace storm
+
+extern "C" int STORM_b200_microbench(int kind, double* rate, double* sm_mhz) {
+    using namespace storm;
+    if (!rate) { set_error("rate is NULL"); return STORM_B200_EINVAL; }
+    switch (kind) {
+        case 0: return run_kind<0>(rate, sm_mhz, 8.0);
+        case 1: return run_kind<1>(rate, sm_mhz, 8.0);
+        case 2: return run_kind<2>(rate, sm_mhz, 8.0);
+        case 3: return run_kind<3>(rate, sm_mhz, 6.0);   // 2 POPC + 4 LOP3 per inner step
+        default: set_error("unknown microbench kind %d", kind); return STORM_B200_EINVAL;
+    }
+}

@@ -1,0 +1,38 @@
+// runtime.h -- host-side helpers shared by the C-ABI translation units.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace storm {
+
+int require_device();
+int default_kernel();
+
+TileShape tile_shape_for(int kernel);
+uint64_t triangle_prefix(uint64_t n_rows, TileShape ts, std::vector<uint64_t>* prefix, uint32_t* n_bi, uint32_t* n_bj);
+void shard_range(uint64_t n_tiles, uint32_t shard, uint32_t n_shards, uint64_t* begin, uint64_t* end);
+int resolve_kernel(int kernel, const DenseJob& job);
+int launch_dense(int kernel, const DenseJob& job, cudaStream_t stream);
+
+// Upper-triangle total of a device matrix (shard of the tile raster), accumulated into *d_total.
+int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
+                   uint32_t shard, uint32_t n_shards, int kernel, uint64_t* d_total, cudaStream_t stream);
+// All pairs of A rows x B rows (optionally only global j > i), counts and/or total.
+int pairw_rect(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off,
+               const uint64_t* dB, uint64_t nB, uint64_t strideB, uint64_t j_off,
+               uint32_t n_words, int strict_upper, int kernel,
+               uint32_t* d_out, uint64_t ld, uint64_t* d_total, cudaStream_t stream);
+
+// Sparse-row probe (storm.c:108-129) for the contiguous *_list entry points: pairs
+// (s, x) where s walks `d_sparse_rows` and x every row that pairs with it once.
+int launch_contig_probe(const uint64_t* d_rows, uint64_t stride, uint64_t n_rows,
+                        const uint32_t* d_is_sparse, const uint32_t* d_sparse_rows, uint64_t n_sparse,
+                        const uint32_t* d_pos, const uint64_t* d_pos_off,
+                        unsigned long long* d_total, cudaStream_t stream);
+// Gather rows idx[0..n) of src into a compact arena dst (same stride).
+int launch_gather_rows(uint64_t* dst, const uint64_t* src, uint64_t stride, const uint32_t* d_idx, uint64_t n,
+                       cudaStream_t stream);
+
+}  // namespace storm

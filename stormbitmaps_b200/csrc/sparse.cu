@@ -1,0 +1,646 @@
+// sparse.cu -- STORM_t: the Roaring-like sparse model.
+//
+// Host side: the public containers of storm.h:158-178 rebuilt from scratch
+// (reference builders: storm.c:398-569 blocks, :659-758 rows, :827-875 top).
+// Device side: a flattened mirror (CSR of blocks + one u16 pool + one bitmap
+// pool) and the pairwise kernel that replaces storm.c:877-961 with its per-block
+// 4-way dispatch (storm.c:618-656) and block-id merge (storm.c:75-106, 790-814).
+//
+// Kernel shape: one CTA owns row i and a slice of partner
+// rows j.  Unless row i is tiny, its blocks are expanded once into shared-memory
+// bitmaps (8 KiB per block); each warp then walks partner rows, merges the two
+// sorted block-id lists and, per shared block, dispatches on density:
+//     j list            -> probe j's values into i's shared bitmap
+//     j bitmap, i list (<= 256 values) -> probe i's values into j's global bitmap
+//     j bitmap otherwise -> AND + POPC over the 1024 words
+//     i tiny (<= 64 values in the row, never expanded):
+//         j bitmap      -> probe i's values into j's bitmap
+//         j list        -> sorted-list search intersection (the GPU form of the
+//                          reference's merge, storm.c:4-73)
+// All four give the exact |i AND j| for sorted unique inputs; the reference's
+// probe defect D1 (storm.c:636,644) is not reproduced.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "runtime.h"
+
+namespace storm {
+namespace {
+
+constexpr uint32_t BLOCK_BITS = STORM_DEFAULT_BLOCK_SIZE;          // 65536
+constexpr uint32_t BLOCK_WORDS = BLOCK_BITS / 64;                  // 1024
+constexpr uint32_t LIST_THRESHOLD = STORM_DEFAULT_SCALAR_THRESHOLD;  // 4096
+constexpr uint32_t BITMAP_FLAG = 0x80000000u;
+
+constexpr int SP_THREADS = 256;
+constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr uint32_t SP_SLICE = 1024;        // partner rows per CTA
+constexpr uint32_t SP_MAXB_CAP = 24;       // row-i blocks resident in shared memory per pass (24 x 8 KiB)
+constexpr uint32_t SP_TINY_NNZ = 64;       // rows with <= this many values are never expanded
+constexpr uint32_t SP_PROBE_I_MAX = 256;   // i-list probes into a j-bitmap up to this length
+
+// Flattened device view of one STORM_t.
+struct SparseView {
+    const uint32_t* row_ptr;   // n_rows + 1: first block of each row
+    const uint32_t* row_nnz;   // values handed to the builder per row
+    const uint32_t* blk_id;    // block index (value / 65536), ascending within a row
+    const uint32_t* blk_len;   // number of values; BITMAP_FLAG set for bitmap blocks
+    const uint64_t* blk_off;   // list: element offset into `lists`; bitmap: word offset into `words`
+    const uint16_t* lists;
+    const uint64_t* words;
+    uint32_t n_rows;
+};
+
+struct SparseJob {
+    SparseView A, B;
+    uint64_t i0, i1, j0, j1;
+    int strict_upper;          // same container: only pairs with j > i
+    uint32_t shard, n_shards;  // rows i are dealt round-robin to shards
+    uint32_t maxb;             // shared-memory slots (<= SP_MAXB_CAP)
+    uint32_t* out; uint64_t ld;
+    unsigned long long* total;
+};
+
+__device__ __forceinline__ uint32_t probe_bit64(const uint64_t* words, uint32_t v) {
+    return (uint32_t)((words[v >> 6] >> (v & 63)) & 1ull);
+}
+
+// |a-list ∩ b-list| contribution of one lane: values a[k], k = lane, lane+32, ... searched in sorted b.
+__device__ __forceinline__ uint32_t search_intersect(const uint16_t* a, uint32_t na, const uint16_t* b, uint32_t nb, uint32_t lane) {
+    uint32_t c = 0;
+    for (uint32_t k = lane; k < na; k += 32) {
+        const uint16_t v = a[k];
+        uint32_t lo = 0, hi = nb;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (b[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        c += (lo < nb && b[lo] == v);
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(SP_THREADS) sparse_pairs_kernel(const SparseJob job) {
+    extern __shared__ __align__(16) uint32_t s_bits[];            // maxb x 2048 32-bit words
+    __shared__ uint32_t s_id[SP_MAXB_CAP], s_len[SP_MAXB_CAP];
+    __shared__ uint64_t s_off[SP_MAXB_CAP];
+    __shared__ unsigned long long warp_part[SP_WARPS];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t i = job.i0 + job.shard + (uint64_t)blockIdx.x * job.n_shards;
+    if (i >= job.i1) return;
+    uint64_t jbeg = job.j0;
+    if (job.strict_upper && jbeg < i + 1) jbeg = i + 1;
+    const uint64_t js0 = jbeg + (uint64_t)blockIdx.y * SP_SLICE;
+    if (js0 >= job.j1) return;
+    const uint64_t js1 = min(js0 + (uint64_t)SP_SLICE, job.j1);
+
+    const SparseView& A = job.A;
+    const SparseView& B = job.B;
+    const uint32_t rb = A.row_ptr[i], nbi = A.row_ptr[i + 1] - rb;
+    if (nbi == 0) return;                                          // empty row: all counts 0 (out is pre-zeroed)
+    const bool tiny = A.row_nnz[i] <= SP_TINY_NNZ;
+
+    unsigned long long cta_lane_total = 0;
+    for (uint32_t g = 0; g < nbi; g += job.maxb) {
+        const uint32_t ng = min(job.maxb, nbi - g);
+        __syncthreads();                                           // previous pass is done with shared memory
+        if (tid < ng) {
+            s_id[tid] = A.blk_id[rb + g + tid];
+            s_len[tid] = A.blk_len[rb + g + tid];
+            s_off[tid] = A.blk_off[rb + g + tid];
+        }
+        if (!tiny) {
+            uint4* z = reinterpret_cast<uint4*>(s_bits);
+            for (uint32_t k = tid; k < ng * 512; k += SP_THREADS) z[k] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        if (!tiny) {
+            for (uint32_t s = 0; s < ng; ++s) {
+                const uint32_t len = s_len[s];
+                if (len & BITMAP_FLAG) {
+                    const uint4* src = reinterpret_cast<const uint4*>(A.words + s_off[s]);
+                    uint4* dst = reinterpret_cast<uint4*>(s_bits + s * 2048);
+                    for (uint32_t k = tid; k < 512; k += SP_THREADS) dst[k] = src[k];
+                } else {
+                    const uint16_t* src = A.lists + s_off[s];
+                    for (uint32_t k = tid; k < len; k += SP_THREADS) {
+                        const uint32_t v = src[k];
+                        atomicOr(&s_bits[s * 2048 + (v >> 5)], 1u << (v & 31));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        for (uint64_t j = js0 + warp; j < js1; j += SP_WARPS) {
+            uint32_t c = 0;
+            uint32_t y = B.row_ptr[j];
+            const uint32_t ye = B.row_ptr[j + 1];
+            uint32_t x = 0;
+            while (x < ng && y < ye) {                             // storm.c:75-106: merge of sorted block ids
+                const uint32_t ida = s_id[x], idb = B.blk_id[y];
+                if (ida < idb) { ++x; continue; }
+                if (ida > idb) { ++y; continue; }
+                const uint32_t la = s_len[x], lb = B.blk_len[y];
+                const uint32_t na = la & ~BITMAP_FLAG, nb = lb & ~BITMAP_FLAG;
+                const uint64_t ob = B.blk_off[y];
+                if (lb & BITMAP_FLAG) {
+                    const uint64_t* bw = B.words + ob;
+                    if (!(la & BITMAP_FLAG) && (tiny || na <= SP_PROBE_I_MAX)) {
+                        const uint16_t* al = A.lists + s_off[x];   // list -> bitmap probe (storm.c:632-646, exact)
+                        for (uint32_t k = lane; k < na; k += 32) c += probe_bit64(bw, al[k]);
+                    } else {                                       // bitmap x bitmap (storm.c:648-650)
+                        const uint4* b4 = reinterpret_cast<const uint4*>(bw);
+                        const uint4* a4 = reinterpret_cast<const uint4*>(s_bits + x * 2048);
+#pragma unroll 4
+                        for (uint32_t k = lane; k < 512; k += 32) {
+                            const uint4 p = b4[k], q = a4[k];
+                            c += __popc(p.x & q.x) + __popc(p.y & q.y) + __popc(p.z & q.z) + __popc(p.w & q.w);
+                        }
+                    }
+                } else {
+                    const uint16_t* bl = B.lists + ob;
+                    if (tiny) {                                    // list x list (storm.c:628-630)
+                        c += search_intersect(A.lists + s_off[x], na, bl, nb, lane);
+                    } else {                                       // j's values probed into i's shared bitmap
+                        const uint32_t* ab = s_bits + x * 2048;
+                        for (uint32_t k = lane; k < nb; k += 32) {
+                            const uint32_t v = bl[k];
+                            c += (ab[v >> 5] >> (v & 31)) & 1u;
+                        }
+                    }
+                }
+                ++x; ++y;
+            }
+            cta_lane_total += c;
+            if (job.out) {
+                c = (uint32_t)warp_sum(c);
+                if (lane == 0) {
+                    uint32_t* o = job.out + (i - job.i0) * job.ld + (j - job.j0);
+                    *o = (g == 0) ? c : *o + c;
+                }
+            }
+        }
+    }
+    if (job.total) {
+        const unsigned long long w = warp_sum(cta_lane_total);
+        if (lane == 0) warp_part[warp] = w;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t = 0;
+            for (int k = 0; k < SP_WARPS; ++k) t += warp_part[k];
+            if (t) atomicAdd(job.total, t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// device mirror
+// ---------------------------------------------------------------------------------
+struct StormState {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    bool dirty = true;
+    uint32_t n_rows = 0, max_blocks = 0;
+    uint32_t *d_row_ptr = nullptr, *d_row_nnz = nullptr, *d_blk_id = nullptr, *d_blk_len = nullptr;
+    uint64_t* d_blk_off = nullptr; uint16_t* d_lists = nullptr; uint64_t* d_words = nullptr;
+    unsigned long long* d_total = nullptr; unsigned long long* h_total = nullptr;
+};
+
+struct DeviceGuard {
+    int prev = -1; bool active = false;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); active = true; }
+    }
+    ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+};
+
+inline StormState* state_of(const STORM_t* s) { return static_cast<StormState*>(s->b200); }
+
+void free_mirror(StormState* st) {
+    for (void* p : {(void*)st->d_row_ptr, (void*)st->d_row_nnz, (void*)st->d_blk_id, (void*)st->d_blk_len,
+                    (void*)st->d_blk_off, (void*)st->d_lists, (void*)st->d_words})
+        if (p) cudaFree(p);
+    st->d_row_ptr = st->d_row_nnz = st->d_blk_id = st->d_blk_len = nullptr;
+    st->d_blk_off = nullptr; st->d_lists = nullptr; st->d_words = nullptr;
+}
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src, cudaStream_t stream) {
+    const size_t n = std::max<size_t>(src.size(), 1);
+    STORM_CUDA_TRY(cudaMalloc(dst, n * sizeof(T)));
+    if (!src.empty()) STORM_CUDA_TRY(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return STORM_B200_OK;
+}
+
+int ensure_state(StormState* st) {
+    if (st->device >= 0 && st->d_total) return STORM_B200_OK;
+    int rc = require_device();
+    if (rc) return rc;
+    STORM_CUDA_TRY(cudaGetDevice(&st->device));
+    STORM_CUDA_TRY(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    STORM_CUDA_TRY(cudaMalloc(&st->d_total, 8));
+    STORM_CUDA_TRY(cudaMallocHost(&st->h_total, 8));
+    return STORM_B200_OK;
+}
+
+// Flatten the host containers and upload them (whole-container rebuild on change).
+int sync_mirror(const STORM_t* s, StormState* st) {
+    int rc = ensure_state(st);
+    if (rc) return rc;
+    if (!st->dirty && st->n_rows == s->n_conts) return STORM_B200_OK;
+    free_mirror(st);
+    std::vector<uint32_t> row_ptr(s->n_conts + 1, 0), row_nnz(s->n_conts, 0), blk_id, blk_len;
+    std::vector<uint64_t> blk_off, words;
+    std::vector<uint16_t> lists;
+    uint32_t max_blocks = 0;
+    for (uint32_t r = 0; r < s->n_conts; ++r) {
+        const STORM_bitmap_cont_t* row = &s->conts[r];
+        row_ptr[r] = (uint32_t)blk_id.size();
+        max_blocks = std::max(max_blocks, row->n_bitmaps);
+        for (uint32_t b = 0; b < row->n_bitmaps; ++b) {
+            const STORM_bitmap_t* k = &row->bitmaps[b];
+            blk_id.push_back(k->id);
+            if (k->n_bitmap) {
+                blk_len.push_back(k->n_bits_set | BITMAP_FLAG);
+                blk_off.push_back(words.size());
+                words.insert(words.end(), k->data, k->data + BLOCK_WORDS);
+                row_nnz[r] += k->n_bits_set;
+            } else {
+                blk_len.push_back(k->n_scalar);
+                while (lists.size() % 8) lists.push_back(0);       // 16-byte aligned lists
+                blk_off.push_back(lists.size());
+                lists.insert(lists.end(), k->scalar, k->scalar + k->n_scalar);
+                row_nnz[r] += k->n_scalar;
+            }
+        }
+    }
+    row_ptr[s->n_conts] = (uint32_t)blk_id.size();
+    if ((rc = upload(&st->d_row_ptr, row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, row_nnz, st->stream)) ||
+        (rc = upload(&st->d_blk_id, blk_id, st->stream)) || (rc = upload(&st->d_blk_len, blk_len, st->stream)) ||
+        (rc = upload(&st->d_blk_off, blk_off, st->stream)) || (rc = upload(&st->d_lists, lists, st->stream)) ||
+        (rc = upload(&st->d_words, words, st->stream)))
+        return rc;
+    STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));              // host vectors die here
+    st->n_rows = s->n_conts;
+    st->max_blocks = max_blocks;
+    st->dirty = false;
+    return STORM_B200_OK;
+}
+
+SparseView view_of(const StormState* st) {
+    return SparseView{st->d_row_ptr, st->d_row_nnz, st->d_blk_id, st->d_blk_len, st->d_blk_off, st->d_lists, st->d_words, st->n_rows};
+}
+
+int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t stream) {
+    SparseJob job = job_in;
+    if (job.i1 <= job.i0 || job.j1 <= job.j0) return STORM_B200_OK;
+    job.maxb = std::max<uint32_t>(1, std::min<uint32_t>(max_blocks, SP_MAXB_CAP));
+    const size_t smem = (size_t)job.maxb * 8192;
+    STORM_CUDA_TRY(cudaFuncSetAttribute(sparse_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_MAXB_CAP * 8192)));
+    const uint64_t rows_i = (job.i1 - job.i0 + job.n_shards - 1 - job.shard) / job.n_shards;   // rows of this shard
+    if (rows_i == 0) return STORM_B200_OK;
+    const uint64_t slices = (job.j1 - job.j0 + SP_SLICE - 1) / SP_SLICE;
+    if (slices > 65535) { set_error("too many partner rows for one launch (%llu)", (unsigned long long)(job.j1 - job.j0)); return STORM_B200_EINVAL; }
+    dim3 grid((unsigned)rows_i, (unsigned)slices);
+    sparse_pairs_kernel<<<grid, SP_THREADS, smem, stream>>>(job);
+    STORM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return STORM_B200_OK;
+}
+
+uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
+    if (s == nullptr) return (uint64_t)-1;                          // storm.c:878,898
+    if (s->n_conts < 2) return 0;
+    StormState* st = state_of(s);
+    DeviceGuard guard(st->device);
+    if (sync_mirror(s, st)) return (uint64_t)-1;
+    if (cudaMemsetAsync(st->d_total, 0, 8, st->stream) != cudaSuccess) return (uint64_t)-1;
+    SparseJob job{};
+    job.A = job.B = view_of(st);
+    job.i0 = 0; job.i1 = s->n_conts; job.j0 = 0; job.j1 = s->n_conts;
+    job.strict_upper = 1;
+    job.shard = shard; job.n_shards = n_shards;
+    job.total = st->d_total;
+    if (launch_sparse(job, st->max_blocks, st->stream)) return (uint64_t)-1;
+    if (cudaMemcpyAsync(st->h_total, st->d_total, 8, cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
+        cudaStreamSynchronize(st->stream) != cudaSuccess) {
+        set_error("STORM_t query failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return (uint64_t)-1;
+    }
+    return *st->h_total;
+}
+
+void mark_dirty(STORM_t* s) { if (s && s->b200) state_of(s)->dirty = true; }
+
+}  // namespace
+}  // namespace storm
+
+// =================================================================================
+// C ABI: host containers
+// =================================================================================
+using namespace storm;
+
+extern "C" {
+
+// ---- block (storm.c:398-569) -------------------------------------------------------
+void STORM_bitmap_init(STORM_bitmap_t* b) {                                // storm.c:416-430
+    if (b == nullptr) return;
+    memset(b, 0, sizeof(*b));
+    b->own_data = 1;
+    b->own_scalar = 1;
+}
+
+STORM_bitmap_t* STORM_bitmap_new(void) {                                    // storm.c:398-413
+    void* p = nullptr;
+    if (posix_memalign(&p, 64, sizeof(STORM_bitmap_t))) return nullptr;
+    STORM_bitmap_init((STORM_bitmap_t*)p);
+    return (STORM_bitmap_t*)p;
+}
+
+static void bitmap_release(STORM_bitmap_t* b) {
+    if (b->own_data) free(b->data);
+    if (b->own_scalar) free(b->scalar);
+    b->data = nullptr; b->scalar = nullptr;
+}
+
+void STORM_bitmap_free(STORM_bitmap_t* b) {                                 // storm.c:433-438
+    if (b == nullptr) return;
+    bitmap_release(b);
+    free(b);
+}
+
+int STORM_bitmap_add(STORM_bitmap_t* b, const uint32_t* values, const uint32_t n_values) {   // storm.c:442-465
+    if (b == nullptr) return -1;
+    if (values == nullptr) return -2;
+    if (n_values == 0) return -3;
+    const uint32_t adjust = b->id * BLOCK_BITS;
+    if (b->data == nullptr) {
+        void* p = nullptr;
+        if (posix_memalign(&p, 64, BLOCK_WORDS * sizeof(uint64_t))) return -4;
+        memset(p, 0, BLOCK_WORDS * sizeof(uint64_t));
+        b->data = (uint64_t*)p;
+    }
+    b->n_bitmap = BLOCK_WORDS;
+    for (uint32_t i = 0; i < n_values; ++i) {
+        const uint32_t v = values[i] - adjust;
+        if (v >= BLOCK_BITS) return -5;                                   // reference: assert, compiled out
+        const uint64_t bit = 1ull << (v & 63);
+        b->n_bits_set += (b->data[v >> 6] & bit) == 0;
+        b->data[v >> 6] |= bit;
+    }
+    return (int)n_values;
+}
+
+int STORM_bitmap_add_scalar_only(STORM_bitmap_t* b, const uint32_t* values, const uint32_t n_values) {  // :521-558
+    if (b == nullptr) return -1;
+    if (values == nullptr) return -3;
+    if (n_values == 0) return -4;
+    const uint32_t need = b->n_scalar + n_values;
+    if (b->scalar == nullptr || need > b->m_scalar) {                     // capacity checked against the need (D9)
+        const uint32_t cap = std::max<uint32_t>(256, need + (need >> 2));
+        uint16_t* p = (uint16_t*)realloc(b->own_scalar ? b->scalar : nullptr, cap * sizeof(uint16_t));
+        if (p == nullptr) return -5;
+        b->scalar = p; b->m_scalar = cap; b->own_scalar = 1;
+    }
+    const uint32_t adjust = b->id * BLOCK_BITS;
+    b->n_scalar_set = 1;
+    uint32_t n = b->n_scalar;
+    for (uint32_t i = 0; i < n_values; ++i) {
+        const uint32_t v = values[i] - adjust;
+        if (v >= BLOCK_BITS) return -5;
+        b->scalar[n++] = (uint16_t)v;
+        ++b->n_bits_set;
+    }
+    b->n_scalar = n;
+    return (int)n_values;
+}
+
+int STORM_bitmap_clear(STORM_bitmap_t* b) {                                 // storm.c:561-569
+    if (b == nullptr) return -1;
+    if (b->data != nullptr) memset(b->data, 0, sizeof(uint64_t) * BLOCK_WORDS);
+    b->n_scalar = 0;
+    b->n_bits_set = 0;
+    b->n_bitmap = 0;
+    return 1;
+}
+
+uint32_t STORM_bitmap_serialized_size(STORM_bitmap_t* b) {                  // storm.c:372-381
+    uint32_t total = (uint32_t)sizeof(uint64_t) * b->n_bitmap;
+    if (b->n_scalar_set) total += (uint32_t)sizeof(uint16_t) * b->n_scalar;
+    return total + 4 * (uint32_t)sizeof(uint32_t);
+}
+
+// ---- row (storm.c:659-824) ---------------------------------------------------------
+void STORM_bitmap_cont_init(STORM_bitmap_cont_t* r) {                       // storm.c:670-677
+    if (r == nullptr) return;
+    memset(r, 0, sizeof(*r));
+}
+
+STORM_bitmap_cont_t* STORM_bitmap_cont_new(void) {                          // storm.c:659-668
+    STORM_bitmap_cont_t* r = (STORM_bitmap_cont_t*)malloc(sizeof(STORM_bitmap_cont_t));
+    STORM_bitmap_cont_init(r);
+    return r;
+}
+
+static void cont_release(STORM_bitmap_cont_t* r) {
+    for (uint32_t i = 0; i < r->m_bitmaps; ++i) bitmap_release(&r->bitmaps[i]);
+    free(r->bitmaps);
+    free(r->block_ids);
+    r->bitmaps = nullptr; r->block_ids = nullptr; r->n_bitmaps = r->m_bitmaps = 0;
+}
+
+void STORM_bitmap_cont_free(STORM_bitmap_cont_t* r) {                       // storm.c:679-689
+    if (r == nullptr) return;
+    cont_release(r);
+    free(r);
+}
+
+static int cont_reserve(STORM_bitmap_cont_t* r, uint32_t need) {
+    if (need <= r->m_bitmaps) return 0;
+    const uint32_t cap = std::max<uint32_t>(need, r->m_bitmaps ? r->m_bitmaps + 8 : 2);   // :699,:728-735
+    void* p = nullptr;                                                     // STORM_bitmap_t is 64-byte aligned
+    if (posix_memalign(&p, 64, cap * sizeof(STORM_bitmap_t))) return -1;
+    if (r->bitmaps) memcpy(p, r->bitmaps, r->m_bitmaps * sizeof(STORM_bitmap_t));
+    free(r->bitmaps);
+    r->bitmaps = (STORM_bitmap_t*)p;
+    for (uint32_t i = r->m_bitmaps; i < cap; ++i) STORM_bitmap_init(&r->bitmaps[i]);
+    uint32_t* ids = (uint32_t*)realloc(r->block_ids, cap * sizeof(uint32_t));
+    if (ids == nullptr) return -1;
+    r->block_ids = ids;
+    r->m_bitmaps = cap;
+    return 0;
+}
+
+int STORM_bitmap_cont_add(STORM_bitmap_cont_t* r, const uint32_t* values, const uint32_t n_values) {  // :692-758
+    if (r == nullptr) return -1;
+    if (values == nullptr) return -2;
+    if (n_values == 0) return 0;
+    uint32_t start = 0;
+    while (start < n_values) {
+        const uint32_t target = values[start] / BLOCK_BITS;
+        uint32_t stop = start;
+        while (stop < n_values && values[stop] / BLOCK_BITS == target) ++stop;
+        if (cont_reserve(r, r->n_bitmaps + 1)) return -3;
+        STORM_bitmap_t* x = &r->bitmaps[r->n_bitmaps];
+        x->id = target;
+        r->block_ids[r->n_bitmaps] = target;
+        int rc;
+        if (stop - start < LIST_THRESHOLD) rc = STORM_bitmap_add_scalar_only(x, values + start, stop - start);  // :745-746
+        else rc = STORM_bitmap_add(x, values + start, stop - start);                                          // :747-748
+        if (rc < 0) return -3;
+        ++r->n_bitmaps;
+        r->prev_inserted_value = values[stop - 1];
+        start = stop;
+    }
+    return 1;
+}
+
+int STORM_bitmap_cont_clear(STORM_bitmap_cont_t* r) {                       // storm.c:816-824
+    if (r == nullptr) return -1;
+    for (uint32_t i = 0; i < r->n_bitmaps; ++i) STORM_bitmap_clear(&r->bitmaps[i]);
+    r->n_bitmaps = 0;
+    r->prev_inserted_value = 0;
+    return 1;
+}
+
+uint32_t STORM_bitmap_cont_serialized_size(STORM_bitmap_cont_t* r) {        // storm.c:384-394
+    uint32_t total = 0;
+    if (r->bitmaps != nullptr)
+        for (uint32_t i = 0; i < r->n_bitmaps; ++i) total += STORM_bitmap_serialized_size(&r->bitmaps[i]);
+    return total + (uint32_t)sizeof(uint32_t) * r->n_bitmaps + 3 * (uint32_t)sizeof(uint32_t);
+}
+
+// ---- top (storm.c:827-973) ---------------------------------------------------------
+STORM_t* STORM_new(void) {                                                  // storm.c:827-834
+    STORM_t* s = (STORM_t*)calloc(1, sizeof(STORM_t));
+    if (s == nullptr) return nullptr;
+    StormState* st = new (std::nothrow) StormState();
+    if (st == nullptr) { free(s); return nullptr; }
+    s->b200 = st;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) cudaGetDevice(&st->device); else cudaGetLastError();
+    return s;
+}
+
+void STORM_free(STORM_t* s) {                                               // storm.c:836-842 (+ D8)
+    if (s == nullptr) return;
+    StormState* st = state_of(s);
+    if (st) {
+        DeviceGuard guard(st->device);
+        if (st->stream) cudaStreamSynchronize(st->stream);
+        free_mirror(st);
+        if (st->d_total) cudaFree(st->d_total);
+        if (st->h_total) cudaFreeHost(st->h_total);
+        if (st->stream) cudaStreamDestroy(st->stream);
+        delete st;
+    }
+    for (uint32_t i = 0; i < s->m_conts; ++i) cont_release(&s->conts[i]);
+    free(s->conts);
+    free(s);
+}
+
+int STORM_add(STORM_t* s, const uint32_t* values, const uint32_t n_values) {   // storm.c:844-866
+    if (s == nullptr) return -1;
+    if (s->n_conts == s->m_conts) {
+        const uint32_t cap = s->m_conts + 1024;
+        STORM_bitmap_cont_t* c = (STORM_bitmap_cont_t*)realloc(s->conts, cap * sizeof(STORM_bitmap_cont_t));
+        if (c == nullptr) return -3;
+        for (uint32_t i = s->m_conts; i < cap; ++i) STORM_bitmap_cont_init(&c[i]);
+        s->conts = c; s->m_conts = cap;
+    }
+    STORM_bitmap_cont_add(&s->conts[s->n_conts++], values, n_values);      // an empty list still appends a row
+    mark_dirty(s);
+    return 1;
+}
+
+int STORM_clear(STORM_t* s) {                                               // storm.c:868-875
+    if (s == nullptr) return -1;
+    for (uint32_t i = 0; i < s->n_conts; ++i) STORM_bitmap_cont_clear(&s->conts[i]);
+    s->n_conts = 0;
+    mark_dirty(s);
+    return 1;
+}
+
+uint64_t STORM_serialized_size(const STORM_t* s) {                          // storm.c:963-973
+    if (s == nullptr) return 0;
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < s->n_conts; ++i) tot += STORM_bitmap_cont_serialized_size(&s->conts[i]);
+    return tot + 2 * sizeof(uint32_t);
+}
+
+uint64_t STORM_pairw_intersect_cardinality(STORM_t* s) {                    // storm.c:877-895
+    return storm_query(s, 0, 1);
+}
+
+uint64_t STORM_pairw_intersect_cardinality_blocked(STORM_t* s, uint32_t bsize) {   // storm.c:897-961
+    (void)bsize;   // 0 = auto on the CPU (storm.c:903-914); a hint only, the total does not depend on it
+    return storm_query(s, 0, 1);
+}
+
+uint64_t STORM_b200_storm_pairw_shard(STORM_t* s, uint32_t shard, uint32_t n_shards) {
+    if (s == nullptr) return (uint64_t)-1;
+    if (n_shards == 0 || shard >= n_shards) { set_error("shard %u of %u", shard, n_shards); return (uint64_t)-1; }
+    return storm_query(s, shard, n_shards);
+}
+
+int STORM_b200_storm_pairw_rect(STORM_t* s, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, uint32_t* out) {
+    if (s == nullptr || out == nullptr) { set_error("NULL argument"); return STORM_B200_EINVAL; }
+    if (i0 > i1 || j0 > j1 || i1 > s->n_conts || j1 > s->n_conts) { set_error("rectangle outside the %u rows", s->n_conts); return STORM_B200_EINVAL; }
+    if (i0 == i1 || j0 == j1) return STORM_B200_OK;
+    StormState* st = state_of(s);
+    DeviceGuard guard(st->device);
+    int rc = sync_mirror(s, st);
+    if (rc) return rc;
+    const uint64_t ni = i1 - i0, nj = j1 - j0;
+    uint32_t* d_out = nullptr;
+    if (cudaMalloc(&d_out, ni * nj * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); set_error("device allocation for %llu x %llu counts failed", (unsigned long long)ni, (unsigned long long)nj); return STORM_B200_ENOMEM; }
+    SparseJob job{};
+    job.A = job.B = view_of(st);
+    job.i0 = i0; job.i1 = i1; job.j0 = j0; job.j1 = j1;
+    job.strict_upper = 1; job.shard = 0; job.n_shards = 1;
+    job.out = d_out; job.ld = nj;
+    if (cudaMemsetAsync(d_out, 0, ni * nj * sizeof(uint32_t), st->stream) != cudaSuccess) rc = STORM_B200_ECUDA;
+    if (!rc) rc = launch_sparse(job, st->max_blocks, st->stream);
+    if (!rc && (cudaMemcpyAsync(out, d_out, ni * nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
+                cudaStreamSynchronize(st->stream) != cudaSuccess)) {
+        set_error("STORM_t rect query failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = STORM_B200_ECUDA;
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+// Declared in the reference (storm.h:229) but never defined there (storm.c:975).
+uint64_t STORM_intersect_cardinality_square(const STORM_t* STORM_RESTRICT s1, const STORM_t* STORM_RESTRICT s2) {
+    if (s1 == nullptr || s2 == nullptr) return (uint64_t)-1;
+    if (s1->n_conts == 0 || s2->n_conts == 0) return 0;
+    StormState* a = state_of(s1);
+    StormState* b = state_of(s2);
+    DeviceGuard guard(a->device);
+    if (sync_mirror(s1, a) || sync_mirror(s2, b)) return (uint64_t)-1;
+    if (a->device != b->device) { set_error("the two containers live on different devices"); return (uint64_t)-1; }
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) return (uint64_t)-1;
+    if (cudaMemsetAsync(a->d_total, 0, 8, a->stream) != cudaSuccess) return (uint64_t)-1;
+    SparseJob job{};
+    job.A = view_of(a); job.B = view_of(b);
+    job.i0 = 0; job.i1 = s1->n_conts; job.j0 = 0; job.j1 = s2->n_conts;
+    job.strict_upper = 0; job.shard = 0; job.n_shards = 1;
+    job.total = a->d_total;
+    if (launch_sparse(job, a->max_blocks, a->stream)) return (uint64_t)-1;
+    if (cudaMemcpyAsync(a->h_total, a->d_total, 8, cudaMemcpyDeviceToHost, a->stream) != cudaSuccess ||
+        cudaStreamSynchronize(a->stream) != cudaSuccess) {
+        set_error("square query failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return (uint64_t)-1;
+    }
+    return *a->h_total;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""CPU tests of the drop-in boundary: the library loads without a GPU, exports
+every symbol include/*.h declares, keeps the reference's public struct layout,
+mirrors its host-side error conventions, and fails loudly (no CPU fallback) when
+a query needs a device that is not there."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from stormbitmaps_b200 import build
+    build.build()
+    import stormbitmaps_b200 as sb
+    return sb.load()
+
+
+def _declared_functions(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(STORM_[A-Za-z0-9_]+)\s*\(", text)) - {"STORM_ALIGN"}
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from stormbitmaps_b200 import _lib
+    declared = _declared_functions("storm.h") | _declared_functions("storm_b200.h")
+    assert len(declared) > 50
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, f"declared in include/*.h but not exported: {missing}"
+    unbound = sorted(declared - set(_lib.SIGNATURES))
+    assert not unbound, f"declared but without a ctypes signature: {unbound}"
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    assert "orc_" not in exported, "the product library must not contain oracle code"
+
+
+LAYOUT_C = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "storm.h"
+#define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  printf("sizeof.STORM_contiguous_t %zu\n", sizeof(STORM_contiguous_t));
+  P(STORM_contiguous_t, data); P(STORM_contiguous_t, scalar); P(STORM_contiguous_t, n_scalar);
+  P(STORM_contiguous_t, bitmaps); P(STORM_contiguous_t, n_data); P(STORM_contiguous_t, m_data);
+  P(STORM_contiguous_t, tot_scalar); P(STORM_contiguous_t, m_scalar); P(STORM_contiguous_t, vector_length);
+  P(STORM_contiguous_t, n_bitmaps_vector); P(STORM_contiguous_t, intsec_func); P(STORM_contiguous_t, alignment);
+  P(STORM_contiguous_t, scalar_cutoff); P(STORM_contiguous_t, b200);
+  printf("sizeof.STORM_contiguous_bitmap_t %zu\n", sizeof(STORM_contiguous_bitmap_t));
+  P(STORM_contiguous_bitmap_t, data); P(STORM_contiguous_bitmap_t, scalar); P(STORM_contiguous_bitmap_t, n_scalar);
+  printf("sizeof.STORM_t %zu\n", sizeof(STORM_t));
+  P(STORM_t, conts); P(STORM_t, n_conts); P(STORM_t, m_conts); P(STORM_t, b200);
+  printf("sizeof.STORM_bitmap_cont_t %zu\n", sizeof(STORM_bitmap_cont_t));
+  P(STORM_bitmap_cont_t, bitmaps); P(STORM_bitmap_cont_t, block_ids); P(STORM_bitmap_cont_t, n_bitmaps);
+  P(STORM_bitmap_cont_t, m_bitmaps); P(STORM_bitmap_cont_t, prev_inserted_value);
+  printf("sizeof.STORM_bitmap_t %zu\n", sizeof(STORM_bitmap_t));
+  printf("alignof.STORM_bitmap_t %zu\n", _Alignof(STORM_bitmap_t));
+  P(STORM_bitmap_t, data); P(STORM_bitmap_t, scalar); P(STORM_bitmap_t, n_bits_set); P(STORM_bitmap_t, n_missing);
+  P(STORM_bitmap_t, m_scalar); P(STORM_bitmap_t, id);
+  return 0;
+}
+"""
+
+# offsets of the reference structs on x86-64 (gcc C99/C11 and g++).
+REFERENCE_LAYOUT = {
+    "STORM_contiguous_t.data": 0, "STORM_contiguous_t.scalar": 8, "STORM_contiguous_t.n_scalar": 16,
+    "STORM_contiguous_t.bitmaps": 24, "STORM_contiguous_t.n_data": 32, "STORM_contiguous_t.m_data": 40,
+    "STORM_contiguous_t.tot_scalar": 48, "STORM_contiguous_t.m_scalar": 56, "STORM_contiguous_t.vector_length": 64,
+    "STORM_contiguous_t.n_bitmaps_vector": 72, "STORM_contiguous_t.intsec_func": 80,
+    "STORM_contiguous_t.alignment": 88, "STORM_contiguous_t.scalar_cutoff": 92,
+    "STORM_contiguous_t.b200": 96,                      # appended after the reference's 96 bytes
+    "sizeof.STORM_contiguous_bitmap_t": 24, "STORM_contiguous_bitmap_t.data": 0,
+    "STORM_contiguous_bitmap_t.scalar": 8, "STORM_contiguous_bitmap_t.n_scalar": 16,
+    "STORM_t.conts": 0, "STORM_t.n_conts": 8, "STORM_t.m_conts": 12, "STORM_t.b200": 16,
+    "sizeof.STORM_bitmap_cont_t": 32, "STORM_bitmap_cont_t.bitmaps": 0, "STORM_bitmap_cont_t.block_ids": 8,
+    "STORM_bitmap_cont_t.n_bitmaps": 16, "STORM_bitmap_cont_t.m_bitmaps": 20,
+    "STORM_bitmap_cont_t.prev_inserted_value": 24,
+    "sizeof.STORM_bitmap_t": 128, "alignof.STORM_bitmap_t": 64, "STORM_bitmap_t.data": 0,
+    "STORM_bitmap_t.scalar": 64, "STORM_bitmap_t.n_bits_set": 76, "STORM_bitmap_t.n_missing": 84,
+    "STORM_bitmap_t.m_scalar": 88, "STORM_bitmap_t.id": 92,
+}
+
+
+@pytest.mark.parametrize("compiler,std", [("gcc", "-std=c11"), ("g++", "-std=c++17")])
+def test_public_struct_layout_matches_reference(compiler, std):
+    with tempfile.TemporaryDirectory() as d:
+        ext = ".c" if compiler == "gcc" else ".cpp"
+        src = os.path.join(d, "layout" + ext)
+        code = LAYOUT_C if compiler == "gcc" else LAYOUT_C.replace("_Alignof", "alignof")
+        open(src, "w").write(code)
+        exe = os.path.join(d, "layout")
+        subprocess.check_call([compiler, std, "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        got = dict((k, int(v)) for k, v in (l.split() for l in subprocess.check_output([exe], text=True).splitlines()))
+    for k, v in REFERENCE_LAYOUT.items():
+        assert got[k] == v, (k, got[k], v)
+
+
+def test_host_side_conventions_without_gpu(lib):
+    """storm.c:1001-1018,1031-1137,1139-1147,844-875: construction is pure host work."""
+    import stormbitmaps_b200 as sb
+    u32p = C.POINTER(C.c_uint32)
+    assert lib.STORM_contig_add(None, None, 0) == -1
+    assert lib.STORM_contig_clear(None) == -1
+    assert lib.STORM_contig_pairw_intersect_cardinality(None) == 2**64 - 1
+    assert lib.STORM_pairw_intersect_cardinality(None) == 2**64 - 1
+    assert lib.STORM_add(None, None, 0) == -1
+    c = sb.StormContiguous(65536)
+    assert lib.STORM_contig_add(c._h, None, 3) == -2
+    assert c.clear() == 0                                  # nothing allocated yet
+    assert c.add([]) == 0                                  # empty list: no row (D7)
+    assert c.add([1, 5, 9]) == 3
+    assert c.add([5, 5, 9, 10]) == 4                       # returns n_values, duplicates collapse
+    with pytest.raises(sb.StormError):
+        c.add([65536])                                     # out of range is rejected, not written
+    # public fields are populated like the reference's
+    class Contig(C.Structure):
+        _fields_ = [("data", C.POINTER(C.c_uint64)), ("scalar", u32p), ("n_scalar", u32p), ("bitmaps", C.c_void_p),
+                    ("n_data", C.c_uint64), ("m_data", C.c_uint64), ("tot_scalar", C.c_uint64), ("m_scalar", C.c_uint64),
+                    ("vector_length", C.c_uint64), ("n_bitmaps_vector", C.c_uint32), ("intsec_func", C.c_void_p),
+                    ("alignment", C.c_uint32), ("scalar_cutoff", C.c_uint32)]
+    s = Contig.from_address(c._h)
+    assert (s.n_data, s.vector_length, s.n_bitmaps_vector, s.scalar_cutoff) == (2, 65536, 1024, 200)
+    assert s.data[0] == (1 << 1) | (1 << 5) | (1 << 9) and s.data[1024] == (1 << 5) | (1 << 9) | (1 << 10)
+    assert [s.n_scalar[0], s.n_scalar[1]] == [3, 3] and s.tot_scalar == 6
+    assert [s.scalar[i] for i in range(6)] == [1, 5, 9, 5, 9, 10]
+    fn = C.CFUNCTYPE(C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t)(s.intsec_func)
+    a = (C.c_uint64 * 2)(0b1011, 1 << 63)
+    b = (C.c_uint64 * 2)(0b0110, 1 << 63)
+    assert fn(a, b, 2) == 2                                # the kept host function pointer is callable
+    assert c.clear() == 1 and s.n_data == 0
+    c.free()
+    # cutoff rule min(200, M/200) (storm.c:1016)
+    for M, want in [(65536, 200), (4096, 20), (100, 0), (1 << 20, 200)]:
+        k = sb.StormContiguous(M)
+        assert Contig.from_address(k._h).scalar_cutoff == want
+        k.free()
+
+
+def test_storm_t_host_builder_matches_oracle_sizes(lib, orc, golden):
+    """Block splitting / list-vs-bitmap threshold / serialized size (storm.c:692-758,372-394,963-973)."""
+    import stormbitmaps_b200 as sb
+    from conftest import case_rows
+    for name in ("mix_65536x200_1000_30000", "edge_block_boundaries", "edge_empty_row_middle", "c2s_524288x120_d20971"):
+        case = next(c for c in golden["cases"] if c["name"] == name)
+        with sb.Storm() as s:
+            for p in case_rows(orc, case):
+                assert s.add(p) == 1
+            assert s.serialized_size() == case["ref"]["storm_serialized_size"], name
+
+
+def test_queries_fail_loudly_without_a_device(lib):
+    import stormbitmaps_b200 as sb
+    if lib.STORM_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    c = sb.StormContiguous(256)
+    c.add([1, 2]); c.add([2, 3])
+    with pytest.raises(sb.StormError, match="no CUDA device"):
+        c.pairw_intersect_cardinality()
+    with pytest.raises(sb.StormError):
+        sb.wrapper_diag(np.ones((4, 4), dtype=np.uint64))
+    s = sb.Storm()
+    s.add([1, 2]); s.add([2, 3])
+    with pytest.raises(sb.StormError):
+        s.pairw_intersect_cardinality()

@@ -1,0 +1,12 @@
+#!/usr/bin/env python
+"""Print the CUDA-core issue rates measured by STORM_b200_microbench (run on the GPU box)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import stormbitmaps_b200 as sb
+info = sb.device_info(0)
+out = {"device": info}
+for kind, name in [(0, "popc32"), (1, "lop3_32"), (2, "iadd32"), (3, "mix_1popc_2lop3")]:
+    rate, mhz = sb.microbench(kind)
+    out[name] = {"thread_instr_per_s": rate, "sm_mhz": mhz,
+                 "per_clk_per_sm": rate / (mhz * 1e6) / info["sm_count"]}
+print(json.dumps(out, indent=1))
