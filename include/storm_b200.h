@@ -132,6 +132,9 @@ int STORM_b200_synth_geno_device(uint64_t* d_rows, uint64_t n_rows, uint32_t n_w
  * 1 LOP3.32, 2 IADD3, 3 POPC+LOP3 mixed.  Returns thread-instructions per
  * second over the whole device in *rate and the SM clock (MHz) it ran at. */
 int STORM_b200_microbench(int kind, double* rate, double* sm_mhz);
+/* cta_group of the UMMA kernel: 2 (default) = CTA pair per 256 x 256 tile, 1 = one CTA per
+ * 128 x 256 tile.  Returns the previous value. */
+int STORM_b200_set_umma_cta_group(int cg);
 /* Number of kernel launches issued by this library since load (for bench.py). */
 uint64_t STORM_b200_launch_count(void);
 

@@ -327,6 +327,10 @@ def set_default_kernel(kernel) -> int:
     return _lib.load().STORM_b200_set_default_kernel(_kernel_id(kernel))
 
 
+def set_umma_cta_group(cg: int) -> int:
+    return _lib.load().STORM_b200_set_umma_cta_group(int(cg))
+
+
 def device_info(dev: int = 0) -> dict:
     L = _lib.load()
     name = C.create_string_buffer(128)

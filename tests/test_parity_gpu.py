@@ -29,6 +29,8 @@ def sb():
     assert torch.cuda.is_available(), "these tests need a CUDA device"
     import stormbitmaps_b200 as sb
     sb.load()
+    if os.environ.get("STORM_UMMA_CG"):
+        sb.set_umma_cta_group(int(os.environ["STORM_UMMA_CG"]))
     info = sb.device_info(0)
     assert info["cc"] // 10 == 10, f"libstorm_b200 targets sm_100a, got {info}"
     return sb
