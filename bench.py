@@ -255,6 +255,8 @@ def main_ours(args, rows, bits, gen):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sb.load()
+    if args.umma_cg:
+        sb.set_umma_cta_group(args.umma_cg)
     dev = torch.device("cuda", local_rank)
     W = (bits + 63) // 64
     kernel = args.kernel
@@ -407,6 +409,7 @@ def main():
     ap.add_argument("--bits", type=int, default=None)
     ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "umma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--umma-cg", type=int, default=0, help="cta_group of the UMMA kernel (1 or 2; 0 = library default)")
     args = ap.parse_args()
     if args.workload == "custom":
         rows, bits, gen = args.rows or 20000, args.bits or 131072, "geno"

@@ -35,7 +35,6 @@ namespace storm {
 namespace {
 
 constexpr int UM_N = 256;               // B rows (accumulator columns) per tile
-constexpr int UM_STAGES = 4;            // k-blocks in flight
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_COL = 0;           // accumulator: columns [0, 256)
 constexpr int UM_A_COL = 256;           // A stage s: columns [256 + 32 s, 256 + 32 s + 32)
@@ -44,6 +43,10 @@ constexpr int UM_PREFETCH = 4;          // packed k-blocks each expander keeps i
 template <int CG>
 struct Cfg {
     static constexpr int A_WARPS = 4;
+    // k-blocks in flight.  The pair kernel hands stages over through cluster-scope barriers (remote
+    // arrive, multicast commit), so it needs a deeper ring to cover that latency; 8 stages of A fill
+    // the 256 TMEM columns next to the accumulator.
+    static constexpr int STAGES = CG == 2 ? 8 : 6;
     static constexpr int B_ROWS = UM_N / CG;                 // B rows expanded by this CTA
     static constexpr int B_WARPS = B_ROWS / 32;
     static constexpr int MMA_WARP = A_WARPS + B_WARPS;
@@ -51,7 +54,7 @@ struct Cfg {
     static constexpr int STAGE_BYTES = B_ROWS * 128;         // expanded B rows of one k-block
     static constexpr int TM = 128 * CG, TN = UM_N;
     static constexpr int PRODUCER_ARRIVALS = CG * (A_WARPS + B_WARPS);
-    static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + UM_STAGES * STAGE_BYTES + 256;
+    static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256;
     // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor bit layout):
     //   [4,6) c_format = 2 (S32); [7,10) a_format = 0 (u8); [10,13) b_format = 0 (u8);
     //   [15] a_major = 0 (K); [16] b_major = 0 (K); [17,23) N >> 3; [24,29) M >> 4
@@ -65,20 +68,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // Bounded spin: a protocol bug traps (CUDA error) instead of hanging the device.
+// Default (.acquire.cta) semantics on purpose: an explicit .acquire.cluster makes ptxas emit
+// CCTL.IVALL (L1 invalidate) per wait and .release.cluster a MEMBAR.ALL.GPU per arrive, which
+// more than halved the pair kernel.  The data handed over is ordered by its own fences
+// (tcgen05.wait::st + tcgen05.fence for TMEM, fence.proxy.async for shared memory).
 template <bool CLUSTER>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
-        if (CLUSTER)
-            asm volatile("{\n\t.reg .pred p;\n\t"
-                         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        else
-            asm volatile("{\n\t.reg .pred p;\n\t"
-                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (spin > (1u << 26)) __trap();
     }
 }
@@ -89,7 +90,7 @@ __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile("{\n\t.reg .b32 r;\n\t"
                  "mapa.shared::cluster.u32 r, %0, %1;\n\t"
-                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}"
+                 "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}"
                  ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -187,14 +188,14 @@ __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1) dense_umma_kernel(const D
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
-    const uint32_t bar_base = smem_base + UM_STAGES * C::STAGE_BYTES;
-    const uint32_t full_bar = bar_base;                                     // UM_STAGES x 8 B
-    const uint32_t empty_bar = bar_base + 8 * UM_STAGES;
-    const uint32_t acc_bar = bar_base + 16 * UM_STAGES;
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t full_bar = bar_base;                                     // STAGES x 8 B
+    const uint32_t empty_bar = bar_base + 8 * C::STAGES;
+    const uint32_t acc_bar = bar_base + 16 * C::STAGES;
     const uint32_t tmem_slot = acc_bar + 8;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + UM_STAGES * C::STAGE_BYTES + 16 * UM_STAGES + 8);
-    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + UM_STAGES * C::STAGE_BYTES + 16 * UM_STAGES + 16);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 16 * C::STAGES + 8);
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + C::STAGES * C::STAGE_BYTES + 16 * C::STAGES + 16);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1) dense_umma_kernel(const D
     // ---- setup ----------------------------------------------------------------
     if (warp == C::MMA_WARP) tmem_alloc<CG>(tmem_slot);
     if (tid == 0) {
-        for (int s = 0; s < UM_STAGES; ++s) {
+        for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_bar + 8 * s, C::PRODUCER_ARRIVALS);
             mbar_init(empty_bar + 8 * s, 1);
         }
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1) dense_umma_kernel(const D
             for (int u = 0; u < UM_PREFETCH; ++u) {
                 const uint32_t kb = kb0 + u;
                 if (kb < n_kb) {
-                    const uint32_t s = kb % UM_STAGES, it = kb / UM_STAGES;
+                    const uint32_t s = kb % C::STAGES, it = kb / C::STAGES;
                     const uint4 w = pf[u];
                     pf[u] = load_kblock(src, kb + UM_PREFETCH, n_kb, job.n_words);
                     mbar_wait<CG == 2>(empty_bar + 8 * s, (it & 1) ^ 1);
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1) dense_umma_kernel(const D
             for (int u = 0; u < UM_PREFETCH; ++u) {
                 const uint32_t kb = kb0 + u;
                 if (kb < n_kb) {
-                    const uint32_t s = kb % UM_STAGES, it = kb / UM_STAGES;
+                    const uint32_t s = kb % C::STAGES, it = kb / C::STAGES;
                     const uint4 w = pf[u];
                     pf[u] = load_kblock(src, kb + UM_PREFETCH, n_kb, job.n_words);
                     mbar_wait<CG == 2>(empty_bar + 8 * s, (it & 1) ^ 1);
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1) dense_umma_kernel(const D
         //   between 8-row groups); [46,48) version = 1; [61,64) layout = 2 (SWIZZLE_128B)
         const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
         for (uint32_t kb = 0; kb < n_kb; ++kb) {
-            const uint32_t s = kb % UM_STAGES, it = kb / UM_STAGES;
+            const uint32_t s = kb % C::STAGES, it = kb / C::STAGES;
             mbar_wait<CG == 2>(full_bar + 8 * s, it & 1);
             tc_fence_after();
             const uint32_t b_addr = smem_base + s * C::STAGE_BYTES;

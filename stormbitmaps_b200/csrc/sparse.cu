@@ -274,11 +274,15 @@ int sync_mirror(const STORM_t* s, StormState* st) {
                 words.insert(words.end(), k->data, k->data + BLOCK_WORDS);
                 row_nnz[r] += k->n_bits_set;
             } else {
-                blk_len.push_back(k->n_scalar);
                 while (lists.size() % 8) lists.push_back(0);       // 16-byte aligned lists
                 blk_off.push_back(lists.size());
-                lists.insert(lists.end(), k->scalar, k->scalar + k->n_scalar);
-                row_nnz[r] += k->n_scalar;
+                // set semantics on the device: adjacent duplicates (which the reference's list
+                // builder keeps, storm.c:548-556) collapse, as they do in a bitmap block
+                uint32_t kept = 0;
+                for (uint32_t v = 0; v < k->n_scalar; ++v)
+                    if (v == 0 || k->scalar[v] != k->scalar[v - 1]) { lists.push_back(k->scalar[v]); ++kept; }
+                blk_len.push_back(kept);
+                row_nnz[r] += kept;
             }
         }
     }
