@@ -3,24 +3,31 @@
 //
 // XX^T over a binary matrix is an integer GEMM: popcount(row_i & row_j) =
 // sum_k bit(i,k) * bit(j,k).  Replaces the same loop nest as dense_popc.cu
-// (storm.c:1165-1169 / 1199-1238 + libalgebra.h:2684-2744) with one UMMA tile per
-// CTA (pair).  Accumulation is exact: u8 x u8 products into s32 accumulators in
-// tensor memory, and a pair count is at most M < 2^31.
+// (storm.c:1165-1169 / 1199-1238 + libalgebra.h:2684-2744) with UMMA tiles.
+// Accumulation is exact: u8 x u8 products into s32 accumulators in tensor memory,
+// and a pair count is at most M < 2^31.
 //
-// Structure, per CTA:
-//   warps 0-3   "A expanders": thread = one A row = one TMEM lane.  Each k-block
-//               (128 bits) is loaded packed (16 B, ld.global.nc), expanded with
-//               (w >> j) & 0x01010101 into 32 registers and written to tensor memory
-//               with tcgen05.st (A operand lives in TMEM: no shared-memory traffic).
-//               After the K loop the same warps run the epilogue (tcgen05.ld).
+// Structure.  Persistent CTAs (one per SM, or one CTA pair
+// per SM pair) walk the tile list; per CTA:
+//   TMA warp    one thread streams PACKED rows into shared memory with
+//               cp.async.bulk.tensor (SWIZZLE_128B boxes of 128 rows x 128 bytes =
+//               8 k-blocks of 128 bits), double buffered, completion on an mbarrier.
+//               Out-of-range rows / columns are zero-filled by the TMA unit.
+//   warps 0-3   "A expanders": thread = one A row = one TMEM lane.  Each k-block is
+//               read back from the staged box (16 B, conflict-free thanks to the
+//               swizzle), expanded with (w >> j) & 0x01010101 into 32 registers and
+//               written to tensor memory with tcgen05.st (the A operand lives in TMEM:
+//               no shared-memory write + read for it).  After the K loop of a tile the
+//               same warps run its epilogue (tcgen05.ld, mask, sum / per-pair store).
 //   warps 4..   "B expanders": thread = one B row.  Same expansion, written with
 //               st.shared.v4 into the canonical K-major SWIZZLE_128B layout the UMMA
 //               shared-memory descriptor expects (16-byte chunk c of row r lands at
 //               chunk c ^ (r & 7) of its 128-byte line; 8-row groups are 1024 B apart).
-//   last warp   TMEM allocation and, in the leader CTA, the single thread that issues
+//   MMA warp    TMEM allocation and, in the leader CTA, the single thread that issues
 //               tcgen05.mma (4 per k-block, K = 32 bytes each) and tcgen05.commit.
-//   Stages are handed over with mbarriers: full[s] (expanders -> MMA), empty[s]
-//   (tcgen05.commit -> expanders), acc_full (last commit -> epilogue).
+//   Hand-over is by mbarriers only: raw_full/raw_empty (TMA <-> expanders),
+//   full[s]/empty[s] (expanders <-> MMA, tcgen05.commit), acc_full/acc_empty
+//   (MMA <-> epilogue).
 //
 // Bit order: within a 32-bit word, output register j holds bits j, j+8, j+16, j+24 as
 // its four bytes.  A and B use the same permutation of K, and a dot product is
@@ -29,6 +36,8 @@
 // CG = 2 (cta_group::2): two CTAs of a cluster share one 256 x 256 tile; each holds
 // 128 A rows in its own TMEM and supplies 128 of the 256 B rows from its own shared
 // memory, which halves the per-SM expansion work and shared-memory reads per MMA.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace storm {
@@ -38,23 +47,27 @@ constexpr int UM_N = 256;               // B rows (accumulator columns) per tile
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_COL = 0;           // accumulator: columns [0, 256)
 constexpr int UM_A_COL = 256;           // A stage s: columns [256 + 32 s, 256 + 32 s + 32)
-constexpr int UM_PREFETCH = 4;          // packed k-blocks each expander keeps in registers
+constexpr int UM_CHUNK_KB = 8;          // k-blocks per TMA box (8 x 16 B = one 128-byte swizzle line)
 
 template <int CG>
 struct Cfg {
     static constexpr int A_WARPS = 4;
-    // k-blocks in flight.  The pair kernel hands stages over through cluster-scope barriers (remote
-    // arrive, multicast commit), so it needs a deeper ring to cover that latency; 8 stages of A fill
-    // the 256 TMEM columns next to the accumulator.
-    static constexpr int STAGES = CG == 2 ? 8 : 6;
     static constexpr int B_ROWS = UM_N / CG;                 // B rows expanded by this CTA
     static constexpr int B_WARPS = B_ROWS / 32;
     static constexpr int MMA_WARP = A_WARPS + B_WARPS;
-    static constexpr int THREADS = (A_WARPS + B_WARPS + 1) * 32;
+    static constexpr int TMA_WARP = MMA_WARP + 1;
+    static constexpr int THREADS = (A_WARPS + B_WARPS + 2) * 32;
+    // expanded k-blocks in flight between the expanders and the MMA thread
+    static constexpr int STAGES = CG == 2 ? 6 : 3;
     static constexpr int STAGE_BYTES = B_ROWS * 128;         // expanded B rows of one k-block
+    static constexpr int RAW_A_BYTES = 128 * 128;            // one box of packed A rows
+    static constexpr int RAW_B_BYTES = B_ROWS * 128;
+    static constexpr int RAW_BYTES = RAW_A_BYTES + RAW_B_BYTES;
     static constexpr int TM = 128 * CG, TN = UM_N;
-    static constexpr int PRODUCER_ARRIVALS = CG * (A_WARPS + B_WARPS);
-    static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256;
+    static constexpr int EXPANDER_WARPS = A_WARPS + B_WARPS;
+    static constexpr uint32_t OFF_RAW = STAGES * STAGE_BYTES;
+    static constexpr uint32_t OFF_BAR = OFF_RAW + 2 * RAW_BYTES;
+    static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 256;
     // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor bit layout):
     //   [4,6) c_format = 2 (S32); [7,10) a_format = 0 (u8); [10,13) b_format = 0 (u8);
     //   [15] a_major = 0 (K); [16] b_major = 0 (K); [17,23) N >> 3; [24,29) M >> 4
@@ -72,7 +85,6 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // CCTL.IVALL (L1 invalidate) per wait and .release.cluster a MEMBAR.ALL.GPU per arrive, which
 // more than halved the pair kernel.  The data handed over is ordered by its own fences
 // (tcgen05.wait::st + tcgen05.fence for TMEM, fence.proxy.async for shared memory).
-template <bool CLUSTER>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
@@ -86,12 +98,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 // Arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile("{\n\t.reg .b32 r;\n\t"
                  "mapa.shared::cluster.u32 r, %0, %1;\n\t"
                  "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}"
                  ::"r"(bar), "r"(cta) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    if (CG == 2) mbar_arrive_cluster(bar, 0); else mbar_arrive_local(bar);
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -106,6 +125,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// One TMA box: packed rows [y, y + box rows) x bytes [x, x + 128) -> shared memory (SWIZZLE_128B).
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t x, uint32_t y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
 template <int CG>
@@ -163,17 +191,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-
-// One packed k-block (128 bits) of a row; `words` = how many of its 64-bit words carry data.
-__device__ __forceinline__ uint4 load_kblock(const uint4* row, uint32_t kb, uint32_t n_kb, uint32_t n_words) {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row == nullptr || kb >= n_kb) return v;
-    const uint4* p = row + kb;
-    if (2 * kb + 2 <= n_words) {
-        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    } else {                                   // last k-block of an odd-width row: one word only
-        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
 
@@ -184,163 +204,186 @@ __device__ __forceinline__ void expand32(uint32_t w, uint32_t (&r)[8]) {
 }
 
 template <int CG>
-__global__ void __launch_bounds__(Cfg<CG>::THREADS, 1) dense_umma_kernel(const DenseJob job) {
+__global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
+dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DenseJob job) {
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
-    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
-    const uint32_t full_bar = bar_base;                                     // STAGES x 8 B
-    const uint32_t empty_bar = bar_base + 8 * C::STAGES;
-    const uint32_t acc_bar = bar_base + 16 * C::STAGES;
-    const uint32_t tmem_slot = acc_bar + 8;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 16 * C::STAGES + 8);
-    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + C::STAGES * C::STAGE_BYTES + 16 * C::STAGES + 16);
+    const uint32_t raw_base = smem_base + C::OFF_RAW;                       // [2][A box | B box]
+    const uint32_t bar_base = smem_base + C::OFF_BAR;
+    const uint32_t full_bar = bar_base;                                     // STAGES x 8 B
+    const uint32_t empty_bar = full_bar + 8 * C::STAGES;
+    const uint32_t raw_full_bar = empty_bar + 8 * C::STAGES;                // 2 x 8 B
+    const uint32_t raw_empty_bar = raw_full_bar + 16;                       // 2 x 8 B
+    const uint32_t acc_full_bar = raw_empty_bar + 16;
+    const uint32_t acc_empty_bar = acc_full_bar + 8;
+    const uint32_t tmem_slot = acc_empty_bar + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + (tmem_slot + 8 - smem_base));
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
-    const uint64_t tile = job.tile_begin + (CG == 2 ? (blockIdx.x >> 1) : blockIdx.x);
-    uint32_t bi, bj;
-    tile_coords(job, tile, C::TM, C::TN, bi, bj);
-    const uint64_t rowA0 = (uint64_t)bi * C::TM + rank * 128u;              // this CTA's 128 A rows
-    const uint64_t rowB0 = (uint64_t)bj * C::TN;                            // the tile's 256 B rows
+    const uint64_t cluster_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+    const uint64_t n_clusters = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
     const uint32_t n_kb = (job.n_words + 1) / 2;
+    const uint32_t n_chunks = (n_kb + UM_CHUNK_KB - 1) / UM_CHUNK_KB;
 
     // ---- setup ----------------------------------------------------------------
     if (warp == C::MMA_WARP) tmem_alloc<CG>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(full_bar + 8 * s, C::PRODUCER_ARRIVALS);
-            mbar_init(empty_bar + 8 * s, 1);
+            mbar_init(full_bar + 8 * s, CG * C::EXPANDER_WARPS);           // every expander warp of the pair
+            mbar_init(empty_bar + 8 * s, 1);                               // tcgen05.commit
         }
-        mbar_init(acc_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(raw_full_bar + 8 * b, 1);                            // expect_tx arrive + TMA bytes
+            mbar_init(raw_empty_bar + 8 * b, C::EXPANDER_WARPS);
+        }
+        mbar_init(acc_full_bar, 1);                                        // tcgen05.commit
+        mbar_init(acc_empty_bar, CG * C::A_WARPS);                         // every epilogue warp of the pair
         fence_mbar_init();
+    }
+    if (warp == C::TMA_WARP && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < C::A_WARPS) {
-        // ===== A expander: row -> TMEM lane ========================================
-        const uint64_t r = rowA0 + warp * 32 + lane;
-        const uint4* src = (r < job.nA) ? reinterpret_cast<const uint4*>(job.A + r * job.strideA) : nullptr;
-        const uint32_t lane_base = tmem_base + ((warp * 32u) << 16);
-        uint4 pf[UM_PREFETCH];
-#pragma unroll
-        for (int u = 0; u < UM_PREFETCH; ++u) pf[u] = load_kblock(src, u, n_kb, job.n_words);
-        for (uint32_t kb0 = 0; kb0 < n_kb; kb0 += UM_PREFETCH) {
-#pragma unroll
-            for (int u = 0; u < UM_PREFETCH; ++u) {
-                const uint32_t kb = kb0 + u;
-                if (kb < n_kb) {
-                    const uint32_t s = kb % C::STAGES, it = kb / C::STAGES;
-                    const uint4 w = pf[u];
-                    pf[u] = load_kblock(src, kb + UM_PREFETCH, n_kb, job.n_words);
-                    mbar_wait<CG == 2>(empty_bar + 8 * s, (it & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t t = lane_base + UM_A_COL + s * 32;
-                    uint32_t e[8];
-                    expand32(w.x, e); tmem_st8(t + 0, e);
-                    expand32(w.y, e); tmem_st8(t + 8, e);
-                    expand32(w.z, e); tmem_st8(t + 16, e);
-                    expand32(w.w, e); tmem_st8(t + 24, e);
-                    tc_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CG == 2) mbar_arrive_cluster(full_bar + 8 * s, 0); else mbar_arrive_local(full_bar + 8 * s);
-                    }
-                }
-            }
-        }
-    } else if (warp < C::MMA_WARP) {
-        // ===== B expander: row -> swizzled shared-memory line =======================
-        const uint32_t idx = tid - C::A_WARPS * 32;                        // 0 .. B_ROWS-1
-        const uint64_t r = rowB0 + rank * C::B_ROWS + idx;
-        const uint4* src = (r < job.nB) ? reinterpret_cast<const uint4*>(job.B + r * job.strideB) : nullptr;
-        const uint32_t line = (idx >> 3) * 1024u + (idx & 7u) * 128u;      // 8-row groups are 1024 B apart
-        const uint32_t sw = idx & 7u;
-        uint4 pf[UM_PREFETCH];
-#pragma unroll
-        for (int u = 0; u < UM_PREFETCH; ++u) pf[u] = load_kblock(src, u, n_kb, job.n_words);
-        for (uint32_t kb0 = 0; kb0 < n_kb; kb0 += UM_PREFETCH) {
-#pragma unroll
-            for (int u = 0; u < UM_PREFETCH; ++u) {
-                const uint32_t kb = kb0 + u;
-                if (kb < n_kb) {
-                    const uint32_t s = kb % C::STAGES, it = kb / C::STAGES;
-                    const uint4 w = pf[u];
-                    pf[u] = load_kblock(src, kb + UM_PREFETCH, n_kb, job.n_words);
-                    mbar_wait<CG == 2>(empty_bar + 8 * s, (it & 1) ^ 1);
-                    const uint32_t dst = smem_base + s * C::STAGE_BYTES + line;
-                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {                          // K step k = bytes [32k, 32k+32) of the line
-                        uint32_t e[8];
-                        expand32(ws[k], e);
-                        st_shared_v4(dst + (((2 * k) ^ sw) << 4), e[0], e[1], e[2], e[3]);
-                        st_shared_v4(dst + (((2 * k + 1) ^ sw) << 4), e[4], e[5], e[6], e[7]);
-                    }
-                    fence_proxy_async_smem();                              // generic writes -> visible to the UMMA (async proxy)
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CG == 2) mbar_arrive_cluster(full_bar + 8 * s, 0); else mbar_arrive_local(full_bar + 8 * s);
-                    }
-                }
-            }
-        }
-    } else if (rank == 0 && lane == 0) {
-        // ===== MMA issuer: one thread of the leader CTA ==============================
-        // K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor):
-        //   [0,14) addr >> 4; [16,30) LBO >> 4 = 1 (unused for swizzled K-major); [32,46) SBO >> 4 = 64 (1024 B
-        //   between 8-row groups); [46,48) version = 1; [61,64) layout = 2 (SWIZZLE_128B)
-        const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-        for (uint32_t kb = 0; kb < n_kb; ++kb) {
-            const uint32_t s = kb % C::STAGES, it = kb / C::STAGES;
-            mbar_wait<CG == 2>(full_bar + 8 * s, it & 1);
-            tc_fence_after();
-            const uint32_t b_addr = smem_base + s * C::STAGE_BYTES;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
-                umma_i8_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
-                               (kb | (uint32_t)k) != 0);
-            }
-            umma_commit<CG>(empty_bar + 8 * s);                            // frees the stage when these MMAs are done
-        }
-        umma_commit<CG>(acc_bar);                                          // accumulator complete
-    }
-    __syncwarp();                                                          // re-converge the MMA warp (aligned ops follow)
-
-    // ---- epilogue: TMEM -> registers -> masked sum / per-pair store ---------------
     unsigned long long sum = 0;
-    if (warp < C::A_WARPS) {
-        mbar_wait<CG == 2>(acc_bar, 0);
-        tc_fence_after();
-        const uint64_t li = rowA0 + warp * 32 + lane;                      // A row of this thread (= its TMEM lane)
-        const uint64_t gi = job.i_off + li;
-        const bool row_ok = li < job.nA;
-        const uint32_t lane_base = tmem_base + ((warp * 32u) << 16) + UM_ACC_COL;
-#pragma unroll 1
-        for (int c0 = 0; c0 < UM_N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(lane_base + c0, v);
-            tc_wait_ld();
-            if (row_ok) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const uint64_t lj = rowB0 + c0 + c;
-                    if (lj < job.nB) {
-                        uint32_t x = v[c];
-                        if (job.strict_upper && job.j_off + lj <= gi) x = 0;
-                        sum += x;
-                        if (job.out) job.out[li * job.ld + lj] = x;
-                    }
+
+    if (warp == C::TMA_WARP) {
+        // ===== TMA producer: packed rows -> shared memory ==============================
+        if (lane == 0) {
+            uint32_t gc = 0;                                               // chunks issued so far (all tiles)
+            for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters) {
+                uint32_t bi, bj;
+                tile_coords(job, tile, C::TM, C::TN, bi, bj);
+                const uint32_t ya = bi * C::TM + rank * 128u;
+                const uint32_t yb = bj * C::TN + rank * C::B_ROWS;
+                for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
+                    const uint32_t buf = gc & 1;
+                    mbar_wait(raw_empty_bar + 8 * buf, ((gc >> 1) & 1) ^ 1);
+                    mbar_expect_tx(raw_full_bar + 8 * buf, C::RAW_BYTES);
+                    const uint32_t dst = raw_base + buf * C::RAW_BYTES;
+                    tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
+                    tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
                 }
             }
         }
+    } else if (warp == C::MMA_WARP) {
+        // ===== MMA issuer: one thread of the leader CTA ================================
+        if (rank == 0 && lane == 0) {
+            // K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor):
+            //   [0,14) addr >> 4; [16,30) LBO >> 4 = 1 (unused for swizzled K-major); [32,46) SBO >> 4 = 64
+            //   (1024 B between 8-row groups); [46,48) version = 1; [61,64) layout = 2 (SWIZZLE_128B)
+            const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+            uint32_t gk = 0, t_iter = 0;
+            for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
+                mbar_wait(acc_empty_bar, (t_iter & 1) ^ 1);                // epilogue of the previous tile drained TMEM
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < n_kb; ++kb, ++gk) {
+                    const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
+                    mbar_wait(full_bar + 8 * s, it & 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_base + s * C::STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
+                        umma_i8_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
+                                       (kb | (uint32_t)k) != 0);
+                    }
+                    umma_commit<CG>(empty_bar + 8 * s);                    // frees the stage when these MMAs are done
+                }
+                umma_commit<CG>(acc_full_bar);                             // accumulator of this tile complete
+            }
+        }
+    } else {
+        // ===== expanders (A: warps 0-3 -> TMEM, B: warps 4.. -> shared memory) ==========
+        const bool is_a = warp < C::A_WARPS;
+        const uint32_t idx = is_a ? tid : tid - C::A_WARPS * 32;           // row within this CTA's A / B slice
+        const uint32_t raw_row = (is_a ? 0u : (uint32_t)C::RAW_A_BYTES) + idx * 128u;
+        const uint32_t sw = idx & 7u;
+        const uint32_t b_line = (idx >> 3) * 1024u + (idx & 7u) * 128u;    // 8-row groups are 1024 B apart
+        const uint32_t a_lane = tmem_base + ((warp * 32u) << 16);
+        uint32_t gk = 0, gc = 0, t_iter = 0;
+        for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
+            for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
+                const uint32_t buf = gc & 1;
+                mbar_wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
+                const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
+                const uint32_t nq = min((uint32_t)UM_CHUNK_KB, n_kb - c * UM_CHUNK_KB);
+                for (uint32_t q = 0; q < nq; ++q, ++gk) {
+                    const uint4 w = ld_shared_v4(src + ((q ^ sw) << 4));
+                    const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
+                    mbar_wait(empty_bar + 8 * s, (it & 1) ^ 1);
+                    uint32_t e[8];
+                    if (is_a) {
+                        tc_fence_after();
+                        const uint32_t t = a_lane + UM_A_COL + s * 32;
+                        expand32(w.x, e); tmem_st8(t + 0, e);
+                        expand32(w.y, e); tmem_st8(t + 8, e);
+                        expand32(w.z, e); tmem_st8(t + 16, e);
+                        expand32(w.w, e); tmem_st8(t + 24, e);
+                        tc_wait_st();
+                        tc_fence_before();
+                    } else {
+                        const uint32_t dst = smem_base + s * C::STAGE_BYTES + b_line;
+                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {                      // K step k = bytes [32k, 32k+32) of the line
+                            expand32(ws[k], e);
+                            st_shared_v4(dst + (((2 * k) ^ sw) << 4), e[0], e[1], e[2], e[3]);
+                            st_shared_v4(dst + (((2 * k + 1) ^ sw) << 4), e[4], e[5], e[6], e[7]);
+                        }
+                        fence_proxy_async_smem();                          // generic writes -> visible to the UMMA (async proxy)
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader<CG>(full_bar + 8 * s);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
+            }
+            if (is_a) {
+                // ---- epilogue of this tile: TMEM -> registers -> masked sum / per-pair store ----
+                uint32_t bi, bj;
+                tile_coords(job, tile, C::TM, C::TN, bi, bj);
+                const uint64_t rowB0 = (uint64_t)bj * C::TN;
+                const uint64_t li = (uint64_t)bi * C::TM + rank * 128u + idx;  // A row of this thread (= its TMEM lane)
+                const uint64_t gi = job.i_off + li;
+                const bool row_ok = li < job.nA;
+                mbar_wait(acc_full_bar, t_iter & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < UM_N; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(a_lane + UM_ACC_COL + c0, v);
+                    tc_wait_ld();
+                    if (row_ok) {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) {
+                            const uint64_t lj = rowB0 + c0 + cc;
+                            if (lj < job.nB) {
+                                uint32_t x = v[cc];
+                                if (job.strict_upper && job.j_off + lj <= gi) x = 0;
+                                sum += x;
+                                if (job.out) job.out[li * job.ld + lj] = x;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
+            }
+        }
     }
+    __syncwarp();                                                          // re-converge (aligned ops follow)
+
+    // ---- one atomic per CTA, then teardown --------------------------------------------
     if (job.total) {
         sum = warp_sum(sum);
         if (lane == 0 && warp < C::A_WARPS) red[warp] = sum;
@@ -354,33 +397,66 @@ __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1) dense_umma_kernel(const D
     if (warp == C::MMA_WARP) tmem_free<CG>(tmem_base);
 }
 
+// ---- host side --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// Packed rows as a 2-D byte tensor: inner = n_words * 8 bytes, outer = rows; box = 128 bytes x box_rows.
+int make_row_map(CUtensorMap* map, const uint64_t* base, uint64_t n_rows, uint64_t stride_words, uint32_t n_words, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return STORM_B200_ECUDA; }
+    const cuuint64_t dims[2] = {(cuuint64_t)n_words * 8, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride_words * 8};
+    const cuuint32_t box[2] = {128, box_rows};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint64_t*>(base), dims, strides, box, elem,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return STORM_B200_ECUDA; }
+    return STORM_B200_OK;
+}
+
 template <int CG>
 int launch_cg(const DenseJob& job, cudaStream_t stream) {
     using C = Cfg<CG>;
+    alignas(64) CUtensorMap map_a, map_b;
+    int rc = make_row_map(&map_a, job.A, job.nA, job.strideA, job.n_words, 128);
+    if (!rc) rc = make_row_map(&map_b, job.B, job.nB, job.strideB, job.n_words, C::B_ROWS);
+    if (rc) return rc;
     STORM_CUDA_TRY(cudaFuncSetAttribute(dense_umma_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    uint64_t remaining = job.tile_end - job.tile_begin, begin = job.tile_begin;
-    while (remaining) {
-        const uint64_t n = remaining > 0x20000000ull ? 0x20000000ull : remaining;
-        DenseJob j = job;
-        j.tile_begin = begin;
-        j.tile_end = begin + n;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(n * CG));
-        cfg.blockDim = dim3(C::THREADS);
-        cfg.dynamicSmemBytes = C::SMEM_BYTES;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CG;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_umma_kernel<CG>, j));
-        count_launch();
-        begin += n;
-        remaining -= n;
-    }
+    int dev = 0, sms = 0;
+    STORM_CUDA_TRY(cudaGetDevice(&dev));
+    STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const uint64_t n_tiles = job.tile_end - job.tile_begin;
+    const uint64_t clusters = n_tiles < (uint64_t)(sms / CG) ? n_tiles : (uint64_t)(sms / CG);   // persistent: one per SM (pair)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clusters * CG));
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_umma_kernel<CG>, map_a, map_b, job));
+    count_launch();
     return STORM_B200_OK;
 }
 
@@ -392,9 +468,10 @@ TileShape umma_tile_shape() { return {(uint32_t)(128 * g_umma_cg), (uint32_t)UM_
 
 bool umma_supports(const DenseJob& job) {
     if (job.n_words == 0 || job.n_words >= (1u << 25)) return false;        // counts stay below 2^31
-    if ((job.strideA & 1) || (job.strideB & 1)) return false;
+    if ((job.strideA & 1) || (job.strideB & 1)) return false;               // TMA: 16-byte row pitch and base
     if (job.A && ((uintptr_t)job.A & 15)) return false;
     if (job.B && ((uintptr_t)job.B & 15)) return false;
+    if (job.nA >= (1ull << 31) || job.nB >= (1ull << 31)) return false;
     return true;
 }
 
