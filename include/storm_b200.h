@@ -129,12 +129,19 @@ int STORM_b200_synth_geno_device(uint64_t* d_rows, uint64_t n_rows, uint32_t n_w
 /* ---- measurement helpers -------------------------------------------------- */
 /* Issue-rate micro-benchmarks used as roofline denominators for the CUDA-core
  * kernels (MEASURED_PEAKS.json only has HBM and bf16).  kind: 0 POPC.32,
- * 1 LOP3.32, 2 IADD3, 3 POPC+LOP3 mixed.  Returns thread-instructions per
- * second over the whole device in *rate and the SM clock (MHz) it ran at. */
+ * 1 LOP3.32, 2 IADD3, 3 POPC+LOP3 mixed: thread-instructions per second over the
+ * whole device in *rate (and a clock64-derived SM clock in *sm_mhz, indicative
+ * only).  kind 4 / 5: the UMMA kernel's own tcgen05.mma kind::i8 instruction
+ * (cta_group 1 / 2) issued back to back with no operand production: int8 ops per
+ * second (2 per MAC) in *rate -- the tensor-pipe ceiling of dense_umma_kernel. */
 int STORM_b200_microbench(int kind, double* rate, double* sm_mhz);
 /* cta_group of the UMMA kernel: 2 (default) = CTA pair per 256 x 256 tile, 1 = one CTA per
  * 128 x 256 tile.  Returns the previous value. */
 int STORM_b200_set_umma_cta_group(int cg);
+/* Code variant of the UMMA kernel (bit 0: hardware-suspended mbarrier waits; bit 1: scaled
+ * bit expansion, see dense_umma.cu).  Results are identical for every value.  Returns the
+ * previous value. */
+int STORM_b200_set_umma_variant(int variant);
 /* Number of kernel launches issued by this library since load (for bench.py). */
 uint64_t STORM_b200_launch_count(void);
 

@@ -87,6 +87,7 @@ SIGNATURES = {
     "STORM_b200_synth_geno_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "STORM_b200_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "STORM_b200_set_umma_cta_group": (C.c_int, [C.c_int]),
+    "STORM_b200_set_umma_variant": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),
 }
 

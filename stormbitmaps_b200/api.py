@@ -331,6 +331,11 @@ def set_umma_cta_group(cg: int) -> int:
     return _lib.load().STORM_b200_set_umma_cta_group(int(cg))
 
 
+def set_umma_variant(variant: int) -> int:
+    """Code variant of the UMMA kernel (bit 0: suspended waits, bit 1: scaled expansion)."""
+    return _lib.load().STORM_b200_set_umma_variant(int(variant))
+
+
 def device_info(dev: int = 0) -> dict:
     L = _lib.load()
     name = C.create_string_buffer(128)

@@ -87,6 +87,8 @@ TileShape umma_tile_shape();
 int launch_dense_umma(const DenseJob& job, cudaStream_t stream);
 // UMMA needs at least one full K step of 128 bits and 16-byte aligned rows.
 bool umma_supports(const DenseJob& job);
+// int8 ops per second of the UMMA kernel's own instruction issued back to back (cta_group 1 or 2).
+int umma_peak_ops(int cg, double* ops_per_s);
 
 int launch_synth_uniform(uint64_t* d_rows, uint64_t n_rows, uint64_t stride, uint32_t M,
                          uint32_t n_draws, uint64_t seed, uint64_t row0, cudaStream_t stream);

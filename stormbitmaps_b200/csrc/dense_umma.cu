@@ -80,21 +80,39 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded spin: a protocol bug traps (CUDA error) instead of hanging the device.
+// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the device.
 // Default (.acquire.cta) semantics on purpose: an explicit .acquire.cluster makes ptxas emit
 // CCTL.IVALL (L1 invalidate) per wait and .release.cluster a MEMBAR.ALL.GPU per arrive, which
 // more than halved the pair kernel.  The data handed over is ordered by its own fences
 // (tcgen05.wait::st + tcgen05.fence for TMEM, fence.proxy.async for shared memory).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+//
+// SUSPEND = true passes a suspend-time hint so that the hardware parks the warp until the
+// phase completes (or ~1 ms passes) instead of returning at once: without it the MMA thread
+// re-issued try_wait + counter + branch ~44 times per k-block (ncu, profiles/r01_umma_v1.md)
+// and those instructions competed with the expander warps of its scheduler for issue slots
+// and for the ALU pipe.
+template <bool SUSPEND>
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 26)) __trap();
+    if (SUSPEND) {
+        for (uint32_t spin = 0; !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                         "selp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+            if (spin > (1u << 12)) __trap();                               // ~4 s of 1 ms suspensions
+        }
+    } else {
+        for (uint32_t spin = 0; !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            if (spin > (1u << 26)) __trap();
+        }
     }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_t<false>(bar, parity); }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -202,8 +220,25 @@ __device__ __forceinline__ void expand32(uint32_t w, uint32_t (&r)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = (w >> j) & 0x01010101u;
 }
+// Scaled expansion (VAR_SCALED): the shift is dropped on the A side.  A byte is 2^j where the plain
+// form has 1 (one LOP3 per register), the matching B byte is 2^(7-j), so every matching bit
+// contributes exactly 128 to the s32 accumulator and the epilogue shifts the count right by 7.
+// Exact while 128 * M < 2^31.  The B side gets bit 7-j of each byte by reversing the bits of the
+// word (BREV) and restoring the byte order (PRMT): two extra instructions per eight registers.
+__device__ __forceinline__ void expand32_a_scaled(uint32_t w, uint32_t (&r)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = w & (0x01010101u << j);
+}
+__device__ __forceinline__ void expand32_b_scaled(uint32_t w, uint32_t (&r)[8]) {
+    const uint32_t wr = __byte_perm(__brev(w), 0u, 0x0123);                // byte b keeps its place, bits reversed inside it
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = wr & (0x01010101u << (7 - j));
+}
 
-template <int CG>
+constexpr int VAR_SUSPEND = 1;          // hardware-suspended mbarrier waits
+constexpr int VAR_SCALED = 2;           // scaled expansion (counts accumulate x128)
+
+template <int CG, int VAR>
 __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
 dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DenseJob job) {
     using C = Cfg<CG>;
@@ -221,6 +256,9 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_slot = acc_empty_bar + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
     unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + (tmem_slot + 8 - smem_base));
+
+    auto wait = [](uint32_t bar, uint32_t parity) { mbar_wait_t<(VAR & VAR_SUSPEND) != 0>(bar, parity); };
+    constexpr bool SCALED = (VAR & VAR_SCALED) != 0;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -266,7 +304,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t yb = bj * C::TN + rank * C::B_ROWS;
                 for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
                     const uint32_t buf = gc & 1;
-                    mbar_wait(raw_empty_bar + 8 * buf, ((gc >> 1) & 1) ^ 1);
+                    wait(raw_empty_bar + 8 * buf, ((gc >> 1) & 1) ^ 1);
                     mbar_expect_tx(raw_full_bar + 8 * buf, C::RAW_BYTES);
                     const uint32_t dst = raw_base + buf * C::RAW_BYTES;
                     tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
@@ -283,11 +321,11 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
             uint32_t gk = 0, t_iter = 0;
             for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
-                mbar_wait(acc_empty_bar, (t_iter & 1) ^ 1);                // epilogue of the previous tile drained TMEM
+                wait(acc_empty_bar, (t_iter & 1) ^ 1);                // epilogue of the previous tile drained TMEM
                 tc_fence_after();
                 for (uint32_t kb = 0; kb < n_kb; ++kb, ++gk) {
                     const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
-                    mbar_wait(full_bar + 8 * s, it & 1);
+                    wait(full_bar + 8 * s, it & 1);
                     tc_fence_after();
                     const uint32_t b_addr = smem_base + s * C::STAGE_BYTES;
 #pragma unroll
@@ -313,21 +351,23 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
             for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
                 const uint32_t buf = gc & 1;
-                mbar_wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
+                wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min((uint32_t)UM_CHUNK_KB, n_kb - c * UM_CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q, ++gk) {
                     const uint4 w = ld_shared_v4(src + ((q ^ sw) << 4));
                     const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
-                    mbar_wait(empty_bar + 8 * s, (it & 1) ^ 1);
+                    wait(empty_bar + 8 * s, (it & 1) ^ 1);
                     uint32_t e[8];
                     if (is_a) {
                         tc_fence_after();
                         const uint32_t t = a_lane + UM_A_COL + s * 32;
-                        expand32(w.x, e); tmem_st8(t + 0, e);
-                        expand32(w.y, e); tmem_st8(t + 8, e);
-                        expand32(w.z, e); tmem_st8(t + 16, e);
-                        expand32(w.w, e); tmem_st8(t + 24, e);
+                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (SCALED) expand32_a_scaled(ws[k], e); else expand32(ws[k], e);
+                            tmem_st8(t + 8 * k, e);
+                        }
                         tc_wait_st();
                         tc_fence_before();
                     } else {
@@ -335,7 +375,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {                      // K step k = bytes [32k, 32k+32) of the line
-                            expand32(ws[k], e);
+                            if (SCALED) expand32_b_scaled(ws[k], e); else expand32(ws[k], e);
                             st_shared_v4(dst + (((2 * k) ^ sw) << 4), e[0], e[1], e[2], e[3]);
                             st_shared_v4(dst + (((2 * k + 1) ^ sw) << 4), e[4], e[5], e[6], e[7]);
                         }
@@ -355,7 +395,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint64_t li = (uint64_t)bi * C::TM + rank * 128u + idx;  // A row of this thread (= its TMEM lane)
                 const uint64_t gi = job.i_off + li;
                 const bool row_ok = li < job.nA;
-                mbar_wait(acc_full_bar, t_iter & 1);
+                wait(acc_full_bar, t_iter & 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (int c0 = 0; c0 < UM_N; c0 += 32) {
@@ -367,7 +407,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int cc = 0; cc < 32; ++cc) {
                             const uint64_t lj = rowB0 + c0 + cc;
                             if (lj < job.nB) {
-                                uint32_t x = v[cc];
+                                uint32_t x = SCALED ? (v[cc] >> 7) : v[cc];
                                 if (job.strict_upper && job.j_off + lj <= gi) x = 0;
                                 sum += x;
                                 if (job.out) job.out[li * job.ld + lj] = x;
@@ -395,6 +435,93 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (t) atomicAdd(job.total, t);
     }
     if (warp == C::MMA_WARP) tmem_free<CG>(tmem_base);
+}
+
+// ---- tensor-pipe peak probe ----------------------------------------------------------
+// Issues the production kernel's exact instruction (kind::i8, M = 128 * CG, N = 256, K = 32, A from
+// tensor memory, B from SWIZZLE_128B shared memory) back to back with no operand production at
+// all, so that its rate is the ceiling the tile kernel can reach on this device at its clocks.
+// Operands are whatever the (zeroed) shared memory and tensor memory hold; results are discarded.
+template <int CG>
+__global__ void __launch_bounds__(128, 1) umma_peak_kernel(uint32_t iters) {
+    using C = Cfg<CG>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    constexpr uint32_t RING = 4;
+    const uint32_t bar_base = smem_base + C::STAGE_BYTES;                   // RING barriers, then the TMEM slot
+    const uint32_t tmem_slot = bar_base + 8 * RING;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+
+    for (uint32_t i = tid; i < C::STAGE_BYTES / 16; i += blockDim.x) st_shared_v4(smem_base + i * 16, 0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (warp == 0) tmem_alloc<CG>(tmem_slot);
+    if (tid == 0) {
+        for (uint32_t b = 0; b < RING; ++b) mbar_init(bar_base + 8 * b, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    if (rank == 0 && tid == 0) {
+        const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+        for (uint32_t it = 0; it < iters; ++it) {
+            if (it >= RING) mbar_wait(bar_base + 8 * (it % RING), ((it / RING) - 1) & 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t b_desc = desc_hi | (uint64_t)(((smem_base + k * 32) >> 4) & 0x3FFF);
+                umma_i8_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + k * 8, b_desc, C::IDESC, 1u);
+            }
+            umma_commit<CG>(bar_base + 8 * (it % RING));
+        }
+        for (uint32_t it = iters > RING ? iters - RING : 0; it < iters; ++it)   // drain
+            mbar_wait(bar_base + 8 * (it % RING), (it / RING) & 1);
+    }
+    __syncwarp();
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 0) tmem_free<CG>(tmem_base);
+}
+
+template <int CG>
+int run_umma_peak(double* ops_per_s) {
+    using C = Cfg<CG>;
+    int dev = 0, sms = 0;
+    STORM_CUDA_TRY(cudaGetDevice(&dev));
+    STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int smem_bytes = 1024 + C::STAGE_BYTES + 256;
+    STORM_CUDA_TRY(cudaFuncSetAttribute(umma_peak_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(sms / CG * CG));
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaEvent_t e0, e1;
+    STORM_CUDA_TRY(cudaEventCreate(&e0));
+    STORM_CUDA_TRY(cudaEventCreate(&e1));
+    const uint32_t iters = 100000;                                        // ~50 M clocks: tens of milliseconds
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {                                   // rep 0 is the warm-up
+        STORM_CUDA_TRY(cudaEventRecord(e0));
+        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_peak_kernel<CG>, iters));
+        STORM_CUDA_TRY(cudaEventRecord(e1));
+        STORM_CUDA_TRY(cudaEventSynchronize(e1));
+        count_launch();
+        float ms = 0;
+        STORM_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        // per SM and instruction: 128 x 256 x 32 MACs = 2 ops each
+        const double ops = (double)cfg.gridDim.x * iters * 4.0 * 128.0 * 256.0 * 32.0 * 2.0;
+        if (rep > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ops_per_s = best;
+    return STORM_B200_OK;
 }
 
 // ---- host side --------------------------------------------------------------------
@@ -430,14 +557,14 @@ int make_row_map(CUtensorMap* map, const uint64_t* base, uint64_t n_rows, uint64
     return STORM_B200_OK;
 }
 
-template <int CG>
+template <int CG, int VAR>
 int launch_cg(const DenseJob& job, cudaStream_t stream) {
     using C = Cfg<CG>;
     alignas(64) CUtensorMap map_a, map_b;
     int rc = make_row_map(&map_a, job.A, job.nA, job.strideA, job.n_words, 128);
     if (!rc) rc = make_row_map(&map_b, job.B, job.nB, job.strideB, job.n_words, C::B_ROWS);
     if (rc) return rc;
-    STORM_CUDA_TRY(cudaFuncSetAttribute(dense_umma_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    STORM_CUDA_TRY(cudaFuncSetAttribute(dense_umma_kernel<CG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     int dev = 0, sms = 0;
     STORM_CUDA_TRY(cudaGetDevice(&dev));
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -455,12 +582,25 @@ int launch_cg(const DenseJob& job, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_umma_kernel<CG>, map_a, map_b, job));
+    STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_umma_kernel<CG, VAR>, map_a, map_b, job));
     count_launch();
     return STORM_B200_OK;
 }
 
-int g_umma_cg = 2;   // cta_group used by launch_dense_umma (1 or 2); see STORM_b200_set_umma_cta_group
+int g_umma_cg = 2;        // cta_group used by launch_dense_umma (1 or 2); see STORM_b200_set_umma_cta_group
+int g_umma_variant = 0;   // VAR_* bits; see STORM_b200_set_umma_variant
+
+template <int CG>
+int launch_var(const DenseJob& job, cudaStream_t stream) {
+    int var = g_umma_variant & 3;
+    if ((uint64_t)job.n_words * 64 * 128 >= (1ull << 31)) var &= ~VAR_SCALED;   // x128 counts must stay below 2^31
+    switch (var) {
+        case 0: return launch_cg<CG, 0>(job, stream);
+        case 1: return launch_cg<CG, 1>(job, stream);
+        case 2: return launch_cg<CG, 2>(job, stream);
+        default: return launch_cg<CG, 3>(job, stream);
+    }
+}
 
 }  // namespace
 
@@ -475,9 +615,13 @@ bool umma_supports(const DenseJob& job) {
     return true;
 }
 
+int umma_peak_ops(int cg, double* ops_per_s) {
+    return cg == 1 ? run_umma_peak<1>(ops_per_s) : run_umma_peak<2>(ops_per_s);
+}
+
 int launch_dense_umma(const DenseJob& job, cudaStream_t stream) {
     if (job.tile_end <= job.tile_begin) return STORM_B200_OK;
-    return g_umma_cg == 2 ? launch_cg<2>(job, stream) : launch_cg<1>(job, stream);
+    return g_umma_cg == 2 ? launch_var<2>(job, stream) : launch_var<1>(job, stream);
 }
 
 }  // namespace storm
@@ -487,5 +631,13 @@ int launch_dense_umma(const DenseJob& job, cudaStream_t stream) {
 extern "C" int STORM_b200_set_umma_cta_group(int cg) {
     const int prev = storm::g_umma_cg;
     if (cg == 1 || cg == 2) storm::g_umma_cg = cg;
+    return prev;
+}
+
+// Development / measurement knob: bit 0 = hardware-suspended mbarrier waits, bit 1 = scaled expansion.
+// Returns the previous value.
+extern "C" int STORM_b200_set_umma_variant(int variant) {
+    const int prev = storm::g_umma_variant;
+    if (variant >= 0 && variant <= 3) storm::g_umma_variant = variant;
     return prev;
 }

@@ -9,4 +9,8 @@ for kind, name in [(0, "popc32"), (1, "lop3_32"), (2, "iadd32"), (3, "mix_1popc_
     rate, mhz = sb.microbench(kind)
     out[name] = {"thread_instr_per_s": rate, "sm_mhz": mhz,
                  "per_clk_per_sm": rate / (mhz * 1e6) / info["sm_count"]}
+for kind, name in [(4, "umma_i8_cta_group1"), (5, "umma_i8_cta_group2")]:
+    rate, _ = sb.microbench(kind)
+    out[name] = {"int8_ops_per_s": rate, "tops": rate / 1e12,
+                 "mac_per_clk_per_sm_at_1965mhz": rate / 2 / 1.965e9 / info["sm_count"]}
 print(json.dumps(out, indent=1))
