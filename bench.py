@@ -243,6 +243,17 @@ def colcount_total_torch(rows_t, W, chunk=16384):
     return int((counts * (counts - 1) // 2).sum().item())
 
 
+def ncu_traffic(workload: str, kernel: str, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json), or None if none was taken."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(f"{workload}:{kernel}:gpus{world}", {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def main_ours(args, rows, bits, gen):
     import torch
     import torch.distributed as dist
@@ -343,25 +354,36 @@ def main_ours(args, rows, bits, gen):
     # dominant kernel: one launch per step per rank; its duration is the step time
     # minus the 8-byte all-reduce (N>1), measured by the same CUDA events
     launch_ms = elapsed_ms / args.steps
+    traffic = ncu_traffic(args.workload, used_kernel, world)
     if used_kernel == "umma":
-        # algorithmic work: 64 int8 MACs = 128 ops per 64-bit word pair
+        # algorithmic work: 64 int8 MACs = 128 ops per 64-bit word pair.
+        # Denominator: the kernel's own tcgen05.mma kind::i8 instruction issued back to back on THIS
+        # device (STORM_b200_microbench kind 5) -- MEASURED_PEAKS.json has no int8 figure, and the
+        # cuBLAS bf16 number is taken under the 1 kW power cap at ~1.3 GHz while this kernel's 0/1
+        # operands leave the part at its 1965 MHz boost clock; 2 x bf16 is reported beside it.
         ops_per_launch = wp / world * 128.0
         achieved = ops_per_launch / (launch_ms * 1e-3) / 1e12
-        peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "dense_umma_kernel",
-                    "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peak_src}); kind::i8 issues at "
-                                   "twice the bf16 rate, 1 MAC = 2 ops",
-                    "algorithmic": "128 int8 ops per 64-bit word pair"}
+        i8_peak = sb.microbench(5)[0] / 1e12
+        bf16x2 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TFLOP/s", "frac": achieved / i8_peak,
+                    "traffic": traffic, "kernel": "dense_umma_kernel",
+                    "unit_note": "int8 tensor ops per second / 1e12 (1 MAC = 2 ops), not floating point",
+                    "peak_source": "tcgen05.mma.kind::i8 M256 N256 K32 issue-rate probe on this device (measured, "
+                                   "STORM_b200_microbench(5)); nominal 4500 dense",
+                    "peak_2x_bf16": bf16x2, "frac_of_2x_bf16": achieved / bf16x2,
+                    "peak_2x_bf16_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peak_src})",
+                    "algorithmic": "128 int8 ops per 64-bit word pair x wp per launch",
+                    "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
     else:
         # CUDA-core kernels: bound by the POPC issue rate, measured on this device
-        popc_rate, mhz = sb.microbench(0)
+        popc_rate, _ = sb.microbench(0)
         per_wp = 2.0                                       # 2 POPC.32 per 64-bit word pair (direct form)
         achieved = wp / world * per_wp / (launch_ms * 1e-3)
         roofline = {"bound": "issue", "achieved": achieved / 1e12, "peak": popc_rate / 1e12, "unit": "T POPC.32/s",
-                    "frac": achieved / popc_rate, "traffic": None, "kernel": f"dense_{used_kernel}_kernel",
-                    "peak_source": f"STORM_b200_microbench(POPC) on this device at {mhz:.0f} MHz",
-                    "algorithmic": "2 LOP3.32 + 2 POPC.32 per 64-bit word pair (SURVEY.md 8(d))",
+                    "frac": achieved / popc_rate, "traffic": traffic, "kernel": "dense_tile_kernel",
+                    "peak_source": "STORM_b200_microbench(POPC) on this device (measured)",
+                    "algorithmic": "2 LOP3.32 + 2 POPC.32 per 64-bit word pair (SURVEY.md 8(d)); the carry-save kernel "
+                                   "issues fewer POPC than that, so its fraction can exceed 1",
                     "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
 
     line = {

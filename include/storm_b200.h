@@ -81,6 +81,16 @@ int STORM_b200_square_device(const uint64_t* d_rows1, uint64_t n1, uint64_t stri
  * reason about shard balance), and the tile edge lengths it uses. */
 uint64_t STORM_b200_tile_count(uint64_t n_rows, int kernel, uint32_t* tile_rows, uint32_t* tile_cols);
 
+/* Host-only bookkeeping of the same raster (no device needed): the tile range
+ * [*tile_begin, *tile_end) that shard `shard` of `n_shards` owns, and the row
+ * rectangle [i0,i1) x [j0,j1) (clipped to n_rows) a tile index covers; a tile
+ * contributes its pairs with j > i.  Multi-GPU callers and the CPU tests use
+ * these to check that the shards partition the triangle. */
+int STORM_b200_shard_tiles(uint64_t n_rows, int kernel, uint32_t shard, uint32_t n_shards,
+                           uint64_t* tile_begin, uint64_t* tile_end);
+int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile,
+                         uint64_t* i0, uint64_t* i1, uint64_t* j0, uint64_t* j1);
+
 /* Which kernel id AUTO (or the process default) resolves to for rows of n_words. */
 int STORM_b200_resolve_kernel(int kernel, uint32_t n_words);
 

@@ -75,6 +75,8 @@ SIGNATURES = {
     "STORM_b200_resolve_kernel": (C.c_int, [C.c_int, C.c_uint32]),
     "STORM_b200_wrapper_diag_shard": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),
     "STORM_b200_tile_count": (C.c_uint64, [C.c_uint64, C.c_int, u32p, u32p]),
+    "STORM_b200_shard_tiles": (C.c_int, [C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, u64p, u64p]),
+    "STORM_b200_tile_rect": (C.c_int, [C.c_uint64, C.c_int, C.c_uint64, u64p, u64p, u64p, u64p]),
     "STORM_b200_contig_pairw_shard": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     "STORM_b200_contig_pairw_rect": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u32p]),
     "STORM_b200_contig_device_rows": (C.c_void_p, [C.c_void_p, u64p]),

@@ -312,6 +312,23 @@ def tile_count(n_rows: int, kernel=KERNEL_AUTO):
     return int(n), tm.value, tn.value
 
 
+def shard_tiles(n_rows: int, shard: int, n_shards: int, kernel=KERNEL_AUTO):
+    """``STORM_b200_shard_tiles`` (host only): tile range [begin, end) owned by one shard."""
+    L = _lib.load()
+    b, e = C.c_uint64(), C.c_uint64()
+    _lib.check(L.STORM_b200_shard_tiles(n_rows, _kernel_id(kernel), shard, n_shards, C.byref(b), C.byref(e)),
+               "STORM_b200_shard_tiles")
+    return int(b.value), int(e.value)
+
+
+def tile_rect(n_rows: int, tile: int, kernel=KERNEL_AUTO):
+    """``STORM_b200_tile_rect`` (host only): rows (i0, i1, j0, j1) a tile covers."""
+    L = _lib.load()
+    v = [C.c_uint64() for _ in range(4)]
+    _lib.check(L.STORM_b200_tile_rect(n_rows, _kernel_id(kernel), tile, *[C.byref(x) for x in v]), "STORM_b200_tile_rect")
+    return tuple(int(x.value) for x in v)
+
+
 def microbench(kind: int):
     L = _lib.load()
     rate, mhz = C.c_double(), C.c_double()

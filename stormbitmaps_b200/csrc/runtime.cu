@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -267,6 +268,29 @@ uint64_t STORM_b200_tile_count(uint64_t n_rows, int kernel, uint32_t* tile_rows,
     if (tile_rows) *tile_rows = ts.tm;
     if (tile_cols) *tile_cols = ts.tn;
     return triangle_prefix(n_rows, ts, nullptr, nullptr, nullptr);
+}
+
+int STORM_b200_shard_tiles(uint64_t n_rows, int kernel, uint32_t shard, uint32_t n_shards,
+                           uint64_t* tile_begin, uint64_t* tile_end) {
+    if (n_shards == 0 || shard >= n_shards || !tile_begin || !tile_end) { set_error("shard %u of %u", shard, n_shards); return STORM_B200_EINVAL; }
+    const uint64_t n_tiles = STORM_b200_tile_count(n_rows, kernel, nullptr, nullptr);
+    shard_range(n_tiles, shard, n_shards, tile_begin, tile_end);
+    return STORM_B200_OK;
+}
+
+int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile, uint64_t* i0, uint64_t* i1, uint64_t* j0, uint64_t* j1) {
+    if (kernel == STORM_B200_KERNEL_AUTO) kernel = STORM_b200_resolve_kernel(kernel, 1024);
+    const TileShape ts = tile_shape_for(kernel);
+    std::vector<uint64_t> prefix;
+    uint32_t nbi = 0, nbj = 0;
+    const uint64_t n_tiles = triangle_prefix(n_rows, ts, &prefix, &nbi, &nbj);
+    if (tile >= n_tiles || !i0 || !i1 || !j0 || !j1) { set_error("tile %llu of %llu", (unsigned long long)tile, (unsigned long long)n_tiles); return STORM_B200_EINVAL; }
+    // same search as tile_coords() on the device: largest bi with prefix[bi] <= tile
+    const uint32_t bi = (uint32_t)(std::upper_bound(prefix.begin(), prefix.begin() + nbi, tile) - prefix.begin()) - 1;
+    const uint32_t bj = tri_jstart(bi, ts.tm, ts.tn) + (uint32_t)(tile - prefix[bi]);
+    *i0 = (uint64_t)bi * ts.tm; *i1 = std::min<uint64_t>(*i0 + ts.tm, n_rows);
+    *j0 = (uint64_t)bj * ts.tn; *j1 = std::min<uint64_t>(*j0 + ts.tn, n_rows);
+    return STORM_B200_OK;
 }
 
 int STORM_b200_synth_uniform_device(uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,

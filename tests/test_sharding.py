@@ -1,0 +1,94 @@
+"""Multi-GPU sharding logic on CPU: world_size-2 gloo processes (no GPU needed).
+
+Every rank owns a contiguous range of the tile raster (STORM_b200_shard_tiles);
+the only exchange on the path is the all-reduce of the 64-bit partial totals.
+Here each rank evaluates its tiles with the CPU oracle (the checker standing in
+for the kernel), so the test pins the raster, the shard ranges and the reduce --
+the host logic bench.py and a multi-GPU caller rely on.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rank_main(rank, world, port, kernel, n_rows, M, draws, seed, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import stormbitmaps_b200 as sb
+    from oracle import oracle as O
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        orc = O.Oracle()
+        vals = orc.gen_dense_uniform(seed, n_rows, draws, M)        # every rank holds the full matrix
+        begin, end = sb.shard_tiles(n_rows, rank, world, kernel)
+        part, pairs = 0, 0
+        for t in range(begin, end):
+            i0, i1, j0, j1 = sb.tile_rect(n_rows, t, kernel)
+            part += orc.rect_total(vals, i0, i1, j0, j1)             # strict upper triangle of the rectangle
+            ii, jj = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), indexing="ij")
+            pairs += int((jj > ii).sum())
+        t = torch.tensor([part, pairs, end - begin], dtype=torch.int64)
+        dist.all_reduce(t)                                            # the path's only collective
+        if rank == 0:
+            out.put((int(t[0]), int(t[1]), int(t[2]), orc.wrapper_diag(vals)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kernel,n_rows", [("popc", 700), ("umma", 1100), ("csa", 513)])
+def test_two_ranks_partition_the_triangle(kernel, n_rows):
+    import torch.multiprocessing as mp
+    import stormbitmaps_b200 as sb
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    M, draws, seed, world = 2048, 700, 5, 2
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, kernel, n_rows, M, draws, seed, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    total, pairs, tiles, exact = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert total == exact
+    assert pairs == n_rows * (n_rows - 1) // 2
+    assert tiles == sb.tile_count(n_rows, kernel)[0]
+
+
+def test_shard_ranges_are_balanced_and_contiguous():
+    import stormbitmaps_b200 as sb
+    for kernel in ("popc", "umma"):
+        for n_rows in (2, 255, 256, 257, 10_000, 200_000):
+            n_tiles = sb.tile_count(n_rows, kernel)[0]
+            for world in (1, 2, 3, 8):
+                prev_end, sizes = 0, []
+                for r in range(world):
+                    b, e = sb.shard_tiles(n_rows, r, world, kernel)
+                    assert b == prev_end and e >= b
+                    prev_end = e
+                    sizes.append(e - b)
+                assert prev_end == n_tiles
+                assert max(sizes) - min(sizes) <= 1
+
+
+def test_tiles_cover_every_pair_once():
+    import stormbitmaps_b200 as sb
+    for kernel, n_rows in (("popc", 300), ("umma", 600), ("umma", 256), ("popc", 129)):
+        seen = np.zeros((n_rows, n_rows), dtype=np.int32)
+        for t in range(sb.tile_count(n_rows, kernel)[0]):
+            i0, i1, j0, j1 = sb.tile_rect(n_rows, t, kernel)
+            seen[i0:i1, j0:j1] += 1
+        iu = np.triu_indices(n_rows, k=1)
+        assert (seen[iu] == 1).all()
