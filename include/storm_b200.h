@@ -122,6 +122,12 @@ int STORM_b200_contig_add_bulk(STORM_contiguous_t* bitmap, const uint32_t* posit
 int STORM_b200_contig_last_timing(STORM_contiguous_t* bitmap, double out_seconds[3]);
 
 uint64_t STORM_b200_storm_pairw_shard(STORM_t* bitmap, uint32_t shard, uint32_t n_shards);
+/* How whole-container STORM_t queries are answered: 0 = cost model (default), 1 = the sparse
+ * merge/probe kernel, 2 = rows densified on the device + the dense tile kernel (falls back to
+ * 1 if the dense form does not fit in device memory).  Results are identical.  Returns the
+ * previous value; STORM_b200_storm_last_route tells which one the last query of `bitmap` took. */
+int STORM_b200_set_storm_route(int route);
+int STORM_b200_storm_last_route(const STORM_t* bitmap);
 /* Per-pair counts of a STORM_t rectangle into a HOST buffer (strict upper). */
 int STORM_b200_storm_pairw_rect(STORM_t* bitmap, uint64_t i0, uint64_t i1,
                                 uint64_t j0, uint64_t j1, uint32_t* out);

@@ -143,6 +143,10 @@ class Storm:
         return _query(self._L.STORM_pairw_intersect_cardinality_blocked(self._h, bsize),
                       "STORM_pairw_intersect_cardinality_blocked")
 
+    def last_route(self) -> str:
+        """Which kernel family answered the last whole-container query: 'sparse' or 'dense'."""
+        return {0: "none", 1: "sparse", 2: "dense"}[self._L.STORM_b200_storm_last_route(self._h)]
+
     def pairw_shard(self, shard: int, n_shards: int) -> int:
         return _query(self._L.STORM_b200_storm_pairw_shard(self._h, shard, n_shards), "STORM_b200_storm_pairw_shard")
 
@@ -346,6 +350,12 @@ def set_default_kernel(kernel) -> int:
 
 def set_umma_cta_group(cg: int) -> int:
     return _lib.load().STORM_b200_set_umma_cta_group(int(cg))
+
+
+def set_storm_route(route) -> int:
+    """``STORM_b200_set_storm_route``: 'auto' | 'sparse' | 'dense' for whole-container STORM_t queries."""
+    r = {"auto": 0, "sparse": 1, "dense": 2}[route] if isinstance(route, str) else int(route)
+    return _lib.load().STORM_b200_set_storm_route(r)
 
 
 def set_umma_variant(variant: int) -> int:

@@ -33,9 +33,16 @@ void count_launch(uint64_t n = 1);
 //
 // A and B are row-major bitmaps (64-bit words).  A tile (bi, bj) covers A rows
 // [bi*TM, bi*TM+TM) x B rows [bj*TN, bj*TN+TN) where TM/TN belong to the kernel.
-// Tiles are numbered row-block-major; in triangle mode only tiles that intersect
-// the strict upper triangle exist and `row_prefix[bi]` is the number of tiles in
-// row blocks < bi (n_bi + 1 entries, device memory).
+// Rectangle mode numbers tiles row-block-major.  Triangle mode (A == B, strict upper
+// triangle) only has the tiles that intersect the triangle and numbers them in an
+// L2-friendly raster: row blocks are taken in groups of TRI_GROUP; inside a group the
+// walk is column-block-major (bj outer, bi inner).  Consecutive tile indices -- which is
+// what the CTAs of one wave hold, and what a shard is a range of -- then share their A rows
+// with TRI_GROUP - 1 neighbours and their B rows with ~wave / TRI_GROUP neighbours, so a wave
+// of 74 tiles touches ~17 distinct row blocks instead of 75.
+// `group_prefix[g]` is the number of tiles in groups < g (n_groups + 1 entries, device).
+constexpr uint32_t TRI_GROUP = 8;
+
 struct DenseJob {
     const uint64_t* A;
     const uint64_t* B;
@@ -44,8 +51,8 @@ struct DenseJob {
     uint32_t n_words;            // words per row that carry data
     uint64_t i_off, j_off;       // global row index of A row 0 / B row 0 (for the j>i mask)
     int strict_upper;            // count / emit only pairs with global j > global i
-    int triangle;                // 1: tile list is the triangle raster (needs row_prefix)
-    const uint64_t* row_prefix;  // device, n_bi + 1 entries (triangle mode)
+    int triangle;                // 1: tile list is the triangle raster (needs group_prefix)
+    const uint64_t* group_prefix;  // device, n_groups + 1 entries (triangle mode)
     uint32_t n_bi, n_bj;         // tile grid extents
     uint64_t tile_begin, tile_end;  // this launch handles tiles [begin, end)
     uint32_t* out;               // optional per-pair counts, out[(i)*ld + j] relative to A/B row 0
@@ -59,7 +66,45 @@ __host__ __device__ inline uint32_t tri_jstart(uint32_t bi, uint32_t TM, uint32_
     return (uint32_t)(((uint64_t)bi * TM + 1) / TN);
 }
 
-// Map a linear tile index to (bi, bj).
+// Number of tiles of the row-block group starting at row block g0 (host builds the prefix with it).
+__host__ __device__ inline uint64_t tri_group_tiles(uint32_t g0, uint32_t n_bi, uint32_t n_bj, uint32_t TM, uint32_t TN) {
+    uint64_t n = 0;
+    for (uint32_t bi = g0; bi < g0 + TRI_GROUP && bi < n_bi; ++bi) {
+        const uint32_t js = tri_jstart(bi, TM, TN);
+        if (js < n_bj) n += n_bj - js;
+    }
+    return n;
+}
+
+// Tile u of the group whose first row block is g0 -> (bi, bj): column-block-major inside the group.
+__host__ __device__ inline void tri_group_coords(uint32_t g0, uint64_t u, uint32_t n_bi, uint32_t TM, uint32_t TN,
+                                                 uint32_t& bi, uint32_t& bj) {
+    const uint32_t rows = (g0 + TRI_GROUP <= n_bi) ? TRI_GROUP : n_bi - g0;      // row blocks in this group
+    const uint32_t jfull = tri_jstart(g0 + rows - 1, TM, TN);                    // from here on every row block has a tile
+    uint32_t j = tri_jstart(g0, TM, TN);
+    for (; j < jfull; ++j) {                                                     // ramp: columns that only some rows reach
+        // (jfull < n_bj for every tile shape in use: the last row block always has its diagonal tile)
+        uint32_t c = 0;
+        while (c < rows && tri_jstart(g0 + c, TM, TN) <= j) ++c;
+        if (u < c) { bi = g0 + (uint32_t)u; bj = j; return; }
+        u -= c;
+    }
+    bj = jfull + (uint32_t)(u / rows);
+    bi = g0 + (uint32_t)(u % rows);
+}
+
+// Map a linear tile index to (bi, bj).  `prefix` is job.group_prefix (device) or its host copy.
+__host__ __device__ inline void tile_coords_tri(const uint64_t* prefix, uint32_t n_bi, uint64_t t, uint32_t TM, uint32_t TN,
+                                                uint32_t& bi, uint32_t& bj) {
+    const uint32_t n_groups = (n_bi + TRI_GROUP - 1) / TRI_GROUP;
+    uint32_t lo = 0, hi = n_groups;          // largest g with prefix[g] <= t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    tri_group_coords(lo * TRI_GROUP, t - prefix[lo], n_bi, TM, TN, bi, bj);
+}
+
 __device__ inline void tile_coords(const DenseJob& job, uint64_t t, uint32_t TM, uint32_t TN,
                                    uint32_t& bi, uint32_t& bj) {
     if (!job.triangle) {
@@ -67,13 +112,7 @@ __device__ inline void tile_coords(const DenseJob& job, uint64_t t, uint32_t TM,
         bj = (uint32_t)(t % job.n_bj);
         return;
     }
-    uint32_t lo = 0, hi = job.n_bi;          // largest bi with prefix[bi] <= t
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (job.row_prefix[mid] <= t) lo = mid; else hi = mid;
-    }
-    bi = lo;
-    bj = tri_jstart(lo, TM, TN) + (uint32_t)(t - job.row_prefix[lo]);
+    tile_coords_tri(job.group_prefix, job.n_bi, t, TM, TN, bi, bj);
 }
 
 // ---- launchers (one per kernel family) ---------------------------------------

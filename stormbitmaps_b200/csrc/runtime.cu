@@ -57,14 +57,14 @@ TileShape tile_shape_for(int kernel) {
 uint64_t triangle_prefix(uint64_t n_rows, TileShape ts, std::vector<uint64_t>* prefix, uint32_t* n_bi, uint32_t* n_bj) {
     const uint32_t nbi = (uint32_t)((n_rows + ts.tm - 1) / ts.tm);
     const uint32_t nbj = (uint32_t)((n_rows + ts.tn - 1) / ts.tn);
-    if (prefix) prefix->assign((size_t)nbi + 1, 0);
+    const uint32_t n_groups = (nbi + TRI_GROUP - 1) / TRI_GROUP;
+    if (prefix) prefix->assign((size_t)n_groups + 1, 0);
     uint64_t acc = 0;
-    for (uint32_t bi = 0; bi < nbi; ++bi) {
-        if (prefix) (*prefix)[bi] = acc;
-        const uint32_t js = tri_jstart(bi, ts.tm, ts.tn);
-        if (js < nbj) acc += nbj - js;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        if (prefix) (*prefix)[g] = acc;
+        acc += tri_group_tiles(g * TRI_GROUP, nbi, nbj, ts.tm, ts.tn);
     }
-    if (prefix) (*prefix)[nbi] = acc;
+    if (prefix) (*prefix)[n_groups] = acc;
     if (n_bi) *n_bi = nbi;
     if (n_bj) *n_bj = nbj;
     return acc;
@@ -163,7 +163,7 @@ int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, ui
     kernel = resolve_kernel(kernel, job);
     const TileShape ts = tile_shape_for(kernel);
     uint64_t n_tiles = 0;
-    if ((rc = get_triangle_prefix(n_rows, ts, stream, &job.row_prefix, &n_tiles, &job.n_bi, &job.n_bj))) return rc;
+    if ((rc = get_triangle_prefix(n_rows, ts, stream, &job.group_prefix, &n_tiles, &job.n_bi, &job.n_bj))) return rc;
     shard_range(n_tiles, shard, n_shards, &job.tile_begin, &job.tile_end);
     return launch_dense(kernel, job, stream);
 }
@@ -285,9 +285,8 @@ int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile, uint64_t* i
     uint32_t nbi = 0, nbj = 0;
     const uint64_t n_tiles = triangle_prefix(n_rows, ts, &prefix, &nbi, &nbj);
     if (tile >= n_tiles || !i0 || !i1 || !j0 || !j1) { set_error("tile %llu of %llu", (unsigned long long)tile, (unsigned long long)n_tiles); return STORM_B200_EINVAL; }
-    // same search as tile_coords() on the device: largest bi with prefix[bi] <= tile
-    const uint32_t bi = (uint32_t)(std::upper_bound(prefix.begin(), prefix.begin() + nbi, tile) - prefix.begin()) - 1;
-    const uint32_t bj = tri_jstart(bi, ts.tm, ts.tn) + (uint32_t)(tile - prefix[bi]);
+    uint32_t bi = 0, bj = 0;
+    tile_coords_tri(prefix.data(), nbi, tile, ts.tm, ts.tn, bi, bj);      // the function the kernels call
     *i0 = (uint64_t)bi * ts.tm; *i1 = std::min<uint64_t>(*i0 + ts.tm, n_rows);
     *j0 = (uint64_t)bj * ts.tn; *j1 = std::min<uint64_t>(*j0 + ts.tn, n_rows);
     return STORM_B200_OK;

@@ -200,6 +200,29 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_pairs_kernel(const SparseJo
     }
 }
 
+// Dense route: one CTA per row writes the row's blocks into a zeroed row-major arena in the
+// layout of the contiguous model (bit v -> word v/64, bit v%64; storm.c:1114), after which
+// the query is the dense tile kernel's.  A bitmap block is a 8 KiB copy; a list block sets
+// its bits with 64-bit atomic ORs (two values of a list may share a word).
+__global__ void __launch_bounds__(256) densify_rows_kernel(const SparseView v, uint64_t* dense, uint64_t stride) {
+    const uint32_t row = blockIdx.x;
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(dense + (uint64_t)row * stride);
+    for (uint32_t b = v.row_ptr[row]; b < v.row_ptr[row + 1]; ++b) {
+        const uint32_t len = v.blk_len[b];
+        unsigned long long* blk = out + (uint64_t)v.blk_id[b] * BLOCK_WORDS;
+        if (len & BITMAP_FLAG) {
+            const uint64_t* src = v.words + v.blk_off[b];
+            for (uint32_t w = threadIdx.x; w < BLOCK_WORDS; w += blockDim.x) blk[w] = src[w];
+        } else {
+            const uint16_t* src = v.lists + v.blk_off[b];
+            for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) {
+                const uint32_t x = src[k];
+                atomicOr(blk + (x >> 6), 1ull << (x & 63));
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // device mirror
 // ---------------------------------------------------------------------------------
@@ -208,6 +231,10 @@ struct StormState {
     cudaStream_t stream = nullptr;
     bool dirty = true;
     uint32_t n_rows = 0, max_blocks = 0;
+    uint32_t max_blk_id = 0;             // largest block index of any row (row width of the dense form)
+    uint64_t total_nnz = 0;
+    uint64_t* d_dense = nullptr; uint64_t dense_cap_words = 0; bool dense_valid = false;   // densified rows (dense route)
+    int last_route = 0;                  // 1 = sparse kernel, 2 = densified + dense tile kernel
     uint32_t *d_row_ptr = nullptr, *d_row_nnz = nullptr, *d_blk_id = nullptr, *d_blk_len = nullptr;
     uint64_t* d_blk_off = nullptr; uint16_t* d_lists = nullptr; uint64_t* d_words = nullptr;
     unsigned long long* d_total = nullptr; unsigned long long* h_total = nullptr;
@@ -230,6 +257,7 @@ void free_mirror(StormState* st) {
         if (p) cudaFree(p);
     st->d_row_ptr = st->d_row_nnz = st->d_blk_id = st->d_blk_len = nullptr;
     st->d_blk_off = nullptr; st->d_lists = nullptr; st->d_words = nullptr;
+    st->dense_valid = false;
 }
 
 template <typename T>
@@ -260,7 +288,7 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     std::vector<uint32_t> row_ptr(s->n_conts + 1, 0), row_nnz(s->n_conts, 0), blk_id, blk_len;
     std::vector<uint64_t> blk_off, words;
     std::vector<uint16_t> lists;
-    uint32_t max_blocks = 0;
+    uint32_t max_blocks = 0, max_blk_id = 0;
     for (uint32_t r = 0; r < s->n_conts; ++r) {
         const STORM_bitmap_cont_t* row = &s->conts[r];
         row_ptr[r] = (uint32_t)blk_id.size();
@@ -268,6 +296,7 @@ int sync_mirror(const STORM_t* s, StormState* st) {
         for (uint32_t b = 0; b < row->n_bitmaps; ++b) {
             const STORM_bitmap_t* k = &row->bitmaps[b];
             blk_id.push_back(k->id);
+            max_blk_id = std::max(max_blk_id, k->id);
             if (k->n_bitmap) {
                 blk_len.push_back(k->n_bits_set | BITMAP_FLAG);
                 blk_off.push_back(words.size());
@@ -295,6 +324,9 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));              // host vectors die here
     st->n_rows = s->n_conts;
     st->max_blocks = max_blocks;
+    st->max_blk_id = max_blk_id;
+    st->total_nnz = 0;
+    for (uint32_t v : row_nnz) st->total_nnz += v;
     st->dirty = false;
     return STORM_B200_OK;
 }
@@ -320,6 +352,49 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
     return STORM_B200_OK;
 }
 
+// Route of a whole-container query.  The dense tile kernel costs W / 3e13 s per pair whatever the
+// density (tensor pipe, bench.py); the sparse kernel costs about one probe per value of the partner
+// row, ~1e12 probes/s.  Dense wins unless rows are nearly empty -- the threshold is a cost model,
+// not the reference's CPU-tuned 4096 / 200 constants, and it cannot change a result.
+int g_storm_route = 0;   // 0 auto, 1 sparse kernel, 2 densify + dense tile kernel (STORM_b200_set_storm_route)
+
+bool choose_dense_route(const StormState* st, uint64_t n_rows) {
+    if (g_storm_route == 1) return false;
+    const uint64_t W = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
+    if (W >= (1u << 25)) return false;                                   // per-pair counts must stay below 2^31
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+    const uint64_t need = n_rows * W * 8;
+    const uint64_t have = free_b + (st->d_dense ? st->dense_cap_words * 8 : 0);
+    if (need > have / 10 * 8) return false;                              // keep 20 % of the free memory
+    if (g_storm_route == 2) return true;
+    const double avg_nnz = (double)st->total_nnz / (double)n_rows;
+    return avg_nnz * 30.0 > (double)W;                                   // W / 3e13  <  avg_nnz / 1e12
+}
+
+int ensure_dense(StormState* st, uint64_t n_rows, uint64_t* stride_out) {
+    const uint64_t stride = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;   // a multiple of 16 words
+    *stride_out = stride;
+    if (st->dense_valid) return STORM_B200_OK;
+    const uint64_t words = n_rows * stride;
+    if (words > st->dense_cap_words) {
+        if (st->d_dense) cudaFree(st->d_dense);
+        st->d_dense = nullptr; st->dense_cap_words = 0;
+        if (cudaMalloc(&st->d_dense, words * 8) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("dense form of the STORM_t rows (%llu bytes) does not fit", (unsigned long long)(words * 8));
+            return STORM_B200_ENOMEM;
+        }
+        st->dense_cap_words = words;
+    }
+    STORM_CUDA_TRY(cudaMemsetAsync(st->d_dense, 0, words * 8, st->stream));
+    densify_rows_kernel<<<(unsigned)n_rows, 256, 0, st->stream>>>(view_of(st), st->d_dense, stride);
+    STORM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    st->dense_valid = true;
+    return STORM_B200_OK;
+}
+
 uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     if (s == nullptr) return (uint64_t)-1;                          // storm.c:878,898
     if (s->n_conts < 2) return 0;
@@ -327,13 +402,21 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     DeviceGuard guard(st->device);
     if (sync_mirror(s, st)) return (uint64_t)-1;
     if (cudaMemsetAsync(st->d_total, 0, 8, st->stream) != cudaSuccess) return (uint64_t)-1;
-    SparseJob job{};
-    job.A = job.B = view_of(st);
-    job.i0 = 0; job.i1 = s->n_conts; job.j0 = 0; job.j1 = s->n_conts;
-    job.strict_upper = 1;
-    job.shard = shard; job.n_shards = n_shards;
-    job.total = st->d_total;
-    if (launch_sparse(job, st->max_blocks, st->stream)) return (uint64_t)-1;
+    uint64_t stride = 0;
+    if (choose_dense_route(st, s->n_conts) && ensure_dense(st, s->n_conts, &stride) == STORM_B200_OK) {
+        st->last_route = 2;
+        if (pairw_triangle(st->d_dense, s->n_conts, (uint32_t)stride, stride, shard, n_shards, STORM_B200_KERNEL_AUTO,
+                           reinterpret_cast<uint64_t*>(st->d_total), st->stream)) return (uint64_t)-1;
+    } else {
+        st->last_route = 1;
+        SparseJob job{};
+        job.A = job.B = view_of(st);
+        job.i0 = 0; job.i1 = s->n_conts; job.j0 = 0; job.j1 = s->n_conts;
+        job.strict_upper = 1;
+        job.shard = shard; job.n_shards = n_shards;
+        job.total = st->d_total;
+        if (launch_sparse(job, st->max_blocks, st->stream)) return (uint64_t)-1;
+    }
     if (cudaMemcpyAsync(st->h_total, st->d_total, 8, cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
         cudaStreamSynchronize(st->stream) != cudaSuccess) {
         set_error("STORM_t query failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -541,6 +624,7 @@ void STORM_free(STORM_t* s) {                                               // s
         DeviceGuard guard(st->device);
         if (st->stream) cudaStreamSynchronize(st->stream);
         free_mirror(st);
+        if (st->d_dense) cudaFree(st->d_dense);
         if (st->d_total) cudaFree(st->d_total);
         if (st->h_total) cudaFreeHost(st->h_total);
         if (st->stream) cudaStreamDestroy(st->stream);
@@ -593,6 +677,17 @@ uint64_t STORM_b200_storm_pairw_shard(STORM_t* s, uint32_t shard, uint32_t n_sha
     if (s == nullptr) return (uint64_t)-1;
     if (n_shards == 0 || shard >= n_shards) { set_error("shard %u of %u", shard, n_shards); return (uint64_t)-1; }
     return storm_query(s, shard, n_shards);
+}
+
+int STORM_b200_set_storm_route(int route) {
+    const int prev = g_storm_route;
+    if (route >= 0 && route <= 2) g_storm_route = route;
+    return prev;
+}
+
+int STORM_b200_storm_last_route(const STORM_t* s) {
+    if (s == nullptr || s->b200 == nullptr) return 0;
+    return state_of(s)->last_route;
 }
 
 int STORM_b200_storm_pairw_rect(STORM_t* s, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, uint32_t* out) {

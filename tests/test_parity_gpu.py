@@ -223,6 +223,38 @@ def test_storm_t_dispatch_regimes(sb, orc):
         assert s.pairw_intersect_cardinality() == orc.wrapper_diag(vals[100:160])
 
 
+@pytest.mark.parametrize("route", ["sparse", "dense", "auto"])
+def test_storm_t_routes_agree(sb, orc, route):
+    """Whole-container STORM_t queries: the sparse merge/probe kernel and the densified +
+    dense-tile route return the same exact total on every density regime of config C2
+    (scaled to 120 rows) and on the C4-like 1 % rows."""
+    M = 524288
+    prev = sb.set_storm_route(route)
+    try:
+        for draws in (262144, 20971, 5242, 524, 104, 5, 1):
+            rows = [orc.gen_row_positions(77, i, draws, M) for i in range(120)]
+            with O.OracleStorm(orc) as ref_s, sb.Storm() as s:
+                for p in rows:
+                    ref_s.add(p)
+                    s.add(p)
+                exact = ref_s.pairw(False)
+                assert s.pairw_intersect_cardinality_blocked(0) == exact, (route, draws)
+                took = s.last_route()
+                if route != "auto":
+                    assert took == route
+                else:                                  # cost model: dense unless rows are nearly empty
+                    assert took == ("dense" if draws >= 524 else "sparse"), (draws, took)
+                # shards add up on either route
+                assert sum(s.pairw_shard(r, 3) for r in range(3)) == exact
+                # a second query reuses the resident mirror; a mutation invalidates it
+                assert s.pairw_intersect_cardinality() == exact
+                s.add(rows[0])
+                ref_s.add(rows[0])
+                assert s.pairw_intersect_cardinality() == ref_s.pairw(False)
+    finally:
+        sb.set_storm_route(prev)
+
+
 # --------------------------------------------------------------------------- #
 # full-size configurations: size-independent properties
 # --------------------------------------------------------------------------- #
