@@ -279,7 +279,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_init(raw_empty_bar + 8 * b, C::EXPANDER_WARPS);
         }
         mbar_init(acc_full_bar, 1);                                        // tcgen05.commit
-        mbar_init(acc_empty_bar, CG * C::A_WARPS);                         // every epilogue warp of the pair
+        mbar_init(acc_empty_bar, CG * C::EXPANDER_WARPS);                  // every epilogue warp of the pair
         fence_mbar_init();
     }
     if (warp == C::TMA_WARP && lane == 0) {
@@ -387,22 +387,41 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
             }
-            if (is_a) {
+            {
                 // ---- epilogue of this tile: TMEM -> registers -> masked sum / per-pair store ----
+                // Every expander warp takes part: warp w may read TMEM lanes 32 (w % 4) .. +31, so the
+                // A warp and the B warp(s) of one lane quarter split the 256 accumulator columns between
+                // them (32-column chunks dealt round-robin) and the drain takes half (a third) as long.
                 uint32_t bi, bj;
                 tile_coords(job, tile, C::TM, C::TN, bi, bj);
-                const uint64_t rowB0 = (uint64_t)bj * C::TN;
-                const uint64_t li = (uint64_t)bi * C::TM + rank * 128u + idx;  // A row of this thread (= its TMEM lane)
+                const uint32_t quarter = warp & 3u, sharer = warp >> 2;
+                constexpr uint32_t N_SHARERS = C::EXPANDER_WARPS / 4;
+                const uint64_t rowA0 = (uint64_t)bi * C::TM, rowB0 = (uint64_t)bj * C::TN;
+                const uint64_t li = rowA0 + rank * 128u + quarter * 32u + lane;  // accumulator row of this thread (= its TMEM lane)
                 const uint64_t gi = job.i_off + li;
                 const bool row_ok = li < job.nA;
+                const uint32_t acc_lane = tmem_base + ((quarter * 32u) << 16) + UM_ACC_COL;
+                // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
+                const bool interior = job.out == nullptr && rowA0 + C::TM <= job.nA && rowB0 + C::TN <= job.nB &&
+                                      (!job.strict_upper || job.j_off + rowB0 >= job.i_off + rowA0 + C::TM);
                 wait(acc_full_bar, t_iter & 1);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < UM_N; c0 += 32) {
+                for (uint32_t c0 = sharer * 32u; c0 < (uint32_t)UM_N; c0 += 32u * N_SHARERS) {
                     uint32_t v[32];
-                    tmem_ld32(a_lane + UM_ACC_COL + c0, v);
+                    tmem_ld32(acc_lane + c0, v);
                     tc_wait_ld();
-                    if (row_ok) {
+                    if (interior) {
+                        if (SCALED) {                                      // 32 counts of at most 2^24 each fit 32 bits
+                            uint32_t part = 0;
+#pragma unroll
+                            for (int cc = 0; cc < 32; ++cc) part += v[cc] >> 7;
+                            sum += part;
+                        } else {
+#pragma unroll
+                            for (int cc = 0; cc < 32; ++cc) sum += v[cc];
+                        }
+                    } else if (row_ok) {
 #pragma unroll
                         for (int cc = 0; cc < 32; ++cc) {
                             const uint64_t lj = rowB0 + c0 + cc;
@@ -426,12 +445,14 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ---- one atomic per CTA, then teardown --------------------------------------------
     if (job.total) {
         sum = warp_sum(sum);
-        if (lane == 0 && warp < C::A_WARPS) red[warp] = sum;
+        if (lane == 0 && warp < C::EXPANDER_WARPS) red[warp] = sum;
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();                 // everyone is done with TMEM / smem
     if (job.total && tid == 0) {
-        const unsigned long long t = red[0] + red[1] + red[2] + red[3];
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < C::EXPANDER_WARPS; ++w) t += red[w];
         if (t) atomicAdd(job.total, t);
     }
     if (warp == C::MMA_WARP) tmem_free<CG>(tmem_base);
