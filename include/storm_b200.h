@@ -32,6 +32,8 @@ extern "C" {
 #define STORM_B200_KERNEL_POPC 1   /* CUDA cores: LOP3 + POPC register tiles          */
 #define STORM_B200_KERNEL_UMMA 2   /* tcgen05.mma kind::i8 on bits unpacked on the fly */
 #define STORM_B200_KERNEL_CSA  3   /* CUDA cores: carry-save adders feeding POPC        */
+#define STORM_B200_KERNEL_FP4  4   /* tcgen05.mma kind::mxf4 on bits unpacked to E2M1 nibbles, fp32 accumulators
+                                      (exact below 2^24 bits per row; twice the rate of kind::i8) */
 
 /* ---- library / device ---------------------------------------------------- */
 const char* STORM_b200_last_error(void);
@@ -151,6 +153,15 @@ int STORM_b200_synth_geno_device(uint64_t* d_rows, uint64_t n_rows, uint32_t n_w
  * (cta_group 1 / 2) issued back to back with no operand production: int8 ops per
  * second (2 per MAC) in *rate -- the tensor-pipe ceiling of dense_umma_kernel. */
 int STORM_b200_microbench(int kind, double* rate, double* sm_mhz);
+/* kind 6 / 7 of STORM_b200_microbench: tcgen05.mma kind::mxf4 (block-scaled E2M1, K = 64) at
+ * cta_group 1 / 2, ops per second (2 per MAC).
+ *
+ * Exactness probe of that instruction for bit counting (fp4_probe.cu): each case is three
+ * uint32 {n_full, n_single, pattern}: n_full instructions that add 64 to each of the 128 x 256
+ * fp32 accumulators, then n_single that add 1; pattern 0..3 picks the operand encodings
+ * (1.0 x 1.0, 0.5 x 2.0, 2.0 x 0.5, alternating).  Per case four 32-bit results: expected value,
+ * smallest and largest accumulator (floats) and the number of accumulators != expected (uint32). */
+int STORM_b200_fp4_probe(const uint32_t* cases, uint32_t n_cases, float* results);
 /* cta_group of the UMMA kernel: 2 (default) = CTA pair per 256 x 256 tile, 1 = one CTA per
  * 128 x 256 tile.  Returns the previous value. */
 int STORM_b200_set_umma_cta_group(int cg);

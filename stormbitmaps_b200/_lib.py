@@ -16,8 +16,8 @@ u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
 UINT64_MAX = 2**64 - 1
 
-KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_CSA = 0, 1, 2, 3
-KERNEL_NAMES = {"auto": 0, "popc": 1, "umma": 2, "csa": 3}
+KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_CSA, KERNEL_FP4 = 0, 1, 2, 3, 4
+KERNEL_NAMES = {"auto": 0, "popc": 1, "umma": 2, "csa": 3, "fp4": 4}
 
 
 class StormError(RuntimeError):
@@ -90,6 +90,7 @@ SIGNATURES = {
     "STORM_b200_synth_uniform_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "STORM_b200_synth_geno_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "STORM_b200_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "STORM_b200_fp4_probe": (C.c_int, [u32p, C.c_uint32, C.POINTER(C.c_float)]),
     "STORM_b200_set_umma_cta_group": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_variant": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),

@@ -126,8 +126,11 @@ TileShape umma_tile_shape();
 int launch_dense_umma(const DenseJob& job, cudaStream_t stream);
 // UMMA needs at least one full K step of 128 bits and 16-byte aligned rows.
 bool umma_supports(const DenseJob& job);
+bool umma_fp4_supports(const DenseJob& job);          // + every pair count below 2^24 (fp32-exact)
+int launch_dense_fp4(const DenseJob& job, cudaStream_t stream);   // same kernel, kind::mxf4 form
 // int8 ops per second of the UMMA kernel's own instruction issued back to back (cta_group 1 or 2).
 int umma_peak_ops(int cg, double* ops_per_s);
+int fp4_peak_ops(int cg, double* ops_per_s);   // tcgen05.mma kind::mxf4 issue-rate probe (fp4_probe.cu)
 
 int launch_synth_uniform(uint64_t* d_rows, uint64_t n_rows, uint64_t stride, uint32_t M,
                          uint32_t n_draws, uint64_t seed, uint64_t row0, cudaStream_t stream);

@@ -39,15 +39,21 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace storm {
 namespace {
 
 constexpr int UM_N = 256;               // B rows (accumulator columns) per tile
-constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_ACC_COL = 0;           // accumulator: columns [0, 256)
 constexpr int UM_A_COL = 256;           // A stage s: columns [256 + 32 s, 256 + 32 s + 32)
-constexpr int UM_CHUNK_KB = 8;          // k-blocks per TMA box (8 x 16 B = one 128-byte swizzle line)
+constexpr int UM_SF_COL = 448;          // FP4 form: 64 columns of UE8M0 scale factors, all 127 (x 1.0)
+constexpr int UM_SF_COLS = 64;
+// k-block = the packed bits of one row that expand to one 128-byte swizzle line (4 MMAs):
+// 128 bits (16 B) as bytes for kind::i8, 256 bits (32 B) as nibbles for kind::mxf4.  A TMA box is
+// 128 packed bytes wide, i.e. 8 resp. 4 k-blocks.
+constexpr int UM_CHUNK_KB = 8;
+constexpr int UM_CHUNK_KB_FP4 = 4;
 
 template <int CG>
 struct Cfg {
@@ -72,148 +78,11 @@ struct Cfg {
     //   [4,6) c_format = 2 (S32); [7,10) a_format = 0 (u8); [10,13) b_format = 0 (u8);
     //   [15] a_major = 0 (K); [16] b_major = 0 (K); [17,23) N >> 3; [24,29) M >> 4
     static constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(UM_N >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+    // kind::mxf4 block-scaled descriptor (cute::UMMA::InstrDescriptorBlockScaled): [7,10) a_format = 1 (E2M1);
+    //   [10,13) b_format = 1; K-major; [17,23) N >> 3; [23] scale format 1 (UE8M0); [24,29) M >> 4; [31] 0 = K 64
+    static constexpr uint32_t IDESC_FP4 = (1u << 7) | (1u << 10) | ((uint32_t)(UM_N >> 3) << 17) | (1u << 23) |
+                                          ((uint32_t)((128 * CG) >> 4) << 24);
 };
-
-// ---- PTX wrappers -----------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the device.
-// Default (.acquire.cta) semantics on purpose: an explicit .acquire.cluster makes ptxas emit
-// CCTL.IVALL (L1 invalidate) per wait and .release.cluster a MEMBAR.ALL.GPU per arrive, which
-// more than halved the pair kernel.  The data handed over is ordered by its own fences
-// (tcgen05.wait::st + tcgen05.fence for TMEM, fence.proxy.async for shared memory).
-//
-// SUSPEND = true passes a suspend-time hint so that the hardware parks the warp until the
-// phase completes (or ~1 ms passes) instead of returning at once: without it the MMA thread
-// re-issued try_wait + counter + branch ~44 times per k-block (ncu, profiles/r01_umma_v1.md)
-// and those instructions competed with the expander warps of its scheduler for issue slots
-// and for the ALU pipe.
-template <bool SUSPEND>
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    if (SUSPEND) {
-        for (uint32_t spin = 0; !done; ++spin) {
-            asm volatile("{\n\t.reg .pred p;\n\t"
-                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                         "selp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
-            if (spin > (1u << 12)) __trap();                               // ~4 s of 1 ms suspensions
-        }
-    } else {
-        for (uint32_t spin = 0; !done; ++spin) {
-            asm volatile("{\n\t.reg .pred p;\n\t"
-                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-            if (spin > (1u << 26)) __trap();
-        }
-    }
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_t<false>(bar, parity); }
-__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
-    asm volatile("{\n\t.reg .b32 r;\n\t"
-                 "mapa.shared::cluster.u32 r, %0, %1;\n\t"
-                 "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}"
-                 ::"r"(bar), "r"(cta) : "memory");
-}
-template <int CG>
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-    if (CG == 2) mbar_arrive_cluster(bar, 0); else mbar_arrive_local(bar);
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// One TMA box: packed rows [y, y + box rows) x bytes [x, x + 128) -> shared memory (SWIZZLE_128B).
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t x, uint32_t y, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-template <int CG>
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
-    if (CG == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(UM_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(UM_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-}
-template <int CG>
-__device__ __forceinline__ void tmem_free(uint32_t taddr) {
-    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(UM_TMEM_COLS) : "memory");
-    else         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(UM_TMEM_COLS) : "memory");
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]^T, A and B K-major u8, D s32.
-template <int CG>
-__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    if (CG == 1)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-                     ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-                     ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Arrive on `bar` (in every CTA of the pair for CG = 2) once all MMAs issued so far have completed.
-template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    if (CG == 1)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-    else
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
 
 // 32 bits -> 32 bytes of {0,1}: register j holds bits j, j+8, j+16, j+24.
 __device__ __forceinline__ void expand32(uint32_t w, uint32_t (&r)[8]) {
@@ -235,8 +104,44 @@ __device__ __forceinline__ void expand32_b_scaled(uint32_t w, uint32_t (&r)[8]) 
     for (int j = 0; j < 8; ++j) r[j] = wr & (0x01010101u << (7 - j));
 }
 
+// FP4 form (VAR_FP4): 32 bits -> 32 E2M1 nibbles in four registers; register j holds bit j of every
+// nibble of the word, moved to a nibble position whose E2M1 reading (0001 = 0.5, 0010 = 1, 0100 = 2)
+// multiplies to exactly 1.0 with its partner on the other side:
+//     A: 0.5, 1, 2, 2      B: 2, 1, 0.5, 0.5
+// so the A side needs one shift and the B side three (bit 3 of a nibble is the E2M1 sign and cannot be
+// used in place).  Every matching bit adds exactly 1.0f to an fp32 accumulator; integers below 2^24 are
+// exact in fp32 and the tensor core's accumulation of them was measured to be exact (fp4_probe.cu).
+__device__ __forceinline__ void expand32_a_fp4(uint32_t w, uint32_t* r) {
+    r[0] = w & 0x11111111u;
+    r[1] = w & 0x22222222u;
+    r[2] = w & 0x44444444u;
+    r[3] = (w >> 1) & 0x44444444u;
+}
+__device__ __forceinline__ void expand32_b_fp4(uint32_t w, uint32_t* r) {
+    r[0] = (w << 2) & 0x44444444u;
+    r[1] = w & 0x22222222u;
+    r[2] = (w >> 2) & 0x11111111u;
+    r[3] = (w >> 3) & 0x11111111u;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T with E2M1 operands, UE8M0 scale factors per 32 elements from tensor
+// memory (all 1.0 here), fp32 accumulation, K = 64 per instruction: twice the bits of kind::i8.
+template <int CG>
+__device__ __forceinline__ void umma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%5], [%6], p;\n\t}"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%5], [%6], p;\n\t}"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+}
+
 constexpr int VAR_SUSPEND = 1;          // hardware-suspended mbarrier waits
-constexpr int VAR_SCALED = 2;           // scaled expansion (counts accumulate x128)
+constexpr int VAR_SCALED = 2;           // scaled expansion (counts accumulate x128); kind::i8 only
+constexpr int VAR_FP4 = 4;              // bits -> E2M1 nibbles, tcgen05.mma kind::mxf4, fp32 accumulators
 
 template <int CG, int VAR>
 __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
@@ -258,14 +163,16 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + (tmem_slot + 8 - smem_base));
 
     auto wait = [](uint32_t bar, uint32_t parity) { mbar_wait_t<(VAR & VAR_SUSPEND) != 0>(bar, parity); };
-    constexpr bool SCALED = (VAR & VAR_SCALED) != 0;
+    constexpr bool FP4 = (VAR & VAR_FP4) != 0;
+    constexpr bool SCALED = !FP4 && (VAR & VAR_SCALED) != 0;
+    constexpr uint32_t CHUNK_KB = FP4 ? UM_CHUNK_KB_FP4 : UM_CHUNK_KB;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
     const uint64_t cluster_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
     const uint64_t n_clusters = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
-    const uint32_t n_kb = (job.n_words + 1) / 2;
-    const uint32_t n_chunks = (n_kb + UM_CHUNK_KB - 1) / UM_CHUNK_KB;
+    const uint32_t n_kb = FP4 ? (job.n_words + 3) / 4 : (job.n_words + 1) / 2;
+    const uint32_t n_chunks = (n_kb + CHUNK_KB - 1) / CHUNK_KB;
 
     // ---- setup ----------------------------------------------------------------
     if (warp == C::MMA_WARP) tmem_alloc<CG>(tmem_slot);
@@ -292,6 +199,20 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     unsigned long long sum = 0;
+
+    if (FP4 && warp < C::A_WARPS) {
+        // Scale factors of the block-scaled MMA: every byte of the region is UE8M0 127 = 2^0, so whatever
+        // lane / column / byte the hardware layout of SFA and SFB assigns to a (row, 32-element block),
+        // it reads 1.0.  Written once; the MMA thread first touches it after the full-barrier hand-over.
+        uint32_t sf[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sf[j] = 0x7F7F7F7Fu;
+        const uint32_t sf_lane = tmem_base + ((warp * 32u) << 16) + UM_SF_COL;
+#pragma unroll
+        for (int c = 0; c < UM_SF_COLS; c += 8) tmem_st8(sf_lane + c, sf);
+        tc_wait_st();
+        tc_fence_before();
+    }
 
     if (warp == C::TMA_WARP) {
         // ===== TMA producer: packed rows -> shared memory ==============================
@@ -331,8 +252,12 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
-                        umma_i8_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
-                                       (kb | (uint32_t)k) != 0);
+                        if (FP4)
+                            umma_mxf4_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC_FP4,
+                                             tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + UM_SF_COLS / 2, (kb | (uint32_t)k) != 0);
+                        else
+                            umma_i8_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
+                                           (kb | (uint32_t)k) != 0);
                     }
                     umma_commit<CG>(empty_bar + 8 * s);                    // frees the stage when these MMAs are done
                 }
@@ -353,29 +278,41 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t buf = gc & 1;
                 wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
-                const uint32_t nq = min((uint32_t)UM_CHUNK_KB, n_kb - c * UM_CHUNK_KB);
+                const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q, ++gk) {
-                    const uint4 w = ld_shared_v4(src + ((q ^ sw) << 4));
+                    // the packed bits of this row for one k-block: 16 B (i8 form) or 32 B (FP4 form)
+                    uint32_t ws[FP4 ? 8 : 4];
+                    if constexpr (FP4) {
+                        const uint4 w0 = ld_shared_v4(src + (((2 * q) ^ sw) << 4));
+                        const uint4 w1 = ld_shared_v4(src + (((2 * q + 1) ^ sw) << 4));
+                        ws[0] = w0.x; ws[1] = w0.y; ws[2] = w0.z; ws[3] = w0.w;
+                        ws[4] = w1.x; ws[5] = w1.y; ws[6] = w1.z; ws[7] = w1.w;
+                    } else {
+                        const uint4 w = ld_shared_v4(src + ((q ^ sw) << 4));
+                        ws[0] = w.x; ws[1] = w.y; ws[2] = w.z; ws[3] = w.w;
+                    }
                     const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
                     wait(empty_bar + 8 * s, (it & 1) ^ 1);
                     uint32_t e[8];
                     if (is_a) {
                         tc_fence_after();
                         const uint32_t t = a_lane + UM_A_COL + s * 32;
-                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (SCALED) expand32_a_scaled(ws[k], e); else expand32(ws[k], e);
+                        for (int k = 0; k < 4; ++k) {                      // K step k = TMEM columns [8k, 8k + 8) of the stage
+                            if constexpr (FP4) { expand32_a_fp4(ws[2 * k], e); expand32_a_fp4(ws[2 * k + 1], e + 4); }
+                            else if (SCALED) expand32_a_scaled(ws[k], e);
+                            else expand32(ws[k], e);
                             tmem_st8(t + 8 * k, e);
                         }
                         tc_wait_st();
                         tc_fence_before();
                     } else {
                         const uint32_t dst = smem_base + s * C::STAGE_BYTES + b_line;
-                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {                      // K step k = bytes [32k, 32k+32) of the line
-                            if (SCALED) expand32_b_scaled(ws[k], e); else expand32(ws[k], e);
+                            if constexpr (FP4) { expand32_b_fp4(ws[2 * k], e); expand32_b_fp4(ws[2 * k + 1], e + 4); }
+                            else if (SCALED) expand32_b_scaled(ws[k], e);
+                            else expand32(ws[k], e);
                             st_shared_v4(dst + (((2 * k) ^ sw) << 4), e[0], e[1], e[2], e[3]);
                             st_shared_v4(dst + (((2 * k + 1) ^ sw) << 4), e[4], e[5], e[6], e[7]);
                         }
@@ -404,6 +341,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
                 const bool interior = job.out == nullptr && rowA0 + C::TM <= job.nA && rowB0 + C::TN <= job.nB &&
                                       (!job.strict_upper || job.j_off + rowB0 >= job.i_off + rowA0 + C::TM);
+                const bool fp4_sum_exact = (uint64_t)job.n_words * 64 * 32 <= (1ull << 24);
                 wait(acc_full_bar, t_iter & 1);
                 tc_fence_after();
 #pragma unroll 1
@@ -412,7 +350,19 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tmem_ld32(acc_lane + c0, v);
                     tc_wait_ld();
                     if (interior) {
-                        if (SCALED) {                                      // 32 counts of at most 2^24 each fit 32 bits
+                        if constexpr (FP4) {
+                            // fp32 accumulators holding exact integers.  While 32 counts cannot exceed 2^24 their
+                            // float sum is exact too (one conversion per 32 columns); otherwise convert one by one.
+                            if (fp4_sum_exact) {
+                                float part = 0.0f;
+#pragma unroll
+                                for (int cc = 0; cc < 32; ++cc) part += __uint_as_float(v[cc]);
+                                sum += __float2uint_rn(part);
+                            } else {
+#pragma unroll
+                                for (int cc = 0; cc < 32; ++cc) sum += __float2uint_rn(__uint_as_float(v[cc]));
+                            }
+                        } else if (SCALED) {                               // 32 counts of at most 2^24 each fit 32 bits
                             uint32_t part = 0;
 #pragma unroll
                             for (int cc = 0; cc < 32; ++cc) part += v[cc] >> 7;
@@ -426,7 +376,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int cc = 0; cc < 32; ++cc) {
                             const uint64_t lj = rowB0 + c0 + cc;
                             if (lj < job.nB) {
-                                uint32_t x = SCALED ? (v[cc] >> 7) : v[cc];
+                                uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
                                 if (job.strict_upper && job.j_off + lj <= gi) x = 0;
                                 sum += x;
                                 if (job.out) job.out[li * job.ld + lj] = x;
@@ -612,8 +562,15 @@ int g_umma_cg = 2;        // cta_group used by launch_dense_umma (1 or 2); see S
 int g_umma_variant = 3;   // VAR_* bits (both on: 4.27 vs 3.60 POP/s on 30k x 131072); see STORM_b200_set_umma_variant
 
 template <int CG>
-int launch_var(const DenseJob& job, cudaStream_t stream) {
+int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
     int var = g_umma_variant & 3;
+    if (fp4) {
+        if (!umma_fp4_supports(job)) {
+            set_error("FP4 kernel: a pair count must stay below 2^24 for exact fp32 accumulation (n_words %u)", job.n_words);
+            return STORM_B200_EINVAL;
+        }
+        return launch_cg<CG, VAR_FP4 | VAR_SUSPEND>(job, stream);
+    }
     if ((uint64_t)job.n_words * 64 * 128 >= (1ull << 31)) var &= ~VAR_SCALED;   // x128 counts must stay below 2^31
     switch (var) {
         case 0: return launch_cg<CG, 0>(job, stream);
@@ -636,13 +593,23 @@ bool umma_supports(const DenseJob& job) {
     return true;
 }
 
+// The FP4 form accumulates in fp32: exact while a pair count (at most 64 * n_words) stays below 2^24.
+bool umma_fp4_supports(const DenseJob& job) {
+    return umma_supports(job) && (uint64_t)job.n_words * 64 <= (1ull << 24);
+}
+
 int umma_peak_ops(int cg, double* ops_per_s) {
     return cg == 1 ? run_umma_peak<1>(ops_per_s) : run_umma_peak<2>(ops_per_s);
 }
 
 int launch_dense_umma(const DenseJob& job, cudaStream_t stream) {
     if (job.tile_end <= job.tile_begin) return STORM_B200_OK;
-    return g_umma_cg == 2 ? launch_var<2>(job, stream) : launch_var<1>(job, stream);
+    return g_umma_cg == 2 ? launch_var<2>(job, stream, false) : launch_var<1>(job, stream, false);
+}
+
+int launch_dense_fp4(const DenseJob& job, cudaStream_t stream) {
+    if (job.tile_end <= job.tile_begin) return STORM_B200_OK;
+    return g_umma_cg == 2 ? launch_var<2>(job, stream, true) : launch_var<1>(job, stream, true);
 }
 
 }  // namespace storm

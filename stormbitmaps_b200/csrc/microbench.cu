@@ -93,6 +93,8 @@ extern "C" int STORM_b200_microbench(int kind, double* rate, double* sm_mhz) {
         case 3: return run_kind<3>(rate, sm_mhz, 6.0);   // 2 POPC + 4 LOP3 per inner step
         case 4: if (sm_mhz) *sm_mhz = 0; return umma_peak_ops(1, rate);   // tcgen05.mma kind::i8, cta_group::1
         case 5: if (sm_mhz) *sm_mhz = 0; return umma_peak_ops(2, rate);   // tcgen05.mma kind::i8, cta_group::2
+        case 6: if (sm_mhz) *sm_mhz = 0; return fp4_peak_ops(1, rate);    // tcgen05.mma kind::mxf4 (E2M1, K 64), cta_group::1
+        case 7: if (sm_mhz) *sm_mhz = 0; return fp4_peak_ops(2, rate);    // tcgen05.mma kind::mxf4, cta_group::2
         default: set_error("unknown microbench kind %d", kind); return STORM_B200_EINVAL;
     }
 }

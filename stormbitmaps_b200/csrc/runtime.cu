@@ -48,7 +48,8 @@ int require_device() {
 // ---- tile rasters ---------------------------------------------------------------
 TileShape tile_shape_for(int kernel) {
     switch (kernel) {
-        case STORM_B200_KERNEL_UMMA: return umma_tile_shape();
+        case STORM_B200_KERNEL_UMMA:
+        case STORM_B200_KERNEL_FP4:  return umma_tile_shape();
         case STORM_B200_KERNEL_CSA:  return csa_tile_shape();
         default:                     return popc_tile_shape();
     }
@@ -125,6 +126,12 @@ int launch_dense(int kernel, const DenseJob& job, cudaStream_t stream) {
                 return STORM_B200_EINVAL;
             }
             return launch_dense_umma(job, stream);
+        case STORM_B200_KERNEL_FP4:
+            if (!umma_fp4_supports(job)) {
+                set_error("FP4 kernel needs what the UMMA kernel needs and n_words <= 262144 (pair counts below 2^24)");
+                return STORM_B200_EINVAL;
+            }
+            return launch_dense_fp4(job, stream);
         default:
             set_error("unknown kernel id %d", kernel);
             return STORM_B200_EINVAL;
