@@ -268,6 +268,7 @@ def main_ours(args, rows, bits, gen):
     sb.load()
     if args.umma_cg:
         sb.set_umma_cta_group(args.umma_cg)
+    sb.set_umma_wave_sync(bool(args.wave_sync))
     dev = torch.device("cuda", local_rank)
     W = (bits + 63) // 64
     kernel = args.kernel
@@ -320,7 +321,7 @@ def main_ours(args, rows, bits, gen):
     e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step():
-        part = sb.wrapper_diag_shard_ptr(host.data_ptr(), rows, W, rank, world)   # H2D + kernels + D2H inside
+        part = sb.wrapper_diag_shard_ptr(host.data_ptr(), rows, W, rank, world, kernel=kernel)   # H2D + kernels + D2H inside
         if world > 1:
             t = torch.tensor([part], dtype=torch.int64, device=dev)
             dist.all_reduce(t)
@@ -355,7 +356,24 @@ def main_ours(args, rows, bits, gen):
     # minus the 8-byte all-reduce (N>1), measured by the same CUDA events
     launch_ms = elapsed_ms / args.steps
     traffic = ncu_traffic(args.workload, used_kernel, world)
-    if used_kernel == "umma":
+    if used_kernel == "fp4":
+        # Same algorithmic work (64 one-bit MACs = 128 ops per 64-bit word pair), carried by tcgen05.mma
+        # kind::mxf4 on bits unpacked to E2M1 nibbles (K = 64 per instruction, fp32 accumulators that hold
+        # exact integers).  Denominator: that instruction issued back to back on THIS device
+        # (STORM_b200_microbench kind 7); nominal dense fp4 peak 9000.
+        ops_per_launch = wp / world * 128.0
+        achieved = ops_per_launch / (launch_ms * 1e-3) / 1e12
+        fp4_peak = sb.microbench(7)[0] / 1e12
+        i8_peak = sb.microbench(5)[0] / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": fp4_peak, "unit": "TFLOP/s", "frac": achieved / fp4_peak,
+                    "traffic": traffic, "kernel": "dense_umma_kernel<2, FP4>",
+                    "unit_note": "tensor ops per second / 1e12 (1 MAC = 2 ops) on E2M1 operands holding bits",
+                    "peak_source": "tcgen05.mma.kind::mxf4 M256 N256 K64 issue-rate probe on this device (measured, "
+                                   "STORM_b200_microbench(7)); nominal 9000 dense",
+                    "peak_i8_probe": i8_peak, "frac_of_i8_probe": achieved / i8_peak,
+                    "algorithmic": "128 ops per 64-bit word pair x wp per launch",
+                    "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
+    elif used_kernel == "umma":
         # algorithmic work: 64 int8 MACs = 128 ops per 64-bit word pair.
         # Denominator: the kernel's own tcgen05.mma kind::i8 instruction issued back to back on THIS
         # device (STORM_b200_microbench kind 5) -- MEASURED_PEAKS.json has no int8 figure, and the
@@ -391,7 +409,7 @@ def main_ours(args, rows, bits, gen):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: dense {rows}x{bits} XX^T upper triangle", "rows": rows, "bits": bits,
-                   "generator": gen, "seed": SEED, "kernel": used_kernel, "tile": [tm, tn], "tiles": n_tiles,
+                   "generator": gen, "seed": SEED, "kernel": used_kernel, "tile": [tm, tn], "tiles": n_tiles, "wave_sync": bool(args.wave_sync),
                    "parallelism": f"tile-raster shards x{world}, rows replicated",
                    "l2": "inputs larger than L2 (%.2f GB vs 126 MB)" % (rows * W * 8 / 1e9)},
         "clocks": clocks,
@@ -429,7 +447,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "custom"])
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--bits", type=int, default=None)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "umma"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "umma", "fp4"])
+    ap.add_argument("--wave-sync", type=int, default=1, help="UMMA kernel: keep the tiles of a wave in step (L2 reuse); 0 = off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--umma-cg", type=int, default=0, help="cta_group of the UMMA kernel (1 or 2; 0 = library default)")
     args = ap.parse_args()

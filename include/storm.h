@@ -62,6 +62,14 @@ extern "C" {
 /* Per-pair kernel signature (libalgebra.h:3035).  Kept so that callers which
  * store or pass such pointers still compile; the GPU path ignores them. */
 typedef uint64_t (*STORM_compute_func)(const uint64_t*, const uint64_t*, const size_t);
+/* The kernel choosers of libalgebra.h:3094-3140 (intersect), 3142-3188 (union) and 3190-3236
+ * (diff), which the reference's storm.h pulls in.  Here they return exported host functions of
+ * this library (plain popcount loops with the same results); a raw-buffer wrapper that is handed
+ * the union or diff one answers with that set operation on the GPU, any other pointer
+ * (including NULL and foreign functions) means intersect. */
+STORM_compute_func STORM_get_intersect_count_func(const size_t n_bitmaps_vector);
+STORM_compute_func STORM_get_union_count_func(const size_t n_bitmaps_vector);
+STORM_compute_func STORM_get_diff_count_func(const size_t n_bitmaps_vector);
 /* Sparse-aware per-pair signature (storm.h:66-67). */
 typedef uint64_t (*STORM_compute_lfunc)(const uint64_t*, const uint64_t*,
                                         const uint32_t*, const uint32_t*,
@@ -210,9 +218,11 @@ uint32_t STORM_bitmap_serialized_size(STORM_bitmap_t* bitmap);
  *  Raw-buffer wrappers (storm.h:95-148 -> storm.c:132-369)
  *
  *  `vals` is a caller-owned HOST buffer of n_vectors x n_ints words; the call
- *  uploads it, runs the tile kernels and returns the total.  The kernel
- *  pointers f / fl and block_size are accepted for source compatibility and
- *  ignored (they select CPU code in the reference).
+ *  uploads it, runs the tile kernels and returns the total.  `f` selects the
+ *  set operation when it is one of this library's STORM_get_{union,diff}_count_func
+ *  results (sum of popcount(a|b) resp. popcount(a^b) over the same pairs) and
+ *  means intersect otherwise; fl and block_size only steer CPU code in the
+ *  reference and are ignored.
  * ========================================================================== */
 uint64_t STORM_wrapper_diag(const uint32_t n_vectors, const uint64_t* vals,
                             const uint32_t n_ints, const STORM_compute_func f);

@@ -35,6 +35,12 @@ extern "C" {
 #define STORM_B200_KERNEL_FP4  4   /* tcgen05.mma kind::mxf4 on bits unpacked to E2M1 nibbles, fp32 accumulators
                                       (exact below 2^24 bits per row; twice the rate of kind::i8) */
 
+/* Set operation of a pairwise query (libalgebra's three per-pair kernel families,
+ * libalgebra.h:2985-3008): |a & b|, |a | b| = |a| + |b| - |a & b|, |a ^ b| = |a| + |b| - 2 |a & b|. */
+#define STORM_B200_OP_INTERSECT 0
+#define STORM_B200_OP_UNION     1
+#define STORM_B200_OP_DIFF      2
+
 /* ---- library / device ---------------------------------------------------- */
 const char* STORM_b200_last_error(void);
 const char* STORM_b200_version(void);
@@ -78,6 +84,25 @@ int STORM_b200_square_device(const uint64_t* d_rows1, uint64_t n1, uint64_t stri
                              const uint64_t* d_rows2, uint64_t n2, uint64_t stride2,
                              uint32_t n_words, int kernel,
                              uint32_t* d_out, uint64_t ld, uint64_t* d_total, void* stream);
+
+/* Set bits per row: d_counts[r] = popcount(row r) (uint32, device). */
+int STORM_b200_row_popcounts_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                    uint64_t row_stride_words, uint32_t* d_counts, void* stream);
+/* Upper-triangle total under a set operation `op` (STORM_B200_OP_*), ACCUMULATED into *d_total:
+ * row popcounts (one HBM pass) + the intersection tiles.  What STORM_wrapper_diag computes in the
+ * reference when handed STORM_get_union_count_func / STORM_get_diff_count_func (storm.c:132-150). */
+int STORM_b200_pairw_op_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                               uint64_t row_stride_words, int op, int kernel, uint64_t* d_total, void* stream);
+/* STORM_b200_pairw_rect_device under a set operation (at most 65535 rows i1 - i0 when d_out is given). */
+int STORM_b200_pairw_rect_op_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                    uint64_t row_stride_words,
+                                    uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1,
+                                    int strict_upper, int op, int kernel,
+                                    uint32_t* d_out, uint64_t ld, uint64_t* d_total, void* stream);
+/* The host functions behind STORM_get_{intersect,union,diff}_count_func (storm.h). */
+uint64_t STORM_b200_host_intersect_count(const uint64_t* a, const uint64_t* b, const size_t n_words);
+uint64_t STORM_b200_host_union_count(const uint64_t* a, const uint64_t* b, const size_t n_words);
+uint64_t STORM_b200_host_diff_count(const uint64_t* a, const uint64_t* b, const size_t n_words);
 
 /* Number of tiles the triangle raster of `kernel` has for n_rows (so callers can
  * reason about shard balance), and the tile edge lengths it uses. */
@@ -162,6 +187,9 @@ int STORM_b200_microbench(int kind, double* rate, double* sm_mhz);
  * (1.0 x 1.0, 0.5 x 2.0, 2.0 x 0.5, alternating).  Per case four 32-bit results: expected value,
  * smallest and largest accumulator (floats) and the number of accumulators != expected (uint32). */
 int STORM_b200_fp4_probe(const uint32_t* cases, uint32_t n_cases, float* results);
+/* The one-time per-device check behind KERNEL_AUTO's choice of the FP4 form: 1 if accumulators driven
+ * to 2^24 - 1 in steps of 64 and of 1 came out exact for every operand encoding, else 0. */
+int STORM_b200_fp4_selftest(void);
 /* cta_group of the UMMA kernel: 2 (default) = CTA pair per 256 x 256 tile, 1 = one CTA per
  * 128 x 256 tile.  Returns the previous value. */
 int STORM_b200_set_umma_cta_group(int cg);
@@ -169,6 +197,10 @@ int STORM_b200_set_umma_cta_group(int cg);
  * bit expansion, see dense_umma.cu).  Results are identical for every value.  Returns the
  * previous value. */
 int STORM_b200_set_umma_variant(int variant);
+/* 1 (default): the persistent UMMA kernel keeps the tiles of a wave in step through K so that
+ * they share their row blocks in L2 (a bounded wait on a device counter, results never depend
+ * on it); 0: free-running CTAs.  Returns the previous value. */
+int STORM_b200_set_umma_wave_sync(int on);
 /* Number of kernel launches issued by this library since load (for bench.py). */
 uint64_t STORM_b200_launch_count(void);
 

@@ -59,6 +59,9 @@ class Oracle:
             "orc_rect_total": (C.c_uint64, [u64p, C.c_uint64] + [C.c_uint64] * 4),
             "orc_rect_counts": (None, [u64p, C.c_uint64] + [C.c_uint64] * 4 + [u32p]),
             "orc_wrapper_square": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64, u64p, C.c_uint64]),
+            "orc_wrapper_diag_op": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64, C.c_int]),
+            "orc_rect_counts_op": (None, [u64p, C.c_uint64] + [C.c_uint64] * 4 + [C.c_int, u32p]),
+            "orc_wrapper_square_op": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int]),
             "orc_colcount_total": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64]),
             "orc_colcount_rect": (C.c_uint64, [u64p, C.c_uint64] + [C.c_uint64] * 4),
             "orc_contig_new": (C.c_void_p, [C.c_size_t]),
@@ -108,6 +111,21 @@ class Oracle:
         out = np.zeros((i1 - i0, j1 - j0), dtype=np.uint32)
         self.lib.orc_rect_counts(_ptr(vals, u64p), vals.shape[1], i0, i1, j0, j1, _ptr(out, u32p))
         return out
+
+    # set operations: op 0 intersect, 1 union, 2 diff (libalgebra.h:2985-3008 under storm.c:132-150)
+    def wrapper_diag_op(self, vals, op: int) -> int:
+        vals = _u64(vals)
+        return int(self.lib.orc_wrapper_diag_op(vals.shape[0], _ptr(vals, u64p), vals.shape[1], op))
+
+    def rect_counts_op(self, vals, i0, i1, j0, j1, op: int) -> np.ndarray:
+        vals = _u64(vals)
+        out = np.zeros((i1 - i0, j1 - j0), dtype=np.uint32)
+        self.lib.orc_rect_counts_op(_ptr(vals, u64p), vals.shape[1], i0, i1, j0, j1, op, _ptr(out, u32p))
+        return out
+
+    def wrapper_square_op(self, v1, v2, op: int) -> int:
+        v1, v2 = _u64(v1), _u64(v2)
+        return int(self.lib.orc_wrapper_square_op(v1.shape[0], _ptr(v1, u64p), v2.shape[0], _ptr(v2, u64p), v1.shape[1], op))
 
     def wrapper_square(self, v1, v2) -> int:
         v1, v2 = _u64(v1), _u64(v2)
@@ -215,6 +233,8 @@ class Reference:
             "REF_wrapper_diag_blocked": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, C.c_uint32]),
             "REF_diag_rows": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64, C.c_uint64, C.c_uint64]),
             "REF_rect_blocked": (C.c_uint64, [u64p, C.c_uint64] + [C.c_uint64] * 4 + [C.c_uint32]),
+            "REF_wrapper_diag_op": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, C.c_int]),
+            "REF_count_op": (C.c_uint64, [u64p, u64p, C.c_size_t, C.c_int]),
             "REF_cpuid": (C.c_int, []),
             "REF_kernel_name": (C.c_char_p, [C.c_size_t]),
             "REF_contig_scalar_cutoff": (C.c_uint32, [C.c_void_p]),
@@ -248,6 +268,10 @@ class Reference:
     def wrapper_diag(self, vals) -> int:
         vals = _u64(vals)
         return int(self.lib.REF_wrapper_diag(vals.shape[0], _ptr(vals, u64p), vals.shape[1]))
+
+    def wrapper_diag_op(self, vals, op: int) -> int:
+        vals = _u64(vals)
+        return int(self.lib.REF_wrapper_diag_op(vals.shape[0], _ptr(vals, u64p), vals.shape[1], op))
 
     def wrapper_diag_blocked(self, vals, bsize) -> int:
         vals = _u64(vals)

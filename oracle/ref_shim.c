@@ -21,6 +21,21 @@ uint64_t REF_wrapper_diag(uint32_t n_vectors, const uint64_t* vals, uint32_t n_w
     return STORM_wrapper_diag(n_vectors, vals, n_words, STORM_get_intersect_count_func(n_words));
 }
 
+/* storm.c:132-150 driven with the reference's own union / diff kernel choosers
+ * (libalgebra.h:3142-3188, 3190-3236): op 0 intersect, 1 union, 2 diff. */
+uint64_t REF_wrapper_diag_op(uint32_t n_vectors, const uint64_t* vals, uint32_t n_words, int op) {
+    const STORM_compute_func f = op == 1 ? STORM_get_union_count_func(n_words)
+                               : op == 2 ? STORM_get_diff_count_func(n_words)
+                                         : STORM_get_intersect_count_func(n_words);
+    return STORM_wrapper_diag(n_vectors, vals, n_words, f);
+}
+uint64_t REF_count_op(const uint64_t* a, const uint64_t* b, size_t n_words, int op) {
+    const STORM_compute_func f = op == 1 ? STORM_get_union_count_func(n_words)
+                               : op == 2 ? STORM_get_diff_count_func(n_words)
+                                         : STORM_get_intersect_count_func(n_words);
+    return (*f)(a, b, n_words);
+}
+
 /* storm.c:222-279. */
 uint64_t REF_wrapper_diag_blocked(uint32_t n_vectors, const uint64_t* vals, uint32_t n_words, uint32_t bsize) {
     return STORM_wrapper_diag_blocked(n_vectors, vals, n_words, STORM_get_intersect_count_func(n_words), bsize);

@@ -67,6 +67,46 @@ void orc_rect_counts(const uint64_t* vals, uint64_t n_words,
                 : 0u;
 }
 
+/* libalgebra.h:2994-3000 / 3002-3008: the union and diff per-pair kernels. */
+uint64_t orc_union_count(const uint64_t* a, const uint64_t* b, size_t n_words) {
+    uint64_t count = 0;
+    for (size_t k = 0; k < n_words; ++k) count += (uint64_t)__builtin_popcountll(a[k] | b[k]);
+    return count;
+}
+uint64_t orc_diff_count(const uint64_t* a, const uint64_t* b, size_t n_words) {
+    uint64_t count = 0;
+    for (size_t k = 0; k < n_words; ++k) count += (uint64_t)__builtin_popcountll(a[k] ^ b[k]);
+    return count;
+}
+static uint64_t orc_count_op(const uint64_t* a, const uint64_t* b, size_t n_words, int op) {
+    return op == 1 ? orc_union_count(a, b, n_words) : op == 2 ? orc_diff_count(a, b, n_words)
+                                                               : orc_intersect_count(a, b, n_words);
+}
+/* storm.c:132-150 with the kernel pointer f chosen by op. */
+uint64_t orc_wrapper_diag_op(uint64_t n_vectors, const uint64_t* vals, uint64_t n_words, int op) {
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n_vectors; ++i)
+        for (uint64_t j = i + 1; j < n_vectors; ++j)
+            total += orc_count_op(vals + i * n_words, vals + j * n_words, n_words, op);
+    return total;
+}
+void orc_rect_counts_op(const uint64_t* vals, uint64_t n_words,
+                        uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, int op, uint32_t* out) {
+    const uint64_t nj = j1 - j0;
+    for (uint64_t i = i0; i < i1; ++i)
+        for (uint64_t j = j0; j < j1; ++j)
+            out[(i - i0) * nj + (j - j0)] = (j > i)
+                ? (uint32_t)orc_count_op(vals + i * n_words, vals + j * n_words, n_words, op) : 0u;
+}
+uint64_t orc_wrapper_square_op(uint64_t n1, const uint64_t* vals1, uint64_t n2,
+                               const uint64_t* vals2, uint64_t n_words, int op) {
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n1; ++i)
+        for (uint64_t j = 0; j < n2; ++j)
+            total += orc_count_op(vals1 + i * n_words, vals2 + j * n_words, n_words, op);
+    return total;
+}
+
 /* Documented intent of storm.c:153-171 (storm.h:72-76). */
 uint64_t orc_wrapper_square(uint64_t n1, const uint64_t* vals1, uint64_t n2,
                             const uint64_t* vals2, uint64_t n_words) {

@@ -38,6 +38,18 @@ extern "C" {
  * of the CSA kernels at :2684-2744,2872-2890, which compute the same value). */
 uint64_t orc_intersect_count(const uint64_t* a, const uint64_t* b, size_t n_words);
 
+/* sum_k popcount(a[k] | b[k])  -- libalgebra.h:2994-3000 (scalar), 521-540 (unrolled).
+ * sum_k popcount(a[k] ^ b[k])  -- libalgebra.h:3002-3008 (scalar), 543-563 (unrolled). */
+uint64_t orc_union_count(const uint64_t* a, const uint64_t* b, size_t n_words);
+uint64_t orc_diff_count(const uint64_t* a, const uint64_t* b, size_t n_words);
+/* storm.c:132-150 with f = the intersect (op 0), union (1) or diff (2) kernel. */
+uint64_t orc_wrapper_diag_op(uint64_t n_vectors, const uint64_t* vals, uint64_t n_words, int op);
+/* orc_rect_counts / orc_wrapper_square under the same choice of f. */
+void orc_rect_counts_op(const uint64_t* vals, uint64_t n_words,
+                        uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, int op, uint32_t* out);
+uint64_t orc_wrapper_square_op(uint64_t n1, const uint64_t* vals1, uint64_t n2,
+                               const uint64_t* vals2, uint64_t n_words, int op);
+
 /* ---- raw-buffer loops --------------------------------------------------- */
 /* storm.c:132-150 (STORM_wrapper_diag) with 64-bit offsets (defect D5). */
 uint64_t orc_wrapper_diag(uint64_t n_vectors, const uint64_t* vals, uint64_t n_words);

@@ -63,7 +63,16 @@ SIGNATURES = {
     "STORM_wrapper_square": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, u64p, C.c_uint32, C.c_void_p]),
     "STORM_wrapper_diag_list": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, u32p, u32p, u32p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "STORM_wrapper_diag_list_blocked": (C.c_uint64, [C.c_uint32, u64p, C.c_uint32, u32p, u32p, u32p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "STORM_get_intersect_count_func": (C.c_void_p, [C.c_size_t]),
+    "STORM_get_union_count_func": (C.c_void_p, [C.c_size_t]),
+    "STORM_get_diff_count_func": (C.c_void_p, [C.c_size_t]),
     # ---- storm_b200.h
+    "STORM_b200_row_popcounts_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "STORM_b200_pairw_op_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "STORM_b200_pairw_rect_op_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "STORM_b200_host_intersect_count": (C.c_uint64, [u64p, u64p, C.c_size_t]),
+    "STORM_b200_host_union_count": (C.c_uint64, [u64p, u64p, C.c_size_t]),
+    "STORM_b200_host_diff_count": (C.c_uint64, [u64p, u64p, C.c_size_t]),
     "STORM_b200_last_error": (C.c_char_p, []),
     "STORM_b200_version": (C.c_char_p, []),
     "STORM_b200_device_count": (C.c_int, []),
@@ -91,8 +100,10 @@ SIGNATURES = {
     "STORM_b200_synth_geno_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "STORM_b200_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "STORM_b200_fp4_probe": (C.c_int, [u32p, C.c_uint32, C.POINTER(C.c_float)]),
+    "STORM_b200_fp4_selftest": (C.c_int, []),
     "STORM_b200_set_umma_cta_group": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_variant": (C.c_int, [C.c_int]),
+    "STORM_b200_set_umma_wave_sync": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),
 }
 

@@ -185,11 +185,25 @@ class Storm:
 # ---------------------------------------------------------------------------
 # raw host buffers (storm.h:95-148)
 # ---------------------------------------------------------------------------
-def wrapper_diag(vals: np.ndarray) -> int:
-    """``STORM_wrapper_diag``: caller-owned host matrix (n_vectors, n_ints) of uint64 -> total."""
+OPS = {"intersect": 0, "union": 1, "diff": 2}
+
+
+def _compute_func(op):
+    """The STORM_compute_func a C caller would pass for a set operation (libalgebra.h:3094-3236)."""
+    L = _lib.load()
+    getter = {"intersect": L.STORM_get_intersect_count_func, "union": L.STORM_get_union_count_func,
+              "diff": L.STORM_get_diff_count_func}[op]
+    return getter(0)
+
+
+def wrapper_diag(vals: np.ndarray, op: str = "intersect") -> int:
+    """``STORM_wrapper_diag``: caller-owned host matrix (n_vectors, n_ints) of uint64 -> total.
+    ``op`` picks the per-pair kernel pointer handed to it, exactly as a C caller would
+    (``STORM_get_{intersect,union,diff}_count_func``)."""
     L = _lib.load()
     v = np.ascontiguousarray(vals, dtype=np.uint64)
-    return _query(L.STORM_wrapper_diag(v.shape[0], v.ctypes.data_as(u64p), v.shape[1], None), "STORM_wrapper_diag")
+    f = None if op == "intersect" else _compute_func(op)
+    return _query(L.STORM_wrapper_diag(v.shape[0], v.ctypes.data_as(u64p), v.shape[1], f), "STORM_wrapper_diag")
 
 
 def wrapper_diag_ptr(ptr: int, n_vectors: int, n_ints: int, bsize: int = 0) -> int:
@@ -212,14 +226,14 @@ def resolved_kernel_name(kernel, n_words: int) -> str:
     return {v: k for k, v in KERNEL_NAMES.items()}[kid]
 
 
-def wrapper_square(v1: np.ndarray, v2: np.ndarray) -> int:
+def wrapper_square(v1: np.ndarray, v2: np.ndarray, op: str = "intersect") -> int:
     L = _lib.load()
     a = np.ascontiguousarray(v1, dtype=np.uint64)
     b = np.ascontiguousarray(v2, dtype=np.uint64)
     if a.shape[1] != b.shape[1]:
         raise ValueError("row widths differ")
     return _query(L.STORM_wrapper_square(a.shape[0], a.ctypes.data_as(u64p), b.shape[0], b.ctypes.data_as(u64p),
-                                         a.shape[1], None), "STORM_wrapper_square")
+                                         a.shape[1], None if op == "intersect" else _compute_func(op)), "STORM_wrapper_square")
 
 
 # ---------------------------------------------------------------------------
@@ -269,6 +283,42 @@ def pairw_rect_device(rows, i0, i1, j0, j1, n_words: Optional[int] = None, stric
                                               total.data_ptr(), _stream_handle(stream)),
                "STORM_b200_pairw_rect_device")
     return out, total
+
+
+def pairw_op_device(rows, op: str, n_words: Optional[int] = None, kernel=KERNEL_AUTO, stream=None):
+    """``STORM_b200_pairw_op_device``: upper-triangle total of |a&b|, |a|b| or |a^b| (1-elem int64 CUDA tensor)."""
+    import torch
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    total = torch.zeros(1, dtype=torch.int64, device=rows.device)
+    _lib.check(L.STORM_b200_pairw_op_device(ptr, n_rows, n_words or rows.shape[1], stride, OPS[op], _kernel_id(kernel),
+                                            total.data_ptr(), _stream_handle(stream)), "STORM_b200_pairw_op_device")
+    return total
+
+
+def pairw_rect_op_device(rows, op: str, i0, i1, j0, j1, n_words: Optional[int] = None, strict_upper: bool = True,
+                         kernel=KERNEL_AUTO, stream=None):
+    """``STORM_b200_pairw_rect_op_device``: (counts, total) of a rectangle of pairs under a set operation."""
+    import torch
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    out = torch.zeros((i1 - i0, j1 - j0), dtype=torch.int32, device=rows.device)
+    total = torch.zeros(1, dtype=torch.int64, device=rows.device)
+    _lib.check(L.STORM_b200_pairw_rect_op_device(ptr, n_rows, n_words or rows.shape[1], stride, i0, i1, j0, j1,
+                                                 int(strict_upper), OPS[op], _kernel_id(kernel), out.data_ptr(), j1 - j0,
+                                                 total.data_ptr(), _stream_handle(stream)), "STORM_b200_pairw_rect_op_device")
+    return out, total
+
+
+def row_popcounts_device(rows, n_words: Optional[int] = None, stream=None):
+    """``STORM_b200_row_popcounts_device``: set bits per row (int32 CUDA tensor)."""
+    import torch
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    out = torch.zeros(n_rows, dtype=torch.int32, device=rows.device)
+    _lib.check(L.STORM_b200_row_popcounts_device(ptr, n_rows, n_words or rows.shape[1], stride, out.data_ptr(),
+                                                 _stream_handle(stream)), "STORM_b200_row_popcounts_device")
+    return out
 
 
 def square_device(rows1, rows2, n_words: Optional[int] = None, kernel=KERNEL_AUTO, want_counts: bool = False, stream=None):
@@ -361,6 +411,11 @@ def set_storm_route(route) -> int:
 def set_umma_variant(variant: int) -> int:
     """Code variant of the UMMA kernel (bit 0: suspended waits, bit 1: scaled expansion)."""
     return _lib.load().STORM_b200_set_umma_variant(int(variant))
+
+
+def set_umma_wave_sync(on: bool) -> int:
+    """Wave-synchronous tile schedule of the UMMA kernel (default on); returns the previous value."""
+    return _lib.load().STORM_b200_set_umma_wave_sync(int(bool(on)))
 
 
 def device_info(dev: int = 0) -> dict:

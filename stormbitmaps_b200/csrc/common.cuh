@@ -58,6 +58,11 @@ struct DenseJob {
     uint32_t* out;               // optional per-pair counts, out[(i)*ld + j] relative to A/B row 0
     uint64_t ld;
     unsigned long long* total;   // optional, accumulated with atomicAdd
+    // Optional wave counter of the persistent UMMA kernel (zeroed before the launch): CTAs start the
+    // loads of their next tile only when every CTA has issued the loads of the current one, so the
+    // tiles of a wave walk K in step and share their row blocks in L2.  A performance hint only:
+    // the wait is bounded and results never depend on it.
+    unsigned int* wave_sync;
 };
 
 // First column block of row block bi that intersects the strict upper triangle
@@ -130,6 +135,7 @@ bool umma_fp4_supports(const DenseJob& job);          // + every pair count belo
 int launch_dense_fp4(const DenseJob& job, cudaStream_t stream);   // same kernel, kind::mxf4 form
 // int8 ops per second of the UMMA kernel's own instruction issued back to back (cta_group 1 or 2).
 int umma_peak_ops(int cg, double* ops_per_s);
+int fp4_selftest_ok();                          // 1 if this device accumulates E2M1 bit products exactly (cached)
 int fp4_peak_ops(int cg, double* ops_per_s);   // tcgen05.mma kind::mxf4 issue-rate probe (fp4_probe.cu)
 
 int launch_synth_uniform(uint64_t* d_rows, uint64_t n_rows, uint64_t stride, uint32_t M,

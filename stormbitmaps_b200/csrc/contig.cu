@@ -404,7 +404,8 @@ int scratch_upload(const uint64_t* vals, uint64_t n_vectors, uint64_t n_ints, ui
 }
 
 uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_ints,
-                           uint32_t shard = 0, uint32_t n_shards = 1, int kernel = STORM_B200_KERNEL_AUTO) {
+                           uint32_t shard = 0, uint32_t n_shards = 1, int kernel = STORM_B200_KERNEL_AUTO,
+                           int op = STORM_B200_OP_INTERSECT) {
     if (vals == nullptr || n_ints == 0) { set_error("STORM_wrapper_diag: NULL buffer or zero width"); return (uint64_t)-1; }
     if (n_shards == 0 || shard >= n_shards) { set_error("shard %u of %u", shard, n_shards); return (uint64_t)-1; }
     if (n_vectors < 2) return 0;
@@ -414,8 +415,12 @@ uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_
     Scratch& s = g_scratch;
     if (scratch_upload(vals, n_vectors, n_ints, stride, 0)) return (uint64_t)-1;
     if (cudaMemsetAsync(s.d_total, 0, 8, s.stream) != cudaSuccess) return (uint64_t)-1;
-    if (pairw_triangle(s.d_rows, n_vectors, (uint32_t)n_ints, stride, shard, n_shards, kernel,
-                       reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
+    if (op != STORM_B200_OP_INTERSECT) {
+        if (n_shards != 1) { set_error("set operations other than intersect are not sharded"); return (uint64_t)-1; }
+        if (pairw_rect_op(s.d_rows, n_vectors, stride, 0, s.d_rows, n_vectors, stride, 0, (uint32_t)n_ints, 1, op, kernel, true,
+                          nullptr, 0, reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
+    } else if (pairw_triangle(s.d_rows, n_vectors, (uint32_t)n_ints, stride, shard, n_shards, kernel,
+                              reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
     if (cudaMemcpyAsync(s.h_total, s.d_total, 8, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
         cudaStreamSynchronize(s.stream) != cudaSuccess) {
         set_error("STORM_wrapper_diag failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -430,6 +435,18 @@ uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_
 // =================================================================================
 // C ABI: storm.h contiguous entry points
 // =================================================================================
+extern "C" {
+uint64_t STORM_b200_host_union_count(const uint64_t* a, const uint64_t* b, const size_t n);
+uint64_t STORM_b200_host_diff_count(const uint64_t* a, const uint64_t* b, const size_t n);
+}
+namespace storm {
+int op_of_compute_func(const STORM_compute_func f) {
+    if (f == &STORM_b200_host_union_count) return STORM_B200_OP_UNION;
+    if (f == &STORM_b200_host_diff_count) return STORM_B200_OP_DIFF;
+    return STORM_B200_OP_INTERSECT;
+}
+}  // namespace storm
+
 using namespace storm;
 
 extern "C" {
@@ -544,21 +561,43 @@ uint64_t STORM_contig_pairw_intersect_cardinality_blocked_list(STORM_contiguous_
 }
 
 // ---- raw-buffer wrappers (storm.c:132-369) ---------------------------------------
+// ---- per-pair kernel pointers (libalgebra.h:3035, 3094-3236) ----------------------------------
+// The reference's raw-buffer loops apply whatever STORM_compute_func the caller hands them.  Host code
+// cannot run on the device, but the three families libalgebra offers can be told apart by address:
+// these exported functions are what the STORM_get_*_count_func choosers of this library return, and a
+// wrapper that receives the union or diff one answers with that set operation (setops.cu).  Any other
+// pointer, including NULL and the reference's own static kernels, means intersect.
+uint64_t STORM_b200_host_intersect_count(const uint64_t* a, const uint64_t* b, const size_t n) {
+    return host_intersect_count(a, b, n);
+}
+uint64_t STORM_b200_host_union_count(const uint64_t* a, const uint64_t* b, const size_t n) {       // libalgebra.h:2994-3000
+    uint64_t c = 0;
+    for (size_t k = 0; k < n; ++k) c += (uint64_t)__builtin_popcountll(a[k] | b[k]);
+    return c;
+}
+uint64_t STORM_b200_host_diff_count(const uint64_t* a, const uint64_t* b, const size_t n) {        // libalgebra.h:3002-3008
+    uint64_t c = 0;
+    for (size_t k = 0; k < n; ++k) c += (uint64_t)__builtin_popcountll(a[k] ^ b[k]);
+    return c;
+}
+STORM_compute_func STORM_get_intersect_count_func(const size_t n_bitmaps_vector) { (void)n_bitmaps_vector; return &STORM_b200_host_intersect_count; }
+STORM_compute_func STORM_get_union_count_func(const size_t n_bitmaps_vector) { (void)n_bitmaps_vector; return &STORM_b200_host_union_count; }
+STORM_compute_func STORM_get_diff_count_func(const size_t n_bitmaps_vector) { (void)n_bitmaps_vector; return &STORM_b200_host_diff_count; }
+
 uint64_t STORM_wrapper_diag(const uint32_t n_vectors, const uint64_t* vals, const uint32_t n_ints, const STORM_compute_func f) {
-    (void)f;
-    return wrapper_diag_impl(n_vectors, vals, n_ints);
+    return wrapper_diag_impl(n_vectors, vals, n_ints, 0, 1, STORM_B200_KERNEL_AUTO, op_of_compute_func(f));
 }
 
 uint64_t STORM_wrapper_diag_blocked(const uint32_t n_vectors, const uint64_t* vals, const uint32_t n_ints,
                                     const STORM_compute_func f, uint32_t block_size) {
-    (void)f; (void)block_size;
-    return wrapper_diag_impl(n_vectors, vals, n_ints);
+    (void)block_size;
+    return wrapper_diag_impl(n_vectors, vals, n_ints, 0, 1, STORM_B200_KERNEL_AUTO, op_of_compute_func(f));
 }
 
 uint64_t STORM_wrapper_square(const uint32_t n_vectors1, const uint64_t* STORM_RESTRICT vals1,
                               const uint32_t n_vectors2, const uint64_t* STORM_RESTRICT vals2,
                               const uint32_t n_ints, const STORM_compute_func f) {
-    (void)f;
+    const int op = op_of_compute_func(f);
     if (!vals1 || !vals2 || n_ints == 0) { set_error("STORM_wrapper_square: NULL buffer or zero width"); return (uint64_t)-1; }
     if (n_vectors1 == 0 || n_vectors2 == 0) return 0;
     std::lock_guard<std::mutex> lock(g_scratch.mu);
@@ -568,8 +607,8 @@ uint64_t STORM_wrapper_square(const uint32_t n_vectors1, const uint64_t* STORM_R
     const uint64_t at2 = (uint64_t)n_vectors1 * stride;
     if (scratch_upload(vals1, n_vectors1, n_ints, stride, 0) || scratch_upload(vals2, n_vectors2, n_ints, stride, at2)) return (uint64_t)-1;
     if (cudaMemsetAsync(s.d_total, 0, 8, s.stream) != cudaSuccess) return (uint64_t)-1;
-    if (pairw_rect(s.d_rows, n_vectors1, stride, 0, s.d_rows + at2, n_vectors2, stride, 0, n_ints, 0,
-                   STORM_B200_KERNEL_AUTO, nullptr, 0, reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
+    if (pairw_rect_op(s.d_rows, n_vectors1, stride, 0, s.d_rows + at2, n_vectors2, stride, 0, n_ints, 0, op,
+                      STORM_B200_KERNEL_AUTO, false, nullptr, 0, reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
     if (cudaMemcpyAsync(s.h_total, s.d_total, 8, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
         cudaStreamSynchronize(s.stream) != cudaSuccess) {
         set_error("STORM_wrapper_square failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -38,6 +38,9 @@
 // memory, which halves the per-SM expansion work and shared-memory reads per MMA.
 #include <cuda.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -47,24 +50,30 @@ namespace {
 constexpr int UM_N = 256;               // B rows (accumulator columns) per tile
 constexpr int UM_ACC_COL = 0;           // accumulator: columns [0, 256)
 constexpr int UM_A_COL = 256;           // A stage s: columns [256 + 32 s, 256 + 32 s + 32)
-constexpr int UM_SF_COL = 448;          // FP4 form: 64 columns of UE8M0 scale factors, all 127 (x 1.0)
-constexpr int UM_SF_COLS = 64;
+constexpr int UM_SF_COL = 480;          // FP4 form: 32 columns of UE8M0 scale factors, all 127 (x 1.0)
+constexpr int UM_SF_COLS = 32;
 // k-block = the packed bits of one row that expand to one 128-byte swizzle line (4 MMAs):
 // 128 bits (16 B) as bytes for kind::i8, 256 bits (32 B) as nibbles for kind::mxf4.  A TMA box is
 // 128 packed bytes wide, i.e. 8 resp. 4 k-blocks.
 constexpr int UM_CHUNK_KB = 8;
 constexpr int UM_CHUNK_KB_FP4 = 4;
 
-template <int CG>
+// XW = expander warps per 32 rows: 1 = a thread expands its row's whole k-block (4 K steps), 2 = two
+// threads of different warps expand K steps {0, 1} and {2, 3} of it, which halves the time from "stage free"
+// to "stage full" (the FP4 form expands twice the bits per MMA and fell 15 % short of the pipe with XW = 1).
+template <int CG, int XW = 1, bool FP4 = false>
 struct Cfg {
-    static constexpr int A_WARPS = 4;
+    static constexpr int A_ROW_WARPS = 4;                    // 128 A rows = TMEM lanes
     static constexpr int B_ROWS = UM_N / CG;                 // B rows expanded by this CTA
-    static constexpr int B_WARPS = B_ROWS / 32;
+    static constexpr int B_ROW_WARPS = B_ROWS / 32;
+    static constexpr int A_WARPS = A_ROW_WARPS * XW;
+    static constexpr int B_WARPS = B_ROW_WARPS * XW;
     static constexpr int MMA_WARP = A_WARPS + B_WARPS;
     static constexpr int TMA_WARP = MMA_WARP + 1;
     static constexpr int THREADS = (A_WARPS + B_WARPS + 2) * 32;
-    // expanded k-blocks in flight between the expanders and the MMA thread
-    static constexpr int STAGES = CG == 2 ? 6 : 3;
+    // expanded k-blocks in flight between the expanders and the MMA thread (A: 32 TMEM columns each,
+    // next to the 256 accumulator columns and, in the FP4 form, 32 scale-factor columns)
+    static constexpr int STAGES = CG == 2 ? (FP4 ? 7 : 6) : 3;
     static constexpr int STAGE_BYTES = B_ROWS * 128;         // expanded B rows of one k-block
     static constexpr int RAW_A_BYTES = 128 * 128;            // one box of packed A rows
     static constexpr int RAW_B_BYTES = B_ROWS * 128;
@@ -73,7 +82,9 @@ struct Cfg {
     static constexpr int EXPANDER_WARPS = A_WARPS + B_WARPS;
     static constexpr uint32_t OFF_RAW = STAGES * STAGE_BYTES;
     static constexpr uint32_t OFF_BAR = OFF_RAW + 2 * RAW_BYTES;
-    static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 256;
+    static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 512;
+    static_assert(UM_A_COL + 32 * STAGES <= (FP4 ? UM_SF_COL : 512), "A stages overflow tensor memory");
+    static_assert(XW == 1 || XW == 2, "one or two expander warps per 32 rows");
     // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor bit layout):
     //   [4,6) c_format = 2 (S32); [7,10) a_format = 0 (u8); [10,13) b_format = 0 (u8);
     //   [15] a_major = 0 (K); [16] b_major = 0 (K); [17,23) N >> 3; [24,29) M >> 4
@@ -142,11 +153,13 @@ __device__ __forceinline__ void umma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, u
 constexpr int VAR_SUSPEND = 1;          // hardware-suspended mbarrier waits
 constexpr int VAR_SCALED = 2;           // scaled expansion (counts accumulate x128); kind::i8 only
 constexpr int VAR_FP4 = 4;              // bits -> E2M1 nibbles, tcgen05.mma kind::mxf4, fp32 accumulators
+constexpr int VAR_WIDE = 8;             // two expander warps per 32 rows (Cfg::XW = 2)
 
 template <int CG, int VAR>
-__global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
+__global__ void __launch_bounds__((Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0>::THREADS), 1)
 dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DenseJob job) {
-    using C = Cfg<CG>;
+    using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0>;
+    constexpr int XW = (VAR & VAR_WIDE) ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
@@ -200,7 +213,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     unsigned long long sum = 0;
 
-    if (FP4 && warp < C::A_WARPS) {
+    if (FP4 && warp < C::A_ROW_WARPS) {
         // Scale factors of the block-scaled MMA: every byte of the region is UE8M0 127 = 2^0, so whatever
         // lane / column / byte the hardware layout of SFA and SFB assigns to a (row, 32-element block),
         // it reads 1.0.  Written once; the MMA thread first touches it after the full-barrier hand-over.
@@ -218,7 +231,22 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== TMA producer: packed rows -> shared memory ==============================
         if (lane == 0) {
             uint32_t gc = 0;                                               // chunks issued so far (all tiles)
-            for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters) {
+            uint32_t t_iter = 0;
+            bool in_step = job.wave_sync != nullptr;
+            for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
+                if (in_step && t_iter > 0) {
+                    // Wave barrier.  The tiles of one wave share 8 A and ~9 B row blocks; they only find each
+                    // other's lines in L2 if they walk K in step, and without this the CTAs drift apart over
+                    // the thousands of tiles of a large query (ncu: 50 % L2 hits, 1.2 TB of DRAM reads on C3).
+                    // Everything staged so far keeps the MMA busy while this thread waits.  Bounded: if some
+                    // CTA is not resident (SMs taken by another kernel) the hint is dropped, not the query.
+                    const uint32_t target = t_iter * gridDim.x;
+                    uint32_t spins = 0;
+                    while (*reinterpret_cast<volatile unsigned int*>(job.wave_sync) < target) {
+                        if (++spins > 8192u) { in_step = false; break; }
+                        __nanosleep(64);
+                    }
+                }
                 uint32_t bi, bj;
                 tile_coords(job, tile, C::TM, C::TN, bi, bj);
                 const uint32_t ya = bi * C::TM + rank * 128u;
@@ -231,6 +259,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
                     tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
                 }
+                if (job.wave_sync) atomicAdd(job.wave_sync, 1u);            // this CTA's loads of the wave are in flight
             }
         }
     } else if (warp == C::MMA_WARP) {
@@ -266,12 +295,17 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else {
         // ===== expanders (A: warps 0-3 -> TMEM, B: warps 4.. -> shared memory) ==========
+        // warp -> (side, K half, 32-row group): A warps [0, 4 XW), then B warps; within a side the row group
+        // varies fastest, so that an A warp's TMEM lane quarter (warp % 4) is its row group
         const bool is_a = warp < C::A_WARPS;
-        const uint32_t idx = is_a ? tid : tid - C::A_WARPS * 32;           // row within this CTA's A / B slice
+        const uint32_t side_warp = is_a ? warp : warp - C::A_WARPS;
+        const uint32_t row_warps = is_a ? (uint32_t)C::A_ROW_WARPS : (uint32_t)C::B_ROW_WARPS;
+        const uint32_t half = side_warp / row_warps;                       // which K steps of a k-block (always 0 for XW = 1)
+        const uint32_t idx = (side_warp % row_warps) * 32u + lane;         // row within this CTA's A / B slice
         const uint32_t raw_row = (is_a ? 0u : (uint32_t)C::RAW_A_BYTES) + idx * 128u;
         const uint32_t sw = idx & 7u;
         const uint32_t b_line = (idx >> 3) * 1024u + (idx & 7u) * 128u;    // 8-row groups are 1024 B apart
-        const uint32_t a_lane = tmem_base + ((warp * 32u) << 16);
+        const uint32_t a_lane = tmem_base + (((warp & 3u) * 32u) << 16);
         uint32_t gk = 0, gc = 0, t_iter = 0;
         for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
             for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
@@ -280,41 +314,47 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q, ++gk) {
-                    // the packed bits of this row for one k-block: 16 B (i8 form) or 32 B (FP4 form)
-                    uint32_t ws[FP4 ? 8 : 4];
-                    if constexpr (FP4) {
+                    // the packed bits of this row that this thread expands: the whole k-block (16 B in the i8 form,
+                    // 32 B in the FP4 form) or, with two warps per row group, the half that feeds its two K steps
+                    constexpr int NW = (FP4 ? 8 : 4) / XW;                 // 32-bit words per thread and k-block
+                    constexpr int KS = 4 / XW;                             // K steps (MMAs) per thread and k-block
+                    static_assert(!(XW == 2 && !FP4), "two expander warps per row group: FP4 form only");
+                    uint32_t ws[NW];
+                    if constexpr (FP4 && XW == 1) {
                         const uint4 w0 = ld_shared_v4(src + (((2 * q) ^ sw) << 4));
                         const uint4 w1 = ld_shared_v4(src + (((2 * q + 1) ^ sw) << 4));
                         ws[0] = w0.x; ws[1] = w0.y; ws[2] = w0.z; ws[3] = w0.w;
                         ws[4] = w1.x; ws[5] = w1.y; ws[6] = w1.z; ws[7] = w1.w;
                     } else {
-                        const uint4 w = ld_shared_v4(src + ((q ^ sw) << 4));
+                        const uint32_t chunk = FP4 ? 2 * q + half : q;
+                        const uint4 w = ld_shared_v4(src + ((chunk ^ sw) << 4));
                         ws[0] = w.x; ws[1] = w.y; ws[2] = w.z; ws[3] = w.w;
                     }
                     const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
                     wait(empty_bar + 8 * s, (it & 1) ^ 1);
                     uint32_t e[8];
+                    const uint32_t k0 = half * KS;                         // first K step of this thread
                     if (is_a) {
                         tc_fence_after();
                         const uint32_t t = a_lane + UM_A_COL + s * 32;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {                      // K step k = TMEM columns [8k, 8k + 8) of the stage
+                        for (int k = 0; k < KS; ++k) {                     // K step k0 + k = TMEM columns [8 (k0 + k), +8) of the stage
                             if constexpr (FP4) { expand32_a_fp4(ws[2 * k], e); expand32_a_fp4(ws[2 * k + 1], e + 4); }
                             else if (SCALED) expand32_a_scaled(ws[k], e);
                             else expand32(ws[k], e);
-                            tmem_st8(t + 8 * k, e);
+                            tmem_st8(t + 8 * (k0 + k), e);
                         }
                         tc_wait_st();
                         tc_fence_before();
                     } else {
                         const uint32_t dst = smem_base + s * C::STAGE_BYTES + b_line;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {                      // K step k = bytes [32k, 32k+32) of the line
+                        for (int k = 0; k < KS; ++k) {                     // K step k0 + k = bytes [32 (k0 + k), +32) of the line
                             if constexpr (FP4) { expand32_b_fp4(ws[2 * k], e); expand32_b_fp4(ws[2 * k + 1], e + 4); }
                             else if (SCALED) expand32_b_scaled(ws[k], e);
                             else expand32(ws[k], e);
-                            st_shared_v4(dst + (((2 * k) ^ sw) << 4), e[0], e[1], e[2], e[3]);
-                            st_shared_v4(dst + (((2 * k + 1) ^ sw) << 4), e[4], e[5], e[6], e[7]);
+                            st_shared_v4(dst + (((2 * (k0 + k)) ^ sw) << 4), e[0], e[1], e[2], e[3]);
+                            st_shared_v4(dst + (((2 * (k0 + k) + 1) ^ sw) << 4), e[4], e[5], e[6], e[7]);
                         }
                         fence_proxy_async_smem();                          // generic writes -> visible to the UMMA (async proxy)
                     }
@@ -528,9 +568,30 @@ int make_row_map(CUtensorMap* map, const uint64_t* base, uint64_t n_rows, uint64
     return STORM_B200_OK;
 }
 
+// Wave counters: a small ring per device, one slot per launch, zeroed on the launch's stream.
+int wave_counter(cudaStream_t stream, unsigned int** slot) {
+    constexpr int MAX_DEV = 16, RING = 256;
+    static unsigned int* pool[MAX_DEV] = {};
+    static std::atomic<unsigned> next[MAX_DEV];
+    static std::mutex mu;
+    int dev = 0;
+    STORM_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= MAX_DEV) { *slot = nullptr; return STORM_B200_OK; }
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pool[dev]) STORM_CUDA_TRY(cudaMalloc(&pool[dev], RING * sizeof(unsigned int)));
+    }
+    *slot = pool[dev] + (next[dev].fetch_add(1) % RING);
+    STORM_CUDA_TRY(cudaMemsetAsync(*slot, 0, sizeof(unsigned int), stream));
+    return STORM_B200_OK;
+}
+
+int g_umma_wave_sync = 1;   // STORM_b200_set_umma_wave_sync
+
 template <int CG, int VAR>
-int launch_cg(const DenseJob& job, cudaStream_t stream) {
-    using C = Cfg<CG>;
+int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
+    using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0>;
+    DenseJob job = job_in;
     alignas(64) CUtensorMap map_a, map_b;
     int rc = make_row_map(&map_a, job.A, job.nA, job.strideA, job.n_words, 128);
     if (!rc) rc = make_row_map(&map_b, job.B, job.nB, job.strideB, job.n_words, C::B_ROWS);
@@ -541,6 +602,11 @@ int launch_cg(const DenseJob& job, cudaStream_t stream) {
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const uint64_t n_tiles = job.tile_end - job.tile_begin;
     const uint64_t clusters = n_tiles < (uint64_t)(sms / CG) ? n_tiles : (uint64_t)(sms / CG);   // persistent: one per SM (pair)
+    job.wave_sync = nullptr;
+    if (g_umma_wave_sync && n_tiles > clusters) {                           // more than one wave
+        int rc2 = wave_counter(stream, &job.wave_sync);
+        if (rc2) return rc2;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
     cfg.blockDim = dim3(C::THREADS);
@@ -559,6 +625,7 @@ int launch_cg(const DenseJob& job, cudaStream_t stream) {
 }
 
 int g_umma_cg = 2;        // cta_group used by launch_dense_umma (1 or 2); see STORM_b200_set_umma_cta_group
+int g_umma_fp4_wide = 1;  // FP4 form, cta_group 2: two expander warps per 32 rows (STORM_b200_set_umma_variant bit 3)
 int g_umma_variant = 3;   // VAR_* bits (both on: 4.27 vs 3.60 POP/s on 30k x 131072); see STORM_b200_set_umma_variant
 
 template <int CG>
@@ -568,6 +635,9 @@ int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
         if (!umma_fp4_supports(job)) {
             set_error("FP4 kernel: a pair count must stay below 2^24 for exact fp32 accumulation (n_words %u)", job.n_words);
             return STORM_B200_EINVAL;
+        }
+        if constexpr (CG == 2) {
+            if (g_umma_fp4_wide) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_WIDE>(job, stream);
         }
         return launch_cg<CG, VAR_FP4 | VAR_SUSPEND>(job, stream);
     }
@@ -622,10 +692,18 @@ extern "C" int STORM_b200_set_umma_cta_group(int cg) {
     return prev;
 }
 
+// Development / measurement knob: 1 (default) = the CTAs of the persistent UMMA kernel keep their tile
+// waves in step (L2 reuse of the shared row blocks), 0 = free-running.  Returns the previous value.
+extern "C" int STORM_b200_set_umma_wave_sync(int on) {
+    const int prev = storm::g_umma_wave_sync;
+    storm::g_umma_wave_sync = on ? 1 : 0;
+    return prev;
+}
+
 // Development / measurement knob: bit 0 = hardware-suspended mbarrier waits, bit 1 = scaled expansion.
 // Returns the previous value.
 extern "C" int STORM_b200_set_umma_variant(int variant) {
-    const int prev = storm::g_umma_variant;
-    if (variant >= 0 && variant <= 3) storm::g_umma_variant = variant;
+    const int prev = storm::g_umma_variant | (storm::g_umma_fp4_wide ? 8 : 0);
+    if (variant >= 0 && variant <= 15) { storm::g_umma_variant = variant & 3; storm::g_umma_fp4_wide = (variant >> 3) & 1; }
     return prev;
 }

@@ -17,6 +17,9 @@
 //   fp4_peak_kernel    the same instruction back to back on every SM: the pipe's ceiling.
 //
 // Results go to STORM_b200_fp4_probe() / STORM_b200_microbench(6|7); tools/fp4_probe.py prints them.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "runtime.h"
 #include "umma_ptx.cuh"
@@ -265,14 +268,7 @@ int run_fp4_peak(double* ops_per_s) {
 
 int fp4_peak_ops(int cg, double* ops_per_s) { return cg == 1 ? run_fp4_peak<1>(ops_per_s) : run_fp4_peak<2>(ops_per_s); }
 
-}  // namespace storm
-
-// cases: n_cases x {n_full, n_single, pattern}; results: n_cases x {expect, min, max (as float), mismatches (u32 bits)}.
-extern "C" int STORM_b200_fp4_probe(const uint32_t* cases, uint32_t n_cases, float* results) {
-    using namespace storm;
-    int rc = require_device();
-    if (rc) return rc;
-    if (!cases || !results || n_cases == 0) { set_error("fp4 probe: bad arguments"); return STORM_B200_EINVAL; }
+static int run_fp4_cases(const Fp4Case* cases, uint32_t n_cases, Fp4Result* results) {
     Fp4Case* d_cases = nullptr; Fp4Result* d_res = nullptr;
     STORM_CUDA_TRY(cudaMalloc(&d_cases, n_cases * sizeof(Fp4Case)));
     STORM_CUDA_TRY(cudaMalloc(&d_res, n_cases * sizeof(Fp4Result)));
@@ -282,8 +278,52 @@ extern "C" int STORM_b200_fp4_probe(const uint32_t* cases, uint32_t n_cases, flo
     fp4_exact_kernel<<<1, 128, smem_bytes>>>(d_cases, d_res, n_cases);
     count_launch();
     STORM_CUDA_TRY(cudaGetLastError());
-    STORM_CUDA_TRY(cudaDeviceSynchronize());
     STORM_CUDA_TRY(cudaMemcpy(results, d_res, n_cases * sizeof(Fp4Result), cudaMemcpyDeviceToHost));
     cudaFree(d_cases); cudaFree(d_res);
     return STORM_B200_OK;
+}
+
+// One-time check per device that the tensor core's fp32 accumulation of E2M1 products is exact for
+// the integer sums the FP4 tile kernel produces: accumulators driven up to 2^24 - 1 in steps of 64
+// and of 1, with every operand encoding the kernel uses.  AUTO only picks the FP4 form on a device
+// that passed; 1 = exact, 0 = not (or the probe could not run).
+int fp4_selftest_ok() {
+    constexpr int MAX_DEV = 16;
+    static int state[MAX_DEV] = {};                 // 0 unknown, 1 exact, 2 inexact
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (state[dev] == 0) {
+        std::vector<Fp4Case> cases;
+        for (uint32_t p = 0; p < 4; ++p) {
+            cases.push_back({1u, 1u, p});
+            cases.push_back({2048u, 3u, p});
+            cases.push_back({32767u, 63u, p});       // 2^21 - 1
+            cases.push_back({262143u, 63u, p});      // 2^24 - 1: the largest count the kernel accepts
+        }
+        std::vector<Fp4Result> res(cases.size());
+        bool ok = run_fp4_cases(cases.data(), (uint32_t)cases.size(), res.data()) == STORM_B200_OK;
+        for (const Fp4Result& r : res) ok = ok && r.mismatches == 0;
+        state[dev] = ok ? 1 : 2;
+    }
+    return state[dev] == 1;
+}
+
+}  // namespace storm
+
+// cases: n_cases x {n_full, n_single, pattern}; results: n_cases x {expect, min, max (as float), mismatches (u32 bits)}.
+extern "C" int STORM_b200_fp4_probe(const uint32_t* cases, uint32_t n_cases, float* results) {
+    using namespace storm;
+    int rc = require_device();
+    if (rc) return rc;
+    if (!cases || !results || n_cases == 0) { set_error("fp4 probe: bad arguments"); return STORM_B200_EINVAL; }
+    static_assert(sizeof(Fp4Case) == 12 && sizeof(Fp4Result) == 16, "C-ABI layout of the probe records");
+    return run_fp4_cases(reinterpret_cast<const Fp4Case*>(cases), n_cases, reinterpret_cast<Fp4Result*>(results));
+}
+
+extern "C" int STORM_b200_fp4_selftest(void) {
+    using namespace storm;
+    if (require_device()) return 0;
+    return fp4_selftest_ok();
 }

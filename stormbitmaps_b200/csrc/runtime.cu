@@ -111,8 +111,12 @@ void shard_range(uint64_t n_tiles, uint32_t shard, uint32_t n_shards, uint64_t* 
 
 int resolve_kernel(int kernel, const DenseJob& job) {
     if (kernel == STORM_B200_KERNEL_AUTO) kernel = default_kernel();
-    if (kernel == STORM_B200_KERNEL_AUTO)
-        kernel = umma_supports(job) ? STORM_B200_KERNEL_UMMA : STORM_B200_KERNEL_POPC;
+    if (kernel == STORM_B200_KERNEL_AUTO) {
+        // tensor-core forms first: FP4 (twice the rate of i8) where every pair count stays fp32-exact and the
+        // device passed the accumulation self-test, else i8; CUDA cores for shapes the TMA path cannot take
+        if (umma_fp4_supports(job) && fp4_selftest_ok()) kernel = STORM_B200_KERNEL_FP4;
+        else kernel = umma_supports(job) ? STORM_B200_KERNEL_UMMA : STORM_B200_KERNEL_POPC;
+    }
     return kernel;
 }
 

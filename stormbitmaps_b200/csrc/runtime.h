@@ -25,6 +25,14 @@ int pairw_rect(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off
                uint32_t n_words, int strict_upper, int kernel,
                uint32_t* d_out, uint64_t ld, uint64_t* d_total, cudaStream_t stream);
 
+// The same rectangle (or whole triangle) under a set operation STORM_B200_OP_* (setops.cu).
+int pairw_rect_op(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off,
+                  const uint64_t* dB, uint64_t nB, uint64_t strideB, uint64_t j_off,
+                  uint32_t n_words, int strict_upper, int op, int kernel, bool triangle,
+                  uint32_t* d_out, uint64_t ld, uint64_t* d_total, cudaStream_t stream);
+// Which set operation a caller-supplied per-pair kernel pointer stands for (contig.cu).
+int op_of_compute_func(const STORM_compute_func f);
+
 // Sparse-row probe (storm.c:108-129) for the contiguous *_list entry points: pairs
 // (s, x) where s walks `d_sparse_rows` and x every row that pairs with it once.
 int launch_contig_probe(const uint64_t* d_rows, uint64_t stride, uint64_t n_rows,

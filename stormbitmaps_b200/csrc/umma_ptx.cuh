@@ -17,7 +17,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the device.
+// Bounded wait: a protocol bug traps (CUDA error) after ten seconds instead of hanging the device.
 // Default (.acquire.cta) semantics on purpose: an explicit .acquire.cluster makes ptxas emit
 // CCTL.IVALL (L1 invalidate) per wait and .release.cluster a MEMBAR.ALL.GPU per arrive, which
 // more than halved the pair kernel.  The data handed over is ordered by its own fences
@@ -28,24 +28,33 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // re-issued try_wait + counter + branch ~44 times per k-block (ncu, profiles/r01_umma_v1.md)
 // and those instructions competed with the expander warps of its scheduler for issue slots
 // and for the ALU pipe.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <bool SUSPEND>
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    if (SUSPEND) {
-        for (uint32_t spin = 0; !done; ++spin) {
+    uint64_t t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        if (SUSPEND)
             asm volatile("{\n\t.reg .pred p;\n\t"
                          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                          "selp.b32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
-            if (spin > (1u << 12)) __trap();                               // ~4 s of 1 ms suspensions
-        }
-    } else {
-        for (uint32_t spin = 0; !done; ++spin) {
+        else
             asm volatile("{\n\t.reg .pred p;\n\t"
                          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                          "selp.b32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-            if (spin > (1u << 26)) __trap();
+        if (done) break;
+        // Wall-clock bound (the hardware caps the suspend hint well below what is asked for, so a spin
+        // count says little): ten seconds without the phase completing is a protocol bug.
+        if ((spin & 1023u) == 1023u) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) __trap();
         }
     }
 }

@@ -16,7 +16,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = os.environ.get("STORM_TEST_KERNELS", "popc,csa,umma").split(",")
+KERNELS = os.environ.get("STORM_TEST_KERNELS", "popc,csa,umma,fp4").split(",")
 
 
 def _sha(a):
@@ -109,7 +109,7 @@ def test_device_total_and_pairs_match_oracle(sb, orc, kernel, M, N, draws, seed)
     import torch
     vals = orc.gen_dense_uniform(seed, N, draws, M)
     W = vals.shape[1]
-    if kernel == "umma" and W < 2:
+    if kernel in ("umma", "fp4") and W < 2:
         pytest.skip("UMMA needs at least 128 bits per row")
     rows = _device_rows(sb, vals)
     exact = orc.wrapper_diag(vals)
@@ -307,3 +307,65 @@ def test_c3_shape_subsample_and_idempotence(sb, orc):
     got, t = sb.pairw_rect_device(rows, 3000, 3096, 3000, 3096, n_words=W)
     assert (got.cpu().numpy().view(np.uint32) == orc.rect_counts(host, 0, 96, 0, 96)).all()
     assert int(t.item()) == orc.wrapper_diag(host)
+
+
+# --------------------------------------------------------------------------- #
+# FP4 tensor form (tcgen05.mma kind::mxf4, fp32 accumulators): exactness limits
+# --------------------------------------------------------------------------- #
+def test_fp4_accumulation_selftest_and_probe(sb):
+    """The hardware property the FP4 form rests on, measured on this device: fp32 accumulators driven
+    to 2^24 - 1 by +64 and +1 steps stay exact for every operand encoding the kernel uses."""
+    import ctypes as C
+    from stormbitmaps_b200 import _lib
+    lib = sb.load()
+    assert lib.STORM_b200_fp4_selftest() == 1
+    cases = np.asarray([(n_full, n_single, p) for p in range(4)
+                        for (n_full, n_single) in [(0, 1), (1, 0), (3, 5), (4096, 63), (131071, 63), (262143, 63)]],
+                       dtype=np.uint32)
+    res = np.zeros((len(cases), 4), dtype=np.float32)
+    _lib.check(lib.STORM_b200_fp4_probe(cases.ctypes.data_as(_lib.u32p), len(cases),
+                                        res.ctypes.data_as(C.POINTER(C.c_float))), "fp4 probe")
+    for (n_full, n_single, p), r in zip(cases, res):
+        want = 64.0 * n_full + n_single
+        assert r[0] == want and r[1] == want and r[2] == want, (n_full, n_single, p, r[:3])
+        assert r[3:4].view(np.uint32)[0] == 0
+
+
+def test_fp4_largest_counts_and_limit(sb, orc):
+    """Counts of 2^22 (all-ones rows of 4 Mi bits) come out exact; beyond 2^24 bits per row the FP4
+    form refuses and AUTO answers with the int8 form."""
+    import torch
+    N, M = 260, 1 << 22
+    rows, W = sb.alloc_rows(N, M)
+    rows[:, :W] = -1
+    rows[7, 5] = 0x0123456789ABCDEF                  # one row that is not all ones
+    host = rows[:, :W].cpu().numpy().view(np.uint64)
+    exact = orc.wrapper_diag(host)
+    for kernel in ("fp4", "umma", "auto"):
+        assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == exact, kernel
+    got, _ = sb.pairw_rect_device(rows, 0, 16, 0, 16, n_words=W, kernel="fp4")
+    assert (got.cpu().numpy().view(np.uint32) == orc.rect_counts(host, 0, 16, 0, 16)).all()
+    del rows
+    N, M = 3, (1 << 24) + 64
+    rows, W = sb.alloc_rows(N, M)
+    rows[:, :W] = -1
+    assert sb.resolved_kernel_name("auto", W) == "umma"
+    assert sb.resolved_kernel_name("auto", 2048) == "fp4"
+    with pytest.raises(sb.StormError):
+        sb.pairw_device(rows, n_words=W, kernel="fp4")
+    assert int(sb.pairw_device(rows, n_words=W, kernel="auto").item()) == 3 * M
+
+
+def test_wave_sync_is_only_a_hint(sb):
+    """The wave counter of the persistent tensor kernels changes when CTAs load, never what they compute."""
+    N, M = 5000, 8192
+    rows, W = sb.alloc_rows(N, M)
+    sb.synth_uniform_device(rows, M, 3000, 9)
+    closed = _colcount_total_torch(rows, W)
+    for on in (False, True):
+        prev = sb.set_umma_wave_sync(on)
+        try:
+            for kernel in ("umma", "fp4"):
+                assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == closed, (on, kernel)
+        finally:
+            sb.set_umma_wave_sync(bool(prev))
