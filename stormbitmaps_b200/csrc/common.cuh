@@ -35,11 +35,14 @@ void count_launch(uint64_t n = 1);
 // [bi*TM, bi*TM+TM) x B rows [bj*TN, bj*TN+TN) where TM/TN belong to the kernel.
 // Rectangle mode numbers tiles row-block-major.  Triangle mode (A == B, strict upper
 // triangle) only has the tiles that intersect the triangle and numbers them in an
-// L2-friendly raster: row blocks are taken in groups of TRI_GROUP; inside a group the
-// walk is column-block-major (bj outer, bi inner).  Consecutive tile indices -- which is
-// what the CTAs of one wave hold, and what a shard is a range of -- then share their A rows
-// with TRI_GROUP - 1 neighbours and their B rows with ~wave / TRI_GROUP neighbours, so a wave
-// of 74 tiles touches ~17 distinct row blocks instead of 75.
+// L2-friendly raster: COLUMN blocks are taken in groups of TRI_GROUP; inside a group the
+// walk is row-block-major (bi outer, bj inner).  Consecutive tile indices -- which is
+// what the CTAs of one wave hold, and what a shard is a range of -- then share their B rows
+// with the whole group and their A rows with TRI_GROUP - 1 neighbours, so a wave of 74 tiles
+// touches ~17 distinct row blocks instead of 75.  Tile indices are
+// also monotone in the largest row they touch: tiles of groups <= g only read rows below
+// (g + 1) * TRI_GROUP * TN, which is what lets a host-buffer query start computing while the
+// rest of the matrix is still being uploaded (contig.cu: wrapper_diag_impl).
 // `group_prefix[g]` is the number of tiles in groups < g (n_groups + 1 entries, device).
 constexpr uint32_t TRI_GROUP = 8;
 
@@ -65,49 +68,47 @@ struct DenseJob {
     unsigned int* wave_sync;
 };
 
-// First column block of row block bi that intersects the strict upper triangle
-// when A == B (square matrix, same origin).
-__host__ __device__ inline uint32_t tri_jstart(uint32_t bi, uint32_t TM, uint32_t TN) {
-    return (uint32_t)(((uint64_t)bi * TM + 1) / TN);
+// Last row block of column block bj that intersects the strict upper triangle when A == B (square
+// matrix, same origin): the block holding row (bj + 1) * TN - 2, clipped to the matrix.
+__host__ __device__ inline uint32_t tri_iend(uint32_t bj, uint32_t n_bi, uint32_t TM, uint32_t TN) {
+    const uint64_t last = (((uint64_t)bj + 1) * TN - 2) / TM;
+    return last < n_bi ? (uint32_t)last : n_bi - 1;
 }
 
-// Number of tiles of the row-block group starting at row block g0 (host builds the prefix with it).
-__host__ __device__ inline uint64_t tri_group_tiles(uint32_t g0, uint32_t n_bi, uint32_t n_bj, uint32_t TM, uint32_t TN) {
+// Number of tiles of the column-block group starting at column block c0 (host builds the prefix with it).
+__host__ __device__ inline uint64_t tri_group_tiles(uint32_t c0, uint32_t n_bi, uint32_t n_bj, uint32_t TM, uint32_t TN) {
     uint64_t n = 0;
-    for (uint32_t bi = g0; bi < g0 + TRI_GROUP && bi < n_bi; ++bi) {
-        const uint32_t js = tri_jstart(bi, TM, TN);
-        if (js < n_bj) n += n_bj - js;
-    }
+    for (uint32_t bj = c0; bj < c0 + TRI_GROUP && bj < n_bj; ++bj) n += (uint64_t)tri_iend(bj, n_bi, TM, TN) + 1;
     return n;
 }
 
-// Tile u of the group whose first row block is g0 -> (bi, bj): column-block-major inside the group.
-__host__ __device__ inline void tri_group_coords(uint32_t g0, uint64_t u, uint32_t n_bi, uint32_t TM, uint32_t TN,
+// Tile u of the group whose first column block is c0 -> (bi, bj): row-block-major inside the group.
+__host__ __device__ inline void tri_group_coords(uint32_t c0, uint64_t u, uint32_t n_bi, uint32_t n_bj, uint32_t TM, uint32_t TN,
                                                  uint32_t& bi, uint32_t& bj) {
-    const uint32_t rows = (g0 + TRI_GROUP <= n_bi) ? TRI_GROUP : n_bi - g0;      // row blocks in this group
-    const uint32_t jfull = tri_jstart(g0 + rows - 1, TM, TN);                    // from here on every row block has a tile
-    uint32_t j = tri_jstart(g0, TM, TN);
-    for (; j < jfull; ++j) {                                                     // ramp: columns that only some rows reach
-        // (jfull < n_bj for every tile shape in use: the last row block always has its diagonal tile)
+    const uint32_t cols = (c0 + TRI_GROUP <= n_bj) ? TRI_GROUP : n_bj - c0;      // column blocks in this group
+    const uint32_t ifull = tri_iend(c0, n_bi, TM, TN);                           // up to here every column has a tile
+    const uint64_t n_full = ((uint64_t)ifull + 1) * cols;
+    if (u < n_full) { bi = (uint32_t)(u / cols); bj = c0 + (uint32_t)(u % cols); return; }
+    u -= n_full;
+    for (uint32_t i = ifull + 1;; ++i) {                                         // ramp towards the diagonal: a suffix of the columns
         uint32_t c = 0;
-        while (c < rows && tri_jstart(g0 + c, TM, TN) <= j) ++c;
-        if (u < c) { bi = g0 + (uint32_t)u; bj = j; return; }
-        u -= c;
+        while (c < cols && tri_iend(c0 + c, n_bi, TM, TN) < i) ++c;
+        const uint32_t valid = cols - c;
+        if (u < valid || valid == 0) { bi = i; bj = c0 + c + (uint32_t)u; return; }   // (valid == 0 cannot happen for u < group size)
+        u -= valid;
     }
-    bj = jfull + (uint32_t)(u / rows);
-    bi = g0 + (uint32_t)(u % rows);
 }
 
 // Map a linear tile index to (bi, bj).  `prefix` is job.group_prefix (device) or its host copy.
-__host__ __device__ inline void tile_coords_tri(const uint64_t* prefix, uint32_t n_bi, uint64_t t, uint32_t TM, uint32_t TN,
+__host__ __device__ inline void tile_coords_tri(const uint64_t* prefix, uint32_t n_bi, uint32_t n_bj, uint64_t t, uint32_t TM, uint32_t TN,
                                                 uint32_t& bi, uint32_t& bj) {
-    const uint32_t n_groups = (n_bi + TRI_GROUP - 1) / TRI_GROUP;
+    const uint32_t n_groups = (n_bj + TRI_GROUP - 1) / TRI_GROUP;
     uint32_t lo = 0, hi = n_groups;          // largest g with prefix[g] <= t
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (prefix[mid] <= t) lo = mid; else hi = mid;
     }
-    tri_group_coords(lo * TRI_GROUP, t - prefix[lo], n_bi, TM, TN, bi, bj);
+    tri_group_coords(lo * TRI_GROUP, t - prefix[lo], n_bi, n_bj, TM, TN, bi, bj);
 }
 
 __device__ inline void tile_coords(const DenseJob& job, uint64_t t, uint32_t TM, uint32_t TN,
@@ -117,7 +118,7 @@ __device__ inline void tile_coords(const DenseJob& job, uint64_t t, uint32_t TM,
         bj = (uint32_t)(t % job.n_bj);
         return;
     }
-    tile_coords_tri(job.group_prefix, job.n_bi, t, TM, TN, bi, bj);
+    tile_coords_tri(job.group_prefix, job.n_bi, job.n_bj, t, TM, TN, bi, bj);
 }
 
 // ---- launchers (one per kernel family) ---------------------------------------

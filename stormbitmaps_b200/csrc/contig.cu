@@ -353,12 +353,17 @@ int grow_host_scalar(STORM_contiguous_t* c, ContigState* st, uint64_t need) {
 }
 
 // ---- scratch arena for the raw-buffer wrappers ----------------------------------
+constexpr int MAX_UPLOAD_CHUNKS = 16;
+constexpr uint64_t MIN_UPLOAD_CHUNK_BYTES = 32ull << 20;
 struct Scratch {
     std::mutex mu;
     int device = -1;
     uint64_t* d_rows = nullptr; uint64_t cap_words = 0;
     unsigned long long* d_total = nullptr; unsigned long long* h_total = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // uploads of a streamed query run ahead of its kernels here
+    cudaEvent_t chunk_ready[MAX_UPLOAD_CHUNKS] = {};
+    cudaEvent_t idle = nullptr;
 };
 Scratch g_scratch;
 
@@ -373,9 +378,16 @@ int scratch_prepare(uint64_t words) {
         if (s.d_total) cudaFree(s.d_total);
         if (s.h_total) cudaFreeHost(s.h_total);
         if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+        for (cudaEvent_t& e : s.chunk_ready) { if (e) cudaEventDestroy(e); e = nullptr; }
+        if (s.idle) cudaEventDestroy(s.idle);
         s.d_rows = nullptr; s.cap_words = 0; s.d_total = nullptr; s.h_total = nullptr; s.stream = nullptr;
+        s.copy_stream = nullptr; s.idle = nullptr;
         s.device = dev;
         STORM_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        STORM_CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : s.chunk_ready) STORM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        STORM_CUDA_TRY(cudaEventCreateWithFlags(&s.idle, cudaEventDisableTiming));
         STORM_CUDA_TRY(cudaMalloc(&s.d_total, 8));
         STORM_CUDA_TRY(cudaMallocHost(&s.h_total, 8));
     }
@@ -403,6 +415,52 @@ int scratch_upload(const uint64_t* vals, uint64_t n_vectors, uint64_t n_ints, ui
     return STORM_B200_OK;
 }
 
+// Host-buffer query with the upload hidden behind the kernels.  The triangle raster is monotone in the
+// largest row a tile touches (common.cuh), so the matrix is uploaded in row chunks on a copy stream and
+// the tiles that only need the rows uploaded so far are launched as soon as their chunk has landed:
+// the query takes one chunk of PCIe time plus the kernel time instead of the whole upload plus the kernels.
+int streamed_triangle(const uint64_t* vals, uint64_t n_vectors, uint64_t n_ints, uint64_t stride,
+                      uint32_t shard, uint32_t n_shards, int kernel) {
+    Scratch& s = g_scratch;
+    kernel = resolve_kernel_for_rows(kernel, s.d_rows, n_vectors, (uint32_t)n_ints, stride);
+    const TileShape ts = tile_shape_for(kernel);
+    std::vector<uint64_t> prefix;
+    uint32_t nbi = 0, nbj = 0;
+    const uint64_t n_tiles = triangle_prefix(n_vectors, ts, &prefix, &nbi, &nbj);
+    uint64_t tb = 0, te = 0;
+    shard_range(n_tiles, shard, n_shards, &tb, &te);
+    const uint64_t group_rows = (uint64_t)TRI_GROUP * ts.tn;               // rows a raster group adds
+    const uint64_t n_groups = prefix.size() - 1;
+    // chunks of whole groups, at least MIN_UPLOAD_CHUNK_BYTES each, at most MAX_UPLOAD_CHUNKS of them
+    uint64_t groups_per_chunk = std::max<uint64_t>(1, (MIN_UPLOAD_CHUNK_BYTES + group_rows * n_ints * 8 - 1) / (group_rows * n_ints * 8));
+    groups_per_chunk = std::max(groups_per_chunk, (n_groups + MAX_UPLOAD_CHUNKS - 1) / MAX_UPLOAD_CHUNKS);
+    // the copy stream must not overwrite the arena while an earlier query's kernels still read it
+    STORM_CUDA_TRY(cudaEventRecord(s.idle, s.stream));
+    STORM_CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.idle, 0));
+    int chunk = 0;
+    for (uint64_t g0 = 0; g0 < n_groups; g0 += groups_per_chunk, ++chunk) {
+        const uint64_t g1 = std::min(n_groups, g0 + groups_per_chunk);
+        const uint64_t r0 = g0 * group_rows, r1 = std::min<uint64_t>(n_vectors, g1 * group_rows);
+        if (r1 > r0) {
+            uint64_t* dst = s.d_rows + r0 * stride;
+            if (stride != n_ints) STORM_CUDA_TRY(cudaMemsetAsync(dst, 0, (r1 - r0) * stride * 8, s.copy_stream));
+            STORM_CUDA_TRY(cudaMemcpy2DAsync(dst, stride * 8, vals + r0 * n_ints, n_ints * 8, n_ints * 8, r1 - r0,
+                                             cudaMemcpyHostToDevice, s.copy_stream));
+        }
+        STORM_CUDA_TRY(cudaEventRecord(s.chunk_ready[chunk], s.copy_stream));
+        const uint64_t t0 = std::max(tb, prefix[g0]), t1 = std::min(te, prefix[g1]);
+        if (t1 > t0) {
+            STORM_CUDA_TRY(cudaStreamWaitEvent(s.stream, s.chunk_ready[chunk], 0));
+            int rc = pairw_triangle_range(s.d_rows, n_vectors, (uint32_t)n_ints, stride, t0, t1, kernel,
+                                          reinterpret_cast<uint64_t*>(s.d_total), s.stream);
+            if (rc) return rc;
+        }
+    }
+    // later queries on s.stream may reuse the arena: order them after the last upload as well
+    STORM_CUDA_TRY(cudaStreamWaitEvent(s.stream, s.chunk_ready[chunk - 1], 0));
+    return STORM_B200_OK;
+}
+
 uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_ints,
                            uint32_t shard = 0, uint32_t n_shards = 1, int kernel = STORM_B200_KERNEL_AUTO,
                            int op = STORM_B200_OP_INTERSECT) {
@@ -413,9 +471,12 @@ uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_
     const uint64_t stride = padded_stride(n_ints);
     if (scratch_prepare(n_vectors * stride)) return (uint64_t)-1;
     Scratch& s = g_scratch;
-    if (scratch_upload(vals, n_vectors, n_ints, stride, 0)) return (uint64_t)-1;
     if (cudaMemsetAsync(s.d_total, 0, 8, s.stream) != cudaSuccess) return (uint64_t)-1;
-    if (op != STORM_B200_OP_INTERSECT) {
+    if (op == STORM_B200_OP_INTERSECT && n_vectors * n_ints * 8 >= 2 * MIN_UPLOAD_CHUNK_BYTES) {
+        if (streamed_triangle(vals, n_vectors, n_ints, stride, shard, n_shards, kernel)) return (uint64_t)-1;
+    } else if (scratch_upload(vals, n_vectors, n_ints, stride, 0)) {
+        return (uint64_t)-1;
+    } else if (op != STORM_B200_OP_INTERSECT) {
         if (n_shards != 1) { set_error("set operations other than intersect are not sharded"); return (uint64_t)-1; }
         if (pairw_rect_op(s.d_rows, n_vectors, stride, 0, s.d_rows, n_vectors, stride, 0, (uint32_t)n_ints, 1, op, kernel, true,
                           nullptr, 0, reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;

@@ -263,34 +263,45 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
     } else if (warp == C::MMA_WARP) {
-        // ===== MMA issuer: one thread of the leader CTA ================================
-        if (rank == 0 && lane == 0) {
+        // ===== MMA issuer: the MMA warp of the leader CTA ==============================
+        // The whole warp walks the loop (waits included) and one elected lane issues: with warp-uniform
+        // control flow the stage counters, descriptors and tensor-memory addresses live in uniform
+        // registers, where tcgen05.mma wants them.  With a single thread in a divergent branch every
+        // operand took an ELECT + R2UR.BROADCAST detour and the loop needed ~90 % of a k-block's MMA time
+        // (ncu source view, profiles/r01_fp4_c3_ncu_full.md): any hiccup starved the tensor pipe.
+        if (rank == 0) {
+            const bool leader = elect_one();
             // K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor):
             //   [0,14) addr >> 4; [16,30) LBO >> 4 = 1 (unused for swizzled K-major); [32,46) SBO >> 4 = 64
             //   (1024 B between 8-row groups); [46,48) version = 1; [61,64) layout = 2 (SWIZZLE_128B)
             const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-            uint32_t gk = 0, t_iter = 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            uint32_t s = 0, phase = 0, t_iter = 0;                         // stage ring position and its parity
             for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
-                wait(acc_empty_bar, (t_iter & 1) ^ 1);                // epilogue of the previous tile drained TMEM
+                wait(acc_empty_bar, (t_iter & 1) ^ 1);                     // epilogue of the previous tile drained TMEM
                 tc_fence_after();
-                for (uint32_t kb = 0; kb < n_kb; ++kb, ++gk) {
-                    const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
-                    wait(full_bar + 8 * s, it & 1);
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    wait(full_bar + 8 * s, phase);
                     tc_fence_after();
                     const uint32_t b_addr = smem_base + s * C::STAGE_BYTES;
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
-                        if (FP4)
-                            umma_mxf4_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC_FP4,
-                                             tmem_base + UM_SF_COL, tmem_base + UM_SF_COL + UM_SF_COLS / 2, (kb | (uint32_t)k) != 0);
-                        else
-                            umma_i8_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
-                                           (kb | (uint32_t)k) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
+                            if (FP4)
+                                umma_mxf4_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC_FP4,
+                                                 tmem_u + UM_SF_COL, tmem_u + UM_SF_COL + UM_SF_COLS / 2, (kb | (uint32_t)k) != 0);
+                            else
+                                umma_i8_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
+                                               (kb | (uint32_t)k) != 0);
+                        }
+                        umma_commit<CG>(empty_bar + 8 * s);                // frees the stage when these MMAs are done
                     }
-                    umma_commit<CG>(empty_bar + 8 * s);                    // frees the stage when these MMAs are done
+                    __syncwarp();
+                    if (++s == (uint32_t)C::STAGES) { s = 0; phase ^= 1; }
                 }
-                umma_commit<CG>(acc_full_bar);                             // accumulator of this tile complete
+                if (leader) umma_commit<CG>(acc_full_bar);                 // accumulator of this tile complete
+                __syncwarp();
             }
         }
     } else {
@@ -306,14 +317,14 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t sw = idx & 7u;
         const uint32_t b_line = (idx >> 3) * 1024u + (idx & 7u) * 128u;    // 8-row groups are 1024 B apart
         const uint32_t a_lane = tmem_base + (((warp & 3u) * 32u) << 16);
-        uint32_t gk = 0, gc = 0, t_iter = 0;
+        uint32_t s = 0, phase = 0, gc = 0, t_iter = 0;                     // stage ring position and its parity
         for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
             for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
                 const uint32_t buf = gc & 1;
                 wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
-                for (uint32_t q = 0; q < nq; ++q, ++gk) {
+                for (uint32_t q = 0; q < nq; ++q) {
                     // the packed bits of this row that this thread expands: the whole k-block (16 B in the i8 form,
                     // 32 B in the FP4 form) or, with two warps per row group, the half that feeds its two K steps
                     constexpr int NW = (FP4 ? 8 : 4) / XW;                 // 32-bit words per thread and k-block
@@ -330,8 +341,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const uint4 w = ld_shared_v4(src + ((chunk ^ sw) << 4));
                         ws[0] = w.x; ws[1] = w.y; ws[2] = w.z; ws[3] = w.w;
                     }
-                    const uint32_t s = gk % C::STAGES, it = gk / C::STAGES;
-                    wait(empty_bar + 8 * s, (it & 1) ^ 1);
+                    wait(empty_bar + 8 * s, phase ^ 1);
                     uint32_t e[8];
                     const uint32_t k0 = half * KS;                         // first K step of this thread
                     if (is_a) {
@@ -360,6 +370,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader<CG>(full_bar + 8 * s);
+                    if (++s == (uint32_t)C::STAGES) { s = 0; phase ^= 1; }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
@@ -603,7 +614,10 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     const uint64_t n_tiles = job.tile_end - job.tile_begin;
     const uint64_t clusters = n_tiles < (uint64_t)(sms / CG) ? n_tiles : (uint64_t)(sms / CG);   // persistent: one per SM (pair)
     job.wave_sync = nullptr;
-    if (g_umma_wave_sync && n_tiles > clusters) {                           // more than one wave
+    // Worth it when the rows do not fit in L2 anyway and a tile lasts long enough to hide the barrier: below
+    // that it costs up to 10 % (32768 x 4096: 0.79 vs 0.71 ms) and there is no DRAM traffic to save.
+    const uint64_t matrix_bytes = (job.nA + (job.A == job.B ? 0 : job.nB)) * (uint64_t)job.n_words * 8;
+    if (g_umma_wave_sync && n_tiles > clusters && matrix_bytes >= (96ull << 20) && job.n_words >= 512) {
         int rc2 = wave_counter(stream, &job.wave_sync);
         if (rc2) return rc2;
     }
@@ -625,7 +639,10 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
 }
 
 int g_umma_cg = 2;        // cta_group used by launch_dense_umma (1 or 2); see STORM_b200_set_umma_cta_group
-int g_umma_fp4_wide = 1;  // FP4 form, cta_group 2: two expander warps per 32 rows (STORM_b200_set_umma_variant bit 3)
+// FP4 form, cta_group 2: two expander warps per 32 rows (STORM_b200_set_umma_variant bit 3).  Off by default:
+// once the MMA issue loop was made warp-uniform the narrow form reached 95.8 % of the pipe on C3 and the
+// wide one 92.5 % (it only wins by a few percent below 16 Ki bits per row), profiles/r01_fp4_tune.jsonl.
+int g_umma_fp4_wide = 0;
 int g_umma_variant = 3;   // VAR_* bits (both on: 4.27 vs 3.60 POP/s on 30k x 131072); see STORM_b200_set_umma_variant
 
 template <int CG>

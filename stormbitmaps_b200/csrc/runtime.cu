@@ -58,7 +58,7 @@ TileShape tile_shape_for(int kernel) {
 uint64_t triangle_prefix(uint64_t n_rows, TileShape ts, std::vector<uint64_t>* prefix, uint32_t* n_bi, uint32_t* n_bj) {
     const uint32_t nbi = (uint32_t)((n_rows + ts.tm - 1) / ts.tm);
     const uint32_t nbj = (uint32_t)((n_rows + ts.tn - 1) / ts.tn);
-    const uint32_t n_groups = (nbi + TRI_GROUP - 1) / TRI_GROUP;
+    const uint32_t n_groups = (nbj + TRI_GROUP - 1) / TRI_GROUP;
     if (prefix) prefix->assign((size_t)n_groups + 1, 0);
     uint64_t acc = 0;
     for (uint32_t g = 0; g < n_groups; ++g) {
@@ -154,15 +154,7 @@ static int check_rows(const uint64_t* d_rows, uint64_t stride, uint32_t n_words)
     return STORM_B200_OK;
 }
 
-int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
-                   uint32_t shard, uint32_t n_shards, int kernel, uint64_t* d_total, cudaStream_t stream) {
-    int rc = require_device();
-    if (rc) return rc;
-    if (n_shards == 0 || shard >= n_shards) { set_error("shard %u of %u", shard, n_shards); return STORM_B200_EINVAL; }
-    if (!d_total) { set_error("d_total is NULL"); return STORM_B200_EINVAL; }
-    if (n_rows < 2) return STORM_B200_OK;
-    if ((rc = check_rows(d_rows, stride, n_words))) return rc;
-
+static DenseJob triangle_job(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride, uint64_t* d_total) {
     DenseJob job{};
     job.A = job.B = d_rows;
     job.strideA = job.strideB = stride;
@@ -171,12 +163,44 @@ int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, ui
     job.strict_upper = 1;
     job.triangle = 1;
     job.total = reinterpret_cast<unsigned long long*>(d_total);
+    return job;
+}
+
+int resolve_kernel_for_rows(int kernel, const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride) {
+    return resolve_kernel(kernel, triangle_job(d_rows, n_rows, n_words, stride, nullptr));
+}
+
+// shard < n_shards: that shard's range of the raster; n_shards == 0: the explicit range [tile_begin, tile_end)
+static int pairw_triangle_impl(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
+                               uint32_t shard, uint32_t n_shards, uint64_t tile_begin, uint64_t tile_end,
+                               int kernel, uint64_t* d_total, cudaStream_t stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    if (!d_total) { set_error("d_total is NULL"); return STORM_B200_EINVAL; }
+    if (n_rows < 2) return STORM_B200_OK;
+    if ((rc = check_rows(d_rows, stride, n_words))) return rc;
+    DenseJob job = triangle_job(d_rows, n_rows, n_words, stride, d_total);
     kernel = resolve_kernel(kernel, job);
     const TileShape ts = tile_shape_for(kernel);
     uint64_t n_tiles = 0;
     if ((rc = get_triangle_prefix(n_rows, ts, stream, &job.group_prefix, &n_tiles, &job.n_bi, &job.n_bj))) return rc;
-    shard_range(n_tiles, shard, n_shards, &job.tile_begin, &job.tile_end);
+    if (n_shards) shard_range(n_tiles, shard, n_shards, &job.tile_begin, &job.tile_end);
+    else {
+        if (tile_begin > tile_end || tile_end > n_tiles) { set_error("tile range [%llu, %llu) of %llu", (unsigned long long)tile_begin, (unsigned long long)tile_end, (unsigned long long)n_tiles); return STORM_B200_EINVAL; }
+        job.tile_begin = tile_begin; job.tile_end = tile_end;
+    }
     return launch_dense(kernel, job, stream);
+}
+
+int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
+                   uint32_t shard, uint32_t n_shards, int kernel, uint64_t* d_total, cudaStream_t stream) {
+    if (n_shards == 0 || shard >= n_shards) { set_error("shard %u of %u", shard, n_shards); return STORM_B200_EINVAL; }
+    return pairw_triangle_impl(d_rows, n_rows, n_words, stride, shard, n_shards, 0, 0, kernel, d_total, stream);
+}
+
+int pairw_triangle_range(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
+                         uint64_t tile_begin, uint64_t tile_end, int kernel, uint64_t* d_total, cudaStream_t stream) {
+    return pairw_triangle_impl(d_rows, n_rows, n_words, stride, 0, 0, tile_begin, tile_end, kernel, d_total, stream);
 }
 
 int pairw_rect(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off,
@@ -297,7 +321,7 @@ int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile, uint64_t* i
     const uint64_t n_tiles = triangle_prefix(n_rows, ts, &prefix, &nbi, &nbj);
     if (tile >= n_tiles || !i0 || !i1 || !j0 || !j1) { set_error("tile %llu of %llu", (unsigned long long)tile, (unsigned long long)n_tiles); return STORM_B200_EINVAL; }
     uint32_t bi = 0, bj = 0;
-    tile_coords_tri(prefix.data(), nbi, tile, ts.tm, ts.tn, bi, bj);      // the function the kernels call
+    tile_coords_tri(prefix.data(), nbi, nbj, tile, ts.tm, ts.tn, bi, bj);      // the function the kernels call
     *i0 = (uint64_t)bi * ts.tm; *i1 = std::min<uint64_t>(*i0 + ts.tm, n_rows);
     *j0 = (uint64_t)bj * ts.tn; *j1 = std::min<uint64_t>(*j0 + ts.tn, n_rows);
     return STORM_B200_OK;

@@ -19,6 +19,11 @@ int launch_dense(int kernel, const DenseJob& job, cudaStream_t stream);
 // Upper-triangle total of a device matrix (shard of the tile raster), accumulated into *d_total.
 int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
                    uint32_t shard, uint32_t n_shards, int kernel, uint64_t* d_total, cudaStream_t stream);
+// The same over an explicit range [tile_begin, tile_end) of the triangle raster.
+int pairw_triangle_range(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
+                         uint64_t tile_begin, uint64_t tile_end, int kernel, uint64_t* d_total, cudaStream_t stream);
+// Kernel id AUTO resolves to for square-matrix rows of this geometry on the current device.
+int resolve_kernel_for_rows(int kernel, const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride);
 // All pairs of A rows x B rows (optionally only global j > i), counts and/or total.
 int pairw_rect(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off,
                const uint64_t* dB, uint64_t nB, uint64_t strideB, uint64_t j_off,

@@ -352,7 +352,7 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
     return STORM_B200_OK;
 }
 
-// Route of a whole-container query.  The dense tile kernel costs W / 3e13 s per pair whatever the
+// Route of a whole-container query.  The dense tile kernel costs W / 6e13 s per pair whatever the
 // density (tensor pipe, bench.py); the sparse kernel costs about one probe per value of the partner
 // row, ~1e12 probes/s.  Dense wins unless rows are nearly empty -- the threshold is a cost model,
 // not the reference's CPU-tuned 4096 / 200 constants, and it cannot change a result.
@@ -369,7 +369,9 @@ bool choose_dense_route(const StormState* st, uint64_t n_rows) {
     if (need > have / 10 * 8) return false;                              // keep 20 % of the free memory
     if (g_storm_route == 2) return true;
     const double avg_nnz = (double)st->total_nnz / (double)n_rows;
-    return avg_nnz * 30.0 > (double)W;                                   // W / 3e13  <  avg_nnz / 1e12
+    // W / 6e13 (FP4 tensor form; 3.5e13 for the int8 form)  <  avg_nnz / 1e12
+    const double dense_wp_per_probe = (W * 64 <= (1ull << 24) && fp4_selftest_ok()) ? 60.0 : 35.0;
+    return avg_nnz * dense_wp_per_probe > (double)W;
 }
 
 int ensure_dense(StormState* st, uint64_t n_rows, uint64_t* stride_out) {

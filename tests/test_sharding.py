@@ -92,3 +92,59 @@ def test_tiles_cover_every_pair_once():
             seen[i0:i1, j0:j1] += 1
         iu = np.triu_indices(n_rows, k=1)
         assert (seen[iu] == 1).all()
+
+
+def _gather_main(rank, world, port, n_rows, n_words, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from stormbitmaps_b200 import distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1234)                       # every rank holds the same host matrix
+        host = torch.randint(-2**62, 2**62, (n_rows, n_words), dtype=torch.int64, generator=g)
+        arena = D.alloc_gather_arena(n_rows, n_words, world, "cpu")
+        D.gather_rows(host, arena, rank, world)
+        ok = bool((arena[:n_rows, :n_words] == host).all()) and bool((arena[n_rows:] == 0).all()) \
+            and bool((arena[:, n_words:] == 0).all())
+        r0, r1, height = D.slice_bounds(n_rows, rank, world)
+        t = torch.tensor([int(ok), r1 - r0], dtype=torch.int64)
+        dist.all_reduce(t)
+        if rank == 0:
+            out.put((int(t[0]), int(t[1]), height, tuple(arena.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows,n_words", [(1001, 20), (64, 32), (3, 5)])
+def test_two_ranks_gather_row_slices(n_rows, n_words):
+    """Host-matrix query at N > 1: each rank uploads its slice, the all-gather replicates the arena."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_gather_main, args=(r, world, port, n_rows, n_words, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    n_ok, rows_covered, height, shape = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n_ok == world and rows_covered == n_rows
+    assert shape == (world * height, (n_words + 15) // 16 * 16)
+
+
+def test_raster_is_monotone_in_rows():
+    """Tiles of raster groups <= g only touch rows below (g + 1) * 8 * tile_cols: what the streamed
+    host-buffer query relies on to start computing before the upload has finished."""
+    import stormbitmaps_b200 as sb
+    for kernel, n_rows in (("umma", 5000), ("popc", 3000), ("umma", 2049)):
+        n_tiles, tm, tn = sb.tile_count(n_rows, kernel)
+        last_group = 0
+        for t in range(n_tiles):
+            i0, i1, j0, j1 = sb.tile_rect(n_rows, t, kernel)
+            g = j0 // (8 * tn)
+            assert g >= last_group, (kernel, t)
+            last_group = g
+            assert i1 <= min(n_rows, (g + 1) * 8 * tn) and j1 <= min(n_rows, (g + 1) * 8 * tn)

@@ -23,6 +23,25 @@ def timed(rows, W, kernel, reps=3):
     return best, int(total.item())
 
 peak = sb.microbench(7)[0] / 1e12
+peak8 = sb.microbench(5)[0] / 1e12
+for ws in (1, 0):
+    sb.set_umma_wave_sync(bool(ws))
+    for (n, M) in [(30000, 131072), (32768, 4096), (10000, 65536), (200000, 131072)]:
+        if n == 200000 and ws == 0:
+            continue
+        rows, W = sb.alloc_rows(n, M)
+        sb.synth_geno_device(rows, M, 1)
+        torch.cuda.synchronize()
+        wp = n * (n - 1) / 2 * W
+        ms, _ = timed(rows, W, "umma")
+        print(json.dumps({"kernel": "i8", "wave_sync": ws, "rows": n, "bits": M, "ms": ms, "wp_per_s": wp / ms * 1e3,
+                          "frac_of_i8_peak": wp * 128 / ms * 1e3 / 1e12 / peak8}), flush=True)
+        sb.set_umma_variant(3)
+        ms, _ = timed(rows, W, "fp4")
+        print(json.dumps({"kernel": "fp4", "wide": 0, "wave_sync": ws, "rows": n, "bits": M, "ms": ms, "wp_per_s": wp / ms * 1e3,
+                          "frac_of_fp4_peak": wp * 128 / ms * 1e3 / 1e12 / peak}), flush=True)
+        del rows
+sb.set_umma_wave_sync(True)
 for wide in (0, 1):
     sb.set_umma_variant(3 | (8 if wide else 0))
     ok = True
