@@ -201,6 +201,10 @@ int STORM_b200_set_umma_variant(int variant);
  * they share their row blocks in L2 (a bounded wait on a device counter, results never depend
  * on it); 0: free-running CTAs.  Returns the previous value. */
 int STORM_b200_set_umma_wave_sync(int on);
+/* 1 (default): total-only queries with few tiles per SM split (tile, K chunk) units evenly over the
+ * persistent CTAs (stream-K: no tail wave, no idle SMs on small row counts); 0: whole tiles only.
+ * Results are identical.  Returns the previous value. */
+int STORM_b200_set_umma_stream_k(int on);
 /* Number of kernel launches issued by this library since load (for bench.py). */
 uint64_t STORM_b200_launch_count(void);
 

@@ -418,6 +418,11 @@ def set_umma_wave_sync(on: bool) -> int:
     return _lib.load().STORM_b200_set_umma_wave_sync(int(bool(on)))
 
 
+def set_umma_stream_k(on: bool) -> int:
+    """Stream-K split of total-only UMMA queries with few tiles per SM (default on); returns the previous value."""
+    return _lib.load().STORM_b200_set_umma_stream_k(int(bool(on)))
+
+
 def device_info(dev: int = 0) -> dict:
     L = _lib.load()
     name = C.create_string_buffer(128)

@@ -66,6 +66,10 @@ struct DenseJob {
     // tiles of a wave walk K in step and share their row blocks in L2.  A performance hint only:
     // the wait is bounded and results never depend on it.
     unsigned int* wave_sync;
+    // Set by the UMMA launcher for total-only jobs with few tiles per CTA: the persistent CTAs split the
+    // (tile, K chunk) units evenly instead of whole tiles (a total is a sum, so any K split of a tile
+    // is valid); removes the tail wave and keeps every SM busy when there are fewer tiles than SMs.
+    uint32_t stream_k;
 };
 
 // Last row block of column block bj that intersects the strict upper triangle when A == B (square

@@ -63,6 +63,7 @@ constexpr int UM_CHUNK_KB_FP4 = 4;
 // to "stage full" (the FP4 form expands twice the bits per MMA and fell 15 % short of the pipe with XW = 1).
 template <int CG, int XW = 1, bool FP4 = false>
 struct Cfg {
+    static constexpr bool FP4_FORM = FP4;
     static constexpr int A_ROW_WARPS = 4;                    // 128 A rows = TMEM lanes
     static constexpr int B_ROWS = UM_N / CG;                 // B rows expanded by this CTA
     static constexpr int B_ROW_WARPS = B_ROWS / 32;
@@ -150,6 +151,38 @@ __device__ __forceinline__ void umma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, u
                      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
 }
 
+// Work of one persistent CTA (pair) as a sequence of segments: K chunks [c0, c1) of one tile.  Default:
+// whole tiles, dealt round-robin (cluster k takes tiles begin + k, begin + k + n, ...).  Stream-K
+// (DenseJob::stream_k): the n_tiles x n_chunks units are cut into one contiguous range per cluster, sizes
+// differing by at most one chunk, so a cluster's first and last segments may cover part of a tile's K.
+// Every role of the kernel walks the same sequence.
+struct Seg { uint64_t tile; uint32_t c0, c1; };
+struct SegWalk {
+    uint64_t cur, end, step, tile_begin;
+    uint32_t n_chunks, stream_k;
+    __device__ __forceinline__ SegWalk(const DenseJob& job, uint64_t cluster_id, uint64_t n_clusters, uint32_t n_chunks_)
+        : step(n_clusters), tile_begin(job.tile_begin), n_chunks(n_chunks_), stream_k(job.stream_k) {
+        if (stream_k) {
+            const uint64_t units = (job.tile_end - job.tile_begin) * n_chunks;
+            cur = units / n_clusters * cluster_id + min(units % n_clusters, cluster_id);
+            end = cur + units / n_clusters + (cluster_id < units % n_clusters ? 1 : 0);
+        } else {
+            cur = job.tile_begin + cluster_id;
+            end = job.tile_end;
+        }
+    }
+    __device__ __forceinline__ bool next(Seg& s) {
+        if (cur >= end) return false;
+        if (!stream_k) { s.tile = cur; s.c0 = 0; s.c1 = n_chunks; cur += step; return true; }
+        s.tile = tile_begin + cur / n_chunks;
+        s.c0 = (uint32_t)(cur % n_chunks);
+        const uint64_t left = end - cur;
+        s.c1 = left < (uint64_t)(n_chunks - s.c0) ? s.c0 + (uint32_t)left : n_chunks;
+        cur += s.c1 - s.c0;
+        return true;
+    }
+};
+
 constexpr int VAR_SUSPEND = 1;          // hardware-suspended mbarrier waits
 constexpr int VAR_SCALED = 2;           // scaled expansion (counts accumulate x128); kind::i8 only
 constexpr int VAR_FP4 = 4;              // bits -> E2M1 nibbles, tcgen05.mma kind::mxf4, fp32 accumulators
@@ -233,7 +266,10 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t gc = 0;                                               // chunks issued so far (all tiles)
             uint32_t t_iter = 0;
             bool in_step = job.wave_sync != nullptr;
-            for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
+            SegWalk walk(job, cluster_id, n_clusters, n_chunks);
+            Seg seg;
+            for (; walk.next(seg); ++t_iter) {
+                const uint64_t tile = seg.tile;
                 if (in_step && t_iter > 0) {
                     // Wave barrier.  The tiles of one wave share 8 A and ~9 B row blocks; they only find each
                     // other's lines in L2 if they walk K in step, and without this the CTAs drift apart over
@@ -251,7 +287,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tile_coords(job, tile, C::TM, C::TN, bi, bj);
                 const uint32_t ya = bi * C::TM + rank * 128u;
                 const uint32_t yb = bj * C::TN + rank * C::B_ROWS;
-                for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
+                for (uint32_t c = seg.c0; c < seg.c1; ++c, ++gc) {
                     const uint32_t buf = gc & 1;
                     wait(raw_empty_bar + 8 * buf, ((gc >> 1) & 1) ^ 1);
                     mbar_expect_tx(raw_full_bar + 8 * buf, C::RAW_BYTES);
@@ -277,10 +313,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             uint32_t s = 0, phase = 0, t_iter = 0;                         // stage ring position and its parity
-            for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
-                wait(acc_empty_bar, (t_iter & 1) ^ 1);                     // epilogue of the previous tile drained TMEM
+            SegWalk walk(job, cluster_id, n_clusters, n_chunks);
+            Seg seg;
+            for (; walk.next(seg); ++t_iter) {
+                wait(acc_empty_bar, (t_iter & 1) ^ 1);                     // epilogue of the previous segment drained TMEM
                 tc_fence_after();
-                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                const uint32_t kb0 = seg.c0 * CHUNK_KB, kb1 = min(n_kb, seg.c1 * CHUNK_KB);
+                for (uint32_t kb = kb0; kb < kb1; ++kb) {
                     wait(full_bar + 8 * s, phase);
                     tc_fence_after();
                     const uint32_t b_addr = smem_base + s * C::STAGE_BYTES;
@@ -290,10 +329,10 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
                             if (FP4)
                                 umma_mxf4_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC_FP4,
-                                                 tmem_u + UM_SF_COL, tmem_u + UM_SF_COL + UM_SF_COLS / 2, (kb | (uint32_t)k) != 0);
+                                                 tmem_u + UM_SF_COL, tmem_u + UM_SF_COL + UM_SF_COLS / 2, ((kb - kb0) | (uint32_t)k) != 0);
                             else
                                 umma_i8_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
-                                               (kb | (uint32_t)k) != 0);
+                                               ((kb - kb0) | (uint32_t)k) != 0);
                         }
                         umma_commit<CG>(empty_bar + 8 * s);                // frees the stage when these MMAs are done
                     }
@@ -318,8 +357,11 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t b_line = (idx >> 3) * 1024u + (idx & 7u) * 128u;    // 8-row groups are 1024 B apart
         const uint32_t a_lane = tmem_base + (((warp & 3u) * 32u) << 16);
         uint32_t s = 0, phase = 0, gc = 0, t_iter = 0;                     // stage ring position and its parity
-        for (uint64_t tile = job.tile_begin + cluster_id; tile < job.tile_end; tile += n_clusters, ++t_iter) {
-            for (uint32_t c = 0; c < n_chunks; ++c, ++gc) {
+        SegWalk walk(job, cluster_id, n_clusters, n_chunks);
+        Seg seg;
+        for (; walk.next(seg); ++t_iter) {
+            const uint64_t tile = seg.tile;
+            for (uint32_t c = seg.c0; c < seg.c1; ++c, ++gc) {
                 const uint32_t buf = gc & 1;
                 wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
@@ -598,6 +640,7 @@ int wave_counter(cudaStream_t stream, unsigned int** slot) {
 }
 
 int g_umma_wave_sync = 1;   // STORM_b200_set_umma_wave_sync
+int g_umma_stream_k = 1;    // STORM_b200_set_umma_stream_k
 
 template <int CG, int VAR>
 int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
@@ -612,14 +655,30 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     STORM_CUDA_TRY(cudaGetDevice(&dev));
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const uint64_t n_tiles = job.tile_end - job.tile_begin;
-    const uint64_t clusters = n_tiles < (uint64_t)(sms / CG) ? n_tiles : (uint64_t)(sms / CG);   // persistent: one per SM (pair)
+    const uint64_t max_clusters = (uint64_t)(sms / CG);                                            // persistent: one per SM (pair)
+    uint64_t clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
     job.wave_sync = nullptr;
+    job.stream_k = 0;
     // Worth it when the rows do not fit in L2 anyway and a tile lasts long enough to hide the barrier: below
     // that it costs up to 10 % (32768 x 4096: 0.79 vs 0.71 ms) and there is no DRAM traffic to save.
     const uint64_t matrix_bytes = (job.nA + (job.A == job.B ? 0 : job.nB)) * (uint64_t)job.n_words * 8;
     if (g_umma_wave_sync && n_tiles > clusters && matrix_bytes >= (96ull << 20) && job.n_words >= 512) {
         int rc2 = wave_counter(stream, &job.wave_sync);
         if (rc2) return rc2;
+    }
+    // Stream-K for total-only jobs (a total is a sum, so a tile's K range may be split between CTAs): with
+    // fewer than 64 tiles per cluster the tail wave is worth removing (10000 x 65536: 820 tiles on 74 clusters
+    // = 11.08 waves, run as 12), and with fewer tiles than clusters the idle SMs get K slices of the tiles
+    // (at least STREAMK_MIN_CHUNKS TMA boxes each, so that a segment's epilogue stays small beside its MMAs).
+    constexpr uint64_t STREAMK_MIN_CHUNKS = 8;
+    if (g_umma_stream_k && !job.out && !job.wave_sync && n_tiles < 64 * max_clusters) {
+        const uint32_t n_kb = C::FP4_FORM ? (job.n_words + 3) / 4 : (job.n_words + 1) / 2;
+        const uint32_t chunk_kb = C::FP4_FORM ? UM_CHUNK_KB_FP4 : UM_CHUNK_KB;
+        const uint64_t units = n_tiles * ((n_kb + chunk_kb - 1) / chunk_kb);
+        uint64_t want = units / STREAMK_MIN_CHUNKS;
+        if (want < n_tiles) want = n_tiles;
+        const uint64_t sk_clusters = want < max_clusters ? want : max_clusters;
+        if (sk_clusters > clusters || n_tiles % clusters != 0) { clusters = sk_clusters; job.stream_k = 1; }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
@@ -714,6 +773,14 @@ extern "C" int STORM_b200_set_umma_cta_group(int cg) {
 extern "C" int STORM_b200_set_umma_wave_sync(int on) {
     const int prev = storm::g_umma_wave_sync;
     storm::g_umma_wave_sync = on ? 1 : 0;
+    return prev;
+}
+
+// Development / measurement knob: 1 (default) = total-only jobs with few tiles per CTA split (tile, K chunk)
+// units evenly over the persistent CTAs, 0 = whole tiles only.  Returns the previous value.
+extern "C" int STORM_b200_set_umma_stream_k(int on) {
+    const int prev = storm::g_umma_stream_k;
+    storm::g_umma_stream_k = on ? 1 : 0;
     return prev;
 }
 

@@ -356,6 +356,24 @@ def test_fp4_largest_counts_and_limit(sb, orc):
     assert int(sb.pairw_device(rows, n_words=W, kernel="auto").item()) == 3 * M
 
 
+@pytest.mark.parametrize("N,M", [(300, 8192), (700, 65536 + 64), (2000, 4096), (5000, 8192), (1100, 1 << 17)])
+def test_stream_k_split_is_exact(sb, N, M):
+    """Total-only queries split (tile, K chunk) units over the persistent CTAs: fewer tiles than SMs (K slices
+    of a tile on different CTAs), a ragged last chunk, and a tail wave, against whole-tile scheduling."""
+    rows, W = sb.alloc_rows(N, M)
+    sb.synth_uniform_device(rows, M, max(1, M // 3), 21)
+    closed = _colcount_total_torch(rows, W)
+    for on in (True, False):
+        prev = sb.set_umma_stream_k(on)
+        try:
+            for kernel in ("umma", "fp4"):
+                assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == closed, (on, kernel)
+            parts = [int(sb.pairw_device(rows, n_words=W, shard=r, n_shards=3, kernel="fp4").item()) for r in range(3)]
+            assert sum(parts) == closed, (on, parts)
+        finally:
+            sb.set_umma_stream_k(bool(prev))
+
+
 def test_wave_sync_is_only_a_hint(sb):
     """The wave counter of the persistent tensor kernels changes when CTAs load, never what they compute."""
     N, M = 5000, 8192
