@@ -205,10 +205,6 @@ int STORM_b200_set_umma_wave_sync(int on);
  * persistent CTAs (stream-K: no tail wave, no idle SMs on small row counts); 0: whole tiles only.
  * Results are identical.  Returns the previous value. */
 int STORM_b200_set_umma_stream_k(int on);
-/* k-blocks of the next tile that the expander warps stage before draining the finished tile's
- * accumulator (-1 = default: pipeline depth - 2; 0 = drain first).  Results are identical.
- * Returns the previous value. */
-int STORM_b200_set_umma_prefill(int k_blocks);
 /* Number of kernel launches issued by this library since load (for bench.py). */
 uint64_t STORM_b200_launch_count(void);
 

@@ -105,7 +105,6 @@ SIGNATURES = {
     "STORM_b200_set_umma_variant": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_wave_sync": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_stream_k": (C.c_int, [C.c_int]),
-    "STORM_b200_set_umma_prefill": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),
 }
 

@@ -423,11 +423,6 @@ def set_umma_stream_k(on: bool) -> int:
     return _lib.load().STORM_b200_set_umma_stream_k(int(bool(on)))
 
 
-def set_umma_prefill(k_blocks: int) -> int:
-    """k-blocks of the next tile staged before the finished tile's accumulator is drained (-1 = default)."""
-    return _lib.load().STORM_b200_set_umma_prefill(int(k_blocks))
-
-
 def device_info(dev: int = 0) -> dict:
     L = _lib.load()
     name = C.create_string_buffer(128)

@@ -70,9 +70,6 @@ struct DenseJob {
     // (tile, K chunk) units evenly instead of whole tiles (a total is a sum, so any K split of a tile
     // is valid); removes the tail wave and keeps every SM busy when there are fewer tiles than SMs.
     uint32_t stream_k;
-    // UMMA kernel: k-blocks of the next segment that the expanders stage before they drain the accumulator
-    // of the finished one (clamped to STAGES - 1 in the kernel; 0 = drain first).
-    uint32_t prefill;
 };
 
 // Last row block of column block bj that intersects the strict upper triangle when A == B (square

@@ -40,7 +40,6 @@
 
 #include <atomic>
 #include <mutex>
-#include <type_traits>
 
 #include "common.cuh"
 #include "umma_ptx.cuh"
@@ -359,118 +358,16 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t b_line = (idx >> 3) * 1024u + (idx & 7u) * 128u;    // 8-row groups are 1024 B apart
         const uint32_t a_lane = tmem_base + (((warp & 3u) * 32u) << 16);
         uint32_t s = 0, phase = 0, gc = 0, t_iter = 0;                     // stage ring position and its parity
-        // The epilogue of segment t runs after `prefill` k-blocks of segment t + 1 have been expanded (or at that
-        // segment's last k-block, if it is shorter): while the accumulator drains the MMA warp is held at
-        // acc_empty anyway, and with stages already full it restarts at once instead of waiting for the first
-        // expansion of the new segment.  prefill < STAGES: those stages are freed by segment t's own MMAs, so
-        // the expanders never wait on work that itself waits for this drain.
-        // sum += the accumulator columns v[0, 32) (all of them, or with MASK those in [lo, lo + span)).
-        // FP4: fp32 accumulators holding exact integers; while 32 counts cannot exceed 2^24 their float sum is
-        // exact too (one conversion per 32 columns), otherwise convert one by one.  i8: 32-bit partial sums while
-        // 32 counts fit 32 bits.  Four partial sums keep the dependent add chains short.
-        const bool fp4_sum_exact = (uint64_t)job.n_words * 64 * 32 <= (1ull << 24);
-        const bool u32_sum_exact = (uint64_t)job.n_words * 64 * 32 < (1ull << 32);
-        auto add_columns = [&](const uint32_t (&v)[32], auto mask_tag, const int lo, const uint32_t span) {
-            constexpr bool MASK = decltype(mask_tag)::value;
-            if constexpr (FP4) {
-                if (fp4_sum_exact) {
-                    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-                    for (int cc = 0; cc < 32; ++cc)
-                        part[cc & 3] += (!MASK || (uint32_t)(cc - lo) < span) ? __uint_as_float(v[cc]) : 0.0f;
-                    sum += __float2uint_rn((part[0] + part[1]) + (part[2] + part[3]));
-                } else {
-#pragma unroll
-                    for (int cc = 0; cc < 32; ++cc)
-                        sum += (!MASK || (uint32_t)(cc - lo) < span) ? __float2uint_rn(__uint_as_float(v[cc])) : 0u;
-                }
-            } else {
-                if (u32_sum_exact) {
-                    uint32_t part[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int cc = 0; cc < 32; ++cc)
-                        part[cc & 3] += (!MASK || (uint32_t)(cc - lo) < span) ? (SCALED ? v[cc] >> 7 : v[cc]) : 0u;
-                    sum += (unsigned long long)part[0] + part[1] + part[2] + part[3];
-                } else {
-#pragma unroll
-                    for (int cc = 0; cc < 32; ++cc)
-                        sum += (!MASK || (uint32_t)(cc - lo) < span) ? (SCALED ? v[cc] >> 7 : v[cc]) : 0u;
-                }
-            }
-        };
-        auto epilogue = [&](const uint64_t tile, const uint32_t it) {
-            // ---- epilogue of one segment: TMEM -> registers -> masked sum / per-pair store ----
-            // Every expander warp takes part: warp w may read TMEM lanes 32 (w % 4) .. +31, so the
-            // A warp and the B warp(s) of one lane quarter split the 256 accumulator columns between
-            // them (32-column chunks dealt round-robin) and the drain takes half (a third) as long.
-            uint32_t bi, bj;
-            tile_coords(job, tile, C::TM, C::TN, bi, bj);
-            const uint32_t quarter = warp & 3u, sharer = warp >> 2;
-            constexpr uint32_t N_SHARERS = C::EXPANDER_WARPS / 4;
-            const uint64_t rowA0 = (uint64_t)bi * C::TM, rowB0 = (uint64_t)bj * C::TN;
-            const uint64_t li = rowA0 + rank * 128u + quarter * 32u + lane;  // accumulator row of this thread (= its TMEM lane)
-            const uint64_t gi = job.i_off + li;
-            const bool row_ok = li < job.nA;
-            const uint32_t acc_lane = tmem_base + ((quarter * 32u) << 16) + UM_ACC_COL;
-            // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
-            const bool interior = job.out == nullptr && rowA0 + C::TM <= job.nA && rowB0 + C::TN <= job.nB &&
-                                  (!job.strict_upper || job.j_off + rowB0 >= job.i_off + rowA0 + C::TM);
-            wait(acc_full_bar, it & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (uint32_t c0 = sharer * 32u; c0 < (uint32_t)UM_N; c0 += 32u * N_SHARERS) {
-                uint32_t v[32];
-                tmem_ld32(acc_lane + c0, v);
-                tc_wait_ld();
-                if (interior) {
-                    add_columns(v, std::false_type{}, 0, 32u);
-                } else if (job.out == nullptr) {
-                    // Edge and diagonal tiles, total only: the columns of this 32-column chunk that count are
-                    // [lo, hi) -- those below nB, and right of the diagonal for this row.
-                    const long long cb = (long long)(rowB0 + c0);
-                    const long long h = (long long)job.nB - cb;
-                    const int hi = row_ok ? (h < 0 ? 0 : h > 32 ? 32 : (int)h) : 0;
-                    int lo = 0;
-                    if (job.strict_upper) {
-                        const long long l = (long long)gi - (long long)job.j_off - cb + 1;
-                        lo = l < 0 ? 0 : l > 32 ? 32 : (int)l;
-                    }
-                    add_columns(v, std::true_type{}, lo, (uint32_t)(hi > lo ? hi - lo : 0));
-                } else if (row_ok) {
-#pragma unroll
-                    for (int cc = 0; cc < 32; ++cc) {
-                        const uint64_t lj = rowB0 + c0 + cc;
-                        if (lj < job.nB) {
-                            uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
-                            if (job.strict_upper && job.j_off + lj <= gi) x = 0;
-                            sum += x;
-                            if (job.out) job.out[li * job.ld + lj] = x;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
-        };
         SegWalk walk(job, cluster_id, n_clusters, n_chunks);
         Seg seg;
-        const uint32_t prefill = min(job.prefill, (uint32_t)C::STAGES - 1u);
-        bool pending = false;                                              // a finished segment whose accumulator is not drained yet
-        uint64_t pend_tile = 0;
-        uint32_t pend_iter = 0, ahead = 0;
         for (; walk.next(seg); ++t_iter) {
+            const uint64_t tile = seg.tile;
             for (uint32_t c = seg.c0; c < seg.c1; ++c, ++gc) {
                 const uint32_t buf = gc & 1;
                 wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q) {
-                    if (pending && (ahead == prefill || (c + 1 == seg.c1 && q + 1 == nq))) {
-                        epilogue(pend_tile, pend_iter);
-                        pending = false;
-                    }
-                    ++ahead;
                     // the packed bits of this row that this thread expands: the whole k-block (16 B in the i8 form,
                     // 32 B in the FP4 form) or, with two warps per row group, the half that feeds its two K steps
                     constexpr int NW = (FP4 ? 8 : 4) / XW;                 // 32-bit words per thread and k-block
@@ -521,9 +418,90 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
             }
-            pending = true; pend_tile = seg.tile; pend_iter = t_iter; ahead = 0;
+            {
+                const bool fp4_sum_exact = (uint64_t)job.n_words * 64 * 32 <= (1ull << 24);
+                // ---- epilogue of this tile: TMEM -> registers -> masked sum / per-pair store ----
+                // Every expander warp takes part: warp w may read TMEM lanes 32 (w % 4) .. +31, so the
+                // A warp and the B warp(s) of one lane quarter split the 256 accumulator columns between
+                // them (32-column chunks dealt round-robin) and the drain takes half (a third) as long.
+                uint32_t bi, bj;
+                tile_coords(job, tile, C::TM, C::TN, bi, bj);
+                const uint32_t quarter = warp & 3u, sharer = warp >> 2;
+                constexpr uint32_t N_SHARERS = C::EXPANDER_WARPS / 4;
+                const uint64_t rowA0 = (uint64_t)bi * C::TM, rowB0 = (uint64_t)bj * C::TN;
+                const uint64_t li = rowA0 + rank * 128u + quarter * 32u + lane;  // accumulator row of this thread (= its TMEM lane)
+                const uint64_t gi = job.i_off + li;
+                const bool row_ok = li < job.nA;
+                const uint32_t acc_lane = tmem_base + ((quarter * 32u) << 16) + UM_ACC_COL;
+                // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
+                const bool interior = job.out == nullptr && rowA0 + C::TM <= job.nA && rowB0 + C::TN <= job.nB &&
+                                      (!job.strict_upper || job.j_off + rowB0 >= job.i_off + rowA0 + C::TM);
+                wait(acc_full_bar, t_iter & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (uint32_t c0 = sharer * 32u; c0 < (uint32_t)UM_N; c0 += 32u * N_SHARERS) {
+                    uint32_t v[32];
+                    tmem_ld32(acc_lane + c0, v);
+                    tc_wait_ld();
+                    if (interior) {
+                        if constexpr (FP4) {
+                            // fp32 accumulators holding exact integers.  While 32 counts cannot exceed 2^24 their
+                            // float sum is exact too (one conversion per 32 columns); otherwise convert one by one.
+                            if (fp4_sum_exact) {
+                                float part = 0.0f;
+#pragma unroll
+                                for (int cc = 0; cc < 32; ++cc) part += __uint_as_float(v[cc]);
+                                sum += __float2uint_rn(part);
+                            } else {
+#pragma unroll
+                                for (int cc = 0; cc < 32; ++cc) sum += __float2uint_rn(__uint_as_float(v[cc]));
+                            }
+                        } else if (SCALED) {                               // 32 counts of at most 2^24 each fit 32 bits
+                            uint32_t part = 0;
+#pragma unroll
+                            for (int cc = 0; cc < 32; ++cc) part += v[cc] >> 7;
+                            sum += part;
+                        } else {
+#pragma unroll
+                            for (int cc = 0; cc < 32; ++cc) sum += v[cc];
+                        }
+                    } else if (job.out == nullptr) {
+                        // Edge or diagonal tile, total only: the columns of this 32-column chunk that count are
+                        // [lo, lo + span) -- those below nB and right of the diagonal for this row (one range
+                        // compare per column instead of 64-bit index arithmetic: stream-K can hand a run of
+                        // diagonal tiles to one CTA, and the slow path made that CTA the last to finish).
+                        const long long cb = (long long)(rowB0 + c0);
+                        const long long h = (long long)job.nB - cb;
+                        const int hi = row_ok ? (h < 0 ? 0 : h > 32 ? 32 : (int)h) : 0;
+                        int lo = 0;
+                        if (job.strict_upper) {
+                            const long long l = (long long)gi - (long long)job.j_off - cb + 1;
+                            lo = l < 0 ? 0 : l > 32 ? 32 : (int)l;
+                        }
+                        const uint32_t span = (uint32_t)(hi > lo ? hi - lo : 0);
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) {
+                            const uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
+                            sum += ((uint32_t)(cc - lo) < span) ? x : 0u;
+                        }
+                    } else if (row_ok) {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) {
+                            const uint64_t lj = rowB0 + c0 + cc;
+                            if (lj < job.nB) {
+                                uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
+                                if (job.strict_upper && job.j_off + lj <= gi) x = 0;
+                                sum += x;
+                                job.out[li * job.ld + lj] = x;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
+            }
         }
-        if (pending) epilogue(pend_tile, pend_iter);
     }
     __syncwarp();                                                          // re-converge (aligned ops follow)
 
@@ -683,7 +661,6 @@ int wave_counter(cudaStream_t stream, unsigned int** slot) {
 
 int g_umma_wave_sync = 1;   // STORM_b200_set_umma_wave_sync
 int g_umma_stream_k = 1;    // STORM_b200_set_umma_stream_k
-int g_umma_prefill = -1;    // STORM_b200_set_umma_prefill: -1 = STAGES - 2
 
 template <int CG, int VAR>
 int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
@@ -702,7 +679,6 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     uint64_t clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
     job.wave_sync = nullptr;
     job.stream_k = 0;
-    job.prefill = g_umma_prefill < 0 ? (uint32_t)(C::STAGES - 2) : (uint32_t)g_umma_prefill;
     // Worth it when the rows do not fit in L2 anyway and a tile lasts long enough to hide the barrier: below
     // that it costs up to 10 % (32768 x 4096: 0.79 vs 0.71 ms) and there is no DRAM traffic to save.
     const uint64_t matrix_bytes = (job.nA + (job.A == job.B ? 0 : job.nB)) * (uint64_t)job.n_words * 8;
@@ -827,14 +803,6 @@ extern "C" int STORM_b200_set_umma_wave_sync(int on) {
 extern "C" int STORM_b200_set_umma_stream_k(int on) {
     const int prev = storm::g_umma_stream_k;
     storm::g_umma_stream_k = on ? 1 : 0;
-    return prev;
-}
-
-// Development / measurement knob: k-blocks of the next tile (segment) staged before the accumulator of the
-// finished one is drained; -1 (default) = STAGES - 2, 0 = drain first.  Returns the previous value.
-extern "C" int STORM_b200_set_umma_prefill(int k_blocks) {
-    const int prev = storm::g_umma_prefill;
-    storm::g_umma_prefill = k_blocks < 0 ? -1 : k_blocks;
     return prev;
 }
 

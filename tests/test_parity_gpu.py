@@ -374,25 +374,6 @@ def test_stream_k_split_is_exact(sb, N, M):
             sb.set_umma_stream_k(bool(prev))
 
 
-@pytest.mark.parametrize("prefill", [0, 1, 3, 64])
-def test_deferred_epilogue_is_exact(sb, prefill):
-    """The expanders stage `prefill` k-blocks of the next tile before draining the finished one: a schedule
-    knob only.  Short rows (fewer k-blocks than the pipeline depth), ragged rows, per-pair output."""
-    prev = sb.set_umma_prefill(prefill)
-    try:
-        for (N, M) in [(900, 256), (700, 1100), (2100, 4096), (600, 65536 + 64)]:
-            rows, W = sb.alloc_rows(N, M)
-            sb.synth_uniform_device(rows, M, max(1, M // 3), 5)
-            closed = _colcount_total_torch(rows, W)
-            for kernel in ("umma", "fp4"):
-                assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == closed, (N, M, kernel)
-            a, _ = sb.pairw_rect_device(rows, 0, 300, 100, 600, n_words=W, kernel="fp4")
-            b, _ = sb.pairw_rect_device(rows, 0, 300, 100, 600, n_words=W, kernel="popc")
-            assert (a == b).all()
-    finally:
-        sb.set_umma_prefill(prev)
-
-
 def test_wave_sync_is_only_a_hint(sb):
     """The wave counter of the persistent tensor kernels changes when CTAs load, never what they compute."""
     N, M = 5000, 8192
