@@ -17,7 +17,8 @@ the north-star target is quoted on; it fits one GPU (3.28 GB).
           (``STORM_wrapper_diag_blocked``, storm.h:121-125) from PINNED HOST memory:
           H2D of the whole matrix (in chunks that overlap the kernels) + kernels +
           D2H of the total inside the timed region, every step.  For N>1 every rank
-          uploads 1/N of the rows and the slices are all-gathered over NVLink
+          uploads 1/N of each row band, the bands are all-gathered over NVLink and
+          the tiles of the bands that have landed are computed meanwhile
           (stormbitmaps_b200.distributed.pairw_total_from_host).
   N>1     strong scaling: every rank holds the full matrix and owns 1/N of the
           tile raster; the only collective is an 8-byte all-reduce of the total.
@@ -322,12 +323,13 @@ def main_ours(args, rows, bits, gen):
     e2e_steps = max(1, min(args.steps, 3))
 
     from stormbitmaps_b200 import distributed as sbd
-    arena = sbd.alloc_gather_arena(rows, W, world, dev) if world > 1 else None
+    arena = sbd.alloc_stream_arena(rows, W, world, dev, kernel=kernel) if world > 1 else None
     e2e_total_t = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def e2e_step():
         # N = 1: STORM_wrapper_diag_blocked on the pinned host matrix (chunked H2D overlapped with the kernels, D2H of
-        # the total).  N > 1: each rank uploads 1/N of the rows, NVLink all-gather, shard kernels, all-reduce, D2H.
+        # the total).  N > 1: bands of rows, each uploaded 1/N per rank and all-gathered over NVLink on a side stream
+        # while the tiles of the bands already there are being computed; all-reduce, D2H.
         return sbd.pairw_total_from_host(host, kernel=kernel, arena=arena, total=e2e_total_t)
 
     e2e_total = e2e_step()                                   # warm-up (allocates the scratch arena)
@@ -418,7 +420,7 @@ def main_ours(args, rows, bits, gen):
         "e2e": {"value": e2e_value, "unit": "wp/s", "h2d_bytes_per_step": rows * W * 8, "d2h_bytes_per_step": 8,
                 "steps": e2e_steps,
                 "call": "STORM_wrapper_diag_blocked (host buffer, pinned; upload chunks overlap the kernels)" if world == 1 else
-                        "stormbitmaps_b200.distributed.pairw_total_from_host (1/N slice H2D per rank + NVLink all-gather + shard + all-reduce)"},
+                        "stormbitmaps_b200.distributed.pairw_total_from_host (row bands: 1/N slice H2D per rank + NVLink all-gather, pipelined with the tile kernels; all-reduce)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "verified": {"total": got_total, "closed_form_total": closed, "match": ok},

@@ -118,6 +118,19 @@ int STORM_b200_shard_tiles(uint64_t n_rows, int kernel, uint32_t shard, uint32_t
 int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile,
                          uint64_t* i0, uint64_t* i1, uint64_t* j0, uint64_t* j1);
 
+/* The same query over an explicit range [tile_begin, tile_end) of the triangle raster (any
+ * partition of [0, STORM_b200_tile_count) into ranges adds up to the full total).  With
+ * STORM_b200_tiles_below_row this lets a caller start on the tiles whose rows are already
+ * resident while later rows are still arriving (host upload, NVLink all-gather). */
+int STORM_b200_pairw_tiles_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                  uint64_t row_stride_words, uint64_t tile_begin, uint64_t tile_end,
+                                  int kernel, uint64_t* d_total, void* stream);
+/* Host-only: the raster is monotone in the largest row a tile reads.  *tile_end = number of
+ * leading tiles that read only rows below row_limit (all tiles once row_limit >= n_rows);
+ * *band_rows (optional) = the row granularity at which that count grows. */
+int STORM_b200_tiles_below_row(uint64_t n_rows, int kernel, uint64_t row_limit,
+                               uint64_t* tile_end, uint64_t* band_rows);
+
 /* Which kernel id AUTO (or the process default) resolves to for rows of n_words. */
 int STORM_b200_resolve_kernel(int kernel, uint32_t n_words);
 
@@ -205,6 +218,10 @@ int STORM_b200_set_umma_wave_sync(int on);
  * persistent CTAs (stream-K: no tail wave, no idle SMs on small row counts); 0: whole tiles only.
  * Results are identical.  Returns the previous value. */
 int STORM_b200_set_umma_stream_k(int on);
+/* SMs the persistent UMMA kernel leaves free (default 0): a multi-GPU caller that overlaps an NVLink
+ * all-gather with the tile kernel sets this to a small number so that the collective's CTAs find a place
+ * to run beside it.  Clamped to [0, SM count - 2].  Returns the previous value. */
+int STORM_b200_set_umma_reserved_sms(int n);
 /* Number of kernel launches issued by this library since load (for bench.py). */
 uint64_t STORM_b200_launch_count(void);
 

@@ -83,6 +83,8 @@ SIGNATURES = {
     "STORM_b200_square_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "STORM_b200_resolve_kernel": (C.c_int, [C.c_int, C.c_uint32]),
     "STORM_b200_wrapper_diag_shard": (C.c_uint64, [C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),
+    "STORM_b200_pairw_tiles_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
+    "STORM_b200_tiles_below_row": (C.c_int, [C.c_uint64, C.c_int, C.c_uint64, u64p, u64p]),
     "STORM_b200_tile_count": (C.c_uint64, [C.c_uint64, C.c_int, u32p, u32p]),
     "STORM_b200_shard_tiles": (C.c_int, [C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, u64p, u64p]),
     "STORM_b200_tile_rect": (C.c_int, [C.c_uint64, C.c_int, C.c_uint64, u64p, u64p, u64p, u64p]),
@@ -105,6 +107,7 @@ SIGNATURES = {
     "STORM_b200_set_umma_variant": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_wave_sync": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_stream_k": (C.c_int, [C.c_int]),
+    "STORM_b200_set_umma_reserved_sms": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),
 }
 

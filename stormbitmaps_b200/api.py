@@ -269,6 +269,20 @@ def pairw_device(rows, n_words: Optional[int] = None, shard: int = 0, n_shards: 
     return total
 
 
+def pairw_tiles_device(rows, tile_begin: int, tile_end: int, n_words: Optional[int] = None, kernel=KERNEL_AUTO,
+                       total=None, stream=None):
+    """``STORM_b200_pairw_tiles_device``: accumulate the partial total of raster tiles [tile_begin, tile_end)."""
+    import torch
+    L = _lib.load()
+    ptr, n_rows, stride = _rows_args(rows)
+    if total is None:
+        total = torch.zeros(1, dtype=torch.int64, device=rows.device)
+    _lib.check(L.STORM_b200_pairw_tiles_device(ptr, n_rows, n_words or rows.shape[1], stride, tile_begin, tile_end,
+                                               _kernel_id(kernel), total.data_ptr(), _stream_handle(stream)),
+               "STORM_b200_pairw_tiles_device")
+    return total
+
+
 def pairw_rect_device(rows, i0, i1, j0, j1, n_words: Optional[int] = None, strict_upper: bool = True,
                       kernel=KERNEL_AUTO, want_counts: bool = True, stream=None):
     """``STORM_b200_pairw_rect_device``: (counts[int32 view of uint32], total) of a rectangle of pairs."""
@@ -375,6 +389,21 @@ def shard_tiles(n_rows: int, shard: int, n_shards: int, kernel=KERNEL_AUTO):
     return int(b.value), int(e.value)
 
 
+def tiles_below_row(n_rows: int, row_limit: int, kernel=KERNEL_AUTO):
+    """``STORM_b200_tiles_below_row`` (host only): (number of leading raster tiles that read only rows below
+    ``row_limit``, row granularity at which that number grows)."""
+    L = _lib.load()
+    t, band = C.c_uint64(), C.c_uint64()
+    _lib.check(L.STORM_b200_tiles_below_row(n_rows, _kernel_id(kernel), row_limit, C.byref(t), C.byref(band)),
+               "STORM_b200_tiles_below_row")
+    return int(t.value), int(band.value)
+
+
+def resolve_kernel(kernel, n_words: int) -> int:
+    """Kernel id AUTO / the process default resolves to for rows of ``n_words`` (``STORM_b200_resolve_kernel``)."""
+    return int(_lib.load().STORM_b200_resolve_kernel(_kernel_id(kernel), n_words))
+
+
 def tile_rect(n_rows: int, tile: int, kernel=KERNEL_AUTO):
     """``STORM_b200_tile_rect`` (host only): rows (i0, i1, j0, j1) a tile covers."""
     L = _lib.load()
@@ -416,6 +445,11 @@ def set_umma_variant(variant: int) -> int:
 def set_umma_wave_sync(on: bool) -> int:
     """Wave-synchronous tile schedule of the UMMA kernel (default on); returns the previous value."""
     return _lib.load().STORM_b200_set_umma_wave_sync(int(bool(on)))
+
+
+def set_umma_reserved_sms(n: int) -> int:
+    """SMs the persistent UMMA kernel leaves free (for a collective running beside it); returns the previous value."""
+    return _lib.load().STORM_b200_set_umma_reserved_sms(int(n))
 
 
 def set_umma_stream_k(on: bool) -> int:

@@ -660,6 +660,7 @@ int wave_counter(cudaStream_t stream, unsigned int** slot) {
 }
 
 int g_umma_wave_sync = 1;   // STORM_b200_set_umma_wave_sync
+int g_umma_reserved_sms = 0;   // STORM_b200_set_umma_reserved_sms
 int g_umma_stream_k = 1;    // STORM_b200_set_umma_stream_k
 
 template <int CG, int VAR>
@@ -675,7 +676,8 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     STORM_CUDA_TRY(cudaGetDevice(&dev));
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const uint64_t n_tiles = job.tile_end - job.tile_begin;
-    const uint64_t max_clusters = (uint64_t)(sms / CG);                                            // persistent: one per SM (pair)
+    const int reserved = g_umma_reserved_sms < sms - 2 ? g_umma_reserved_sms : sms - 2;
+    const uint64_t max_clusters = (uint64_t)((sms - reserved) / CG);                               // persistent: one per SM (pair)
     uint64_t clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
     job.wave_sync = nullptr;
     job.stream_k = 0;
@@ -795,6 +797,13 @@ extern "C" int STORM_b200_set_umma_cta_group(int cg) {
 extern "C" int STORM_b200_set_umma_wave_sync(int on) {
     const int prev = storm::g_umma_wave_sync;
     storm::g_umma_wave_sync = on ? 1 : 0;
+    return prev;
+}
+
+// SMs the persistent kernel leaves to a collective running beside it (multi-GPU host queries).  Returns the previous value.
+extern "C" int STORM_b200_set_umma_reserved_sms(int n) {
+    const int prev = storm::g_umma_reserved_sms;
+    storm::g_umma_reserved_sms = n < 0 ? 0 : n;
     return prev;
 }
 

@@ -313,6 +313,28 @@ int STORM_b200_shard_tiles(uint64_t n_rows, int kernel, uint32_t shard, uint32_t
     return STORM_B200_OK;
 }
 
+int STORM_b200_tiles_below_row(uint64_t n_rows, int kernel, uint64_t row_limit, uint64_t* tile_end, uint64_t* band_rows) {
+    if (!tile_end) { set_error("tile_end is NULL"); return STORM_B200_EINVAL; }
+    if (kernel == STORM_B200_KERNEL_AUTO) kernel = STORM_b200_resolve_kernel(kernel, 1024);
+    const TileShape ts = tile_shape_for(kernel);
+    const uint64_t group_rows = (uint64_t)TRI_GROUP * ts.tn;                // rows a raster group adds
+    if (band_rows) *band_rows = group_rows;
+    std::vector<uint64_t> prefix;
+    const uint64_t n_tiles = triangle_prefix(n_rows, ts, &prefix, nullptr, nullptr);
+    // tiles of raster groups <= g only read rows below (g + 1) * group_rows (common.cuh)
+    const uint64_t g = row_limit / group_rows;
+    *tile_end = row_limit >= n_rows ? n_tiles : prefix[std::min<uint64_t>(g, prefix.size() - 1)];
+    return STORM_B200_OK;
+}
+
+int STORM_b200_pairw_tiles_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                  uint64_t row_stride_words, uint64_t tile_begin, uint64_t tile_end,
+                                  int kernel, uint64_t* d_total, void* stream) {
+    if (tile_begin == tile_end) return STORM_B200_OK;
+    return pairw_triangle_range(d_rows, n_rows, n_words, row_stride_words, tile_begin, tile_end, kernel, d_total,
+                                (cudaStream_t)stream);
+}
+
 int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile, uint64_t* i0, uint64_t* i1, uint64_t* j0, uint64_t* j1) {
     if (kernel == STORM_B200_KERNEL_AUTO) kernel = STORM_b200_resolve_kernel(kernel, 1024);
     const TileShape ts = tile_shape_for(kernel);

@@ -37,8 +37,13 @@ constexpr uint32_t BLOCK_WORDS = BLOCK_BITS / 64;                  // 1024
 constexpr uint32_t LIST_THRESHOLD = STORM_DEFAULT_SCALAR_THRESHOLD;  // 4096
 constexpr uint32_t BITMAP_FLAG = 0x80000000u;
 
-constexpr int SP_THREADS = 256;
-constexpr int SP_WARPS = SP_THREADS / 32;
+// Threads per CTA: the kernel is latency-bound (dependent global loads of the merge, random probes), so it
+// wants every warp it can get next to one CTA's shared bitmaps: 1024 threads when the shared-memory slots
+// leave room for a single CTA per SM (8 warps gave 12.5 % occupancy and 17 % issue utilisation on a C4-like
+// matrix, profiles/r01_sparse_c4_ncu_full.md), 512 below that (several CTAs per SM).
+constexpr int SP_MAX_THREADS = 1024;
+constexpr int SP_MAX_WARPS = SP_MAX_THREADS / 32;
+constexpr size_t SP_ONE_CTA_SMEM = 100 * 1024;   // above this only one CTA fits on an SM
 constexpr uint32_t SP_SLICE = 1024;        // partner rows per CTA
 constexpr uint32_t SP_MAXB_CAP = 24;       // row-i blocks resident in shared memory per pass (24 x 8 KiB)
 constexpr uint32_t SP_TINY_NNZ = 64;       // rows with <= this many values are never expanded
@@ -85,11 +90,18 @@ __device__ __forceinline__ uint32_t search_intersect(const uint16_t* a, uint32_t
     return c;
 }
 
-__global__ void __launch_bounds__(SP_THREADS) sparse_pairs_kernel(const SparseJob job) {
+// Set bits of the shared bitmap `ab` among the two block-relative values packed in `w`.
+__device__ __forceinline__ uint32_t probe_pair(const uint32_t* ab, uint32_t w) {
+    const uint32_t v0 = w & 0xFFFFu, v1 = w >> 16;
+    return ((ab[v0 >> 5] >> (v0 & 31)) & 1u) + ((ab[v1 >> 5] >> (v1 & 31)) & 1u);
+}
+
+__global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_pairs_kernel(const SparseJob job) {
     extern __shared__ __align__(16) uint32_t s_bits[];            // maxb x 2048 32-bit words
     __shared__ uint32_t s_id[SP_MAXB_CAP], s_len[SP_MAXB_CAP];
     __shared__ uint64_t s_off[SP_MAXB_CAP];
-    __shared__ unsigned long long warp_part[SP_WARPS];
+    __shared__ unsigned long long warp_part[SP_MAX_WARPS];
+    const uint32_t SP_THREADS = blockDim.x, SP_WARPS = blockDim.x >> 5;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t i = job.i0 + job.shard + (uint64_t)blockIdx.x * job.n_shards;
@@ -169,8 +181,15 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_pairs_kernel(const SparseJo
                     if (tiny) {                                    // list x list (storm.c:628-630)
                         c += search_intersect(A.lists + s_off[x], na, bl, nb, lane);
                     } else {                                       // j's values probed into i's shared bitmap
+                        // lists start on 16-byte boundaries of the pool (sync_mirror): eight values per load
                         const uint32_t* ab = s_bits + x * 2048;
-                        for (uint32_t k = lane; k < nb; k += 32) {
+                        const uint4* bl4 = reinterpret_cast<const uint4*>(bl);
+                        const uint32_t n8 = nb >> 3;
+                        for (uint32_t k = lane; k < n8; k += 32) {
+                            const uint4 q = __ldg(bl4 + k);
+                            c += probe_pair(ab, q.x) + probe_pair(ab, q.y) + probe_pair(ab, q.z) + probe_pair(ab, q.w);
+                        }
+                        for (uint32_t k = (n8 << 3) + lane; k < nb; k += 32) {
                             const uint32_t v = bl[k];
                             c += (ab[v >> 5] >> (v & 31)) & 1u;
                         }
@@ -194,7 +213,7 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_pairs_kernel(const SparseJo
         __syncthreads();
         if (tid == 0) {
             unsigned long long t = 0;
-            for (int k = 0; k < SP_WARPS; ++k) t += warp_part[k];
+            for (uint32_t k = 0; k < SP_WARPS; ++k) t += warp_part[k];
             if (t) atomicAdd(job.total, t);
         }
     }
@@ -346,7 +365,7 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
     const uint64_t slices = (job.j1 - job.j0 + SP_SLICE - 1) / SP_SLICE;
     if (slices > 65535) { set_error("too many partner rows for one launch (%llu)", (unsigned long long)(job.j1 - job.j0)); return STORM_B200_EINVAL; }
     dim3 grid((unsigned)rows_i, (unsigned)slices);
-    sparse_pairs_kernel<<<grid, SP_THREADS, smem, stream>>>(job);
+    sparse_pairs_kernel<<<grid, smem > SP_ONE_CTA_SMEM ? SP_MAX_THREADS : SP_MAX_THREADS / 2, smem, stream>>>(job);
     STORM_CUDA_TRY(cudaGetLastError());
     count_launch();
     return STORM_B200_OK;

@@ -387,3 +387,40 @@ def test_wave_sync_is_only_a_hint(sb):
                 assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == closed, (on, kernel)
         finally:
             sb.set_umma_wave_sync(bool(prev))
+
+
+@pytest.mark.parametrize("kernel", ["fp4", "umma", "popc"])
+def test_tile_ranges_and_reserved_sms_add_up(sb, orc, kernel):
+    """STORM_b200_pairw_tiles_device over any partition of the raster = the full total; the band plan of the
+    pipelined multi-GPU host query (distributed.stream_plan) is such a partition, and a band's tiles give the
+    right answer with only the rows of bands <= b resident (later rows poisoned with ones).  Leaving SMs to a
+    collective (STORM_b200_set_umma_reserved_sms) never changes a result."""
+    import torch
+    from stormbitmaps_b200 import distributed as D
+    N, M = 4500, 4096
+    vals = orc.gen_dense_uniform(33, N, 1500, M)
+    exact = orc.wrapper_diag(vals)
+    rows, W = _device_rows(sb, vals), vals.shape[1]
+    kid = sb.resolve_kernel(kernel, W)
+    n_tiles = sb.tile_count(N, kernel)[0]
+    cuts = sorted({0, 1, n_tiles // 3, n_tiles // 3 + 1, n_tiles - 1, n_tiles})
+    parts = [int(sb.pairw_tiles_device(rows, a, b, n_words=W, kernel=kid).item()) for a, b in zip(cuts, cuts[1:])]
+    assert sum(parts) == exact
+    with pytest.raises(sb.StormError):
+        sb.pairw_tiles_device(rows, 0, n_tiles + 1, n_words=W, kernel=kid)
+    for world in (2, 3):
+        plan = D.stream_plan(N, world, kid, 4)
+        got = 0
+        for rsv in (0, 2, 200):
+            prev = sb.set_umma_reserved_sms(rsv)
+            try:
+                got = 0
+                staged = torch.full_like(rows, -1)                     # rows that have "not arrived yet": all ones
+                for (r0, r1, t0, t1) in plan:
+                    staged[r0:r1] = rows[r0:r1]
+                    for r in range(world):
+                        tb, te = D.rank_tiles(t0, t1, r, world)
+                        got += int(sb.pairw_tiles_device(staged, tb, te, n_words=W, kernel=kid).item())
+                assert got == exact, (world, rsv)
+            finally:
+                sb.set_umma_reserved_sms(prev)

@@ -148,3 +148,89 @@ def test_raster_is_monotone_in_rows():
             assert g >= last_group, (kernel, t)
             last_group = g
             assert i1 <= min(n_rows, (g + 1) * 8 * tn) and j1 <= min(n_rows, (g + 1) * 8 * tn)
+
+
+# ---- pipelined host query (distributed.pairw_total_from_host, N > 1) ---------------------------------
+def test_stream_plan_bands_partition_rows_and_tiles():
+    """Bands are contiguous in rows and in raster tiles, every tile of band b reads only rows the bands <= b
+    carry, band heights split into `world` equal slices, and the ranks' shares partition a band's tiles."""
+    import stormbitmaps_b200 as sb
+    from stormbitmaps_b200 import distributed as D
+    for kernel, n_rows, world, bands in (("umma", 9000, 2, 8), ("umma", 9000, 3, 4), ("umma", 2049, 8, 8),
+                                         ("popc", 5000, 2, 3), ("umma", 300, 2, 8), ("umma", 20000, 8, 5)):
+        kid = sb.resolve_kernel(kernel, 1024)
+        plan = D.stream_plan(n_rows, world, kid, bands)
+        n_tiles = sb.tile_count(n_rows, kernel)[0]
+        assert 1 <= len(plan) <= bands
+        assert plan[0][0] == 0 and plan[0][2] == 0 and plan[-1][1] == n_rows and plan[-1][3] == n_tiles
+        for b, (r0, r1, t0, t1) in enumerate(plan):
+            assert r1 > r0 and t1 >= t0
+            if b:
+                assert r0 == plan[b - 1][1] and t0 == plan[b - 1][3]
+            if b < len(plan) - 1:
+                assert (r1 - r0) % world == 0
+            for t in {t0, (t0 + t1) // 2, max(t0, t1 - 1)} if t1 > t0 else ():
+                i0, i1, j0, j1 = sb.tile_rect(n_rows, t, kernel)
+                assert i1 <= r1 and j1 <= r1, (kernel, n_rows, b, t)
+            if b and t1 > t0:                                   # ... and the band's first tile really needs the band
+                i0, i1, j0, j1 = sb.tile_rect(n_rows, t0, kernel)
+                assert max(i1, j1) > r0
+            prev = t0
+            for r in range(world):
+                tb, te = D.rank_tiles(t0, t1, r, world)
+                assert tb == prev and te >= tb
+                prev = te
+            assert prev == t1
+            # slices of the band: equal heights at fixed places, together exactly the band's rows
+            covered = 0
+            for r in range(world):
+                a, e, h = D.band_slice(r0, r1, r, world)
+                assert e - a <= h and (a == r0 + r * h or a == r1)
+                covered += e - a
+            assert covered == r1 - r0
+        assert D.plan_arena_rows(plan, world) >= n_rows
+
+
+def _band_main(rank, world, port, n_rows, n_words, bands, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import stormbitmaps_b200 as sb
+    from stormbitmaps_b200 import distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(99)
+        host = torch.randint(-2**62, 2**62, (n_rows, n_words), dtype=torch.int64, generator=g)
+        kid = sb.resolve_kernel("umma", n_words)
+        plan = D.stream_plan(n_rows, world, kid, bands)
+        arena = D.alloc_stream_arena(n_rows, n_words, world, "cpu", plan)
+        ok = True
+        for (r0, r1, t0, t1) in plan:
+            D.gather_band(host, arena, r0, r1, rank, world)
+            ok &= bool((arena[:r1, :n_words] == host[:r1]).all())     # everything up to this band has landed
+            ok &= bool((arena[r1 + world:] == 0).all())               # later bands untouched (bar slice padding)
+        ok &= bool((arena[n_rows:] == 0).all()) and bool((arena[:, n_words:] == 0).all())
+        t = torch.tensor([int(ok), len(plan)], dtype=torch.int64)
+        dist.all_reduce(t)
+        if rank == 0:
+            out.put((int(t[0]), int(t[1])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows,n_words,bands", [(9001, 4, 4), (5000, 16, 8), (100, 3, 8)])
+def test_two_ranks_gather_row_bands(n_rows, n_words, bands):
+    """Band-wise upload + all-gather of the pipelined host query replicates the matrix band by band."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_band_main, args=(r, world, port, n_rows, n_words, bands, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    n_ok, n_bands = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n_ok == world and n_bands >= world
