@@ -251,7 +251,7 @@ struct StormState {
     bool dirty = true;
     uint32_t n_rows = 0, max_blocks = 0;
     uint32_t max_blk_id = 0;             // largest block index of any row (row width of the dense form)
-    uint64_t total_nnz = 0;
+    uint64_t total_nnz = 0, total_blocks = 0;
     uint64_t* d_dense = nullptr; uint64_t dense_cap_words = 0; bool dense_valid = false;   // densified rows (dense route)
     int last_route = 0;                  // 1 = sparse kernel, 2 = densified + dense tile kernel
     uint32_t *d_row_ptr = nullptr, *d_row_nnz = nullptr, *d_blk_id = nullptr, *d_blk_len = nullptr;
@@ -345,6 +345,7 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     st->max_blocks = max_blocks;
     st->max_blk_id = max_blk_id;
     st->total_nnz = 0;
+    st->total_blocks = blk_id.size();
     for (uint32_t v : row_nnz) st->total_nnz += v;
     st->dirty = false;
     return STORM_B200_OK;
@@ -371,10 +372,13 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
     return STORM_B200_OK;
 }
 
-// Route of a whole-container query.  The dense tile kernel costs W / 6e13 s per pair whatever the
-// density (tensor pipe, bench.py); the sparse kernel costs about one probe per value of the partner
-// row, ~1e12 probes/s.  Dense wins unless rows are nearly empty -- the threshold is a cost model,
-// not the reference's CPU-tuned 4096 / 200 constants, and it cannot change a result.
+// Route of a whole-container query: a cost model, not the reference's CPU-tuned 4096 / 200 constants, and it
+// cannot change a result.  The dense tile kernel costs W / 6e13 s per pair whatever the density (FP4 tensor
+// form; 3.5e13 for the int8 form) plus one pass over the rows to densify them.  The merge-probe kernel costs,
+// per pair, a fixed part, a part per block of the row (block-id merge + dispatch) and a part per value probed:
+// 0.08 + 0.16 blocks + 0.0003 values ns, fitted to 10 000 x 524 288 at 104 / 5 242 values per row and
+// 3 000 x 1 048 576 at 10 486 (profiles/r01_sparse_timing.jsonl).  Dense wins unless rows are nearly empty or
+// very wide: at 524 288 bits the crossover is below one block per row.
 int g_storm_route = 0;   // 0 auto, 1 sparse kernel, 2 densify + dense tile kernel (STORM_b200_set_storm_route)
 
 bool choose_dense_route(const StormState* st, uint64_t n_rows) {
@@ -388,9 +392,12 @@ bool choose_dense_route(const StormState* st, uint64_t n_rows) {
     if (need > have / 10 * 8) return false;                              // keep 20 % of the free memory
     if (g_storm_route == 2) return true;
     const double avg_nnz = (double)st->total_nnz / (double)n_rows;
-    // W / 6e13 (FP4 tensor form; 3.5e13 for the int8 form)  <  avg_nnz / 1e12
-    const double dense_wp_per_probe = (W * 64 <= (1ull << 24) && fp4_selftest_ok()) ? 60.0 : 35.0;
-    return avg_nnz * dense_wp_per_probe > (double)W;
+    const double avg_blocks = (double)st->total_blocks / (double)n_rows;
+    const double pairs = 0.5 * (double)n_rows * (double)(n_rows - 1);
+    const double dense_rate = (W * 64 <= (1ull << 24) && fp4_selftest_ok()) ? 6.0e13 : 3.5e13;
+    const double dense_s = pairs * (double)W / dense_rate + 3e-5 + (st->dense_valid ? 0.0 : (double)need / 2e12);
+    const double sparse_s = pairs * 1e-9 * (0.08 + 0.16 * avg_blocks + 0.0003 * avg_nnz) + 1e-5;
+    return dense_s < sparse_s;
 }
 
 int ensure_dense(StormState* st, uint64_t n_rows, uint64_t* stride_out) {
