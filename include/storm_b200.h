@@ -218,6 +218,11 @@ int STORM_b200_set_umma_wave_sync(int on);
  * persistent CTAs (stream-K: no tail wave, no idle SMs on small row counts); 0: whole tiles only.
  * Results are identical.  Returns the previous value. */
 int STORM_b200_set_umma_stream_k(int on);
+/* 1 (default): total-only queries keep accumulating consecutive interior tiles of a CTA in the same
+ * tensor-memory accumulator and drain it once per run (as many tiles as the accumulator's exact range
+ * allows: 2^24 / (32 M) for the FP4 form) instead of once per tile; 0: one drain per tile.  Results are
+ * identical.  Returns the previous value. */
+int STORM_b200_set_umma_chain(int on);
 /* SMs the persistent UMMA kernel leaves free (default 0): a multi-GPU caller that overlaps an NVLink
  * all-gather with the tile kernel sets this to a small number so that the collective's CTAs find a place
  * to run beside it.  Clamped to [0, SM count - 2].  Returns the previous value. */

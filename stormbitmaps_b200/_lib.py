@@ -107,6 +107,7 @@ SIGNATURES = {
     "STORM_b200_set_umma_variant": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_wave_sync": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_stream_k": (C.c_int, [C.c_int]),
+    "STORM_b200_set_umma_chain": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_reserved_sms": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),
 }

@@ -457,6 +457,11 @@ def set_umma_stream_k(on: bool) -> int:
     return _lib.load().STORM_b200_set_umma_stream_k(int(bool(on)))
 
 
+def set_umma_chain(on: bool) -> int:
+    """Accumulator chaining of total-only UMMA queries (one drain per run of interior tiles, default on); returns the previous value."""
+    return _lib.load().STORM_b200_set_umma_chain(int(bool(on)))
+
+
 def device_info(dev: int = 0) -> dict:
     L = _lib.load()
     name = C.create_string_buffer(128)

@@ -70,6 +70,11 @@ struct DenseJob {
     // (tile, K chunk) units evenly instead of whole tiles (a total is a sum, so any K split of a tile
     // is valid); removes the tail wave and keeps every SM busy when there are fewer tiles than SMs.
     uint32_t stream_k;
+    // Set by the UMMA launcher for total-only jobs: up to chain_max consecutive interior segments of one
+    // CTA (pair) accumulate into the same tensor-memory accumulator and are drained once (a total is a sum,
+    // so the accumulator may hold the sum of several tiles as long as no element can overflow its exact
+    // range); 0 or 1 = every segment is drained on its own.
+    uint32_t chain_max;
 };
 
 // Last row block of column block bj that intersects the strict upper triangle when A == B (square
@@ -92,7 +97,8 @@ __host__ __device__ inline void tri_group_coords(uint32_t c0, uint64_t u, uint32
     const uint32_t cols = (c0 + TRI_GROUP <= n_bj) ? TRI_GROUP : n_bj - c0;      // column blocks in this group
     const uint32_t ifull = tri_iend(c0, n_bi, TM, TN);                           // up to here every column has a tile
     const uint64_t n_full = ((uint64_t)ifull + 1) * cols;
-    if (u < n_full) { bi = (uint32_t)(u / cols); bj = c0 + (uint32_t)(u % cols); return; }
+    // (a group has at most TRI_GROUP * n_bi < 2^32 tiles: 32-bit division)
+    if (u < n_full) { bi = (uint32_t)u / cols; bj = c0 + (uint32_t)u % cols; return; }
     u -= n_full;
     for (uint32_t i = ifull + 1;; ++i) {                                         // ramp towards the diagonal: a suffix of the columns
         uint32_t c = 0;
@@ -124,6 +130,32 @@ __device__ inline void tile_coords(const DenseJob& job, uint64_t t, uint32_t TM,
     }
     tile_coords_tri(job.group_prefix, job.n_bi, job.n_bj, t, TM, TN, bi, bj);
 }
+
+// tile_coords with the last group's bounds kept in registers: a persistent CTA walks its tiles in increasing
+// order, so most lookups stay inside the group of the previous one and need no global load at all.
+struct TileCursor {
+    uint64_t lo = 1, hi = 0;     // tiles [lo, hi) are group g (empty before the first lookup)
+    uint32_t g = 0;
+    __device__ __forceinline__ void coords(const DenseJob& job, uint64_t t, uint32_t TM, uint32_t TN, uint32_t& bi, uint32_t& bj) {
+        if (!job.triangle) {
+            bi = (uint32_t)(t / job.n_bj);
+            bj = (uint32_t)(t % job.n_bj);
+            return;
+        }
+        if (t < lo || t >= hi) {
+            const uint32_t n_groups = (job.n_bj + TRI_GROUP - 1) / TRI_GROUP;
+            uint32_t a = 0, b = n_groups;        // largest g with prefix[g] <= t
+            while (b - a > 1) {
+                const uint32_t mid = (a + b) >> 1;
+                if (job.group_prefix[mid] <= t) a = mid; else b = mid;
+            }
+            g = a;
+            lo = job.group_prefix[a];
+            hi = job.group_prefix[a + 1];
+        }
+        tri_group_coords(g * TRI_GROUP, t - lo, job.n_bi, job.n_bj, TM, TN, bi, bj);
+    }
+};
 
 // ---- launchers (one per kernel family) ---------------------------------------
 struct TileShape { uint32_t tm, tn; };

@@ -184,6 +184,10 @@ struct SegWalk {
     }
 };
 
+// Run flags handed from the expanders to the MMA warp, one ring entry per segment (the expanders are at most
+// STAGES k-blocks, hence STAGES segments, ahead of the MMA warp).
+constexpr uint32_t RUN_FIRST = 1, RUN_LAST = 2, RUN_RING = 16;
+
 constexpr int VAR_SUSPEND = 1;          // hardware-suspended mbarrier waits
 constexpr int VAR_SCALED = 2;           // scaled expansion (counts accumulate x128); kind::i8 only
 constexpr int VAR_FP4 = 4;              // bits -> E2M1 nibbles, tcgen05.mma kind::mxf4, fp32 accumulators
@@ -208,6 +212,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_slot = acc_empty_bar + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
     unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + (tmem_slot + 8 - smem_base));
+    const uint32_t run_ring = tmem_slot + 8 + 8 * 16;                       // RUN_RING x 4 B: run flags, expanders -> MMA warp
 
     auto wait = [](uint32_t bar, uint32_t parity) { mbar_wait_t<(VAR & VAR_SUSPEND) != 0>(bar, parity); };
     constexpr bool FP4 = (VAR & VAR_FP4) != 0;
@@ -269,6 +274,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             bool in_step = job.wave_sync != nullptr;
             SegWalk walk(job, cluster_id, n_clusters, n_chunks);
             Seg seg;
+            TileCursor cursor;
             for (; walk.next(seg); ++t_iter) {
                 const uint64_t tile = seg.tile;
                 if (in_step && t_iter > 0) {
@@ -285,7 +291,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                 }
                 uint32_t bi, bj;
-                tile_coords(job, tile, C::TM, C::TN, bi, bj);
+                cursor.coords(job, tile, C::TM, C::TN, bi, bj);
                 const uint32_t ya = bi * C::TM + rank * 128u;
                 const uint32_t yb = bj * C::TN + rank * C::B_ROWS;
                 for (uint32_t c = seg.c0; c < seg.c1; ++c, ++gc) {
@@ -313,13 +319,21 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             //   (1024 B between 8-row groups); [46,48) version = 1; [61,64) layout = 2 (SWIZZLE_128B)
             const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-            uint32_t s = 0, phase = 0, t_iter = 0;                         // stage ring position and its parity
+            uint32_t s = 0, phase = 0, t_iter = 0, run_iter = 0;           // stage ring position and its parity; runs done
             SegWalk walk(job, cluster_id, n_clusters, n_chunks);
             Seg seg;
             for (; walk.next(seg); ++t_iter) {
-                wait(acc_empty_bar, (t_iter & 1) ^ 1);                     // epilogue of the previous segment drained TMEM
-                tc_fence_after();
                 const uint32_t kb0 = seg.c0 * CHUNK_KB, kb1 = min(n_kb, seg.c1 * CHUNK_KB);
+                // Run flags of this segment, published by the first expander warp before it filled the segment's
+                // first stage (hence the wait for that stage here; the loop's own wait on it then passes at once).
+                // A run = consecutive interior segments of a total-only job that share the accumulator: only its
+                // first segment waits for the drain of the previous run and overwrites, only its last one hands
+                // the accumulator to the epilogue.  Read outside the k loop, which stays as tight as it was.
+                wait(full_bar + 8 * s, phase);
+                const uint32_t flags = ld_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)));
+                const bool run_first = __any_sync(0xffffffffu, (flags & RUN_FIRST) != 0);      // (warp-uniform anyway)
+                if (run_first) wait(acc_empty_bar, (run_iter & 1) ^ 1);    // epilogue of the previous run drained TMEM
+                tc_fence_after();
                 for (uint32_t kb = kb0; kb < kb1; ++kb) {
                     wait(full_bar + 8 * s, phase);
                     tc_fence_after();
@@ -328,19 +342,22 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
+                            const uint32_t accumulate = (((kb - kb0) | (uint32_t)k) != 0 || !run_first) ? 1u : 0u;   // first MMA of a run overwrites
                             if (FP4)
                                 umma_mxf4_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC_FP4,
-                                                 tmem_u + UM_SF_COL, tmem_u + UM_SF_COL + UM_SF_COLS / 2, ((kb - kb0) | (uint32_t)k) != 0);
+                                                 tmem_u + UM_SF_COL, tmem_u + UM_SF_COL + UM_SF_COLS / 2, accumulate);
                             else
-                                umma_i8_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC,
-                                               ((kb - kb0) | (uint32_t)k) != 0);
+                                umma_i8_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC, accumulate);
                         }
                         umma_commit<CG>(empty_bar + 8 * s);                // frees the stage when these MMAs are done
                     }
                     __syncwarp();
                     if (++s == (uint32_t)C::STAGES) { s = 0; phase ^= 1; }
                 }
-                if (leader) umma_commit<CG>(acc_full_bar);                 // accumulator of this tile complete
+                if (flags & RUN_LAST) {
+                    if (leader) umma_commit<CG>(acc_full_bar);             // accumulator of this run complete
+                    ++run_iter;
+                }
                 __syncwarp();
             }
         }
@@ -358,10 +375,36 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t b_line = (idx >> 3) * 1024u + (idx & 7u) * 128u;    // 8-row groups are 1024 B apart
         const uint32_t a_lane = tmem_base + (((warp & 3u) * 32u) << 16);
         uint32_t s = 0, phase = 0, gc = 0, t_iter = 0;                     // stage ring position and its parity
+        uint32_t run_pos = 0, run_iter = 0;                                // segments already in the open run; runs drained
         SegWalk walk(job, cluster_id, n_clusters, n_chunks);
-        Seg seg;
-        for (; walk.next(seg); ++t_iter) {
-            const uint64_t tile = seg.tile;
+        TileCursor cursor;
+        // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
+        auto is_interior = [&](uint32_t bi_, uint32_t bj_) {
+            const uint64_t a0 = (uint64_t)bi_ * C::TM, b0 = (uint64_t)bj_ * C::TN;
+            return job.out == nullptr && a0 + C::TM <= job.nA && b0 + C::TN <= job.nB &&
+                   (!job.strict_upper || job.j_off + b0 >= job.i_off + a0 + C::TM);
+        };
+        Seg seg, seg_next;
+        uint32_t bi = 0, bj = 0, bi_next = 0, bj_next = 0;
+        bool interior = false, interior_next = false;
+        const bool publisher = warp == 0 && lane == 0 && rank == 0;
+        bool have = false, primed = false;
+        for (;;) {
+            // One segment of look-ahead decides where the open run ends: it goes on while this segment and the
+            // next are interior and the accumulator has room (DenseJob::chain_max).  Every expander warp of
+            // the pair takes the same decision; the MMA warp reads it from the flag ring.  (The first pass
+            // only fills the look-ahead: one copy of the tile lookup in the code.)
+            const bool have_next = walk.next(seg_next);
+            if (have_next) { cursor.coords(job, seg_next.tile, C::TM, C::TN, bi_next, bj_next); interior_next = is_interior(bi_next, bj_next); }
+            if (!primed) {
+                primed = true;
+                seg = seg_next; bi = bi_next; bj = bj_next; interior = interior_next; have = have_next;
+                if (!have) break;
+                continue;
+            }
+            const bool run_last = !(have_next && interior && interior_next && run_pos + 1 < job.chain_max);
+            if (publisher)
+                st_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)), (run_pos == 0 ? RUN_FIRST : 0u) | (run_last ? RUN_LAST : 0u));
             for (uint32_t c = seg.c0; c < seg.c1; ++c, ++gc) {
                 const uint32_t buf = gc & 1;
                 wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
@@ -418,14 +461,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
             }
-            {
-                const bool fp4_sum_exact = (uint64_t)job.n_words * 64 * 32 <= (1ull << 24);
+            if (run_last) {
+                const uint64_t run_cap = job.chain_max > 1 ? job.chain_max : 1;    // an accumulator element is at most run_cap x M
+                const bool fp4_sum_exact = (uint64_t)job.n_words * 64 * 32 * run_cap <= (1ull << 24);
                 // ---- epilogue of this tile: TMEM -> registers -> masked sum / per-pair store ----
                 // Every expander warp takes part: warp w may read TMEM lanes 32 (w % 4) .. +31, so the
                 // A warp and the B warp(s) of one lane quarter split the 256 accumulator columns between
                 // them (32-column chunks dealt round-robin) and the drain takes half (a third) as long.
-                uint32_t bi, bj;
-                tile_coords(job, tile, C::TM, C::TN, bi, bj);
                 const uint32_t quarter = warp & 3u, sharer = warp >> 2;
                 constexpr uint32_t N_SHARERS = C::EXPANDER_WARPS / 4;
                 const uint64_t rowA0 = (uint64_t)bi * C::TM, rowB0 = (uint64_t)bj * C::TN;
@@ -433,10 +475,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint64_t gi = job.i_off + li;
                 const bool row_ok = li < job.nA;
                 const uint32_t acc_lane = tmem_base + ((quarter * 32u) << 16) + UM_ACC_COL;
-                // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
-                const bool interior = job.out == nullptr && rowA0 + C::TM <= job.nA && rowB0 + C::TN <= job.nB &&
-                                      (!job.strict_upper || job.j_off + rowB0 >= job.i_off + rowA0 + C::TM);
-                wait(acc_full_bar, t_iter & 1);
+                wait(acc_full_bar, run_iter & 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (uint32_t c0 = sharer * 32u; c0 < (uint32_t)UM_N; c0 += 32u * N_SHARERS) {
@@ -500,7 +539,14 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
+                run_pos = 0;
+                ++run_iter;
+            } else {
+                ++run_pos;
             }
+            seg = seg_next; bi = bi_next; bj = bj_next; interior = interior_next; have = have_next;
+            ++t_iter;
+            if (!have) break;
         }
     }
     __syncwarp();                                                          // re-converge (aligned ops follow)
@@ -662,6 +708,7 @@ int wave_counter(cudaStream_t stream, unsigned int** slot) {
 int g_umma_wave_sync = 1;   // STORM_b200_set_umma_wave_sync
 int g_umma_reserved_sms = 0;   // STORM_b200_set_umma_reserved_sms
 int g_umma_stream_k = 1;    // STORM_b200_set_umma_stream_k
+int g_umma_chain = 1;       // STORM_b200_set_umma_chain
 
 template <int CG, int VAR>
 int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
@@ -703,6 +750,17 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
             if (want > max_clusters) want = max_clusters;
             if (want > n_tiles) { clusters = want; job.stream_k = 1; }
         }
+    }
+    // Accumulator chaining for total-only jobs: consecutive interior segments of a CTA share the accumulator
+    // and are drained once per run.  An element then holds at most chain_max x M, which must stay inside the
+    // exact range of the form: fp32 integers below 2^24 for kind::mxf4 (and 32 of them must still add up
+    // exactly in the epilogue's float sum), s32 for kind::i8 (x 128 in the scaled form).
+    job.chain_max = 1;
+    if (g_umma_chain && !job.out && job.total) {
+        const uint64_t M = (uint64_t)job.n_words * 64;
+        const uint64_t room = C::FP4_FORM ? (1ull << 24) / (M * 32)
+                            : (VAR & VAR_SCALED) ? 0x7FFFFFFFull / (M * 128) : 0x7FFFFFFFull / M;
+        job.chain_max = (uint32_t)(room < 1 ? 1 : room > 4096 ? 4096 : room);
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
@@ -812,6 +870,14 @@ extern "C" int STORM_b200_set_umma_reserved_sms(int n) {
 extern "C" int STORM_b200_set_umma_stream_k(int on) {
     const int prev = storm::g_umma_stream_k;
     storm::g_umma_stream_k = on ? 1 : 0;
+    return prev;
+}
+
+// Development / measurement knob: 1 (default) = total-only jobs drain the accumulator once per run of interior
+// segments (DenseJob::chain_max), 0 = once per segment.  Returns the previous value.
+extern "C" int STORM_b200_set_umma_chain(int on) {
+    const int prev = storm::g_umma_chain;
+    storm::g_umma_chain = on ? 1 : 0;
     return prev;
 }
 

@@ -379,6 +379,33 @@ def test_stream_k_split_is_exact(sb, N, M):
             sb.set_umma_stream_k(bool(prev))
 
 
+@pytest.mark.parametrize("N,M", [(2000, 4096), (5000, 8192), (3000, 1024), (4100, 192), (1500, 65536), (900, 1 << 19)])
+def test_accumulator_chaining_is_exact(sb, orc, N, M):
+    """Total-only queries drain the tensor-memory accumulator once per run of interior tiles (up to
+    2^24 / (32 M) tiles in the FP4 form): same total as one drain per tile, for both tensor forms, with
+    diagonal and ragged edge tiles (which end a run) in between, through shards, and with all-ones rows
+    (every accumulator element at the top of its range)."""
+    rows, W = sb.alloc_rows(N, M)
+    sb.synth_uniform_device(rows, M, max(1, M // 2), 33)
+    closed = _colcount_total_torch(rows, W)
+    if N * W <= 3_000_000:
+        host = rows[:, :W].cpu().numpy().view(np.uint64)
+        assert orc.wrapper_diag(np.ascontiguousarray(host[:600])) == int(sb.pairw_device(rows[:600], n_words=W).item())
+    for on in (True, False):
+        prev = sb.set_umma_chain(on)
+        try:
+            for kernel in ("umma", "fp4"):
+                assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == closed, (on, kernel)
+            parts = [int(sb.pairw_device(rows, n_words=W, shard=r, n_shards=3, kernel="fp4").item()) for r in range(3)]
+            assert sum(parts) == closed, (on, parts)
+        finally:
+            sb.set_umma_chain(bool(prev))
+    rows[:, :W] = -1                                     # every pair count = 64 W: the accumulator's worst case
+    full = N * (N - 1) // 2 * 64 * W
+    for kernel in ("umma", "fp4"):
+        assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == full, kernel
+
+
 def test_wave_sync_is_only_a_hint(sb):
     """The wave counter of the persistent tensor kernels changes when CTAs load, never what they compute."""
     N, M = 5000, 8192

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Dense tile kernel over a grid of shapes, with the schedule knobs A/B'd: JSON lines (run on the GPU box).
 
-    python tools/shape_sweep.py [--knob stream_k|wave_sync|none] [rows:bits ...]
+    python tools/shape_sweep.py [--knob stream_k|wave_sync|chain|none] [rows:bits ...]
 
 Per shape and knob value: best-of-5 CUDA-event time of STORM_b200_pairw_device (rows resident, AUTO kernel),
 the total checked against the column-count closed form, wp/s and the fraction of the measured mxf4 pipe.
@@ -19,7 +19,8 @@ if "--knob" in args:
 shapes = [tuple(int(x) for x in a.split(":")) for a in args] or [
     (300, 65536), (1500, 524288), (2000, 65536), (10000, 65536), (10000, 524288), (16384, 4096), (32768, 4096),
     (65536, 4096), (16384, 16384), (16384, 65536), (30000, 131072), (5000, 1048576)]
-SETTERS = {"stream_k": getattr(sb, "set_umma_stream_k", None), "wave_sync": sb.set_umma_wave_sync, "none": None}
+SETTERS = {"stream_k": getattr(sb, "set_umma_stream_k", None), "wave_sync": sb.set_umma_wave_sync,
+           "chain": getattr(sb, "set_umma_chain", None), "none": None}
 setter = SETTERS[knob]
 
 
