@@ -157,7 +157,7 @@ __device__ __forceinline__ void umma_mxf4_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // wave (all tiles, if there are fewer tiles than clusters) are cut along K: their tiles x n_chunks units
 // are split into one contiguous range per cluster, sizes differing by at most one chunk, so a cluster's
 // first and last tail segments may cover part of a tile's K.  Every role of the kernel walks the same sequence.
-struct Seg { uint64_t tile; uint32_t c0, c1; };
+struct Seg { uint64_t tile; uint32_t c0, c1; bool tail; };
 struct SegWalk {
     uint64_t cur, full_end, step;          // whole tiles: cur, cur + step, ... below full_end
     uint64_t tail_cur, tail_end;           // tail units (tile-major, chunk-minor) of this cluster
@@ -173,8 +173,9 @@ struct SegWalk {
         tail_end = tail_cur + units / n_clusters + (cluster_id < units % n_clusters ? 1 : 0);
     }
     __device__ __forceinline__ bool next(Seg& s) {
-        if (cur < full_end) { s.tile = cur; s.c0 = 0; s.c1 = n_chunks; cur += step; return true; }
+        if (cur < full_end) { s.tile = cur; s.c0 = 0; s.c1 = n_chunks; s.tail = false; cur += step; return true; }
         if (tail_cur >= tail_end) return false;
+        s.tail = true;
         s.tile = full_end + tail_cur / n_chunks;
         s.c0 = (uint32_t)(tail_cur % n_chunks);
         const uint64_t left = tail_end - tail_cur;
@@ -277,6 +278,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             TileCursor cursor;
             for (; walk.next(seg); ++t_iter) {
                 const uint64_t tile = seg.tile;
+                if (seg.tail) in_step = false;                             // stream-K tail: uneven segments, nothing to keep in step
                 if (in_step && t_iter > 0) {
                     // Wave barrier.  The tiles of one wave share 8 A and ~9 B row blocks; they only find each
                     // other's lines in L2 if they walk K in step, and without this the CTAs drift apart over
@@ -302,7 +304,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
                     tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
                 }
-                if (job.wave_sync) atomicAdd(job.wave_sync, 1u);            // this CTA's loads of the wave are in flight
+                if (job.wave_sync && !seg.tail) atomicAdd(job.wave_sync, 1u);   // this CTA's loads of the wave are in flight
             }
         }
     } else if (warp == C::MMA_WARP) {
@@ -320,6 +322,14 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             uint32_t s = 0, phase = 0, t_iter = 0, run_iter = 0;           // stage ring position and its parity; runs done
+            // Everything the four MMAs of a k-block need is carried from iteration to iteration instead of being
+            // rebuilt from s after the wait: low descriptor word of the stage's B lines (LBO | addr >> 4, + 2 per K step
+            // of 32 bytes; shared-memory addresses stay below 2^18, so the 14-bit field cannot carry), tensor-memory
+            // column of its A operand, its two barriers.  The issue loop of this warp runs next to the expander
+            // warps of its scheduler and its length is what the tensor pipe's duty cycle hangs on: three extra
+            // instructions in it cost 2 % on every shape (profiles/r01_ab_chain_v2.jsonl).
+            const uint32_t b_lo0 = ((smem_base >> 4) & 0x3FFFu) | (uint32_t)desc_hi, a_col0 = tmem_u + UM_A_COL;
+            uint32_t b_lo = b_lo0, a_col = a_col0, full_s = full_bar, empty_s = empty_bar;
             SegWalk walk(job, cluster_id, n_clusters, n_chunks);
             Seg seg;
             for (; walk.next(seg); ++t_iter) {
@@ -328,31 +338,37 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 // first stage (hence the wait for that stage here; the loop's own wait on it then passes at once).
                 // A run = consecutive interior segments of a total-only job that share the accumulator: only its
                 // first segment waits for the drain of the previous run and overwrites, only its last one hands
-                // the accumulator to the epilogue.  Read outside the k loop, which stays as tight as it was.
-                wait(full_bar + 8 * s, phase);
+                // the accumulator to the epilogue.  Read outside the k loop.
+                wait(full_s, phase);
                 const uint32_t flags = ld_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)));
                 const bool run_first = __any_sync(0xffffffffu, (flags & RUN_FIRST) != 0);      // (warp-uniform anyway)
                 if (run_first) wait(acc_empty_bar, (run_iter & 1) ^ 1);    // epilogue of the previous run drained TMEM
                 tc_fence_after();
+                uint32_t fresh = run_first ? 0u : 1u;                      // accumulate flag of the segment's first MMA
                 for (uint32_t kb = kb0; kb < kb1; ++kb) {
-                    wait(full_bar + 8 * s, phase);
+                    wait(full_s, phase);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_base + s * C::STAGE_BYTES;
                     if (leader) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t b_desc = desc_hi | (uint64_t)(((b_addr + k * 32) >> 4) & 0x3FFF);
-                            const uint32_t accumulate = (((kb - kb0) | (uint32_t)k) != 0 || !run_first) ? 1u : 0u;   // first MMA of a run overwrites
+                            const uint64_t b_desc = (desc_hi & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + 2 * k);
+                            const uint32_t accumulate = k == 0 ? fresh : 1u;
                             if (FP4)
-                                umma_mxf4_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC_FP4,
+                                umma_mxf4_ts<CG>(tmem_u + UM_ACC_COL, a_col + k * 8, b_desc, C::IDESC_FP4,
                                                  tmem_u + UM_SF_COL, tmem_u + UM_SF_COL + UM_SF_COLS / 2, accumulate);
                             else
-                                umma_i8_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + s * 32 + k * 8, b_desc, C::IDESC, accumulate);
+                                umma_i8_ts<CG>(tmem_u + UM_ACC_COL, a_col + k * 8, b_desc, C::IDESC, accumulate);
                         }
-                        umma_commit<CG>(empty_bar + 8 * s);                // frees the stage when these MMAs are done
+                        umma_commit<CG>(empty_s);                          // frees the stage when these MMAs are done
                     }
                     __syncwarp();
-                    if (++s == (uint32_t)C::STAGES) { s = 0; phase ^= 1; }
+                    fresh = 1u;
+                    if (++s == (uint32_t)C::STAGES) {
+                        s = 0; phase ^= 1;
+                        b_lo = b_lo0; a_col = a_col0; full_s = full_bar; empty_s = empty_bar;
+                    } else {
+                        b_lo += C::STAGE_BYTES >> 4; a_col += 32; full_s += 8; empty_s += 8;
+                    }
                 }
                 if (flags & RUN_LAST) {
                     if (leader) umma_commit<CG>(acc_full_bar);             // accumulator of this run complete
@@ -475,6 +491,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint64_t gi = job.i_off + li;
                 const bool row_ok = li < job.nA;
                 const uint32_t acc_lane = tmem_base + ((quarter * 32u) << 16) + UM_ACC_COL;
+                const bool out_vec = ((reinterpret_cast<uintptr_t>(job.out) | (job.ld * 4)) & 31) == 0;   // 32-byte stores possible
                 wait(acc_full_bar, run_iter & 1);
                 tc_fence_after();
 #pragma unroll 1
@@ -523,6 +540,20 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             const uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
                             sum += ((uint32_t)(cc - lo) < span) ? x : 0u;
                         }
+                    } else if (row_ok && out_vec && rowB0 + c0 + 32 <= job.nB &&
+                               (!job.strict_upper || job.j_off + rowB0 + c0 > gi)) {
+                        // Per-pair output, all 32 columns of the chunk valid and right of the diagonal: this thread's
+                        // 128 consecutive bytes of its output row go out as four 32-byte stores (whole sectors; the
+                        // scalar form below issues 32 stores that each touch 32 different lines across the warp
+                        // and held the tensor pipe up for a third of a 2048-word tile).
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) {
+                            v[cc] = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
+                            sum += v[cc];
+                        }
+                        uint32_t* dst = job.out + li * job.ld + (rowB0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) st_global_v8(dst + 8 * q, &v[8 * q]);
                     } else if (row_ok) {
 #pragma unroll
                         for (int cc = 0; cc < 32; ++cc) {
@@ -740,9 +771,9 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     // with fewer tiles than clusters the idle SMs get K slices of the tiles (at least STREAMK_MIN_CHUNKS TMA
     // boxes each, so that a segment's epilogue stays small beside its MMAs).
     constexpr uint64_t STREAMK_MIN_CHUNKS = 8;
-    if (g_umma_stream_k && !job.out && !job.wave_sync) {
-        if (n_tiles >= max_clusters) job.stream_k = (n_tiles % max_clusters) != 0;
-        else {
+    if (g_umma_stream_k && !job.out) {
+        if (n_tiles >= max_clusters) job.stream_k = (n_tiles % max_clusters) != 0;   // (the wave barrier covers the full waves only)
+        else if (!job.wave_sync) {
             const uint32_t n_kb = C::FP4_FORM ? (job.n_words + 3) / 4 : (job.n_words + 1) / 2;
             const uint32_t chunk_kb = C::FP4_FORM ? UM_CHUNK_KB_FP4 : UM_CHUNK_KB;
             const uint64_t units = n_tiles * ((n_kb + chunk_kb - 1) / chunk_kb);

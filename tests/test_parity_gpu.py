@@ -135,6 +135,27 @@ def test_device_total_and_pairs_match_oracle(sb, orc, kernel, M, N, draws, seed)
     assert int(sq.item()) == orc.wrapper_square(a, b)
 
 
+@pytest.mark.parametrize("kernel", ["umma", "fp4"])
+def test_per_pair_output_vector_and_scalar_stores(sb, orc, kernel):
+    """Per-pair rectangles whose chunks take the 32-byte store path (ld a multiple of 8, whole 32-column chunks
+    right of the diagonal), the scalar path (diagonal / ragged chunks, odd ld), and both inside one tile."""
+    M, N = 2048 + 64, 1100
+    vals = orc.gen_dense_uniform(77, N, 700, M)
+    W = vals.shape[1]
+    rows = _device_rows(sb, vals)
+    for (i0, i1, j0, j1, strict) in [(0, 300, 320, 960, True), (0, 512, 0, 512, True), (0, 520, 0, 1000, True),
+                                     (10, 300, 37, 360, True), (600, 1100, 0, 1096, False), (256, 700, 250, 1100, True)]:
+        counts, total = sb.pairw_rect_device(rows, i0, i1, j0, j1, n_words=W, kernel=kernel, strict_upper=strict)
+        want = orc.rect_counts(vals, i0, i1, j0, j1)
+        if not strict:
+            want = np.array([[orc.pair_count(vals[i], vals[j]) for j in range(j0, j1)] for i in range(i0, i0 + 3)], dtype=np.uint32)
+            assert (counts[:3].cpu().numpy().view(np.uint32) == want).all(), (i0, i1, j0, j1)
+            assert int(total.item()) == int(counts.cpu().numpy().view(np.uint32).sum(dtype=np.uint64))
+            continue
+        assert (counts.cpu().numpy().view(np.uint32) == want).all(), (i0, i1, j0, j1)
+        assert int(total.item()) == int(want.sum(dtype=np.uint64))
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_extreme_rows(sb, orc, kernel):
     """All-ones, all-zero and single-bit rows; counts reach M exactly."""
