@@ -408,6 +408,14 @@ def main_ours(args, rows, bits, gen):
                                    "issues fewer POPC than that, so its fraction can exceed 1",
                     "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
 
+    if roofline.get("bound") == "tensor" and clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz"):
+        # The issue-rate probe runs on zero operands at the part's maximum clock; the tile kernel is power-capped
+        # (sw_power_cap) and holds a lower clock.  The pipe's ceiling AT THE CLOCK SAMPLED DURING THE TIMED REGION
+        # separates "idle pipe cycles" from "fewer cycles per second" (ncu: sm__pipe_tensor_cycles_active,
+        # profiles/r01_fp4_c3_ncu_full_v4.md).  `frac` stays achieved / peak.
+        scale = clocks["sm_mhz"] / clocks["sm_max_mhz"]
+        roofline["peak_at_run_clock"] = roofline["peak"] * scale
+        roofline["frac_at_run_clock"] = roofline["achieved"] / (roofline["peak"] * scale)
     line = {
         "metric": "xxt_wordpair_and_popcnt_per_s", "value": value, "unit": "wp/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,

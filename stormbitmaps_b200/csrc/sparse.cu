@@ -385,11 +385,13 @@ bool choose_dense_route(const StormState* st, uint64_t n_rows) {
     if (g_storm_route == 1) return false;
     const uint64_t W = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
     if (W >= (1u << 25)) return false;                                   // per-pair counts must stay below 2^31
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
     const uint64_t need = n_rows * W * 8;
-    const uint64_t have = free_b + (st->d_dense ? st->dense_cap_words * 8 : 0);
-    if (need > have / 10 * 8) return false;                              // keep 20 % of the free memory
+    if (need > st->dense_cap_words * 8) {                                // (cudaMemGetInfo costs ~0.1 ms: only when the arena must grow)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+        const uint64_t have = free_b + (st->d_dense ? st->dense_cap_words * 8 : 0);
+        if (need > have / 10 * 8) return false;                          // keep 20 % of the free memory
+    }
     if (g_storm_route == 2) return true;
     const double avg_nnz = (double)st->total_nnz / (double)n_rows;
     const double avg_blocks = (double)st->total_blocks / (double)n_rows;

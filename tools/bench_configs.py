@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """Throughput + exactness of the BASELINE.json configurations other than the bench.py headline (C3).
 
-    python tools/bench_configs.py [c1] [c2] [c4] [c5] [--quick]      (JSON lines on stdout)
+    python tools/bench_configs.py [c1] [c2] [c4] [c5] [c5grid] [--quick] [--c2-heavy-rows=N]      (JSON lines on stdout)
 
 C1  benchmark 65536 10000 (benchmark.cpp:693-698 density levels): STORM_contiguous_t through the
     storm.h API, rows ingested with STORM_contig_add / STORM_b200_contig_add_bulk.
 C2  STORM_t 10,000 x 524,288 density sweep (benchmark.cpp:511, README.md:65-80) + one mixed level.
 C4  100,000 x 1,048,576 at ~1 % (10,486 draws per row): STORM_t (all list blocks) and the dense model.
-C5  scaling sweep cells on one GPU, device-resident rows.
+C5  scaling sweep cells on one GPU, device-resident rows (c5grid: all 25 cells of the N x M grid).
+--c2-heavy-rows=N: row count of the C2 levels above 60,000 draws per row (host-side generation and the
+    host closed form of those levels take minutes at 10,000 rows; they take the same code path as 52,428).
 
 Every total is checked against the column-count closed form sum_k C(c_k, 2) (an O(N*W) identity
 that shares no code with the kernels); the timed region is the query call with rows resident
@@ -29,6 +31,7 @@ from oracle import oracle as O  # noqa: E402
 
 QUICK = "--quick" in sys.argv
 which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c2", "c4", "c5"]
+C2_HEAVY_ROWS = next((int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--c2-heavy-rows=")), None)
 orc = O.Oracle()
 
 
@@ -53,12 +56,15 @@ def closed_form_device(rows_t, W):
 
 
 def best_of(fn, reps=3):
+    """Best wall-clock time of fn().  The GPU drops to idle clocks while the host prepares the next level, so
+    short calls are repeated until 0.25 s have passed (at least `reps` times) before the best is taken."""
     fn()                                   # warm-up: uploads / mirrors become resident
-    best, val = 1e30, None
-    for _ in range(reps):
+    best, val, n, t_start = 1e30, None, 0, time.perf_counter()
+    while n < reps or (time.perf_counter() - t_start < 0.25 and n < 200):
         t0 = time.perf_counter()
         val = fn()
         best = min(best, time.perf_counter() - t0)
+        n += 1
     return best, val
 
 
@@ -89,11 +95,12 @@ def run_c1():
 
 
 def run_c2():
-    M, N = 524288, 1500 if QUICK else 10000
+    M, N_all = 524288, 1500 if QUICK else 10000
     W = M // 64
     levels = [262144, 131072, 52428, 20971, 10485, 5242, 2097, 524, 104, 5, 1, "mixed"]
     rng = np.random.default_rng(7)
     for draws in levels:
+        N = C2_HEAVY_ROWS if (C2_HEAVY_ROWS and isinstance(draws, int) and draws > 60000) else N_all
         d = draws if draws != "mixed" else np.exp(rng.uniform(0, np.log(262144), N)).astype(np.int64)
         rows = gen_rows(2, N, d, M)
         exact = closed_form(rows, M)
@@ -147,14 +154,20 @@ def run_c4():
              serialized_size=s.serialized_size(), unit="bitmap-space-equivalent wp/s")
 
 
-def run_c5():
+def run_c5(grid=False):
     cells = [(16384, 4096), (16384, 65536), (65536, 4096), (65536, 16384), (65536, 65536), (16384, 1048576)]
     if not QUICK:
         cells += [(131072, 65536), (262144, 16384), (65536, 262144)]
+    if grid:        # N in 16k..256k x M in 4k..1M (largest cell 34.4 GB of rows)
+        cells = [(N, M) for N in (16384, 32768, 65536, 131072, 262144) for M in (4096, 16384, 65536, 262144, 1048576)]
+    peak = sb.microbench(7)[0] if grid else None
     for N, M in cells:
         W = M // 64
         rows_t, _ = sb.alloc_rows(N, M)
-        sb.synth_uniform_device(rows_t, M, M // 2, 5)
+        if grid:
+            sb.synth_geno_device(rows_t, M, 5)          # (the uniform generator draws M / 2 positions per row: minutes at 34 GB)
+        else:
+            sb.synth_uniform_device(rows_t, M, M // 2, 5)
         torch.cuda.synchronize()
         exact = closed_form_device(rows_t, W)
         total = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -170,7 +183,8 @@ def run_c5():
                 best = min(best, ev0.elapsed_time(ev1) * 1e-3)
         got = int(total.item())
         emit(config="c5", rows=N, bits=M, total=got, exact=exact, match=got == exact, seconds=best,
-             wp_per_s=N * (N - 1) / 2 * W / best, tops=N * (N - 1) / 2 * W * 128 / best / 1e12)
+             wp_per_s=N * (N - 1) / 2 * W / best, tops=N * (N - 1) / 2 * W * 128 / best / 1e12,
+             **({"frac_of_mxf4_pipe": N * (N - 1) / 2 * W * 128 / best / peak, "generator": "geno"} if grid else {}))
         del rows_t
         torch.cuda.empty_cache()
 
@@ -178,4 +192,4 @@ def run_c5():
 if __name__ == "__main__":
     emit(device=sb.device_info(0), quick=QUICK)
     for w in which:
-        {"c1": run_c1, "c2": run_c2, "c4": run_c4, "c5": run_c5}[w]()
+        {"c1": run_c1, "c2": run_c2, "c4": run_c4, "c5": run_c5, "c5grid": lambda: run_c5(grid=True)}[w]()
