@@ -57,6 +57,9 @@ constexpr int UM_SF_COLS = 32;
 // 128 packed bytes wide, i.e. 8 resp. 4 k-blocks.
 constexpr int UM_CHUNK_KB = 8;
 constexpr int UM_CHUNK_KB_FP4 = 4;
+#ifndef STORM_RAW_BUFS
+#define STORM_RAW_BUFS 3
+#endif
 
 // XW = expander warps per 32 rows: 1 = a thread expands its row's whole k-block (4 K steps), 2 = two
 // threads of different warps expand K steps {0, 1} and {2, 3} of it, which halves the time from "stage free"
@@ -82,8 +85,12 @@ struct Cfg {
     static constexpr int TM = 128 * CG, TN = UM_N;
     static constexpr int EXPANDER_WARPS = A_WARPS + B_WARPS;
     static constexpr uint32_t OFF_RAW = STAGES * STAGE_BYTES;
-    static constexpr uint32_t OFF_BAR = OFF_RAW + 2 * RAW_BYTES;
+    // packed-row boxes in flight between the TMA thread and the expanders (how far the loads run ahead of the
+    // expansion: one box = 4 (FP4) or 8 k-blocks); three fit beside the stages of the CTA-pair form
+    static constexpr int RAW_BUFS = CG == 2 ? STORM_RAW_BUFS : 2;
+    static constexpr uint32_t OFF_BAR = OFF_RAW + RAW_BUFS * RAW_BYTES;
     static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 512;
+    static_assert(SMEM_BYTES <= 232448, "shared memory of one CTA");
     static_assert(UM_A_COL + 32 * STAGES <= (FP4 ? UM_SF_COL : 512), "A stages overflow tensor memory");
     static_assert(XW == 1 || XW == 2, "one or two expander warps per 32 rows");
     // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor bit layout):
@@ -202,13 +209,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
-    const uint32_t raw_base = smem_base + C::OFF_RAW;                       // [2][A box | B box]
+    const uint32_t raw_base = smem_base + C::OFF_RAW;                       // [RAW_BUFS][A box | B box]
     const uint32_t bar_base = smem_base + C::OFF_BAR;
     const uint32_t full_bar = bar_base;                                     // STAGES x 8 B
     const uint32_t empty_bar = full_bar + 8 * C::STAGES;
-    const uint32_t raw_full_bar = empty_bar + 8 * C::STAGES;                // 2 x 8 B
-    const uint32_t raw_empty_bar = raw_full_bar + 16;                       // 2 x 8 B
-    const uint32_t acc_full_bar = raw_empty_bar + 16;
+    const uint32_t raw_full_bar = empty_bar + 8 * C::STAGES;                // RAW_BUFS x 8 B
+    const uint32_t raw_empty_bar = raw_full_bar + 8 * C::RAW_BUFS;          // RAW_BUFS x 8 B
+    const uint32_t acc_full_bar = raw_empty_bar + 8 * C::RAW_BUFS;
     const uint32_t acc_empty_bar = acc_full_bar + 8;
     const uint32_t tmem_slot = acc_empty_bar + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -234,7 +241,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_init(full_bar + 8 * s, CG * C::EXPANDER_WARPS);           // every expander warp of the pair
             mbar_init(empty_bar + 8 * s, 1);                               // tcgen05.commit
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < C::RAW_BUFS; ++b) {
             mbar_init(raw_full_bar + 8 * b, 1);                            // expect_tx arrive + TMA bytes
             mbar_init(raw_empty_bar + 8 * b, C::EXPANDER_WARPS);
         }
@@ -270,7 +277,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == C::TMA_WARP) {
         // ===== TMA producer: packed rows -> shared memory ==============================
         if (lane == 0) {
-            uint32_t gc = 0;                                               // chunks issued so far (all tiles)
+            uint32_t buf = 0, buf_phase = 0;                               // ring of packed-row boxes and its parity
             uint32_t t_iter = 0;
             bool in_step = job.wave_sync != nullptr;
             SegWalk walk(job, cluster_id, n_clusters, n_chunks);
@@ -296,13 +303,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 cursor.coords(job, tile, C::TM, C::TN, bi, bj);
                 const uint32_t ya = bi * C::TM + rank * 128u;
                 const uint32_t yb = bj * C::TN + rank * C::B_ROWS;
-                for (uint32_t c = seg.c0; c < seg.c1; ++c, ++gc) {
-                    const uint32_t buf = gc & 1;
-                    wait(raw_empty_bar + 8 * buf, ((gc >> 1) & 1) ^ 1);
+                for (uint32_t c = seg.c0; c < seg.c1; ++c) {
+                    wait(raw_empty_bar + 8 * buf, buf_phase ^ 1);
                     mbar_expect_tx(raw_full_bar + 8 * buf, C::RAW_BYTES);
                     const uint32_t dst = raw_base + buf * C::RAW_BYTES;
                     tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
                     tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
+                    if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
                 }
                 if (job.wave_sync && !seg.tail) atomicAdd(job.wave_sync, 1u);   // this CTA's loads of the wave are in flight
             }
@@ -390,7 +397,8 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t sw = idx & 7u;
         const uint32_t b_line = (idx >> 3) * 1024u + (idx & 7u) * 128u;    // 8-row groups are 1024 B apart
         const uint32_t a_lane = tmem_base + (((warp & 3u) * 32u) << 16);
-        uint32_t s = 0, phase = 0, gc = 0, t_iter = 0;                     // stage ring position and its parity
+        uint32_t s = 0, phase = 0, t_iter = 0;                             // stage ring position and its parity
+        uint32_t buf = 0, buf_phase = 0;                                   // ring of packed-row boxes and its parity
         uint32_t run_pos = 0, run_iter = 0;                                // segments already in the open run; runs drained
         SegWalk walk(job, cluster_id, n_clusters, n_chunks);
         TileCursor cursor;
@@ -421,9 +429,8 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const bool run_last = !(have_next && interior && interior_next && run_pos + 1 < job.chain_max);
             if (publisher)
                 st_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)), (run_pos == 0 ? RUN_FIRST : 0u) | (run_last ? RUN_LAST : 0u));
-            for (uint32_t c = seg.c0; c < seg.c1; ++c, ++gc) {
-                const uint32_t buf = gc & 1;
-                wait(raw_full_bar + 8 * buf, (gc >> 1) & 1);
+            for (uint32_t c = seg.c0; c < seg.c1; ++c) {
+                wait(raw_full_bar + 8 * buf, buf_phase);
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q) {
@@ -476,6 +483,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
+                if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
             }
             if (run_last) {
                 const uint64_t run_cap = job.chain_max > 1 ? job.chain_max : 1;    // an accumulator element is at most run_cap x M
