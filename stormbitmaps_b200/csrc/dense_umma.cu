@@ -11,7 +11,8 @@
 // per SM pair) walk the tile list; per CTA:
 //   TMA warp    one thread streams PACKED rows into shared memory with
 //               cp.async.bulk.tensor (SWIZZLE_128B boxes of 128 rows x 128 bytes =
-//               8 k-blocks of 128 bits), double buffered, completion on an mbarrier.
+//               8 k-blocks of 128 bits), a ring of 2-3 boxes, completion on an mbarrier.  It also decides
+//               where the accumulator runs of total-only jobs end (run flag ring).
 //               Out-of-range rows / columns are zero-filled by the TMA unit.
 //   warps 0-3   "A expanders": thread = one A row = one TMEM lane.  Each k-block is
 //               read back from the staged box (16 B, conflict-free thanks to the
@@ -259,6 +260,12 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     unsigned long long sum = 0;
+    // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
+    auto is_interior = [&](uint32_t bi_, uint32_t bj_) {
+        const uint64_t a0 = (uint64_t)bi_ * C::TM, b0 = (uint64_t)bj_ * C::TN;
+        return job.out == nullptr && a0 + C::TM <= job.nA && b0 + C::TN <= job.nB &&
+               (!job.strict_upper || job.j_off + b0 >= job.i_off + a0 + C::TM);
+    };
 
     if (FP4 && warp < C::A_ROW_WARPS) {
         // Scale factors of the block-scaled MMA: every byte of the region is UE8M0 127 = 2^0, so whatever
@@ -278,40 +285,56 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== TMA producer: packed rows -> shared memory ==============================
         if (lane == 0) {
             uint32_t buf = 0, buf_phase = 0;                               // ring of packed-row boxes and its parity
-            uint32_t t_iter = 0;
+            uint32_t t_iter = 0, run_pos = 0;                              // segments done; segments already in the open run
             bool in_step = job.wave_sync != nullptr;
             SegWalk walk(job, cluster_id, n_clusters, n_chunks);
-            Seg seg;
             TileCursor cursor;
-            for (; walk.next(seg); ++t_iter) {
-                const uint64_t tile = seg.tile;
-                if (seg.tail) in_step = false;                             // stream-K tail: uneven segments, nothing to keep in step
-                if (in_step && t_iter > 0) {
-                    // Wave barrier.  The tiles of one wave share 8 A and ~9 B row blocks; they only find each
-                    // other's lines in L2 if they walk K in step, and without this the CTAs drift apart over
-                    // the thousands of tiles of a large query (ncu: 50 % L2 hits, 1.2 TB of DRAM reads on C3).
-                    // Everything staged so far keeps the MMA busy while this thread waits.  Bounded: if some
-                    // CTA is not resident (SMs taken by another kernel) the hint is dropped, not the query.
-                    const uint32_t target = t_iter * gridDim.x;
-                    uint32_t spins = 0;
-                    while (*reinterpret_cast<volatile unsigned int*>(job.wave_sync) < target) {
-                        if (++spins > 8192u) { in_step = false; break; }
-                        __nanosleep(64);
+            Seg seg, seg_next;
+            uint32_t bi = 0, bj = 0, bi_next = 0, bj_next = 0;
+            bool interior = false, interior_next = false, have = false, primed = false;
+            for (;;) {
+                // This thread runs ahead of everyone else and is idle most of the time, so it also decides where
+                // the accumulator runs of a total-only job end (DenseJob::chain_max): with one segment of
+                // look-ahead, a run goes on while this segment and the next are interior and the accumulator has
+                // room.  {first, last} go into the flag ring before the segment's first box is requested; the
+                // expanders read them after that box has landed, the MMA warp after the segment's first stage is
+                // full (release / acquire through the mbarriers in between).  The first pass only fills the look-ahead.
+                const bool have_next = walk.next(seg_next);
+                if (have_next) { cursor.coords(job, seg_next.tile, C::TM, C::TN, bi_next, bj_next); interior_next = is_interior(bi_next, bj_next); }
+                if (primed) {
+                    const bool run_last = !(have_next && interior && interior_next && run_pos + 1 < job.chain_max);
+                    st_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)), (run_pos == 0 ? RUN_FIRST : 0u) | (run_last ? RUN_LAST : 0u));
+                    run_pos = run_last ? 0 : run_pos + 1;
+                    if (seg.tail) in_step = false;                         // stream-K tail: uneven segments, nothing to keep in step
+                    if (in_step && t_iter > 0) {
+                        // Wave barrier.  The tiles of one wave share 8 A and ~9 B row blocks; they only find each
+                        // other's lines in L2 if they walk K in step, and without this the CTAs drift apart over
+                        // the thousands of tiles of a large query (ncu: 50 % L2 hits, 1.2 TB of DRAM reads on C3).
+                        // Everything staged so far keeps the MMA busy while this thread waits.  Bounded: if some
+                        // CTA is not resident (SMs taken by another kernel) the hint is dropped, not the query.
+                        const uint32_t target = t_iter * gridDim.x;
+                        uint32_t spins = 0;
+                        while (*reinterpret_cast<volatile unsigned int*>(job.wave_sync) < target) {
+                            if (++spins > 8192u) { in_step = false; break; }
+                            __nanosleep(64);
+                        }
                     }
+                    const uint32_t ya = bi * C::TM + rank * 128u;
+                    const uint32_t yb = bj * C::TN + rank * C::B_ROWS;
+                    for (uint32_t c = seg.c0; c < seg.c1; ++c) {
+                        wait(raw_empty_bar + 8 * buf, buf_phase ^ 1);
+                        mbar_expect_tx(raw_full_bar + 8 * buf, C::RAW_BYTES);
+                        const uint32_t dst = raw_base + buf * C::RAW_BYTES;
+                        tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
+                        tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
+                        if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
+                    }
+                    if (job.wave_sync && !seg.tail) atomicAdd(job.wave_sync, 1u);   // this CTA's loads of the wave are in flight
+                    ++t_iter;
                 }
-                uint32_t bi, bj;
-                cursor.coords(job, tile, C::TM, C::TN, bi, bj);
-                const uint32_t ya = bi * C::TM + rank * 128u;
-                const uint32_t yb = bj * C::TN + rank * C::B_ROWS;
-                for (uint32_t c = seg.c0; c < seg.c1; ++c) {
-                    wait(raw_empty_bar + 8 * buf, buf_phase ^ 1);
-                    mbar_expect_tx(raw_full_bar + 8 * buf, C::RAW_BYTES);
-                    const uint32_t dst = raw_base + buf * C::RAW_BYTES;
-                    tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
-                    tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
-                    if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
-                }
-                if (job.wave_sync && !seg.tail) atomicAdd(job.wave_sync, 1u);   // this CTA's loads of the wave are in flight
+                primed = true;
+                seg = seg_next; bi = bi_next; bj = bj_next; interior = interior_next; have = have_next;
+                if (!have) break;
             }
         }
     } else if (warp == C::MMA_WARP) {
@@ -341,8 +364,8 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             Seg seg;
             for (; walk.next(seg); ++t_iter) {
                 const uint32_t kb0 = seg.c0 * CHUNK_KB, kb1 = min(n_kb, seg.c1 * CHUNK_KB);
-                // Run flags of this segment, published by the first expander warp before it filled the segment's
-                // first stage (hence the wait for that stage here; the loop's own wait on it then passes at once).
+                // Run flags of this segment, published by the TMA thread before it requested the segment's first box
+                // (hence the wait for the first stage here; the loop's own wait on it then passes at once).
                 // A run = consecutive interior segments of a total-only job that share the accumulator: only its
                 // first segment waits for the drain of the previous run and overwrites, only its last one hands
                 // the accumulator to the epilogue.  Read outside the k loop.
@@ -399,38 +422,15 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t a_lane = tmem_base + (((warp & 3u) * 32u) << 16);
         uint32_t s = 0, phase = 0, t_iter = 0;                             // stage ring position and its parity
         uint32_t buf = 0, buf_phase = 0;                                   // ring of packed-row boxes and its parity
-        uint32_t run_pos = 0, run_iter = 0;                                // segments already in the open run; runs drained
+        uint32_t run_iter = 0;                                             // runs drained
         SegWalk walk(job, cluster_id, n_clusters, n_chunks);
         TileCursor cursor;
-        // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
-        auto is_interior = [&](uint32_t bi_, uint32_t bj_) {
-            const uint64_t a0 = (uint64_t)bi_ * C::TM, b0 = (uint64_t)bj_ * C::TN;
-            return job.out == nullptr && a0 + C::TM <= job.nA && b0 + C::TN <= job.nB &&
-                   (!job.strict_upper || job.j_off + b0 >= job.i_off + a0 + C::TM);
-        };
-        Seg seg, seg_next;
-        uint32_t bi = 0, bj = 0, bi_next = 0, bj_next = 0;
-        bool interior = false, interior_next = false;
-        const bool publisher = warp == 0 && lane == 0 && rank == 0;
-        bool have = false, primed = false;
-        for (;;) {
-            // One segment of look-ahead decides where the open run ends: it goes on while this segment and the
-            // next are interior and the accumulator has room (DenseJob::chain_max).  Every expander warp of
-            // the pair takes the same decision; the MMA warp reads it from the flag ring.  (The first pass
-            // only fills the look-ahead: one copy of the tile lookup in the code.)
-            const bool have_next = walk.next(seg_next);
-            if (have_next) { cursor.coords(job, seg_next.tile, C::TM, C::TN, bi_next, bj_next); interior_next = is_interior(bi_next, bj_next); }
-            if (!primed) {
-                primed = true;
-                seg = seg_next; bi = bi_next; bj = bj_next; interior = interior_next; have = have_next;
-                if (!have) break;
-                continue;
-            }
-            const bool run_last = !(have_next && interior && interior_next && run_pos + 1 < job.chain_max);
-            if (publisher)
-                st_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)), (run_pos == 0 ? RUN_FIRST : 0u) | (run_last ? RUN_LAST : 0u));
+        Seg seg;
+        for (; walk.next(seg); ++t_iter) {
+            uint32_t flags = RUN_FIRST | RUN_LAST;
             for (uint32_t c = seg.c0; c < seg.c1; ++c) {
                 wait(raw_full_bar + 8 * buf, buf_phase);
+                if (c == seg.c0) flags = ld_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)));   // written before this box was requested
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q) {
@@ -485,7 +485,11 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
                 if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
             }
-            if (run_last) {
+            if (flags & RUN_LAST) {
+                // a run of several segments is interior by construction; a run of one may be a diagonal or edge tile
+                uint32_t bi = 0, bj = 0;
+                bool interior = true;
+                if (flags & RUN_FIRST) { cursor.coords(job, seg.tile, C::TM, C::TN, bi, bj); interior = is_interior(bi, bj); }
                 const uint64_t run_cap = job.chain_max > 1 ? job.chain_max : 1;    // an accumulator element is at most run_cap x M
                 const bool fp4_sum_exact = (uint64_t)job.n_words * 64 * 32 * run_cap <= (1ull << 24);
                 // ---- epilogue of this tile: TMEM -> registers -> masked sum / per-pair store ----
@@ -578,14 +582,8 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
-                run_pos = 0;
                 ++run_iter;
-            } else {
-                ++run_pos;
             }
-            seg = seg_next; bi = bi_next; bj = bj_next; interior = interior_next; have = have_next;
-            ++t_iter;
-            if (!have) break;
         }
     }
     __syncwarp();                                                          // re-converge (aligned ops follow)
