@@ -168,3 +168,43 @@ def test_queries_fail_loudly_without_a_device(lib):
     s.add([1, 2]); s.add([2, 3])
     with pytest.raises(sb.StormError):
         s.pairw_intersect_cardinality()
+
+
+# ---- a C program written against storm.h, linked with libstorm_b200.so -----------------------------------
+HOST_FIELDS = ("rows", "words", "cutoff", "naive", "fptr01", "round2_rows", "null_query", "null_add")
+QUERY_FIELDS = ("contig", "contig_blocked", "storm", "storm_blocked", "wrapper", "round2_contig", "round2_storm")
+
+
+def build_dropin_driver(workdir):
+    """tests/drivers/dropin_driver.c (the calls benchmark.cpp makes, nothing but <storm.h>) against this repo's
+    header and shared library -- the link-time drop-in of INTEGRATION.md section 2."""
+    from stormbitmaps_b200 import build
+    build.build()
+    exe = os.path.join(workdir, "dropin_driver")
+    pkg = os.path.join(ROOT, "stormbitmaps_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "drivers", "dropin_driver.c"), "-L", pkg, "-lstorm_b200",
+                           "-Wl,-rpath," + pkg, "-o", exe])
+    return exe
+
+
+def run_dropin_driver(exe, args):
+    line = subprocess.check_output([exe] + args.split(), text=True, timeout=300).strip()
+    return dict(kv.split("=") for kv in line.split())
+
+
+def test_c_caller_compiles_links_and_keeps_host_semantics(lib):
+    """The same C source gives the same host-visible state (public fields, return codes, kept function pointer)
+    as when it is linked with the reference's storm.c (tests/golden/dropin_driver_v1.json, minted by
+    tools/make_golden_driver.py); without a device every query is the sentinel, never a CPU result."""
+    import json
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "dropin_driver_v1.json")))["cases"]
+    have_gpu = lib.STORM_b200_device_count() > 0
+    with tempfile.TemporaryDirectory() as d:
+        exe = build_dropin_driver(d)
+        for args, want in golden.items():
+            got = run_dropin_driver(exe, args)
+            for k in HOST_FIELDS:
+                assert got[k] == want[k], (args, k, got[k], want[k])
+            for k in QUERY_FIELDS:
+                assert got[k] == (want[k] if have_gpu else str(2**64 - 1)), (args, k, got[k])

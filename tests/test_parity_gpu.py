@@ -477,3 +477,18 @@ def test_tile_ranges_and_reserved_sms_add_up(sb, orc, kernel):
                 assert got == exact, (world, rsv)
             finally:
                 sb.set_umma_reserved_sms(prev)
+
+
+def test_c_caller_linked_with_the_library_prints_the_reference_totals(sb):
+    """tests/drivers/dropin_driver.c -- benchmark.cpp's call sequence in plain C99 -- linked with
+    libstorm_b200.so prints, field for field, what it prints when linked with the reference's storm.c
+    (tests/golden/dropin_driver_v1.json): both models, blocked variants, the raw-buffer wrapper, clear + reuse."""
+    import json, tempfile
+    from test_abi import build_dropin_driver, run_dropin_driver, HOST_FIELDS, QUERY_FIELDS
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dropin_driver_v1.json")))["cases"]
+    with tempfile.TemporaryDirectory() as d:
+        exe = build_dropin_driver(d)
+        for args, want in golden.items():
+            got = run_dropin_driver(exe, args)
+            for k in HOST_FIELDS + QUERY_FIELDS:
+                assert got[k] == want[k], (args, k, got[k], want[k])
