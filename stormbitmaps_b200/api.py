@@ -437,6 +437,11 @@ def set_storm_route(route) -> int:
     return _lib.load().STORM_b200_set_storm_route(r)
 
 
+def set_sparse_flat(on: bool) -> int:
+    """``STORM_b200_set_sparse_flat``: flat probe kernel for containers without bitmap blocks (default on)."""
+    return _lib.load().STORM_b200_set_sparse_flat(int(bool(on)))
+
+
 def set_umma_variant(variant: int) -> int:
     """Code variant of the UMMA kernel (bit 0: suspended waits, bit 1: scaled expansion)."""
     return _lib.load().STORM_b200_set_umma_variant(int(variant))

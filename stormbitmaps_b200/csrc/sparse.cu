@@ -59,6 +59,11 @@ struct SparseView {
     const uint16_t* lists;
     const uint64_t* words;
     uint32_t n_rows;
+    // flat form (ensure_flat; NULL until built): every value of a row as an absolute position, CSR over rows
+    const uint64_t* pos_off;   // n_rows + 1
+    const uint32_t* pos;
+    uint32_t n_blk_span;       // largest block index + 1: positions are below n_blk_span * 65536
+    float avg_nnz;             // values per row on average (sub-warp width of the flat kernel)
 };
 
 struct SparseJob {
@@ -219,6 +224,90 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_pairs_kernel(const S
     }
 }
 
+// ---- flat probe kernel: the merge/probe path for rows that hold FEW values --------------------------------
+// When no row has a bitmap block and a whole row fits shared memory as a bitmap (8 KiB per 65 536 bits), the
+// per-pair block-id merge (storm.c:75-106) and the per-block dispatch (storm.c:618-656) collapse into one case:
+// row i is expanded ONCE per CTA into a shared bitmap over the full row width and every value of a partner row
+// j -- kept as an absolute position in a flat CSR mirror -- is probed into it (the list -> bitmap probe of
+// storm.c:632-646 with the block arithmetic folded into the position).  A sub-warp of G lanes owns one partner
+// row (G = 1 for rows of a few values: 32 pairs per warp step; G = 32 for hundreds), two dependent loads per pair
+// (row offsets -> positions) instead of four per block.  The block kernel above spent ~12 000 cycles per pair
+// on C2's 104-value level (dependent loads of the merge, one warp per pair); this one is bound by the probes.
+constexpr size_t FLAT_MAX_SMEM = 160 * 1024;     // whole-row bitmap: rows up to 1 310 720 bits
+constexpr uint32_t FLAT_SLICE = 4096;            // partner rows per CTA
+
+__global__ void __launch_bounds__(256) flatten_rows_kernel(const SparseView v, const uint64_t* pos_off, uint32_t* pos) {
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= v.n_rows) return;
+    uint64_t o = pos_off[row];
+    for (uint32_t b = v.row_ptr[row]; b < v.row_ptr[row + 1]; ++b) {
+        const uint32_t len = v.blk_len[b];                        // (no bitmap blocks: flat_eligible)
+        const uint32_t base = v.blk_id[b] << 16;
+        const uint16_t* src = v.lists + v.blk_off[b];
+        for (uint32_t k = lane; k < len; k += 32) pos[o + k] = base | src[k];
+        o += len;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_flat_kernel(const SparseJob job, const uint32_t bm_words) {
+    extern __shared__ __align__(16) uint32_t s_bits[];            // bm_words: row i as a bitmap
+    __shared__ unsigned long long warp_part[SP_MAX_WARPS];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t i = job.i0 + job.shard + (uint64_t)blockIdx.x * job.n_shards;
+    if (i >= job.i1) return;
+    uint64_t jbeg = job.j0;
+    if (job.strict_upper && jbeg < i + 1) jbeg = i + 1;
+    const uint64_t js0 = jbeg + (uint64_t)blockIdx.y * FLAT_SLICE;
+    if (js0 >= job.j1) return;
+    const uint64_t js1 = min(js0 + (uint64_t)FLAT_SLICE, job.j1);
+    const uint64_t a0 = job.A.pos_off[i], a1 = job.A.pos_off[i + 1];
+    if (a0 == a1) return;                                          // empty row: all counts 0 (out is pre-zeroed)
+
+    uint4* z = reinterpret_cast<uint4*>(s_bits);
+    for (uint32_t k = tid; k < bm_words / 4; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (uint64_t k = a0 + tid; k < a1; k += blockDim.x) {
+        const uint32_t v = job.A.pos[k];
+        atomicOr(&s_bits[v >> 5], 1u << (v & 31));
+    }
+    __syncthreads();
+
+    constexpr uint32_t SUBS = 32 / G;                             // partner rows per warp step
+    const uint32_t l = lane % G, n_sub = (blockDim.x >> 5) * SUBS;
+    const uint64_t* __restrict__ off = job.B.pos_off;
+    const uint32_t* __restrict__ pos = job.B.pos;
+    unsigned long long acc = 0;
+    for (uint64_t jw = js0 + (uint64_t)warp * SUBS; jw < js1; jw += n_sub) {      // warp-uniform trip count
+        const uint64_t j = jw + lane / G;
+        const bool valid = j < js1;
+        uint32_t c = 0;
+        if (valid) {
+            const uint64_t o0 = off[j], o1 = off[j + 1];
+            for (uint64_t k = o0 + l; k < o1; k += G) {
+                const uint32_t v = __ldg(pos + k);
+                c += (s_bits[v >> 5] >> (v & 31)) & 1u;
+            }
+        }
+        acc += c;
+        if (job.out) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (valid && l == 0) job.out[(i - job.i0) * job.ld + (j - job.j0)] = c;
+        }
+    }
+    if (job.total) {
+        const unsigned long long w = warp_sum(acc);
+        if (lane == 0) warp_part[warp] = w;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t = 0;
+            for (uint32_t k = 0; k < (blockDim.x >> 5); ++k) t += warp_part[k];
+            if (t) atomicAdd(job.total, t);
+        }
+    }
+}
+
 // Dense route: one CTA per row writes the row's blocks into a zeroed row-major arena in the
 // layout of the contiguous model (bit v -> word v/64, bit v%64; storm.c:1114), after which
 // the query is the dense tile kernel's.  A bitmap block is a 8 KiB copy; a list block sets
@@ -257,6 +346,8 @@ struct StormState {
     uint32_t *d_row_ptr = nullptr, *d_row_nnz = nullptr, *d_blk_id = nullptr, *d_blk_len = nullptr;
     uint64_t* d_blk_off = nullptr; uint16_t* d_lists = nullptr; uint64_t* d_words = nullptr;
     unsigned long long* d_total = nullptr; unsigned long long* h_total = nullptr;
+    uint64_t n_bitmap_blocks = 0;        // blocks held as bitmaps (none: the flat probe kernel applies)
+    uint64_t* d_pos_off = nullptr; uint32_t* d_pos = nullptr; bool flat_valid = false;     // flat form (ensure_flat)
 };
 
 struct DeviceGuard {
@@ -272,10 +363,11 @@ inline StormState* state_of(const STORM_t* s) { return static_cast<StormState*>(
 
 void free_mirror(StormState* st) {
     for (void* p : {(void*)st->d_row_ptr, (void*)st->d_row_nnz, (void*)st->d_blk_id, (void*)st->d_blk_len,
-                    (void*)st->d_blk_off, (void*)st->d_lists, (void*)st->d_words})
+                    (void*)st->d_blk_off, (void*)st->d_lists, (void*)st->d_words, (void*)st->d_pos_off, (void*)st->d_pos})
         if (p) cudaFree(p);
     st->d_row_ptr = st->d_row_nnz = st->d_blk_id = st->d_blk_len = nullptr;
     st->d_blk_off = nullptr; st->d_lists = nullptr; st->d_words = nullptr;
+    st->d_pos_off = nullptr; st->d_pos = nullptr; st->flat_valid = false;
     st->dense_valid = false;
 }
 
@@ -308,6 +400,7 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     std::vector<uint64_t> blk_off, words;
     std::vector<uint16_t> lists;
     uint32_t max_blocks = 0, max_blk_id = 0;
+    uint64_t n_bitmap_blocks = 0;
     for (uint32_t r = 0; r < s->n_conts; ++r) {
         const STORM_bitmap_cont_t* row = &s->conts[r];
         row_ptr[r] = (uint32_t)blk_id.size();
@@ -317,6 +410,7 @@ int sync_mirror(const STORM_t* s, StormState* st) {
             blk_id.push_back(k->id);
             max_blk_id = std::max(max_blk_id, k->id);
             if (k->n_bitmap) {
+                ++n_bitmap_blocks;
                 blk_len.push_back(k->n_bits_set | BITMAP_FLAG);
                 blk_off.push_back(words.size());
                 words.insert(words.end(), k->data, k->data + BLOCK_WORDS);
@@ -335,6 +429,10 @@ int sync_mirror(const STORM_t* s, StormState* st) {
         }
     }
     row_ptr[s->n_conts] = (uint32_t)blk_id.size();
+    while (lists.size() % 8) lists.push_back(0);                   // 16-byte loads of the last list stay inside the pool
+    std::vector<uint64_t> pos_off(s->n_conts + 1, 0);              // CSR offsets of the flat form (built on demand)
+    for (uint32_t r = 0; r < s->n_conts; ++r) pos_off[r + 1] = pos_off[r] + row_nnz[r];
+    if ((rc = upload(&st->d_pos_off, pos_off, st->stream))) return rc;
     if ((rc = upload(&st->d_row_ptr, row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, row_nnz, st->stream)) ||
         (rc = upload(&st->d_blk_id, blk_id, st->stream)) || (rc = upload(&st->d_blk_len, blk_len, st->stream)) ||
         (rc = upload(&st->d_blk_off, blk_off, st->stream)) || (rc = upload(&st->d_lists, lists, st->stream)) ||
@@ -346,18 +444,75 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     st->max_blk_id = max_blk_id;
     st->total_nnz = 0;
     st->total_blocks = blk_id.size();
+    st->n_bitmap_blocks = n_bitmap_blocks;
     for (uint32_t v : row_nnz) st->total_nnz += v;
     st->dirty = false;
     return STORM_B200_OK;
 }
 
 SparseView view_of(const StormState* st) {
-    return SparseView{st->d_row_ptr, st->d_row_nnz, st->d_blk_id, st->d_blk_len, st->d_blk_off, st->d_lists, st->d_words, st->n_rows};
+    return SparseView{st->d_row_ptr, st->d_row_nnz, st->d_blk_id, st->d_blk_len, st->d_blk_off, st->d_lists, st->d_words, st->n_rows,
+                      st->flat_valid ? st->d_pos_off : nullptr, st->flat_valid ? st->d_pos : nullptr, st->max_blk_id + 1,
+                      st->n_rows ? (float)((double)st->total_nnz / (double)st->n_rows) : 0.0f};
+}
+
+int g_sparse_flat = 1;   // STORM_b200_set_sparse_flat: 0 = always the block kernel
+
+// The flat probe kernel applies when no block is a bitmap and a whole row fits shared memory as a bitmap.
+bool flat_eligible(const StormState* st) {
+    return g_sparse_flat && st->n_bitmap_blocks == 0 && ((uint64_t)st->max_blk_id + 1) * 8192 <= FLAT_MAX_SMEM;
+}
+
+// Build the flat form (absolute positions, CSR) of an eligible container on the device; a no-op otherwise.
+int ensure_flat(StormState* st) {
+    if (st->flat_valid || !flat_eligible(st) || st->n_rows == 0) return STORM_B200_OK;
+    if (!st->d_pos) {
+        if (cudaMalloc(&st->d_pos, std::max<uint64_t>(st->total_nnz, 1) * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            st->d_pos = nullptr;
+            return STORM_B200_OK;                                  // no room: the block kernel answers
+        }
+    }
+    flatten_rows_kernel<<<(st->n_rows + 7) / 8, 256, 0, st->stream>>>(view_of(st), st->d_pos_off, st->d_pos);
+    STORM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    st->flat_valid = true;
+    return STORM_B200_OK;
+}
+
+template <int G>
+int launch_flat_g(const SparseJob& job, uint32_t bm_words, dim3 grid, cudaStream_t stream) {
+    const size_t smem = (size_t)bm_words * 4;
+    STORM_CUDA_TRY(cudaFuncSetAttribute(sparse_flat_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_MAX_SMEM));
+    sparse_flat_kernel<G><<<grid, smem > SP_ONE_CTA_SMEM / 2 ? SP_MAX_THREADS : SP_MAX_THREADS / 2, smem, stream>>>(job, bm_words);
+    STORM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return STORM_B200_OK;
+}
+
+int launch_flat(const SparseJob& job, cudaStream_t stream) {
+    const uint32_t span = std::max(job.A.n_blk_span, job.B.n_blk_span);       // every probed position is below span * 65536
+    const uint32_t bm_words = span * 2048;
+    const uint64_t rows_i = (job.i1 - job.i0 + job.n_shards - 1 - job.shard) / job.n_shards;
+    if (rows_i == 0) return STORM_B200_OK;
+    const uint64_t slices = (job.j1 - job.j0 + FLAT_SLICE - 1) / FLAT_SLICE;
+    if (slices > 65535) { set_error("too many partner rows for one launch (%llu)", (unsigned long long)(job.j1 - job.j0)); return STORM_B200_EINVAL; }
+    dim3 grid((unsigned)rows_i, (unsigned)slices);
+    // lanes per partner row: about four values per lane
+    const float a = job.B.avg_nnz;
+    if (a <= 4.f) return launch_flat_g<1>(job, bm_words, grid, stream);
+    if (a <= 8.f) return launch_flat_g<2>(job, bm_words, grid, stream);
+    if (a <= 16.f) return launch_flat_g<4>(job, bm_words, grid, stream);
+    if (a <= 32.f) return launch_flat_g<8>(job, bm_words, grid, stream);
+    if (a <= 64.f) return launch_flat_g<16>(job, bm_words, grid, stream);
+    return launch_flat_g<32>(job, bm_words, grid, stream);
 }
 
 int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t stream) {
     SparseJob job = job_in;
     if (job.i1 <= job.i0 || job.j1 <= job.j0) return STORM_B200_OK;
+    if (g_sparse_flat && job.A.pos && job.B.pos &&
+        (uint64_t)std::max(job.A.n_blk_span, job.B.n_blk_span) * 8192 <= FLAT_MAX_SMEM) return launch_flat(job, stream);
     job.maxb = std::max<uint32_t>(1, std::min<uint32_t>(max_blocks, SP_MAXB_CAP));
     const size_t smem = (size_t)job.maxb * 8192;
     STORM_CUDA_TRY(cudaFuncSetAttribute(sparse_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_MAXB_CAP * 8192)));
@@ -439,6 +594,7 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
                            reinterpret_cast<uint64_t*>(st->d_total), st->stream)) return (uint64_t)-1;
     } else {
         st->last_route = 1;
+        if (ensure_flat(st)) return (uint64_t)-1;
         SparseJob job{};
         job.A = job.B = view_of(st);
         job.i0 = 0; job.i1 = s->n_conts; job.j0 = 0; job.j1 = s->n_conts;
@@ -715,6 +871,12 @@ int STORM_b200_set_storm_route(int route) {
     return prev;
 }
 
+int STORM_b200_set_sparse_flat(int on) {
+    const int prev = g_sparse_flat;
+    g_sparse_flat = on ? 1 : 0;
+    return prev;
+}
+
 int STORM_b200_storm_last_route(const STORM_t* s) {
     if (s == nullptr || s->b200 == nullptr) return 0;
     return state_of(s)->last_route;
@@ -731,6 +893,7 @@ int STORM_b200_storm_pairw_rect(STORM_t* s, uint64_t i0, uint64_t i1, uint64_t j
     const uint64_t ni = i1 - i0, nj = j1 - j0;
     uint32_t* d_out = nullptr;
     if (cudaMalloc(&d_out, ni * nj * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); set_error("device allocation for %llu x %llu counts failed", (unsigned long long)ni, (unsigned long long)nj); return STORM_B200_ENOMEM; }
+    if ((rc = ensure_flat(st))) { cudaFree(d_out); return rc; }
     SparseJob job{};
     job.A = job.B = view_of(st);
     job.i0 = i0; job.i1 = i1; job.j0 = j0; job.j1 = j1;
@@ -758,6 +921,8 @@ uint64_t STORM_intersect_cardinality_square(const STORM_t* STORM_RESTRICT s1, co
     if (a->device != b->device) { set_error("the two containers live on different devices"); return (uint64_t)-1; }
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) return (uint64_t)-1;
     if (cudaMemsetAsync(a->d_total, 0, 8, a->stream) != cudaSuccess) return (uint64_t)-1;
+    if (flat_eligible(a) && flat_eligible(b) && (ensure_flat(a) || ensure_flat(b))) return (uint64_t)-1;
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) return (uint64_t)-1;   // b's flat form is built on b's stream
     SparseJob job{};
     job.A = view_of(a); job.B = view_of(b);
     job.i0 = 0; job.i1 = s1->n_conts; job.j0 = 0; job.j1 = s2->n_conts;

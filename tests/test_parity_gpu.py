@@ -281,6 +281,41 @@ def test_storm_t_routes_agree(sb, orc, route):
         sb.set_storm_route(prev)
 
 
+@pytest.mark.parametrize("M", [2 * 65536, 1048576, 20 * 65536, 21 * 65536 + 5])
+def test_storm_t_flat_probe_kernel_equals_block_kernel(sb, orc, M):
+    """Sparse route on containers without bitmap blocks: the flat probe kernel (whole-row shared bitmap, partner
+    positions probed; rows up to 20 blocks wide) and the block merge/probe kernel give the oracle's total, shard
+    sums, per-pair rectangles and XY^T totals; empty rows, single values, duplicates and last-bit values included."""
+    draws = [0, 1, 3, 17, 64, 65, 200, 1000, 3500, 2, 0, 700]
+    rows = [orc.gen_row_positions(91, i, draws[i % len(draws)], M) for i in range(150)]
+    rows[5] = np.array([M - 1], dtype=np.uint32)
+    rows[6] = np.array([0, 0, 7, 7, 65535, 65536, M - 1, M - 1], dtype=np.uint32)      # adjacent duplicates collapse
+    vals = O.positions_to_dense(rows, M)
+    exact = orc.wrapper_diag(vals)
+    prev = sb.set_storm_route("sparse")
+    try:
+        for flat in (True, False):
+            was = sb.set_sparse_flat(flat)
+            try:
+                with sb.Storm() as s, sb.Storm() as t:
+                    for p in rows:
+                        s.add(p)
+                    for p in rows[40:95]:
+                        t.add(p)
+                    assert s.pairw_intersect_cardinality() == exact, (M, flat)
+                    assert s.last_route() == "sparse"
+                    assert sum(s.pairw_shard(r, 4) for r in range(4)) == exact, (M, flat)
+                    assert (s.pairw_rect(0, 150, 0, 150) == orc.rect_counts(vals, 0, 150, 0, 150)).all(), (M, flat)
+                    assert (s.pairw_rect(3, 77, 30, 149) == orc.rect_counts(vals, 3, 77, 30, 149)).all(), (M, flat)
+                    assert s.intersect_cardinality_square(t) == orc.wrapper_square(vals, vals[40:95]), (M, flat)
+                    s.add(rows[8])                                   # a mutation rebuilds both mirrors
+                    assert s.pairw_intersect_cardinality() == orc.wrapper_diag(np.concatenate([vals, vals[8:9]])), (M, flat)
+            finally:
+                sb.set_sparse_flat(bool(was))
+    finally:
+        sb.set_storm_route(prev)
+
+
 # --------------------------------------------------------------------------- #
 # full-size configurations: size-independent properties
 # --------------------------------------------------------------------------- #

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""STORM_t whole-container query through every route on one container: flat probe kernel, block merge/probe
+kernel, densified rows + tensor kernel, and what AUTO picks.  JSON lines (run on the GPU box); the timings are what
+the route cost model in sparse.cu (choose_dense_route) is fitted to.
+
+    python tools/sparse_routes.py [rows:bits:draws ...]
+"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import stormbitmaps_b200 as sb
+from oracle import oracle as O
+
+cases = [tuple(int(x) for x in a.split(":")) for a in sys.argv[1:]] or [
+    (10000, 524288, 1), (10000, 524288, 5), (10000, 524288, 30), (10000, 524288, 104), (10000, 524288, 524),
+    (10000, 524288, 2097), (3000, 1048576, 104), (3000, 1048576, 1000), (3000, 1048576, 10486), (20000, 131072, 16)]
+orc = O.Oracle()
+
+
+def timed(s, min_s=0.2):
+    s.pairw_intersect_cardinality_blocked(0)                      # mirrors resident
+    best, got, n, t_start = 1e30, None, 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t_start < min_s and n < 100):
+        t0 = time.perf_counter()
+        got = s.pairw_intersect_cardinality_blocked(0)
+        best = min(best, time.perf_counter() - t0)
+        n += 1
+    return best, got
+
+
+for rows, bits, draws in cases:
+    pos = [orc.gen_row_positions(2, i, draws, bits) for i in range(rows)]
+    cnt = np.zeros(bits, dtype=np.int64)
+    for p in pos:
+        cnt[p] += 1
+    exact = int((cnt * (cnt - 1) // 2).sum())
+    nnz = int(sum(len(p) for p in pos))
+    rec = {"rows": rows, "bits": bits, "draws": draws, "avg_nnz": nnz / rows, "routes": {}}
+    with sb.Storm() as s:
+        for p in pos:
+            s.add(p)
+        for name, route, flat in (("flat", "sparse", True), ("block", "sparse", False), ("dense", "dense", True), ("auto", "auto", True)):
+            if name == "block" and rows * (rows - 1) / 2 * (1 + nnz / rows / 100) > 4e8:
+                continue                                           # seconds on the block kernel
+            sb.set_storm_route(route)
+            sb.set_sparse_flat(flat)
+            dt, got = timed(s)
+            rec["routes"][name] = {"ms": round(dt * 1e3, 4), "took": s.last_route(), "match": got == exact}
+        sb.set_storm_route("auto")
+        sb.set_sparse_flat(True)
+    print(json.dumps(rec), flush=True)
