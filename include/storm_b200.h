@@ -168,11 +168,13 @@ uint64_t STORM_b200_storm_pairw_shard(STORM_t* bitmap, uint32_t shard, uint32_t 
  * previous value; STORM_b200_storm_last_route tells which one the last query of `bitmap` took. */
 int STORM_b200_set_storm_route(int route);
 int STORM_b200_storm_last_route(const STORM_t* bitmap);
-/* 1 (default): the sparse route answers containers without bitmap blocks whose rows fit shared memory as a
- * bitmap (up to 1 310 720 bits) with the flat probe kernel (positions of a partner row probed into the whole-row
- * shared bitmap of row i; no per-pair block merge); 0: always the block merge/probe kernel.  Results are
- * identical.  Returns the previous value. */
-int STORM_b200_set_sparse_flat(int on);
+/* Kernels of the sparse route for containers without bitmap blocks (their rows are mirrored as flat position
+ * lists on the device).  2 (default): totals through the row-group stream kernel (32 rows i per CTA in a
+ * shared-memory hash position -> row mask, all later rows' positions streamed through it), per-pair rectangles
+ * through the flat probe kernel (positions of a partner row probed into the whole-row shared bitmap of row i,
+ * rows up to 1 310 720 bits); 1: the flat probe kernel for both; 0: always the block merge/probe kernel.
+ * Results are identical.  Returns the previous value. */
+int STORM_b200_set_sparse_flat(int mode);
 /* Per-pair counts of a STORM_t rectangle into a HOST buffer (strict upper). */
 int STORM_b200_storm_pairw_rect(STORM_t* bitmap, uint64_t i0, uint64_t i1,
                                 uint64_t j0, uint64_t j1, uint32_t* out);

@@ -437,9 +437,11 @@ def set_storm_route(route) -> int:
     return _lib.load().STORM_b200_set_storm_route(r)
 
 
-def set_sparse_flat(on: bool) -> int:
-    """``STORM_b200_set_sparse_flat``: flat probe kernel for containers without bitmap blocks (default on)."""
-    return _lib.load().STORM_b200_set_sparse_flat(int(bool(on)))
+def set_sparse_flat(mode) -> int:
+    """``STORM_b200_set_sparse_flat``: 'block' (0) | 'flat' (1) | 'stream' (2, default) kernels of the sparse route
+    for containers without bitmap blocks; returns the previous mode."""
+    m = {"block": 0, "flat": 1, "stream": 2}[mode] if isinstance(mode, str) else int(mode)
+    return _lib.load().STORM_b200_set_sparse_flat(m)
 
 
 def set_umma_variant(variant: int) -> int:

@@ -308,6 +308,126 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_flat_kernel(const Sp
     }
 }
 
+// ---- row-group stream kernel: totals over rows that hold few values ---------------------------------------
+// For a TOTAL the identity of the partner row does not matter, only how many rows i of a group contain each of its
+// positions.  A CTA takes a group of up to 32 consecutive rows i (at most STREAM_ENTRIES values together; groups
+// are cut on the host, StormState::h_group_start), builds position -> row-mask in a shared-memory hash table
+// (open addressing, load <= 1/2), and then streams the positions of ALL later rows -- one contiguous range of the
+// flat mirror, whatever rows they belong to -- through it: total += popc(mask[pos]).  Every (i, j, common position)
+// triple is still counted individually (it is the list -> bitmap probe of storm.c:632-646 against 32 rows at
+// once); per partner position there is one coalesced 4-byte load and one or two shared-memory probes for up to
+// 32 pairs.  Pairs inside a group (j in the group, i < j) take the same table with the mask cut to the rows below j.
+constexpr uint32_t STREAM_CAP = 16384;           // hash slots (keys + masks: 128 KiB)
+constexpr uint32_t STREAM_ENTRIES = STREAM_CAP / 2;
+constexpr uint32_t STREAM_GROUP = 32;            // rows per group (one mask bit each)
+constexpr uint64_t STREAM_SLICE = 1u << 18;      // partner positions per CTA
+
+struct StreamJob {
+    SparseView A, B;
+    const uint32_t* group_start;   // device: first row of each group of A rows, n_groups + 1 entries
+    uint32_t g0, n_groups_job;     // groups [g0, g0 + n_groups_job) overlap rows [i0, i1)
+    uint64_t i0, i1, j0, j1;
+    int strict_upper;
+    uint32_t shard, n_shards;      // groups are dealt round-robin to shards
+    unsigned long long* total;
+};
+
+__device__ __forceinline__ uint32_t stream_slot(uint32_t p) { return (p * 2654435761u) >> 18; }   // 14 bits
+
+__device__ __forceinline__ uint32_t stream_lookup(const uint32_t* keys, const uint32_t* masks, uint32_t p) {
+    uint32_t slot = stream_slot(p);
+    for (;;) {
+        const uint32_t k = keys[slot];
+        if (k == p + 1u) return masks[slot];
+        if (k == 0u) return 0u;
+        slot = (slot + 1u) & (STREAM_CAP - 1u);
+    }
+}
+
+__global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const StreamJob job) {
+    extern __shared__ __align__(16) uint32_t s_tab[];             // keys[STREAM_CAP] | masks[STREAM_CAP]
+    __shared__ uint64_t s_off[STREAM_GROUP + 1];
+    __shared__ unsigned long long warp_part[SP_MAX_WARPS];
+    uint32_t* keys = s_tab;
+    uint32_t* masks = s_tab + STREAM_CAP;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const uint32_t gq = job.shard + blockIdx.x * job.n_shards;
+    if (gq >= job.n_groups_job) return;
+    const uint32_t g = job.g0 + gq;
+    const uint64_t ib = max((uint64_t)job.group_start[g], job.i0), ie = min((uint64_t)job.group_start[g + 1], job.i1);
+    if (ib >= ie) return;
+    const uint32_t R = (uint32_t)(ie - ib);
+    // partner rows all of whose pairs with the group count: [js, j1); rows inside the group: [jin0, jin1)
+    uint64_t js = job.j0, jin0 = 0, jin1 = 0;
+    if (job.strict_upper) {
+        js = max(job.j0, ie);
+        jin0 = max(job.j0, ib + 1);
+        jin1 = min(job.j1, ie);
+    }
+    const uint64_t p_beg = js < job.j1 ? job.B.pos_off[js] : 0, p_end = js < job.j1 ? job.B.pos_off[job.j1] : 0;
+    const uint64_t k0 = p_beg + (uint64_t)blockIdx.y * STREAM_SLICE;
+    const uint64_t k1 = min(k0 + STREAM_SLICE, p_end);
+    const bool inner = blockIdx.y == 0 && jin0 < jin1;
+    if (k0 >= k1 && !inner) return;
+
+    uint4* z = reinterpret_cast<uint4*>(s_tab);
+    for (uint32_t k = tid; k < 2 * STREAM_CAP / 4; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
+    if (tid <= R) s_off[tid] = job.A.pos_off[ib + tid];
+    __syncthreads();
+    const uint64_t e0 = s_off[0], e1 = s_off[R];
+    for (uint64_t e = e0 + tid; e < e1; e += blockDim.x) {
+        uint32_t r = 0;                                            // row of entry e: largest r with s_off[r] <= e
+#pragma unroll
+        for (uint32_t step = 16; step > 0; step >>= 1)
+            if (r + step < R && s_off[r + step] <= e) r += step;
+        const uint32_t p = job.A.pos[e];
+        uint32_t slot = stream_slot(p);
+        for (;;) {
+            const uint32_t old = atomicCAS(&keys[slot], 0u, p + 1u);
+            if (old == 0u || old == p + 1u) { atomicOr(&masks[slot], 1u << r); break; }
+            slot = (slot + 1u) & (STREAM_CAP - 1u);
+        }
+    }
+    __syncthreads();
+
+    unsigned long long acc = 0;
+    const uint32_t* __restrict__ pos = job.B.pos;
+    {   // rows beyond the group: every row of the group pairs with them.  16-byte loads, eight positions in flight
+        // per thread: the loop is bound by the latency of the dependent shared-memory probes.
+        auto hits = [&](uint32_t p) { return (unsigned)__popc(stream_lookup(keys, masks, p)); };
+        const uint64_t ka = min(k1, (uint64_t)((k0 + 3ull) & ~3ull));           // first 16-byte aligned position
+        for (uint64_t k = k0 + tid; k < ka; k += blockDim.x) acc += hits(__ldg(pos + k));
+        const uint4* __restrict__ p4 = reinterpret_cast<const uint4*>(pos + ka);
+        const uint64_t n4 = (k1 - ka) >> 2;
+        uint64_t q = tid;
+        for (; q + blockDim.x < n4; q += 2ull * blockDim.x) {
+            const uint4 a = __ldg(p4 + q), b = __ldg(p4 + q + blockDim.x);
+            acc += hits(a.x) + hits(a.y) + hits(a.z) + hits(a.w) + hits(b.x) + hits(b.y) + hits(b.z) + hits(b.w);
+        }
+        for (; q < n4; q += blockDim.x) {
+            const uint4 a = __ldg(p4 + q);
+            acc += hits(a.x) + hits(a.y) + hits(a.z) + hits(a.w);
+        }
+        for (uint64_t k = ka + 4ull * n4 + tid; k < k1; k += blockDim.x) acc += hits(__ldg(pos + k));
+    }
+    if (inner) {   // rows of the group itself (same container): row j pairs with the group's rows below it
+        for (uint64_t j = jin0 + warp; j < jin1; j += (blockDim.x >> 5)) {
+            const uint32_t below = (1u << (uint32_t)(j - ib)) - 1u;                 // j - ib in [1, 31]
+            for (uint64_t k = job.B.pos_off[j] + lane; k < job.B.pos_off[j + 1]; k += 32)
+                acc += __popc(stream_lookup(keys, masks, __ldg(pos + k)) & below);
+        }
+    }
+    const unsigned long long w = warp_sum(acc);
+    if (lane == 0) warp_part[warp] = w;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+        for (uint32_t k = 0; k < (blockDim.x >> 5); ++k) t += warp_part[k];
+        if (t) atomicAdd(job.total, t);
+    }
+}
+
 // Dense route: one CTA per row writes the row's blocks into a zeroed row-major arena in the
 // layout of the contiguous model (bit v -> word v/64, bit v%64; storm.c:1114), after which
 // the query is the dense tile kernel's.  A bitmap block is a 8 KiB copy; a list block sets
@@ -348,6 +468,9 @@ struct StormState {
     unsigned long long* d_total = nullptr; unsigned long long* h_total = nullptr;
     uint64_t n_bitmap_blocks = 0;        // blocks held as bitmaps (none: the flat probe kernel applies)
     uint64_t* d_pos_off = nullptr; uint32_t* d_pos = nullptr; bool flat_valid = false;     // flat form (ensure_flat)
+    uint32_t max_row_nnz = 0;
+    std::vector<uint32_t> h_group_start; // row groups of the stream kernel (<= 32 rows, <= STREAM_ENTRIES values)
+    uint32_t* d_group_start = nullptr;
 };
 
 struct DeviceGuard {
@@ -363,11 +486,13 @@ inline StormState* state_of(const STORM_t* s) { return static_cast<StormState*>(
 
 void free_mirror(StormState* st) {
     for (void* p : {(void*)st->d_row_ptr, (void*)st->d_row_nnz, (void*)st->d_blk_id, (void*)st->d_blk_len,
-                    (void*)st->d_blk_off, (void*)st->d_lists, (void*)st->d_words, (void*)st->d_pos_off, (void*)st->d_pos})
+                    (void*)st->d_blk_off, (void*)st->d_lists, (void*)st->d_words, (void*)st->d_pos_off, (void*)st->d_pos,
+                    (void*)st->d_group_start})
         if (p) cudaFree(p);
     st->d_row_ptr = st->d_row_nnz = st->d_blk_id = st->d_blk_len = nullptr;
     st->d_blk_off = nullptr; st->d_lists = nullptr; st->d_words = nullptr;
     st->d_pos_off = nullptr; st->d_pos = nullptr; st->flat_valid = false;
+    st->d_group_start = nullptr; st->h_group_start.clear();
     st->dense_valid = false;
 }
 
@@ -433,6 +558,19 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     std::vector<uint64_t> pos_off(s->n_conts + 1, 0);              // CSR offsets of the flat form (built on demand)
     for (uint32_t r = 0; r < s->n_conts; ++r) pos_off[r + 1] = pos_off[r] + row_nnz[r];
     if ((rc = upload(&st->d_pos_off, pos_off, st->stream))) return rc;
+    // row groups of the stream kernel: consecutive rows, at most 32 and at most STREAM_ENTRIES values together
+    uint32_t max_row_nnz = 0;
+    std::vector<uint32_t>& gs = st->h_group_start;
+    gs.assign(1, 0u);
+    uint64_t in_group = 0;
+    for (uint32_t r = 0; r < s->n_conts; ++r) {
+        max_row_nnz = std::max(max_row_nnz, row_nnz[r]);
+        if (r > gs.back() && (r - gs.back() == STREAM_GROUP || in_group + row_nnz[r] > STREAM_ENTRIES)) { gs.push_back(r); in_group = 0; }
+        in_group += row_nnz[r];
+    }
+    gs.push_back(s->n_conts);
+    if ((rc = upload(&st->d_group_start, gs, st->stream))) return rc;
+    st->max_row_nnz = max_row_nnz;
     if ((rc = upload(&st->d_row_ptr, row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, row_nnz, st->stream)) ||
         (rc = upload(&st->d_blk_id, blk_id, st->stream)) || (rc = upload(&st->d_blk_len, blk_len, st->stream)) ||
         (rc = upload(&st->d_blk_off, blk_off, st->stream)) || (rc = upload(&st->d_lists, lists, st->stream)) ||
@@ -456,7 +594,7 @@ SparseView view_of(const StormState* st) {
                       st->n_rows ? (float)((double)st->total_nnz / (double)st->n_rows) : 0.0f};
 }
 
-int g_sparse_flat = 1;   // STORM_b200_set_sparse_flat: 0 = always the block kernel
+int g_sparse_flat = 1;   // STORM_b200_set_sparse_flat(0): always the block kernel
 
 // The flat probe kernel applies when no block is a bitmap and a whole row fits shared memory as a bitmap.
 bool flat_eligible(const StormState* st) {
@@ -508,6 +646,41 @@ int launch_flat(const SparseJob& job, cudaStream_t stream) {
     return launch_flat_g<32>(job, bm_words, grid, stream);
 }
 
+int g_sparse_stream = 1;   // STORM_b200_set_sparse_flat(2): totals of light rows through the row-group stream kernel
+
+// Totals of rows [i0, i1) of `a` against rows [j0, j1) of `b` with the row-group stream kernel.  Needs both flat
+// forms and no row of `a` above STREAM_ENTRIES values.
+bool stream_eligible(const StormState* a, const StormState* b) {
+    return g_sparse_flat && g_sparse_stream && a->flat_valid && b->flat_valid && a->max_row_nnz <= STREAM_ENTRIES &&
+           a->d_group_start != nullptr;
+}
+
+int launch_stream(const StormState* a, const StormState* b, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, int strict_upper,
+                  uint32_t shard, uint32_t n_shards, unsigned long long* d_total, cudaStream_t stream) {
+    if (i1 <= i0 || j1 <= j0) return STORM_B200_OK;
+    const std::vector<uint32_t>& gs = a->h_group_start;            // groups overlapping [i0, i1)
+    const uint32_t g0 = (uint32_t)(std::upper_bound(gs.begin(), gs.end(), (uint32_t)i0) - gs.begin()) - 1;
+    const uint32_t g1 = (uint32_t)(std::lower_bound(gs.begin(), gs.end(), (uint32_t)i1) - gs.begin());
+    StreamJob job{};
+    job.A = view_of(a); job.B = view_of(b);
+    job.group_start = a->d_group_start;
+    job.g0 = g0; job.n_groups_job = g1 - g0;
+    job.i0 = i0; job.i1 = i1; job.j0 = j0; job.j1 = j1;
+    job.strict_upper = strict_upper; job.shard = shard; job.n_shards = n_shards;
+    job.total = d_total;
+    const uint64_t my_groups = (job.n_groups_job + n_shards - 1 - shard) / n_shards;
+    if (my_groups == 0) return STORM_B200_OK;
+    uint64_t slices = (b->total_nnz + STREAM_SLICE - 1) / STREAM_SLICE;      // upper bound on any group's partner stream
+    if (slices == 0) slices = 1;
+    if (slices > 65535) { set_error("partner stream too long for one launch (%llu values)", (unsigned long long)b->total_nnz); return STORM_B200_EINVAL; }
+    const size_t smem = 2 * STREAM_CAP * sizeof(uint32_t);
+    STORM_CUDA_TRY(cudaFuncSetAttribute(sparse_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparse_stream_kernel<<<dim3((unsigned)my_groups, (unsigned)slices), SP_MAX_THREADS, smem, stream>>>(job);
+    STORM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return STORM_B200_OK;
+}
+
 int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t stream) {
     SparseJob job = job_in;
     if (job.i1 <= job.i0 || job.j1 <= job.j0) return STORM_B200_OK;
@@ -532,8 +705,9 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
 // form; 3.5e13 for the int8 form) plus one pass over the rows to densify them.  The merge-probe kernel costs,
 // per pair, a fixed part, a part per block of the row (block-id merge + dispatch) and a part per value probed:
 // 0.08 + 0.16 blocks + 0.0003 values ns, fitted to 10 000 x 524 288 at 104 / 5 242 values per row and
-// 3 000 x 1 048 576 at 10 486 (profiles/r01_sparse_timing.jsonl).  Dense wins unless rows are nearly empty or
-// very wide: at 524 288 bits the crossover is below one block per row.
+// 3 000 x 1 048 576 at 10 486 (profiles/r01_sparse_timing.jsonl).  Containers without bitmap blocks take the
+// row-group stream kernel instead (modelled below), which wins up to a few hundred values per row: at 10 000 x
+// 524 288 the crossover with the tensor kernel is near 450 values per row (0.09 % density).
 int g_storm_route = 0;   // 0 auto, 1 sparse kernel, 2 densify + dense tile kernel (STORM_b200_set_storm_route)
 
 bool choose_dense_route(const StormState* st, uint64_t n_rows) {
@@ -553,7 +727,17 @@ bool choose_dense_route(const StormState* st, uint64_t n_rows) {
     const double pairs = 0.5 * (double)n_rows * (double)(n_rows - 1);
     const double dense_rate = (W * 64 <= (1ull << 24) && fp4_selftest_ok()) ? 6.0e13 : 3.5e13;
     const double dense_s = pairs * (double)W / dense_rate + 3e-5 + (st->dense_valid ? 0.0 : (double)need / 2e12);
-    const double sparse_s = pairs * 1e-9 * (0.08 + 0.16 * avg_blocks + 0.0003 * avg_nnz) + 1e-5;
+    double sparse_s = pairs * 1e-9 * (0.08 + 0.16 * avg_blocks + 0.0003 * avg_nnz) + 1e-5;      // block merge/probe kernel
+    if (g_sparse_flat && g_sparse_stream && st->n_bitmap_blocks == 0 && st->max_row_nnz <= STREAM_ENTRIES) {
+        // Row-group stream kernel: one probe per partner position and GROUP of rows i; a group holds min(32,
+        // 8192 / values per row) rows, and a probe walks (1 + 1 / (1 - load)^2) / 2 slots of the hash table.
+        // 1.9 ps per slot visited, fitted to 10 000 x 524 288 at 5 ... 5 242 values per row and 3 000 x 1 048 576
+        // at 1 000 (profiles/r01_sparse_routes_v2.jsonl: 0.03 / 0.40 / 7.8 / 28 / 112 / 692 ms).
+        const double group = std::min(32.0, std::max(1.0, std::floor((double)STREAM_ENTRIES / std::max(1.0, avg_nnz))));
+        const double load = std::min(0.5, group * avg_nnz / (double)STREAM_CAP);
+        const double walk = 0.5 * (1.0 + 1.0 / ((1.0 - load) * (1.0 - load)));
+        sparse_s = std::min(sparse_s, 1.5e-5 + pairs * avg_nnz / group * walk * 1.9e-12);
+    }
     return dense_s < sparse_s;
 }
 
@@ -595,13 +779,17 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     } else {
         st->last_route = 1;
         if (ensure_flat(st)) return (uint64_t)-1;
-        SparseJob job{};
-        job.A = job.B = view_of(st);
-        job.i0 = 0; job.i1 = s->n_conts; job.j0 = 0; job.j1 = s->n_conts;
-        job.strict_upper = 1;
-        job.shard = shard; job.n_shards = n_shards;
-        job.total = st->d_total;
-        if (launch_sparse(job, st->max_blocks, st->stream)) return (uint64_t)-1;
+        if (stream_eligible(st, st)) {
+            if (launch_stream(st, st, 0, s->n_conts, 0, s->n_conts, 1, shard, n_shards, st->d_total, st->stream)) return (uint64_t)-1;
+        } else {
+            SparseJob job{};
+            job.A = job.B = view_of(st);
+            job.i0 = 0; job.i1 = s->n_conts; job.j0 = 0; job.j1 = s->n_conts;
+            job.strict_upper = 1;
+            job.shard = shard; job.n_shards = n_shards;
+            job.total = st->d_total;
+            if (launch_sparse(job, st->max_blocks, st->stream)) return (uint64_t)-1;
+        }
     }
     if (cudaMemcpyAsync(st->h_total, st->d_total, 8, cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
         cudaStreamSynchronize(st->stream) != cudaSuccess) {
@@ -871,9 +1059,9 @@ int STORM_b200_set_storm_route(int route) {
     return prev;
 }
 
-int STORM_b200_set_sparse_flat(int on) {
-    const int prev = g_sparse_flat;
-    g_sparse_flat = on ? 1 : 0;
+int STORM_b200_set_sparse_flat(int mode) {
+    const int prev = g_sparse_flat ? (g_sparse_stream ? 2 : 1) : 0;
+    if (mode >= 0 && mode <= 2) { g_sparse_flat = mode >= 1; g_sparse_stream = mode == 2; }
     return prev;
 }
 
@@ -923,12 +1111,16 @@ uint64_t STORM_intersect_cardinality_square(const STORM_t* STORM_RESTRICT s1, co
     if (cudaMemsetAsync(a->d_total, 0, 8, a->stream) != cudaSuccess) return (uint64_t)-1;
     if (flat_eligible(a) && flat_eligible(b) && (ensure_flat(a) || ensure_flat(b))) return (uint64_t)-1;
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) return (uint64_t)-1;   // b's flat form is built on b's stream
-    SparseJob job{};
-    job.A = view_of(a); job.B = view_of(b);
-    job.i0 = 0; job.i1 = s1->n_conts; job.j0 = 0; job.j1 = s2->n_conts;
-    job.strict_upper = 0; job.shard = 0; job.n_shards = 1;
-    job.total = a->d_total;
-    if (launch_sparse(job, a->max_blocks, a->stream)) return (uint64_t)-1;
+    if (stream_eligible(a, b)) {
+        if (launch_stream(a, b, 0, s1->n_conts, 0, s2->n_conts, 0, 0, 1, a->d_total, a->stream)) return (uint64_t)-1;
+    } else {
+        SparseJob job{};
+        job.A = view_of(a); job.B = view_of(b);
+        job.i0 = 0; job.i1 = s1->n_conts; job.j0 = 0; job.j1 = s2->n_conts;
+        job.strict_upper = 0; job.shard = 0; job.n_shards = 1;
+        job.total = a->d_total;
+        if (launch_sparse(job, a->max_blocks, a->stream)) return (uint64_t)-1;
+    }
     if (cudaMemcpyAsync(a->h_total, a->d_total, 8, cudaMemcpyDeviceToHost, a->stream) != cudaSuccess ||
         cudaStreamSynchronize(a->stream) != cudaSuccess) {
         set_error("square query failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -283,9 +283,10 @@ def test_storm_t_routes_agree(sb, orc, route):
 
 @pytest.mark.parametrize("M", [2 * 65536, 1048576, 20 * 65536, 21 * 65536 + 5])
 def test_storm_t_flat_probe_kernel_equals_block_kernel(sb, orc, M):
-    """Sparse route on containers without bitmap blocks: the flat probe kernel (whole-row shared bitmap, partner
-    positions probed; rows up to 20 blocks wide) and the block merge/probe kernel give the oracle's total, shard
-    sums, per-pair rectangles and XY^T totals; empty rows, single values, duplicates and last-bit values included."""
+    """Sparse route on containers without bitmap blocks: the row-group stream kernel (totals), the flat probe kernel
+    (whole-row shared bitmap, partner positions probed; rows up to 20 blocks wide) and the block merge/probe kernel
+    give the oracle's total, shard sums, per-pair rectangles and XY^T totals; empty rows, single values, duplicates
+    and last-bit values included."""
     draws = [0, 1, 3, 17, 64, 65, 200, 1000, 3500, 2, 0, 700]
     rows = [orc.gen_row_positions(91, i, draws[i % len(draws)], M) for i in range(150)]
     rows[5] = np.array([M - 1], dtype=np.uint32)
@@ -294,7 +295,7 @@ def test_storm_t_flat_probe_kernel_equals_block_kernel(sb, orc, M):
     exact = orc.wrapper_diag(vals)
     prev = sb.set_storm_route("sparse")
     try:
-        for flat in (True, False):
+        for flat in ("stream", "flat", "block"):
             was = sb.set_sparse_flat(flat)
             try:
                 with sb.Storm() as s, sb.Storm() as t:
@@ -311,7 +312,7 @@ def test_storm_t_flat_probe_kernel_equals_block_kernel(sb, orc, M):
                     s.add(rows[8])                                   # a mutation rebuilds both mirrors
                     assert s.pairw_intersect_cardinality() == orc.wrapper_diag(np.concatenate([vals, vals[8:9]])), (M, flat)
             finally:
-                sb.set_sparse_flat(bool(was))
+                sb.set_sparse_flat(was)
     finally:
         sb.set_storm_route(prev)
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""STORM_t whole-container query through every route on one container: flat probe kernel, block merge/probe
+"""STORM_t whole-container query through every route on one container: row-group stream kernel, flat probe kernel, block merge/probe
 kernel, densified rows + tensor kernel, and what AUTO picks.  JSON lines (run on the GPU box); the timings are what
 the route cost model in sparse.cu (choose_dense_route) is fitted to.
 
@@ -39,13 +39,13 @@ for rows, bits, draws in cases:
     with sb.Storm() as s:
         for p in pos:
             s.add(p)
-        for name, route, flat in (("flat", "sparse", True), ("block", "sparse", False), ("dense", "dense", True), ("auto", "auto", True)):
-            if name == "block" and rows * (rows - 1) / 2 * (1 + nnz / rows / 100) > 4e8:
+        for name, route, flat in (("stream", "sparse", 2), ("flat", "sparse", 1), ("block", "sparse", 0), ("dense", "dense", 2), ("auto", "auto", 2)):
+            if (name == "block" and rows * (rows - 1) / 2 * (1 + nnz / rows / 100) > 2e8) or (name == "flat" and rows * (rows - 1) / 2 * nnz / rows > 3e10):
                 continue                                           # seconds on the block kernel
             sb.set_storm_route(route)
             sb.set_sparse_flat(flat)
             dt, got = timed(s)
             rec["routes"][name] = {"ms": round(dt * 1e3, 4), "took": s.last_route(), "match": got == exact}
         sb.set_storm_route("auto")
-        sb.set_sparse_flat(True)
+        sb.set_sparse_flat(2)
     print(json.dumps(rec), flush=True)
