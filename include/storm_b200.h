@@ -161,6 +161,14 @@ int STORM_b200_contig_add_bulk(STORM_contiguous_t* bitmap, const uint32_t* posit
 /* Seconds spent in the last query of this object: [0] upload (H2D), [1] kernels, [2] total. */
 int STORM_b200_contig_last_timing(STORM_contiguous_t* bitmap, double out_seconds[3]);
 
+/* How the *_list queries of the contiguous model are answered (storm.c:1253-1258 switches per pair between the
+ * probe and the bitmap kernel; both give |i AND j|): 0 = cost model (default), 1 = every pair through the tile
+ * kernel, 2 = dense x dense pairs through the tile kernel and every pair with a sparse row through the probe
+ * kernel, 3 = the row-group stream kernel over the position lists when every row is sparse (else as 2).
+ * Results are identical.  Returns the previous value; ..._last_list_route tells which one the last query took. */
+int STORM_b200_set_contig_list_route(int route);
+int STORM_b200_contig_last_list_route(const STORM_contiguous_t* bitmap);
+
 uint64_t STORM_b200_storm_pairw_shard(STORM_t* bitmap, uint32_t shard, uint32_t n_shards);
 /* How whole-container STORM_t queries are answered: 0 = cost model (default), 1 = the sparse
  * merge/probe kernel, 2 = rows densified on the device + the dense tile kernel (falls back to

@@ -88,6 +88,10 @@ class StormContiguous:
                    "STORM_b200_contig_pairw_rect")
         return out
 
+    def last_list_route(self) -> str:
+        """Which kernels answered the last *_list query: 'tile', 'probe' (tile + probe) or 'stream'."""
+        return {0: "none", 1: "tile", 2: "probe", 3: "stream"}[self._L.STORM_b200_contig_last_list_route(self._h)]
+
     def invalidate_device(self) -> None:
         _lib.check(self._L.STORM_b200_contig_invalidate_device(self._h), "STORM_b200_contig_invalidate_device")
 
@@ -435,6 +439,15 @@ def set_storm_route(route) -> int:
     """``STORM_b200_set_storm_route``: 'auto' | 'sparse' | 'dense' for whole-container STORM_t queries."""
     r = {"auto": 0, "sparse": 1, "dense": 2}[route] if isinstance(route, str) else int(route)
     return _lib.load().STORM_b200_set_storm_route(r)
+
+
+LIST_ROUTES = {"auto": 0, "tile": 1, "probe": 2, "stream": 3}
+
+
+def set_contig_list_route(route) -> int:
+    """``STORM_b200_set_contig_list_route``: 'auto' | 'tile' | 'probe' | 'stream' for the contiguous *_list queries."""
+    r = LIST_ROUTES[route] if isinstance(route, str) else int(route)
+    return _lib.load().STORM_b200_set_contig_list_route(r)
 
 
 def set_sparse_flat(mode) -> int:

@@ -37,6 +37,9 @@ struct ContigState {
     uint32_t* d_dense_rows = nullptr; uint64_t d_meta_cap = 0;
     uint64_t list_rows_synced = 0;     // lists of rows [0, list_rows_synced) are on the device
     uint64_t n_sparse = 0, n_dense = 0;
+    std::vector<uint32_t> h_group_start; uint32_t* d_group_start = nullptr;   // row groups of the stream kernel (all rows sparse)
+    bool stream_ok = false;            // every row is sparse and short enough for the stream kernel
+    int last_list_route = 0;           // 1 tile kernel, 2 tile + probe kernels, 3 stream kernel
     uint64_t* d_gather = nullptr; uint64_t d_gather_cap = 0;   // compact arena of dense rows (list path)
     // result + timing
     unsigned long long* d_total = nullptr;
@@ -142,9 +145,10 @@ int sync_lists(STORM_contiguous_t* c, ContigState* st) {
     // off[r+1]-off[r] must be the list length for sparse rows: dense rows store nothing,
     // so consecutive offsets already delimit each sparse row's list.
     if (st->d_meta_cap < n + 1) {
-        for (void* p : {(void*)st->d_pos_off, (void*)st->d_is_sparse, (void*)st->d_sparse_rows, (void*)st->d_dense_rows})
+        for (void* p : {(void*)st->d_pos_off, (void*)st->d_is_sparse, (void*)st->d_sparse_rows, (void*)st->d_dense_rows, (void*)st->d_group_start})
             if (p) cudaFree(p);
         const uint64_t cap = (n + 1) * 2;
+        STORM_CUDA_TRY(cudaMalloc(&st->d_group_start, (cap + 1) * sizeof(uint32_t)));
         STORM_CUDA_TRY(cudaMalloc(&st->d_pos_off, cap * sizeof(uint64_t)));
         STORM_CUDA_TRY(cudaMalloc(&st->d_is_sparse, cap * sizeof(uint32_t)));
         STORM_CUDA_TRY(cudaMalloc(&st->d_sparse_rows, cap * sizeof(uint32_t)));
@@ -163,6 +167,10 @@ int sync_lists(STORM_contiguous_t* c, ContigState* st) {
         STORM_CUDA_TRY(cudaMemcpy(st->d_pos, c->scalar, c->tot_scalar * sizeof(uint32_t), cudaMemcpyHostToDevice));
     st->n_sparse = sparse_rows.size();
     st->n_dense = dense_rows.size();
+    // every row sparse: the lists are a complete flat form of the matrix, which the row-group stream kernel can answer from
+    st->stream_ok = dense_rows.empty() && stream_groups(c->n_scalar, n, &st->h_group_start);
+    if (st->stream_ok)
+        STORM_CUDA_TRY(cudaMemcpy(st->d_group_start, st->h_group_start.data(), st->h_group_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     st->list_rows_synced = n;
     return STORM_B200_OK;
 }
@@ -255,6 +263,7 @@ int launch_gather_rows(uint64_t* dst, const uint64_t* src, uint64_t stride, cons
 namespace {
 
 enum QueryMode { QUERY_DENSE = 0, QUERY_LIST = 1 };
+int g_list_route = 0;   // STORM_b200_set_contig_list_route: 0 cost model, 1 tile kernel, 2 tile + probe kernels, 3 stream kernel
 
 // Shared body of all contiguous queries.
 uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uint32_t n_shards, int kernel) {
@@ -274,12 +283,34 @@ uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uin
     cudaEventRecord(st->ev[1], st->stream);
 
     int rc = STORM_B200_OK;
-    bool hybrid = false;
+    bool hybrid = false, stream = false;
     if (mode == QUERY_LIST) {
         if ((rc = sync_lists(c, st))) return (uint64_t)-1;
-        hybrid = st->n_sparse > 0;
+        // storm.c:1253-1258 switches per pair between the probe and the bitmap kernel; both give |i AND j|, so the
+        // switch is a cost decision here (fitted: tile kernel 6e13 wp/s; probe kernel 0.08 ns + 1.3 ps per value
+        // and pair, profiles/r01_configs_c1_c4_full.jsonl; stream kernel: stream_seconds): all rows through the
+        // tile kernel, or dense x dense pairs through it and the rest probed, or -- when every row is a list --
+        // the row-group stream kernel over the lists.
+        const double N = (double)c->n_data, W = (double)c->n_bitmaps_vector, pairs = 0.5 * N * (N - 1.0);
+        const double avg = (double)c->tot_scalar / std::max(1.0, (double)st->n_sparse);
+        const double nd = (double)st->n_dense;
+        const double tile_all_s = pairs * W / 6e13 + 3e-5;
+        const double hybrid_s = 0.5 * nd * (nd - 1.0) * W / 6e13 + (nd >= 2 ? 3e-5 + nd * W * 8 / 2e12 : 0.0) +
+                                (pairs - 0.5 * nd * (nd - 1.0)) * (0.08e-9 + 1.3e-12 * avg) + 1e-5;
+        const double stream_s = st->stream_ok ? stream_seconds(pairs, avg) : 1e30;
+        if (st->n_sparse > 0) {
+            stream = stream_s < tile_all_s && stream_s < hybrid_s;
+            hybrid = !stream && hybrid_s < tile_all_s;
+            if (g_list_route == 1) { stream = false; hybrid = false; }
+            if (g_list_route == 2) { stream = false; hybrid = true; }
+            if (g_list_route == 3) { stream = st->stream_ok; hybrid = !stream; }
+        }
+        st->last_list_route = stream ? 3 : hybrid ? 2 : 1;
     }
-    if (!hybrid) {
+    if (stream) {
+        rc = launch_sparse_stream(st->d_pos_off, st->d_pos, st->h_group_start, st->d_group_start, st->d_pos_off, st->d_pos,
+                                  c->tot_scalar, 0, c->n_data, 0, c->n_data, 1, shard, n_shards, st->d_total, st->stream);
+    } else if (!hybrid) {
         rc = pairw_triangle(st->d_rows, c->n_data, c->n_bitmaps_vector, st->stride, shard, n_shards, kernel,
                             reinterpret_cast<uint64_t*>(st->d_total), st->stream);
     } else {
@@ -535,7 +566,7 @@ void STORM_contig_free(STORM_contiguous_t* c) {                             // s
         DeviceGuard guard(st->device);
         if (st->stream) cudaStreamSynchronize(st->stream);
         for (void* p : {(void*)st->d_rows, (void*)st->d_pos, (void*)st->d_pos_off, (void*)st->d_is_sparse,
-                        (void*)st->d_sparse_rows, (void*)st->d_dense_rows, (void*)st->d_gather, (void*)st->d_total})
+                        (void*)st->d_sparse_rows, (void*)st->d_dense_rows, (void*)st->d_group_start, (void*)st->d_gather, (void*)st->d_total})
             if (p) cudaFree(p);
         if (st->h_total) cudaFreeHost(st->h_total);
         for (auto e : st->ev) if (e) cudaEventDestroy(e);
@@ -608,6 +639,17 @@ uint64_t STORM_contig_pairw_intersect_cardinality_blocked(STORM_contiguous_t* c,
     (void)bsize;   // CPU cache-blocking hint; the tile shape is fixed by the kernel
     if (c == nullptr) return (uint64_t)-1;
     return contig_query(c, QUERY_DENSE, 0, 1, STORM_B200_KERNEL_AUTO);
+}
+
+int STORM_b200_set_contig_list_route(int route) {
+    const int prev = g_list_route;
+    if (route >= 0 && route <= 3) g_list_route = route;
+    return prev;
+}
+
+int STORM_b200_contig_last_list_route(const STORM_contiguous_t* c) {
+    if (c == nullptr || c->b200 == nullptr) return 0;
+    return state_of(const_cast<STORM_contiguous_t*>(c))->last_list_route;
 }
 
 uint64_t STORM_contig_pairw_intersect_cardinality_list(STORM_contiguous_t* c) {     // storm.c:1243-1263

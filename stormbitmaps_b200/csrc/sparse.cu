@@ -323,7 +323,8 @@ constexpr uint32_t STREAM_GROUP = 32;            // rows per group (one mask bit
 constexpr uint64_t STREAM_SLICE = 1u << 18;      // partner positions per CTA
 
 struct StreamJob {
-    SparseView A, B;
+    const uint64_t* a_off; const uint32_t* a_pos;     // flat form of the rows i (CSR offsets, absolute positions)
+    const uint64_t* b_off; const uint32_t* b_pos;     // flat form of the partner rows j
     const uint32_t* group_start;   // device: first row of each group of A rows, n_groups + 1 entries
     uint32_t g0, n_groups_job;     // groups [g0, g0 + n_groups_job) overlap rows [i0, i1)
     uint64_t i0, i1, j0, j1;
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
         jin0 = max(job.j0, ib + 1);
         jin1 = min(job.j1, ie);
     }
-    const uint64_t p_beg = js < job.j1 ? job.B.pos_off[js] : 0, p_end = js < job.j1 ? job.B.pos_off[job.j1] : 0;
+    const uint64_t p_beg = js < job.j1 ? job.b_off[js] : 0, p_end = js < job.j1 ? job.b_off[job.j1] : 0;
     const uint64_t k0 = p_beg + (uint64_t)blockIdx.y * STREAM_SLICE;
     const uint64_t k1 = min(k0 + STREAM_SLICE, p_end);
     const bool inner = blockIdx.y == 0 && jin0 < jin1;
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
 
     uint4* z = reinterpret_cast<uint4*>(s_tab);
     for (uint32_t k = tid; k < 2 * STREAM_CAP / 4; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
-    if (tid <= R) s_off[tid] = job.A.pos_off[ib + tid];
+    if (tid <= R) s_off[tid] = job.a_off[ib + tid];
     __syncthreads();
     const uint64_t e0 = s_off[0], e1 = s_off[R];
     for (uint64_t e = e0 + tid; e < e1; e += blockDim.x) {
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
 #pragma unroll
         for (uint32_t step = 16; step > 0; step >>= 1)
             if (r + step < R && s_off[r + step] <= e) r += step;
-        const uint32_t p = job.A.pos[e];
+        const uint32_t p = job.a_pos[e];
         uint32_t slot = stream_slot(p);
         for (;;) {
             const uint32_t old = atomicCAS(&keys[slot], 0u, p + 1u);
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
     __syncthreads();
 
     unsigned long long acc = 0;
-    const uint32_t* __restrict__ pos = job.B.pos;
+    const uint32_t* __restrict__ pos = job.b_pos;
     {   // rows beyond the group: every row of the group pairs with them.  16-byte loads, eight positions in flight
         // per thread: the loop is bound by the latency of the dependent shared-memory probes.
         auto hits = [&](uint32_t p) { return (unsigned)__popc(stream_lookup(keys, masks, p)); };
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
     if (inner) {   // rows of the group itself (same container): row j pairs with the group's rows below it
         for (uint64_t j = jin0 + warp; j < jin1; j += (blockDim.x >> 5)) {
             const uint32_t below = (1u << (uint32_t)(j - ib)) - 1u;                 // j - ib in [1, 31]
-            for (uint64_t k = job.B.pos_off[j] + lane; k < job.B.pos_off[j + 1]; k += 32)
+            for (uint64_t k = job.b_off[j] + lane; k < job.b_off[j + 1]; k += 32)
                 acc += __popc(stream_lookup(keys, masks, __ldg(pos + k)) & below);
         }
     }
@@ -558,17 +559,10 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     std::vector<uint64_t> pos_off(s->n_conts + 1, 0);              // CSR offsets of the flat form (built on demand)
     for (uint32_t r = 0; r < s->n_conts; ++r) pos_off[r + 1] = pos_off[r] + row_nnz[r];
     if ((rc = upload(&st->d_pos_off, pos_off, st->stream))) return rc;
-    // row groups of the stream kernel: consecutive rows, at most 32 and at most STREAM_ENTRIES values together
     uint32_t max_row_nnz = 0;
+    for (uint32_t v : row_nnz) max_row_nnz = std::max(max_row_nnz, v);
     std::vector<uint32_t>& gs = st->h_group_start;
-    gs.assign(1, 0u);
-    uint64_t in_group = 0;
-    for (uint32_t r = 0; r < s->n_conts; ++r) {
-        max_row_nnz = std::max(max_row_nnz, row_nnz[r]);
-        if (r > gs.back() && (r - gs.back() == STREAM_GROUP || in_group + row_nnz[r] > STREAM_ENTRIES)) { gs.push_back(r); in_group = 0; }
-        in_group += row_nnz[r];
-    }
-    gs.push_back(s->n_conts);
+    stream_groups(row_nnz.data(), s->n_conts, &gs);
     if ((rc = upload(&st->d_group_start, gs, st->stream))) return rc;
     st->max_row_nnz = max_row_nnz;
     if ((rc = upload(&st->d_row_ptr, row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, row_nnz, st->stream)) ||
@@ -655,30 +649,66 @@ bool stream_eligible(const StormState* a, const StormState* b) {
            a->d_group_start != nullptr;
 }
 
-int launch_stream(const StormState* a, const StormState* b, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, int strict_upper,
-                  uint32_t shard, uint32_t n_shards, unsigned long long* d_total, cudaStream_t stream) {
+}  // namespace
+
+// Row groups of the stream kernel: consecutive rows, at most 32 and at most STREAM_ENTRIES values together.
+// Returns false if a single row holds more than a group may.
+bool stream_groups(const uint32_t* row_nnz, uint64_t n_rows, std::vector<uint32_t>* group_start) {
+    std::vector<uint32_t>& gs = *group_start;
+    gs.assign(1, 0u);
+    uint64_t in_group = 0;
+    bool ok = true;
+    for (uint64_t r = 0; r < n_rows; ++r) {
+        if (row_nnz[r] > STREAM_ENTRIES) ok = false;
+        if (r > gs.back() && (r - gs.back() == STREAM_GROUP || in_group + row_nnz[r] > STREAM_ENTRIES)) { gs.push_back((uint32_t)r); in_group = 0; }
+        in_group += row_nnz[r];
+    }
+    gs.push_back((uint32_t)n_rows);
+    return ok;
+}
+
+// Seconds the stream kernel needs for `pairs` pairs of rows holding avg_nnz values (fit: choose_dense_route).
+double stream_seconds(double pairs, double avg_nnz) {
+    const double group = std::min(32.0, std::max(1.0, std::floor((double)STREAM_ENTRIES / std::max(1.0, avg_nnz))));
+    const double load = std::min(0.5, group * avg_nnz / (double)STREAM_CAP);
+    const double walk = 0.5 * (1.0 + 1.0 / ((1.0 - load) * (1.0 - load)));
+    return 1.5e-5 + pairs * avg_nnz / group * walk * 1.9e-12;
+}
+
+// Totals of rows [i0, i1) (flat form a_*, row groups h/d_group_start) against rows [j0, j1) (flat form b_*).
+int launch_sparse_stream(const uint64_t* a_off, const uint32_t* a_pos, const std::vector<uint32_t>& gs, const uint32_t* d_group_start,
+                         const uint64_t* b_off, const uint32_t* b_pos, uint64_t b_total_nnz,
+                         uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, int strict_upper,
+                         uint32_t shard, uint32_t n_shards, unsigned long long* d_total, cudaStream_t stream) {
     if (i1 <= i0 || j1 <= j0) return STORM_B200_OK;
-    const std::vector<uint32_t>& gs = a->h_group_start;            // groups overlapping [i0, i1)
-    const uint32_t g0 = (uint32_t)(std::upper_bound(gs.begin(), gs.end(), (uint32_t)i0) - gs.begin()) - 1;
+    const uint32_t g0 = (uint32_t)(std::upper_bound(gs.begin(), gs.end(), (uint32_t)i0) - gs.begin()) - 1;   // groups overlapping [i0, i1)
     const uint32_t g1 = (uint32_t)(std::lower_bound(gs.begin(), gs.end(), (uint32_t)i1) - gs.begin());
     StreamJob job{};
-    job.A = view_of(a); job.B = view_of(b);
-    job.group_start = a->d_group_start;
+    job.a_off = a_off; job.a_pos = a_pos; job.b_off = b_off; job.b_pos = b_pos;
+    job.group_start = d_group_start;
     job.g0 = g0; job.n_groups_job = g1 - g0;
     job.i0 = i0; job.i1 = i1; job.j0 = j0; job.j1 = j1;
     job.strict_upper = strict_upper; job.shard = shard; job.n_shards = n_shards;
     job.total = d_total;
     const uint64_t my_groups = (job.n_groups_job + n_shards - 1 - shard) / n_shards;
     if (my_groups == 0) return STORM_B200_OK;
-    uint64_t slices = (b->total_nnz + STREAM_SLICE - 1) / STREAM_SLICE;      // upper bound on any group's partner stream
+    uint64_t slices = (b_total_nnz + STREAM_SLICE - 1) / STREAM_SLICE;      // upper bound on any group's partner stream
     if (slices == 0) slices = 1;
-    if (slices > 65535) { set_error("partner stream too long for one launch (%llu values)", (unsigned long long)b->total_nnz); return STORM_B200_EINVAL; }
+    if (slices > 65535) { set_error("partner stream too long for one launch (%llu values)", (unsigned long long)b_total_nnz); return STORM_B200_EINVAL; }
     const size_t smem = 2 * STREAM_CAP * sizeof(uint32_t);
     STORM_CUDA_TRY(cudaFuncSetAttribute(sparse_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sparse_stream_kernel<<<dim3((unsigned)my_groups, (unsigned)slices), SP_MAX_THREADS, smem, stream>>>(job);
     STORM_CUDA_TRY(cudaGetLastError());
     count_launch();
     return STORM_B200_OK;
+}
+
+namespace {
+
+int launch_stream(const StormState* a, const StormState* b, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, int strict_upper,
+                  uint32_t shard, uint32_t n_shards, unsigned long long* d_total, cudaStream_t stream) {
+    return launch_sparse_stream(a->d_pos_off, a->d_pos, a->h_group_start, a->d_group_start, b->d_pos_off, b->d_pos, b->total_nnz,
+                                i0, i1, j0, j1, strict_upper, shard, n_shards, d_total, stream);
 }
 
 int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t stream) {
@@ -733,10 +763,7 @@ bool choose_dense_route(const StormState* st, uint64_t n_rows) {
         // 8192 / values per row) rows, and a probe walks (1 + 1 / (1 - load)^2) / 2 slots of the hash table.
         // 1.9 ps per slot visited, fitted to 10 000 x 524 288 at 5 ... 5 242 values per row and 3 000 x 1 048 576
         // at 1 000 (profiles/r01_sparse_routes_v2.jsonl: 0.03 / 0.40 / 7.8 / 28 / 112 / 692 ms).
-        const double group = std::min(32.0, std::max(1.0, std::floor((double)STREAM_ENTRIES / std::max(1.0, avg_nnz))));
-        const double load = std::min(0.5, group * avg_nnz / (double)STREAM_CAP);
-        const double walk = 0.5 * (1.0 + 1.0 / ((1.0 - load) * (1.0 - load)));
-        sparse_s = std::min(sparse_s, 1.5e-5 + pairs * avg_nnz / group * walk * 1.9e-12);
+        sparse_s = std::min(sparse_s, stream_seconds(pairs, avg_nnz));
     }
     return dense_s < sparse_s;
 }

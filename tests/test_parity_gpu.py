@@ -57,8 +57,13 @@ def test_golden_through_storm_h_api(sb, orc, golden, name):
         # list path diverges under D2/D11 -- recorded in the fixture, not reproduced)
         assert c.pairw_intersect_cardinality() == exact
         assert c.pairw_intersect_cardinality_blocked(case["bsize"]) == exact
-        assert c.pairw_intersect_cardinality_list() == exact
-        assert c.pairw_intersect_cardinality_blocked_list(case["bsize"]) == exact
+        for route in ("auto", "tile", "probe", "stream"):                 # every kernel mix behind the *_list calls
+            prev = sb.set_contig_list_route(route)
+            try:
+                assert c.pairw_intersect_cardinality_list() == exact, route
+                assert c.pairw_intersect_cardinality_blocked_list(case["bsize"]) == exact, route
+            finally:
+                sb.set_contig_list_route(prev)
         # sparse model: exact (D1 not reproduced), any bsize
         assert s.pairw_intersect_cardinality() == exact
         assert s.pairw_intersect_cardinality_blocked(0) == exact
@@ -215,6 +220,34 @@ def test_bulk_ingest_equals_row_by_row(sb, orc):
         for r in rows[:100]:
             a.add(r)
         assert a.pairw_intersect_cardinality() == orc.wrapper_diag(O.positions_to_dense([r for r in rows[:100] if len(r)], M))
+
+
+def test_contig_list_routes_agree(sb, orc):
+    """storm.c:1253-1258 switches per pair between the probe and the bitmap kernel; here that is a cost decision
+    between three kernel mixes.  All give the exact total on all-sparse, mixed and all-dense containers, shards add
+    up, and the stream kernel is only taken when every row is a list."""
+    M = 65536
+    for name, draws in (("all_sparse", [1, 5, 60, 150, 199, 3]), ("mixed", [5, 150, 4000, 30000, 90, 250]), ("all_dense", [300, 5000, 40000])):
+        rows = [orc.gen_row_positions(31, i, draws[i % len(draws)], M) for i in range(700)]
+        exact = orc.wrapper_diag(O.positions_to_dense(rows, M))
+        with sb.StormContiguous(M) as c:
+            for r in rows:
+                c.add(r)
+            assert c.pairw_intersect_cardinality() == exact
+            for route in ("auto", "tile", "probe", "stream"):
+                prev = sb.set_contig_list_route(route)
+                try:
+                    assert c.pairw_intersect_cardinality_list() == exact, (name, route)
+                    took = c.last_list_route()
+                    if name == "all_dense":
+                        assert took == "tile"
+                    elif route == "stream":
+                        assert took == ("stream" if name == "all_sparse" else "probe"), (name, took)
+                    elif route != "auto":
+                        assert took == route, (name, route, took)
+                    assert c.pairw_intersect_cardinality_blocked_list(9) == exact, (name, route)
+                finally:
+                    sb.set_contig_list_route(prev)
 
 
 def test_storm_t_dispatch_regimes(sb, orc):
