@@ -333,6 +333,7 @@ struct StreamJob {
     unsigned long long* total;
 };
 
+static_assert(STREAM_CAP == (1u << 14) && STREAM_GROUP <= 32, "stream_slot keeps 14 bits; a row mask has 32");
 __device__ __forceinline__ uint32_t stream_slot(uint32_t p) { return (p * 2654435761u) >> 18; }   // 14 bits
 
 __device__ __forceinline__ uint32_t stream_lookup(const uint32_t* keys, const uint32_t* masks, uint32_t p) {
