@@ -335,9 +335,16 @@ struct StreamJob {
 
 static_assert(STREAM_CAP == (1u << 14) && STREAM_GROUP <= 32, "stream_slot keeps 14 bits; a row mask has 32");
 __device__ __forceinline__ uint32_t stream_slot(uint32_t p) { return (p * 2654435761u) >> 18; }   // 14 bits
+// In front of the table: a hashed bit filter of 2^18 bits (32 KiB).  Nearly every partner position is in none of
+// the group's rows; the filter answers that with one shared-memory load and no loop (at most 8192 of its bits are
+// set: 3 % false positives, which simply go on to the table).
+constexpr uint32_t STREAM_FILTER_WORDS = (1u << 18) / 32;
+__device__ __forceinline__ uint32_t stream_filter_bit(uint32_t p) { return (p * 2654435761u) >> 14; }   // 18 bits
 
 __device__ __forceinline__ uint32_t stream_lookup(const uint32_t* keys, const uint32_t* masks, uint32_t p) {
-    uint32_t slot = stream_slot(p);
+    const uint32_t f = stream_filter_bit(p);
+    if (!((masks[STREAM_CAP + (f >> 5)] >> (f & 31)) & 1u)) return 0u;         // filter words follow the masks
+    uint32_t slot = f >> 4;                                                    // = stream_slot(p)
     for (;;) {
         const uint32_t k = keys[slot];
         if (k == p + 1u) return masks[slot];
@@ -347,7 +354,7 @@ __device__ __forceinline__ uint32_t stream_lookup(const uint32_t* keys, const ui
 }
 
 __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const StreamJob job) {
-    extern __shared__ __align__(16) uint32_t s_tab[];             // keys[STREAM_CAP] | masks[STREAM_CAP]
+    extern __shared__ __align__(16) uint32_t s_tab[];             // keys[STREAM_CAP] | masks[STREAM_CAP] | filter[STREAM_FILTER_WORDS]
     __shared__ uint64_t s_off[STREAM_GROUP + 1];
     __shared__ unsigned long long warp_part[SP_MAX_WARPS];
     uint32_t* keys = s_tab;
@@ -374,7 +381,7 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
     if (k0 >= k1 && !inner) return;
 
     uint4* z = reinterpret_cast<uint4*>(s_tab);
-    for (uint32_t k = tid; k < 2 * STREAM_CAP / 4; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
+    for (uint32_t k = tid; k < (2 * STREAM_CAP + STREAM_FILTER_WORDS) / 4; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
     if (tid <= R) s_off[tid] = job.a_off[ib + tid];
     __syncthreads();
     const uint64_t e0 = s_off[0], e1 = s_off[R];
@@ -384,6 +391,8 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
         for (uint32_t step = 16; step > 0; step >>= 1)
             if (r + step < R && s_off[r + step] <= e) r += step;
         const uint32_t p = job.a_pos[e];
+        const uint32_t f = stream_filter_bit(p);
+        atomicOr(&masks[STREAM_CAP + (f >> 5)], 1u << (f & 31));
         uint32_t slot = stream_slot(p);
         for (;;) {
             const uint32_t old = atomicCAS(&keys[slot], 0u, p + 1u);
@@ -668,12 +677,15 @@ bool stream_groups(const uint32_t* row_nnz, uint64_t n_rows, std::vector<uint32_
     return ok;
 }
 
-// Seconds the stream kernel needs for `pairs` pairs of rows holding avg_nnz values (fit: choose_dense_route).
+// Seconds the stream kernel needs for `pairs` pairs of rows holding avg_nnz values: one probe per partner position
+// and GROUP of rows i (a group holds min(32, 8192 / values per row) rows); a probe is one filter lookup plus, for the
+// hits and the filter's false positives, a walk through the table, both growing with the table's load.  Fitted to
+// 10 000 x 524 288 at 5 / 104 / 300 / 524 / 1 000 values per row (0.03 / 0.22 / 1.19 / 3.46 / 12.4 ms) and
+// 3 000 x 1 048 576 at 1 000 (1.24 ms), profiles/r01_sparse_routes_v4.jsonl.
 double stream_seconds(double pairs, double avg_nnz) {
     const double group = std::min(32.0, std::max(1.0, std::floor((double)STREAM_ENTRIES / std::max(1.0, avg_nnz))));
     const double load = std::min(0.5, group * avg_nnz / (double)STREAM_CAP);
-    const double walk = 0.5 * (1.0 + 1.0 / ((1.0 - load) * (1.0 - load)));
-    return 1.5e-5 + pairs * avg_nnz / group * walk * 1.9e-12;
+    return 1.5e-5 + pairs * avg_nnz / group * (1.1e-12 + 1.8e-12 * load);
 }
 
 // Totals of rows [i0, i1) (flat form a_*, row groups h/d_group_start) against rows [j0, j1) (flat form b_*).
@@ -696,7 +708,7 @@ int launch_sparse_stream(const uint64_t* a_off, const uint32_t* a_pos, const std
     uint64_t slices = (b_total_nnz + STREAM_SLICE - 1) / STREAM_SLICE;      // upper bound on any group's partner stream
     if (slices == 0) slices = 1;
     if (slices > 65535) { set_error("partner stream too long for one launch (%llu values)", (unsigned long long)b_total_nnz); return STORM_B200_EINVAL; }
-    const size_t smem = 2 * STREAM_CAP * sizeof(uint32_t);
+    const size_t smem = (2 * STREAM_CAP + STREAM_FILTER_WORDS) * sizeof(uint32_t);
     STORM_CUDA_TRY(cudaFuncSetAttribute(sparse_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sparse_stream_kernel<<<dim3((unsigned)my_groups, (unsigned)slices), SP_MAX_THREADS, smem, stream>>>(job);
     STORM_CUDA_TRY(cudaGetLastError());
@@ -737,8 +749,8 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
 // per pair, a fixed part, a part per block of the row (block-id merge + dispatch) and a part per value probed:
 // 0.08 + 0.16 blocks + 0.0003 values ns, fitted to 10 000 x 524 288 at 104 / 5 242 values per row and
 // 3 000 x 1 048 576 at 10 486 (profiles/r01_sparse_timing.jsonl).  Containers without bitmap blocks take the
-// row-group stream kernel instead (modelled below), which wins up to a few hundred values per row: at 10 000 x
-// 524 288 the crossover with the tensor kernel is near 450 values per row (0.09 % density).
+// row-group stream kernel instead (stream_seconds), which wins up to several hundred values per row: at 10 000 x
+// 524 288 the crossover with the tensor kernel is near 700 values per row (0.13 % density).
 int g_storm_route = 0;   // 0 auto, 1 sparse kernel, 2 densify + dense tile kernel (STORM_b200_set_storm_route)
 
 bool choose_dense_route(const StormState* st, uint64_t n_rows) {
@@ -760,10 +772,7 @@ bool choose_dense_route(const StormState* st, uint64_t n_rows) {
     const double dense_s = pairs * (double)W / dense_rate + 3e-5 + (st->dense_valid ? 0.0 : (double)need / 2e12);
     double sparse_s = pairs * 1e-9 * (0.08 + 0.16 * avg_blocks + 0.0003 * avg_nnz) + 1e-5;      // block merge/probe kernel
     if (g_sparse_flat && g_sparse_stream && st->n_bitmap_blocks == 0 && st->max_row_nnz <= STREAM_ENTRIES) {
-        // Row-group stream kernel: one probe per partner position and GROUP of rows i; a group holds min(32,
-        // 8192 / values per row) rows, and a probe walks (1 + 1 / (1 - load)^2) / 2 slots of the hash table.
-        // 1.9 ps per slot visited, fitted to 10 000 x 524 288 at 5 ... 5 242 values per row and 3 000 x 1 048 576
-        // at 1 000 (profiles/r01_sparse_routes_v2.jsonl: 0.03 / 0.40 / 7.8 / 28 / 112 / 692 ms).
+        // row-group stream kernel (stream_seconds: its fitted model)
         sparse_s = std::min(sparse_s, stream_seconds(pairs, avg_nnz));
     }
     return dense_s < sparse_s;
