@@ -1,6 +1,6 @@
 /* dropin_driver.c -- a C99 caller of storm.h, written the way the reference's only caller uses the API
- * (benchmark.cpp:710-711 new, :579-580 / :794-795 add with a reused buffer, :898 / :910 queries, :738-739 clear and
- * reuse, :1055-1056 free).  It includes nothing but <storm.h> and links against whatever provides the symbols:
+ * (benchmark.cpp:710-711 new, :579-580 / :794-795 add with a reused buffer, :898 / :910 queries and their list
+ * variants :835 / :845, :738-739 clear and reuse, :1055-1056 free).  It includes nothing but <storm.h> and links against whatever provides the symbols:
  *     gcc -std=c99 -I include tests/drivers/dropin_driver.c -L stormbitmaps_b200 -lstorm_b200      (this repo)
  *     gcc -std=c99 -I /root/reference tests/drivers/dropin_driver.c /root/reference/storm.c        (the reference)
  * Usage: dropin_driver M N draws seed   -> one line "key=value ..." with every total it computed.
@@ -54,9 +54,13 @@ int main(int argc, char** argv) {
     }
     printf(" contig=%llu", (unsigned long long)STORM_contig_pairw_intersect_cardinality(c));
     printf(" contig_blocked=%llu", (unsigned long long)STORM_contig_pairw_intersect_cardinality_blocked(c, 31));
+    printf(" contig_list=%llu", (unsigned long long)STORM_contig_pairw_intersect_cardinality_list(c));
+    printf(" contig_blocked_list=%llu", (unsigned long long)STORM_contig_pairw_intersect_cardinality_blocked_list(c, 31));
     printf(" storm=%llu", (unsigned long long)STORM_pairw_intersect_cardinality(s));
     printf(" storm_blocked=%llu", (unsigned long long)STORM_pairw_intersect_cardinality_blocked(s, 0));
     printf(" wrapper=%llu", (unsigned long long)STORM_wrapper_diag(c->n_data, c->data, c->n_bitmaps_vector, c->intsec_func));
+    printf(" wrapper_blocked=%llu", (unsigned long long)STORM_wrapper_diag_blocked(c->n_data, c->data, c->n_bitmaps_vector, c->intsec_func, 9));
+    printf(" serialized=%llu", (unsigned long long)STORM_serialized_size(s));
     /* clear keeps the objects usable: second, sparser round on the same containers (benchmark.cpp:738-739) */
     STORM_contig_clear(c);
     STORM_clear(s);

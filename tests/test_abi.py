@@ -171,8 +171,9 @@ def test_queries_fail_loudly_without_a_device(lib):
 
 
 # ---- a C program written against storm.h, linked with libstorm_b200.so -----------------------------------
-HOST_FIELDS = ("rows", "words", "cutoff", "naive", "fptr01", "round2_rows", "null_query", "null_add")
-QUERY_FIELDS = ("contig", "contig_blocked", "storm", "storm_blocked", "wrapper", "round2_contig", "round2_storm")
+HOST_FIELDS = ("rows", "words", "cutoff", "naive", "fptr01", "serialized", "round2_rows", "null_query", "null_add")
+QUERY_FIELDS = ("contig", "contig_blocked", "contig_list", "contig_blocked_list", "storm", "storm_blocked", "wrapper", "wrapper_blocked",
+                "round2_contig", "round2_storm")
 
 
 def build_dropin_driver(workdir):

@@ -22,7 +22,8 @@ with tempfile.TemporaryDirectory() as d:
     for args in CASES:
         line = subprocess.check_output([exe] + args.split(), text=True).strip()
         fields = dict(kv.split("=") for kv in line.split())
-        assert fields["naive"] == fields["contig"] == fields["contig_blocked"] == fields["storm"] == fields["storm_blocked"] == fields["wrapper"], line
+        assert (fields["naive"] == fields["contig"] == fields["contig_blocked"] == fields["contig_list"] == fields["contig_blocked_list"]
+                == fields["storm"] == fields["storm_blocked"] == fields["wrapper"] == fields["wrapper_blocked"]), line
         out["cases"][args] = fields
 path = os.path.join(ROOT, "tests", "golden", "dropin_driver_v1.json")
 json.dump(out, open(path, "w"), indent=1)
