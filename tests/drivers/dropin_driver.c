@@ -26,7 +26,8 @@ int main(int argc, char** argv) {
     const uint32_t M = (uint32_t)strtoul(argv[1], 0, 10), N = (uint32_t)strtoul(argv[2], 0, 10);
     const uint32_t draws = (uint32_t)strtoul(argv[3], 0, 10);
     const uint64_t seed = strtoull(argv[4], 0, 10);
-    uint32_t* buf = (uint32_t*)malloc((size_t)(draws ? draws : 1) * sizeof(uint32_t));   /* one buffer, reused per row */
+    /* one buffer, reused per row; one spare element because the reference reads values[n_values] (storm.c:723, D9) */
+    uint32_t* buf = (uint32_t*)calloc((size_t)draws + 1, sizeof(uint32_t));
     uint64_t state, naive = 0;
     uint32_t i, j, k;
 

@@ -17,7 +17,11 @@ with tempfile.TemporaryDirectory() as d:
     subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-march=native", "-DNDEBUG", "-w", "-I", REF,
                            os.path.join(ROOT, "tests", "drivers", "dropin_driver.c"), os.path.join(REF, "storm.c"), "-o", exe])
     out = {"_comment": "dropin_driver.c linked with the reference's storm.c (gcc -std=gnu99 -O2 -march=native); "
-                       "key=value fields of its one output line per argument set 'M N draws seed'",
+                       "key=value fields of its one output line per argument set 'M N draws seed'.  Under "
+                       "-fsanitize=address,undefined -UNDEBUG the reference is clean on these inputs except for its "
+                       "shift by more than 63 in the list probe (storm.c:123, SURVEY.md D10: x86 masks the count, and the "
+                       "values equal the naive count) on the two all-sparse sets; every field is asserted equal to the "
+                       "driver's own naive popcount before it is written",
            "reference": "StormBitmaps @ 2eae567", "cases": {}}
     for args in CASES:
         line = subprocess.check_output([exe] + args.split(), text=True).strip()
