@@ -176,6 +176,11 @@ uint64_t STORM_b200_storm_pairw_shard(STORM_t* bitmap, uint32_t shard, uint32_t 
  * previous value; STORM_b200_storm_last_route tells which one the last query of `bitmap` took. */
 int STORM_b200_set_storm_route(int route);
 int STORM_b200_storm_last_route(const STORM_t* bitmap);
+/* The route cost model as a function (pure arithmetic, no device): expected seconds of a whole-container query of
+ * n_rows rows of n_words 64-bit words holding avg_nnz values in avg_blocks blocks each, out[0] through the
+ * densified rows + tile kernel, out[1] through the sparse kernels.  The query takes the smaller one. */
+int STORM_b200_storm_route_model(uint64_t n_rows, uint32_t n_words, double avg_nnz, double avg_blocks, uint32_t max_row_nnz,
+                                 uint64_t n_bitmap_blocks, int fp4, int dense_resident, double out_seconds[2]);
 /* Kernels of the sparse route for containers without bitmap blocks (their rows are mirrored as flat position
  * lists on the device).  2 (default): totals through the row-group stream kernel (32 rows i per CTA in a
  * shared-memory hash position -> row mask, all later rows' positions streamed through it), per-pair rectangles

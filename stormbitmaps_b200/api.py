@@ -450,6 +450,15 @@ def set_contig_list_route(route) -> int:
     return _lib.load().STORM_b200_set_contig_list_route(r)
 
 
+def storm_route_model(n_rows: int, n_words: int, avg_nnz: float, avg_blocks: float, max_row_nnz: int, n_bitmap_blocks: int = 0,
+                      fp4: bool = True, dense_resident: bool = True) -> dict:
+    """``STORM_b200_storm_route_model``: expected seconds of a STORM_t query on either route (no device needed)."""
+    out = (C.c_double * 2)()
+    _lib.check(_lib.load().STORM_b200_storm_route_model(n_rows, n_words, avg_nnz, avg_blocks, max_row_nnz, n_bitmap_blocks,
+                                                        int(fp4), int(dense_resident), out), "STORM_b200_storm_route_model")
+    return {"dense_s": out[0], "sparse_s": out[1], "route": "dense" if out[0] < out[1] else "sparse"}
+
+
 def set_sparse_flat(mode) -> int:
     """``STORM_b200_set_sparse_flat``: 'block' (0) | 'flat' (1) | 'stream' (2, default) kernels of the sparse route
     for containers without bitmap blocks; returns the previous mode."""

@@ -753,6 +753,18 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
 // 524 288 the crossover with the tensor kernel is near 700 values per row (0.13 % density).
 int g_storm_route = 0;   // 0 auto, 1 sparse kernel, 2 densify + dense tile kernel (STORM_b200_set_storm_route)
 
+// The model itself (pure arithmetic: tests/test_abi.py pins its decisions on the measured cases without a GPU).
+//   dense  = N(N-1)/2 x W / tensor rate (6e13 wp/s FP4 form, 3.5e13 int8 form) + launch + the densify pass
+//   sparse = the cheaper of the block merge/probe kernel and, where it applies, the row-group stream kernel
+void storm_route_model(uint64_t n_rows, uint64_t W, double avg_nnz, double avg_blocks, bool stream_applies, bool fp4,
+                       bool dense_resident, double* dense_s, double* sparse_s) {
+    const double pairs = 0.5 * (double)n_rows * (double)(n_rows - 1);
+    const double dense_rate = fp4 ? 6.0e13 : 3.5e13;
+    *dense_s = pairs * (double)W / dense_rate + 3e-5 + (dense_resident ? 0.0 : (double)n_rows * (double)W * 8.0 / 2e12);
+    *sparse_s = pairs * 1e-9 * (0.08 + 0.16 * avg_blocks + 0.0003 * avg_nnz) + 1e-5;             // block merge/probe kernel
+    if (stream_applies) *sparse_s = std::min(*sparse_s, stream_seconds(pairs, avg_nnz));          // row-group stream kernel
+}
+
 bool choose_dense_route(const StormState* st, uint64_t n_rows) {
     if (g_storm_route == 1) return false;
     const uint64_t W = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
@@ -765,16 +777,10 @@ bool choose_dense_route(const StormState* st, uint64_t n_rows) {
         if (need > have / 10 * 8) return false;                          // keep 20 % of the free memory
     }
     if (g_storm_route == 2) return true;
-    const double avg_nnz = (double)st->total_nnz / (double)n_rows;
-    const double avg_blocks = (double)st->total_blocks / (double)n_rows;
-    const double pairs = 0.5 * (double)n_rows * (double)(n_rows - 1);
-    const double dense_rate = (W * 64 <= (1ull << 24) && fp4_selftest_ok()) ? 6.0e13 : 3.5e13;
-    const double dense_s = pairs * (double)W / dense_rate + 3e-5 + (st->dense_valid ? 0.0 : (double)need / 2e12);
-    double sparse_s = pairs * 1e-9 * (0.08 + 0.16 * avg_blocks + 0.0003 * avg_nnz) + 1e-5;      // block merge/probe kernel
-    if (g_sparse_flat && g_sparse_stream && st->n_bitmap_blocks == 0 && st->max_row_nnz <= STREAM_ENTRIES) {
-        // row-group stream kernel (stream_seconds: its fitted model)
-        sparse_s = std::min(sparse_s, stream_seconds(pairs, avg_nnz));
-    }
+    double dense_s = 0, sparse_s = 0;
+    storm_route_model(n_rows, W, (double)st->total_nnz / (double)n_rows, (double)st->total_blocks / (double)n_rows,
+                      g_sparse_flat && g_sparse_stream && st->n_bitmap_blocks == 0 && st->max_row_nnz <= STREAM_ENTRIES,
+                      W * 64 <= (1ull << 24) && fp4_selftest_ok(), st->dense_valid, &dense_s, &sparse_s);
     return dense_s < sparse_s;
 }
 
@@ -1094,6 +1100,16 @@ int STORM_b200_set_storm_route(int route) {
     const int prev = g_storm_route;
     if (route >= 0 && route <= 2) g_storm_route = route;
     return prev;
+}
+
+// Seconds the route model expects for a whole-container STORM_t query: out[0] densified rows + tile kernel, out[1]
+// sparse kernels.  Pure arithmetic (no device needed); the query takes the smaller one.
+int STORM_b200_storm_route_model(uint64_t n_rows, uint32_t n_words, double avg_nnz, double avg_blocks, uint32_t max_row_nnz,
+                                 uint64_t n_bitmap_blocks, int fp4, int dense_resident, double out_seconds[2]) {
+    if (out_seconds == nullptr || n_rows < 2 || n_words == 0) { set_error("bad argument"); return STORM_B200_EINVAL; }
+    storm_route_model(n_rows, n_words, avg_nnz, avg_blocks, n_bitmap_blocks == 0 && max_row_nnz <= STREAM_ENTRIES, fp4 != 0,
+                      dense_resident != 0, &out_seconds[0], &out_seconds[1]);
+    return STORM_B200_OK;
 }
 
 int STORM_b200_set_sparse_flat(int mode) {
