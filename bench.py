@@ -245,6 +245,82 @@ def colcount_total_torch(rows_t, W, chunk=16384):
     return int((counts * (counts - 1) // 2).sum().item())
 
 
+def sample_tiles(rows: int, tile: int, n: int, seed: int = 7):
+    """`n` tiles (bi, bj), bi <= bj, of the tile x tile raster over `rows` rows: the first diagonal tile, its right
+    neighbour, the last (ragged) diagonal tile, the last column block against the first and the one before it, the
+    rest drawn at random (diagonal and interior)."""
+    import random
+    nb = (rows + tile - 1) // tile
+    picks = [(0, 0), (0, min(1, nb - 1)), (nb - 1, nb - 1), (0, nb - 1), (max(0, nb - 2), nb - 1), (nb // 2, nb // 2)]
+    rng = random.Random(seed)
+    while len(picks) < n:
+        bi = rng.randrange(nb)
+        picks.append((bi, rng.randrange(bi, nb)))
+    seen, out = set(), []
+    for t in picks:
+        if t not in seen:
+            seen.add(t); out.append(t)
+    return out[:n]
+
+
+def verify_pairs(sb, rows_t, rows: int, bits: int, gen: str, kernel, n_tiles: int, tile: int = 256):
+    """Per-pair verification at full size: every pair count of `n_tiles` sampled tile x tile
+    rectangles from the resident matrix (STORM_b200_pairw_rect_device, i.e. the timed kernel with per-pair output)
+    against the CPU oracle's per-pair kernel on the SAME rows regenerated on the host by the oracle's generator.
+    Outside every timed region."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    orc = O.Oracle()
+    W = (bits + 63) // 64
+    t0 = time.perf_counter()
+    pairs = bad = 0
+    cache = {}
+
+    def host_block(b):
+        if b not in cache:
+            r0, n = b * tile, min(tile, rows - b * tile)
+            cache[b] = (orc.gen_dense_geno(SEED, n, bits, row0=r0) if gen == "geno"
+                        else orc.gen_dense_uniform(SEED, n, int(gen[len("uniform"):]), bits, row0=r0))
+        return cache[b]
+
+    tiles = sample_tiles(rows, tile, n_tiles)
+    for bi, bj in tiles:
+        i0, i1, j0, j1 = bi * tile, min(rows, bi * tile + tile), bj * tile, min(rows, bj * tile + tile)
+        a, b = host_block(bi), host_block(bj)
+        both = np.ascontiguousarray(np.concatenate([a, b]))
+        want = orc.rect_counts(both, 0, i1 - i0, i1 - i0, i1 - i0 + (j1 - j0))          # all (i, j) of the rectangle
+        if bi == bj:                                                                  # strict upper triangle on the diagonal
+            want = np.triu(want, 1)
+        got, _ = sb.pairw_rect_device(rows_t, i0, i1, j0, j1, n_words=W, kernel=kernel)
+        got = got.cpu().numpy().view(np.uint32)
+        bad += int((got != want).sum())
+        pairs += (i1 - i0) * (j1 - j0) if bi != bj else (i1 - i0) * (i1 - i0 - 1) // 2
+        if len(cache) > 8:
+            cache.clear()
+    torch.cuda.synchronize()
+    return {"tiles_sampled": len(tiles), "tile": tile, "pairs_sampled": int(pairs), "pairs_wrong": int(bad),
+            "includes": "first diagonal, last ragged diagonal (rows >= %d), last column block, random diagonal + interior" % ((rows - 1) // tile * tile),
+            "checker": "oracle per-pair kernel (oracle/storm_oracle.c) on rows regenerated on the host", "seconds": round(time.perf_counter() - t0, 2)}
+
+
+def contig_api_bench(rows: int, bits: int, reps: int = 3, bulk: bool = True, timeout: int = 900):
+    """The north-star struct API end to end (STORM_contig_new -> rows x STORM_contig_add -> ..._blocked query) through a
+    C99 program linked with the library (tools/contig_api_bench.c): ingest, first and steady query seconds."""
+    from stormbitmaps_b200 import build as B
+    exe = B.tool_path("contig_api_bench")
+    if not os.path.isfile(exe):
+        return {"unavailable": f"{exe} is not built"}
+    try:
+        out = subprocess.run([exe, str(bits), str(rows), str(reps), "1" if bulk else "0"], capture_output=True, text=True, timeout=timeout)
+        line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else ""
+        res = json.loads(line) if line else {"unavailable": out.stderr.strip()[-300:]}
+        res["exit_code"] = out.returncode
+        return res
+    except (subprocess.TimeoutExpired, ValueError, OSError) as e:
+        return {"unavailable": repr(e)[:300]}
+
+
 def ncu_traffic(workload: str, kernel: str, world: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture of this workload (profiles/traffic.json), or None if none was taken."""
@@ -296,6 +372,7 @@ def main_ours(args, rows, bits, gen):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sb.set_clock_probe(True)                              # the tensor kernel records its own clock64 / globaltimer deltas
     for _ in range(args.warmup):
         step()
     barrier()
@@ -309,6 +386,11 @@ def main_ours(args, rows, bits, gen):
     barrier()
     launches = sb.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    try:
+        kclk = sb.last_kernel_clock()                     # of the last timed launch on this rank's device
+    except sb.StormError:
+        kclk = None
+    sb.set_clock_probe(False)
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     elapsed = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -343,6 +425,38 @@ def main_ours(args, rows, bits, gen):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = wp * e2e_steps / float(e2e_s.item())
 
+    # the same call on a PAGEABLE buffer (what a C caller's malloc'd matrix is): staged through pinned slots by host threads
+    e2e_pageable = None
+    if world == 1 and not args.no_extras:
+        import numpy as np
+        pageable = np.empty((rows, W), dtype=np.uint64)
+        pageable[...] = host.numpy().view(np.uint64)
+        sb.wrapper_diag_ptr(pageable.ctypes.data, rows, W, 15)                     # warm-up (staging slots)
+        t0 = time.perf_counter()
+        got_p = 0
+        for _ in range(2):
+            got_p = sb.wrapper_diag_ptr(pageable.ctypes.data, rows, W, 15)
+        dt = (time.perf_counter() - t0) / 2
+        e2e_pageable = {"value": wp / dt, "unit": "wp/s", "seconds": dt, "total": got_p,
+                        "call": "STORM_wrapper_diag_blocked on a pageable (numpy / malloc) buffer, H2D + D2H inside"}
+        del pageable
+
+    # in-library multi-device mode (STORM_B200_DEVICES / STORM_b200_set_devices): one process, all visible GPUs behind storm.h
+    in_lib = None
+    if world == 1 and torch.cuda.device_count() > 1 and not args.no_extras:
+        in_lib = {}
+        for k in [d for d in (2, 4, 8) if d <= torch.cuda.device_count()]:
+            sb.set_devices(k)
+            try:
+                sb.wrapper_diag_ptr(host.data_ptr(), rows, W, 15)                      # warm-up: arenas on every device
+                t0 = time.perf_counter()
+                tot_k = sb.wrapper_diag_ptr(host.data_ptr(), rows, W, 15)
+                dt = time.perf_counter() - t0
+                in_lib[f"devices{k}"] = {"e2e_c_abi": wp / dt, "seconds": dt, "total": tot_k,
+                                         "call": "STORM_wrapper_diag_blocked, pinned host buffer, STORM_b200_set_devices(%d)" % k}
+            finally:
+                sb.set_device_list(())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -351,6 +465,17 @@ def main_ours(args, rows, bits, gen):
     # ---- verification (outside the timed regions) -------------------------------
     closed = colcount_total_torch(rows_t, W)
     ok = (got_total == closed) and (e2e_total == closed)
+    if e2e_pageable is not None:
+        e2e_pageable["match"] = e2e_pageable["total"] == closed
+        ok = ok and e2e_pageable["match"]
+    if in_lib:
+        for v in in_lib.values():
+            v["match"] = v["total"] == closed
+            ok = ok and v["match"]
+    pairs_check = None
+    if args.verify_pairs > 0:
+        pairs_check = verify_pairs(sb, rows_t, rows, bits, gen, kernel, args.verify_pairs)
+        ok = ok and pairs_check["pairs_wrong"] == 0
 
     peaks, peak_src = load_peaks()
     value = wp * args.steps / (elapsed_ms * 1e-3)
@@ -360,42 +485,56 @@ def main_ours(args, rows, bits, gen):
     # minus the 8-byte all-reduce (N>1), measured by the same CUDA events
     launch_ms = elapsed_ms / args.steps
     traffic = ncu_traffic(args.workload, used_kernel, world)
-    if used_kernel == "fp4":
-        # Same algorithmic work (64 one-bit MACs = 128 ops per 64-bit word pair), carried by tcgen05.mma
-        # kind::mxf4 on bits unpacked to E2M1 nibbles (K = 64 per instruction, fp32 accumulators that hold
-        # exact integers).  Denominator: that instruction issued back to back on THIS device
-        # (STORM_b200_microbench kind 7); nominal dense fp4 peak 9000.
+    if used_kernel in ("fp4", "umma"):
+        # Algorithmic work: 64 one-bit MACs = 128 ops per 64-bit word pair, carried by tcgen05.mma
+        # kind::mxf4 on bits unpacked to E2M1 nibbles (fp32 accumulators holding exact integers) or kind::i8 on bits
+        # unpacked to bytes (s32).  MEASURED_PEAKS.json has no fp4 / int8 figure, so the denominator is the tensor
+        # pipe itself: 16384 (mxf4) resp. 8192 (i8) MACs per clock and SM -- the rate ncu reports for this kernel at
+        # 99 % pipe activity (profiles/r01_fp4_c3_ncu_full_v4.md) and the issue probe below reproduces -- x SMs x the
+        # part's MAXIMUM SM clock.  `frac_at_run_clock` divides by the clock the launch actually ran at, measured by
+        # the kernel itself (clock64 delta / globaltimer delta per CTA): under the 1 kW cap the delivered clock is
+        # below what nvidia-smi samples.
+        fp4 = used_kernel == "fp4"
+        info = sb.device_info(local_rank)
+        sms = info["sm_count"]
+        mac_per_clk = 16384.0 if fp4 else 8192.0
+        sm_max = float((clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        # is one clock64 tick one SM cycle?  250 ms spin on the otherwise idle device, nvidia-smi sampled beside it
+        cal_sampler = ClockSampler(local_rank)
+        cal_ticks_mhz = sb.microbench(8)[1]
+        cal = cal_sampler.stop()
+        smi_idle = cal.get("sm_mhz") or sm_max
+        tick_ratio = smi_idle / cal_ticks_mhz if cal_ticks_mhz else 1.0
+        if abs(tick_ratio - round(tick_ratio)) < 0.04 and round(tick_ratio) >= 1:
+            tick_ratio = float(round(tick_ratio))
+        run_mhz = kclk["mhz"] * tick_ratio if kclk else None
+        probe_rate, probe_ticks_mhz = sb.microbench(7 if fp4 else 5)
+        probe_mac_per_clk = probe_rate / 2.0 / (probe_ticks_mhz * tick_ratio * 1e6) / sms if probe_ticks_mhz else None
         ops_per_launch = wp / world * 128.0
         achieved = ops_per_launch / (launch_ms * 1e-3) / 1e12
-        fp4_peak = sb.microbench(7)[0] / 1e12
-        i8_peak = sb.microbench(5)[0] / 1e12
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": fp4_peak, "unit": "TFLOP/s", "frac": achieved / fp4_peak,
-                    "traffic": traffic, "kernel": "dense_umma_kernel<2, FP4>",
-                    "unit_note": "tensor ops per second / 1e12 (1 MAC = 2 ops) on E2M1 operands holding bits",
-                    "peak_source": "tcgen05.mma.kind::mxf4 M256 N256 K64 issue-rate probe on this device (measured, "
-                                   "STORM_b200_microbench(7)); nominal 9000 dense",
-                    "peak_i8_probe": i8_peak, "frac_of_i8_probe": achieved / i8_peak,
+        peak = sms * mac_per_clk * 2.0 * sm_max * 1e6 / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "dense_umma_kernel<2, FP4>" if fp4 else "dense_umma_kernel<2, i8>",
+                    "unit_note": "tensor ops per second / 1e12 (1 MAC = 2 ops) on %s operands holding bits" % ("E2M1" if fp4 else "u8"),
+                    "peak_source": "tensor pipe: %d MAC/clk/SM (%s) x %d SMs x %.0f MHz max SM clock; MEASURED_PEAKS.json has no %s figure "
+                                   "(its bf16 burst x %d = %.0f)" % (mac_per_clk, "kind::mxf4" if fp4 else "kind::i8", sms, sm_max,
+                                                                     "fp4" if fp4 else "int8", 4 if fp4 else 2,
+                                                                     (4 if fp4 else 2) * float(peaks.get("bf16_tflops", 1590.0))),
+                    "peak_nominal_dense": 9000.0 if fp4 else 4500.0, "frac_of_nominal": achieved / (9000.0 if fp4 else 4500.0),
+                    "issue_probe": {"tops": probe_rate / 1e12, "mac_per_clk_per_sm": probe_mac_per_clk,
+                                    "frac_of_pipe": probe_mac_per_clk / mac_per_clk if probe_mac_per_clk else None,
+                                    "what": "the kernel's own tcgen05.mma issued back to back on zero operands, cycles counted by the issuing warp (STORM_b200_microbench(%d))" % (7 if fp4 else 5)},
+                    "clock64_calibration": {"ticks_per_us_idle_spin": cal_ticks_mhz, "nvidia_smi_sm_mhz_during_spin": smi_idle,
+                                            "sm_cycles_per_tick": tick_ratio},
                     "algorithmic": "128 ops per 64-bit word pair x wp per launch",
                     "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
-    elif used_kernel == "umma":
-        # algorithmic work: 64 int8 MACs = 128 ops per 64-bit word pair.
-        # Denominator: the kernel's own tcgen05.mma kind::i8 instruction issued back to back on THIS
-        # device (STORM_b200_microbench kind 5) -- MEASURED_PEAKS.json has no int8 figure, and the
-        # cuBLAS bf16 number is taken under the 1 kW power cap at ~1.3 GHz while this kernel's 0/1
-        # operands leave the part at its 1965 MHz boost clock; 2 x bf16 is reported beside it.
-        ops_per_launch = wp / world * 128.0
-        achieved = ops_per_launch / (launch_ms * 1e-3) / 1e12
-        i8_peak = sb.microbench(5)[0] / 1e12
-        bf16x2 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": i8_peak, "unit": "TFLOP/s", "frac": achieved / i8_peak,
-                    "traffic": traffic, "kernel": "dense_umma_kernel",
-                    "unit_note": "int8 tensor ops per second / 1e12 (1 MAC = 2 ops), not floating point",
-                    "peak_source": "tcgen05.mma.kind::i8 M256 N256 K32 issue-rate probe on this device (measured, "
-                                   "STORM_b200_microbench(5)); nominal 4500 dense",
-                    "peak_2x_bf16": bf16x2, "frac_of_2x_bf16": achieved / bf16x2,
-                    "peak_2x_bf16_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peak_src})",
-                    "algorithmic": "128 int8 ops per 64-bit word pair x wp per launch",
-                    "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
+        if run_mhz:
+            roofline["kernel_clock_mhz"] = run_mhz
+            roofline["kernel_clock_spread_mhz"] = [kclk["min_mhz"] * tick_ratio, kclk["max_mhz"] * tick_ratio]
+            roofline["peak_at_run_clock"] = peak * run_mhz / sm_max
+            roofline["frac_at_run_clock"] = achieved / (peak * run_mhz / sm_max)
+            roofline["mac_per_clk_per_sm"] = ops_per_launch / 2.0 / (launch_ms * 1e-3) / (run_mhz * 1e6) / sms
+            roofline["run_clock_source"] = "in-kernel: clock64 delta / globaltimer delta around the persistent loop, mean over CTAs of the last timed launch"
     else:
         # CUDA-core kernels: bound by the POPC issue rate, measured on this device
         popc_rate, _ = sb.microbench(0)
@@ -408,18 +547,12 @@ def main_ours(args, rows, bits, gen):
                                    "issues fewer POPC than that, so its fraction can exceed 1",
                     "hbm_gbs_compulsory": rows * W * 8 / (launch_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]}
 
-    if roofline.get("bound") == "tensor" and clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz"):
-        # The issue-rate probe runs on zero operands at the part's maximum clock; the tile kernel is power-capped
-        # (sw_power_cap) and holds a lower clock.  The pipe's ceiling AT THE CLOCK SAMPLED DURING THE TIMED REGION
-        # separates "idle pipe cycles" from "fewer cycles per second" (ncu: sm__pipe_tensor_cycles_active,
-        # profiles/r01_fp4_c3_ncu_full_v4.md).  `frac` stays achieved / peak.
-        scale = clocks["sm_mhz"] / clocks["sm_max_mhz"]
-        roofline["peak_at_run_clock"] = roofline["peak"] * scale
-        roofline["frac_at_run_clock"] = roofline["achieved"] / (roofline["peak"] * scale)
+    dtype = {"fp4": "e2m1 x e2m1 -> f32 accumulators holding exact integers < 2^24 (bits unpacked to FP4 nibbles)",
+             "umma": "u8 x u8 -> s32 (bits unpacked to bytes)"}.get(used_kernel, "u64 and + popc")
     line = {
         "metric": "xxt_wordpair_and_popcnt_per_s", "value": value, "unit": "wp/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"{args.workload}: dense {rows}x{bits} XX^T upper triangle", "rows": rows, "bits": bits,
                    "generator": gen, "seed": SEED, "kernel": used_kernel, "tile": [tm, tn], "tiles": n_tiles, "wave_sync": bool(args.wave_sync),
                    "parallelism": f"tile-raster shards x{world}, rows replicated",
@@ -431,9 +564,18 @@ def main_ours(args, rows, bits, gen):
                         "stormbitmaps_b200.distributed.pairw_total_from_host (row bands: 1/N slice H2D per rank + NVLink all-gather, pipelined with the tile kernels; all-reduce)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "verified": {"total": got_total, "closed_form_total": closed, "match": ok},
+        "verified": {"total": got_total, "closed_form_total": closed, "match": ok,
+                     "pairs_sampled": pairs_check["pairs_sampled"] if pairs_check else 0, "pairs": pairs_check},
         "step_ms": step_ms,
     }
+    if e2e_pageable is not None:
+        line["e2e"]["pageable"] = e2e_pageable
+        line["e2e"]["pageable_over_pinned"] = e2e_pageable["value"] / e2e_value
+    if in_lib:
+        line["in_library_devices"] = in_lib
+    if world == 1 and not args.no_extras and args.contig_api_rows != 0:
+        n_api = args.contig_api_rows if args.contig_api_rows > 0 else rows
+        line["contig_api"] = contig_api_bench(n_api, bits)
     if world == 1 and not args.no_cpu_baseline:
         threads = 1                                         # the reference is single-threaded
         ctx = cpu_baseline(rows, bits, gen, 12.0, threads)
@@ -461,9 +603,12 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "custom"])
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--bits", type=int, default=None)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "umma", "fp4"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "csa", "umma", "fp4", "b1"])
     ap.add_argument("--wave-sync", type=int, default=1, help="UMMA kernel: keep the tiles of a wave in step (L2 reuse); 0 = off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify-pairs", type=int, default=64, help="tiles of 256 x 256 pairs checked pair by pair against the oracle after the timed region (0 = off)")
+    ap.add_argument("--contig-api-rows", type=int, default=-1, help="rows of the struct-API end-to-end measurement (-1 = the workload's, 0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the pageable / in-library-devices / struct-API measurements")
     ap.add_argument("--umma-cg", type=int, default=0, help="cta_group of the UMMA kernel (1 or 2; 0 = library default)")
     args = ap.parse_args()
     if args.workload == "custom":

@@ -64,9 +64,10 @@ extern "C" {
 typedef uint64_t (*STORM_compute_func)(const uint64_t*, const uint64_t*, const size_t);
 /* The kernel choosers of libalgebra.h:3094-3140 (intersect), 3142-3188 (union) and 3190-3236
  * (diff), which the reference's storm.h pulls in.  Here they return exported host functions of
- * this library (plain popcount loops with the same results); a raw-buffer wrapper that is handed
- * the union or diff one answers with that set operation on the GPU, any other pointer
- * (including NULL and foreign functions) means intersect. */
+ * this library (plain popcount loops with the same results).  A raw-buffer wrapper answers with the
+ * set operation its `f` stands for: NULL means intersect, these three are known by address, and any
+ * other function (e.g. libalgebra's static kernels compiled into the caller) is identified by what it
+ * returns on three small probe vectors; a function that is none of the three gets UINT64_MAX. */
 STORM_compute_func STORM_get_intersect_count_func(const size_t n_bitmaps_vector);
 STORM_compute_func STORM_get_union_count_func(const size_t n_bitmaps_vector);
 STORM_compute_func STORM_get_diff_count_func(const size_t n_bitmaps_vector);
@@ -213,16 +214,47 @@ int      STORM_bitmap_add(STORM_bitmap_t* bitmap, const uint32_t* values, const 
 int      STORM_bitmap_add_scalar_only(STORM_bitmap_t* bitmap, const uint32_t* values, const uint32_t n_values);
 int      STORM_bitmap_clear(STORM_bitmap_t* bitmap);
 uint32_t STORM_bitmap_serialized_size(STORM_bitmap_t* bitmap);
+/* storm.h:207 -> storm.c:467-519.  Sets the bits AND appends every value not seen before to the block's list. */
+int      STORM_bitmap_add_with_scalar(STORM_bitmap_t* bitmap, const uint32_t* values, const uint32_t n_values);
+
+/* ========================================================================== *
+ *  Per-pair host helpers (storm.h:56-61, 209-210, 220-221 -> storm.c:4-129, 571-656, 761-814)
+ *
+ *  The reference's CPU building blocks for ONE pair of lists / blocks / rows.  They need no device and are
+ *  plain host code here too (host_pairs.cu); the all-vs-all queries above never go through them.  All return
+ *  the exact |a AND b|: the bitmap x list probe defect of storm.c:636,644 (D1) is not reproduced.
+ * ========================================================================== */
+/* storm.c:4-73.  Common values of two sorted unique u16 lists. */
+uint64_t STORM_intersect_vector16_cardinality(const uint16_t* STORM_RESTRICT v1, const uint16_t* STORM_RESTRICT v2,
+                                              const uint32_t len1, const uint32_t len2);
+/* storm.c:75-106.  Merge of two sorted unique u32 lists: out receives (index in v1, index in v2) pairs of the common
+ * values; returns the number of u32 written (2 per match).  `out` must hold 2 * min(len1, len2) entries. */
+uint64_t STORM_intersect_vector32_unsafe(const uint32_t* STORM_RESTRICT v1, const uint32_t* STORM_RESTRICT v2,
+                                         const uint32_t len1, const uint32_t len2, uint32_t* STORM_RESTRICT out);
+/* storm.c:108-129.  The shorter position list probed into the other row's bitmap (n1 < n2: l1 into b2, else l2 into b1). */
+uint64_t STORM_intersect_bitmaps_scalar_list(const uint64_t* STORM_RESTRICT b1, const uint64_t* STORM_RESTRICT b2,
+                                             const uint32_t* l1, const uint32_t* l2, const uint32_t n1, const uint32_t n2);
+/* storm.c:571-614 / 618-656.  Two blocks with the same id: list x list, bitmap x list, list x bitmap or
+ * bitmap x bitmap (through `func`, or a popcount loop); 0 for different ids or NULL. */
+uint64_t STORM_bitmap_intersect_cardinality(STORM_bitmap_t* STORM_RESTRICT bitmap1, STORM_bitmap_t* STORM_RESTRICT bitmap2);
+uint64_t STORM_bitmap_intersect_cardinality_func(STORM_bitmap_t* STORM_RESTRICT bitmap1, STORM_bitmap_t* STORM_RESTRICT bitmap2,
+                                                 const STORM_compute_func func);
+/* storm.c:761-788 / 790-814.  Two rows: merge of the block ids, then the per-block function.  `out` is caller
+ * scratch for the merge (2 * min(n_bitmaps) u32). */
+uint64_t STORM_bitmap_cont_intersect_cardinality(const STORM_bitmap_cont_t* STORM_RESTRICT bitmap1,
+                                                 const STORM_bitmap_cont_t* STORM_RESTRICT bitmap2);
+uint64_t STORM_bitmap_cont_intersect_cardinality_premade(const STORM_bitmap_cont_t* STORM_RESTRICT bitmap1,
+                                                         const STORM_bitmap_cont_t* STORM_RESTRICT bitmap2,
+                                                         const STORM_compute_func func, uint32_t* out);
 
 /* ========================================================================== *
  *  Raw-buffer wrappers (storm.h:95-148 -> storm.c:132-369)
  *
  *  `vals` is a caller-owned HOST buffer of n_vectors x n_ints words; the call
- *  uploads it, runs the tile kernels and returns the total.  `f` selects the
- *  set operation when it is one of this library's STORM_get_{union,diff}_count_func
- *  results (sum of popcount(a|b) resp. popcount(a^b) over the same pairs) and
- *  means intersect otherwise; fl and block_size only steer CPU code in the
- *  reference and are ignored.
+ *  uploads it (over every device of the device set, storm_b200.h), runs the tile
+ *  kernels and returns the total.  `f` selects the set operation (intersect, or sum
+ *  of popcount(a|b) resp. popcount(a^b) over the same pairs; see STORM_compute_func
+ *  above); fl and block_size only steer CPU code in the reference and are ignored.
  * ========================================================================== */
 uint64_t STORM_wrapper_diag(const uint32_t n_vectors, const uint64_t* vals,
                             const uint32_t n_ints, const STORM_compute_func f);

@@ -32,6 +32,8 @@ extern "C" {
 #define STORM_B200_KERNEL_POPC 1   /* CUDA cores: LOP3 + POPC register tiles          */
 #define STORM_B200_KERNEL_UMMA 2   /* tcgen05.mma kind::i8 on bits unpacked on the fly */
 #define STORM_B200_KERNEL_CSA  3   /* CUDA cores: carry-save adders feeding POPC        */
+#define STORM_B200_KERNEL_B1   5   /* mma.sync.m16n8k256 .b1 AND + POPC: the pre-Blackwell one-bit tensor path, which sm_100a
+                                      emulates with IMMA + ALU glue; kept for the record, never chosen by AUTO        */
 #define STORM_B200_KERNEL_FP4  4   /* tcgen05.mma kind::mxf4 on bits unpacked to E2M1 nibbles, fp32 accumulators
                                       (exact below 2^24 bits per row; twice the rate of kind::i8) */
 
@@ -50,6 +52,24 @@ int  STORM_b200_device_info(int dev, char* name, size_t name_len, int* sm_count,
 /* Process-wide default kernel for the storm.h entry points (they have no
  * parameter for it).  Returns the previous value. */
 int  STORM_b200_set_default_kernel(int kernel);
+
+/* ---- devices ---------------------------------------------------------------
+ *
+ * Queries behind storm.h run on a SET of devices (one process, one host thread): every device holds all
+ * rows, device g of G computes shard g of the tile raster, the host adds G totals.  Rows reach the devices in
+ * bands -- 1/G of a band over each device's own PCIe link, the other slices from the peers over NVLink -- and the
+ * tiles of a band start as soon as it is complete on a device.  The set is read when a container first touches a
+ * device (and per call for the raw-buffer wrappers):
+ *   environment STORM_B200_DEVICES = all | <k> | <id>,<id>,...   (read once, before the first query)
+ *   STORM_b200_set_devices(n): n = 0 all visible devices, n >= 1 devices 0 .. n-1; returns the previous count
+ *   STORM_b200_set_device_list(ids, n): explicit ordinals (one may repeat: several replicas on one device, which
+ *     is how the multi-device logic is tested on a one-GPU box); n = 0 restores the default
+ * Default: the calling thread's current device alone (what a multi-process caller with one rank per GPU wants).
+ * STORM_t queries and per-pair rectangles use the first device of the set. */
+int STORM_b200_set_devices(int n);
+int STORM_b200_set_device_list(const int* ids, int n);
+/* The devices a query made now would use: fills ids[0 .. min(cap, count)), returns the count (negative on error). */
+int STORM_b200_get_devices(int* ids, int cap);
 
 /* ---- dense path on device-resident rows ----------------------------------
  *
@@ -125,6 +145,12 @@ int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile,
 int STORM_b200_pairw_tiles_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
                                   uint64_t row_stride_words, uint64_t tile_begin, uint64_t tile_end,
                                   int kernel, uint64_t* d_total, void* stream);
+/* The same with the number of SMs the persistent tensor kernel leaves free passed per launch (reserved_sms >= 0; a
+ * negative value means the process default of STORM_b200_set_umma_reserved_sms): a multi-process caller that overlaps
+ * an NVLink collective with the tile kernel no longer has to flip a process-wide knob around its launches. */
+int STORM_b200_pairw_tiles_device_ex(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                     uint64_t row_stride_words, uint64_t tile_begin, uint64_t tile_end,
+                                     int kernel, int reserved_sms, uint64_t* d_total, void* stream);
 /* Host-only: the raster is monotone in the largest row a tile reads.  *tile_end = number of
  * leading tiles that read only rows below row_limit (all tiles once row_limit >= n_rows);
  * *band_rows (optional) = the row granularity at which that count grows. */
@@ -141,6 +167,8 @@ uint64_t STORM_b200_wrapper_diag_shard(uint64_t n_vectors, const uint64_t* vals,
                                        uint32_t shard, uint32_t n_shards, int kernel);
 
 /* ---- container extensions ------------------------------------------------ */
+/* Device replicas the container's queries run on (0 before it first used a device). */
+int STORM_b200_contig_device_count(const STORM_contiguous_t* bitmap);
 /* Partial total of shard `shard` of `n_shards` (see above); UINT64_MAX on error. */
 uint64_t STORM_b200_contig_pairw_shard(STORM_contiguous_t* bitmap, uint32_t shard, uint32_t n_shards, int kernel);
 /* Per-pair counts into a HOST buffer out[(i-i0)*(j1-j0) + (j-j0)], strict upper triangle. */
@@ -209,7 +237,9 @@ int STORM_b200_synth_geno_device(uint64_t* d_rows, uint64_t n_rows, uint32_t n_w
  * whole device in *rate (and a clock64-derived SM clock in *sm_mhz, indicative
  * only).  kind 4 / 5: the UMMA kernel's own tcgen05.mma kind::i8 instruction
  * (cta_group 1 / 2) issued back to back with no operand production: int8 ops per
- * second (2 per MAC) in *rate -- the tensor-pipe ceiling of dense_umma_kernel. */
+ * second (2 per MAC) in *rate -- the tensor-pipe ceiling of dense_umma_kernel -- and the clock64 ticks per microsecond of
+ * the issue loop in *sm_mhz, so that MACs per clock and SM follow without knowing the clock.  kind 8: clock64 ticks per
+ * second (*rate) and per microsecond (*sm_mhz) over a 250 ms spin. */
 int STORM_b200_microbench(int kind, double* rate, double* sm_mhz);
 /* kind 6 / 7 of STORM_b200_microbench: tcgen05.mma kind::mxf4 (block-scaled E2M1, K = 64) at
  * cta_group 1 / 2, ops per second (2 per MAC).
@@ -220,8 +250,14 @@ int STORM_b200_microbench(int kind, double* rate, double* sm_mhz);
  * (1.0 x 1.0, 0.5 x 2.0, 2.0 x 0.5, alternating).  Per case four 32-bit results: expected value,
  * smallest and largest accumulator (floats) and the number of accumulators != expected (uint32). */
 int STORM_b200_fp4_probe(const uint32_t* cases, uint32_t n_cases, float* results);
+/* The same question with data-dependent increments, as the tile kernel produces them: n_steps (<= 262143) instructions
+ * at cta_group cg (1 or 2) over 4 x 4 pseudo-random operand combinations in the production nibble encoding, every
+ * accumulator element adding 0 .. 64 per instruction (the all-ones element reaches 64 n_steps).  results[0..2]: largest
+ * expected element, smallest and largest (got - expected) as floats; results[3]: number of wrong elements (u32 bits). */
+int STORM_b200_fp4_probe_random(int cg, uint32_t n_steps, uint32_t seed, float* results);
 /* The one-time per-device check behind KERNEL_AUTO's choice of the FP4 form: 1 if accumulators driven
- * to 2^24 - 1 in steps of 64 and of 1 came out exact for every operand encoding, else 0. */
+ * to 2^24 - 1 in steps of 64 and of 1 came out exact for every operand encoding (cta_group 1), and driven to
+ * 2^24 - 64 by data-dependent increments at cta_group 1 and 2 (the probe above), else 0. */
 int STORM_b200_fp4_selftest(void);
 /* cta_group of the UMMA kernel: 2 (default) = CTA pair per 256 x 256 tile, 1 = one CTA per
  * 128 x 256 tile.  Returns the previous value. */
@@ -247,6 +283,13 @@ int STORM_b200_set_umma_chain(int on);
  * all-gather with the tile kernel sets this to a small number so that the collective's CTAs find a place
  * to run beside it.  Clamped to [0, SM count - 2].  Returns the previous value. */
 int STORM_b200_set_umma_reserved_sms(int n);
+/* Clock probe of the tensor kernels: with it on, every launch records per CTA the clock64 and %globaltimer deltas around
+ * its main loop; STORM_b200_last_kernel_clock waits for the device and returns the clock the last probed launch on the
+ * current device ran at, in clock64 ticks per microsecond (mean over CTAs; optional min / max).  STORM_b200_microbench(8)
+ * gives the same figure for a 250 ms spin on an otherwise idle device (to be read beside nvidia-smi's clocks.sm: is one
+ * clock64 tick one SM cycle?).  The roofline of bench.py divides by this clock, not by nvidia-smi's. */
+int STORM_b200_set_clock_probe(int on);
+int STORM_b200_last_kernel_clock(double* mhz, double* min_mhz, double* max_mhz);
 /* Number of kernel launches issued by this library since load (for bench.py). */
 uint64_t STORM_b200_launch_count(void);
 

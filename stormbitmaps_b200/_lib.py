@@ -17,7 +17,7 @@ u32p = C.POINTER(C.c_uint32)
 UINT64_MAX = 2**64 - 1
 
 KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_CSA, KERNEL_FP4 = 0, 1, 2, 3, 4
-KERNEL_NAMES = {"auto": 0, "popc": 1, "umma": 2, "csa": 3, "fp4": 4}
+KERNEL_NAMES = {"auto": 0, "popc": 1, "umma": 2, "csa": 3, "fp4": 4, "b1": 5}
 
 
 class StormError(RuntimeError):
@@ -108,6 +108,7 @@ SIGNATURES = {
     "STORM_b200_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "STORM_b200_fp4_probe": (C.c_int, [u32p, C.c_uint32, C.POINTER(C.c_float)]),
     "STORM_b200_fp4_selftest": (C.c_int, []),
+    "STORM_b200_fp4_probe_random": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "STORM_b200_set_umma_cta_group": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_variant": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_wave_sync": (C.c_int, [C.c_int]),
@@ -115,6 +116,22 @@ SIGNATURES = {
     "STORM_b200_set_umma_chain": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_reserved_sms": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),
+    "STORM_b200_set_clock_probe": (C.c_int, [C.c_int]),
+    "STORM_b200_last_kernel_clock": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "STORM_b200_pairw_tiles_device_ex": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "STORM_b200_set_devices": (C.c_int, [C.c_int]),
+    "STORM_b200_set_device_list": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "STORM_b200_get_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "STORM_b200_contig_device_count": (C.c_int, [C.c_void_p]),
+    # ---- storm.h: per-pair host helpers
+    "STORM_bitmap_add_with_scalar": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
+    "STORM_intersect_vector16_cardinality": (C.c_uint64, [C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_uint32, C.c_uint32]),
+    "STORM_intersect_vector32_unsafe": (C.c_uint64, [u32p, u32p, C.c_uint32, C.c_uint32, u32p]),
+    "STORM_intersect_bitmaps_scalar_list": (C.c_uint64, [u64p, u64p, u32p, u32p, C.c_uint32, C.c_uint32]),
+    "STORM_bitmap_intersect_cardinality": (C.c_uint64, [C.c_void_p, C.c_void_p]),
+    "STORM_bitmap_intersect_cardinality_func": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "STORM_bitmap_cont_intersect_cardinality": (C.c_uint64, [C.c_void_p, C.c_void_p]),
+    "STORM_bitmap_cont_intersect_cardinality_premade": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_void_p, u32p]),
 }
 
 _lib = None

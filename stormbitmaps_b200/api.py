@@ -88,6 +88,10 @@ class StormContiguous:
                    "STORM_b200_contig_pairw_rect")
         return out
 
+    def device_count(self) -> int:
+        """Device replicas this container's queries run on (0 before its first use of a device)."""
+        return int(self._L.STORM_b200_contig_device_count(self._h))
+
     def last_list_route(self) -> str:
         """Which kernels answered the last *_list query: 'tile', 'probe' (tile + probe) or 'stream'."""
         return {0: "none", 1: "tile", 2: "probe", 3: "stream"}[self._L.STORM_b200_contig_last_list_route(self._h)]
@@ -210,6 +214,26 @@ def wrapper_diag(vals: np.ndarray, op: str = "intersect") -> int:
     return _query(L.STORM_wrapper_diag(v.shape[0], v.ctypes.data_as(u64p), v.shape[1], f), "STORM_wrapper_diag")
 
 
+def wrapper_diag_list(vals: np.ndarray, rows_positions, cutoff: int, bsize: Optional[int] = None) -> int:
+    """``STORM_wrapper_diag_list[_blocked]`` (storm.h:104-119, 127-148): host matrix + the caller-built position arrays
+    the reference uses to pick a cheaper per-pair code path (n_alts, concatenated positions, offsets)."""
+    L = _lib.load()
+    v = np.ascontiguousarray(vals, dtype=np.uint64)
+    n_alts = np.asarray([len(p) for p in rows_positions], dtype=np.uint32)
+    offs = np.zeros(len(rows_positions), dtype=np.uint32)
+    if len(rows_positions) > 1:
+        offs[1:] = np.cumsum(n_alts[:-1], dtype=np.uint64).astype(np.uint32)
+    flat = (np.concatenate([np.asarray(p, dtype=np.uint32) for p in rows_positions]) if len(rows_positions) else np.zeros(0, np.uint32))
+    flat = np.ascontiguousarray(flat, dtype=np.uint32)
+    f = _compute_func("intersect")
+    if bsize is None:
+        return _query(L.STORM_wrapper_diag_list(v.shape[0], v.ctypes.data_as(u64p), v.shape[1], n_alts.ctypes.data_as(u32p),
+                                                flat.ctypes.data_as(u32p), offs.ctypes.data_as(u32p), f, None, cutoff), "STORM_wrapper_diag_list")
+    return _query(L.STORM_wrapper_diag_list_blocked(v.shape[0], v.ctypes.data_as(u64p), v.shape[1], n_alts.ctypes.data_as(u32p),
+                                                    flat.ctypes.data_as(u32p), offs.ctypes.data_as(u32p), f, None, cutoff, bsize),
+                  "STORM_wrapper_diag_list_blocked")
+
+
 def wrapper_diag_ptr(ptr: int, n_vectors: int, n_ints: int, bsize: int = 0) -> int:
     """``STORM_wrapper_diag_blocked`` on a raw host pointer (e.g. a pinned torch tensor)."""
     L = _lib.load()
@@ -274,16 +298,22 @@ def pairw_device(rows, n_words: Optional[int] = None, shard: int = 0, n_shards: 
 
 
 def pairw_tiles_device(rows, tile_begin: int, tile_end: int, n_words: Optional[int] = None, kernel=KERNEL_AUTO,
-                       total=None, stream=None):
-    """``STORM_b200_pairw_tiles_device``: accumulate the partial total of raster tiles [tile_begin, tile_end)."""
+                       total=None, stream=None, reserved_sms: Optional[int] = None):
+    """``STORM_b200_pairw_tiles_device[_ex]``: accumulate the partial total of raster tiles [tile_begin, tile_end).
+    ``reserved_sms`` (per launch): SMs the persistent tensor kernel leaves to a collective running beside it."""
     import torch
     L = _lib.load()
     ptr, n_rows, stride = _rows_args(rows)
     if total is None:
         total = torch.zeros(1, dtype=torch.int64, device=rows.device)
-    _lib.check(L.STORM_b200_pairw_tiles_device(ptr, n_rows, n_words or rows.shape[1], stride, tile_begin, tile_end,
-                                               _kernel_id(kernel), total.data_ptr(), _stream_handle(stream)),
-               "STORM_b200_pairw_tiles_device")
+    if reserved_sms is None:
+        _lib.check(L.STORM_b200_pairw_tiles_device(ptr, n_rows, n_words or rows.shape[1], stride, tile_begin, tile_end,
+                                                   _kernel_id(kernel), total.data_ptr(), _stream_handle(stream)),
+                   "STORM_b200_pairw_tiles_device")
+    else:
+        _lib.check(L.STORM_b200_pairw_tiles_device_ex(ptr, n_rows, n_words or rows.shape[1], stride, tile_begin, tile_end,
+                                                      _kernel_id(kernel), int(reserved_sms), total.data_ptr(), _stream_handle(stream)),
+                   "STORM_b200_pairw_tiles_device_ex")
     return total
 
 
@@ -489,6 +519,43 @@ def set_umma_stream_k(on: bool) -> int:
 def set_umma_chain(on: bool) -> int:
     """Accumulator chaining of total-only UMMA queries (one drain per run of interior tiles, default on); returns the previous value."""
     return _lib.load().STORM_b200_set_umma_chain(int(bool(on)))
+
+
+def set_clock_probe(on: bool) -> int:
+    """``STORM_b200_set_clock_probe``: tensor-kernel launches record their clock64 / globaltimer deltas."""
+    return _lib.load().STORM_b200_set_clock_probe(int(bool(on)))
+
+
+def last_kernel_clock() -> dict:
+    """``STORM_b200_last_kernel_clock``: clock64 ticks per microsecond of the last probed launch (mean, min, max over CTAs)."""
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    _lib.check(_lib.load().STORM_b200_last_kernel_clock(C.byref(a), C.byref(b), C.byref(c)), "STORM_b200_last_kernel_clock")
+    return {"mhz": a.value, "min_mhz": b.value, "max_mhz": c.value}
+
+
+def set_devices(n: int) -> int:
+    """``STORM_b200_set_devices``: 0 = every visible device, n >= 1 = devices 0 .. n-1 for containers created and
+    wrapper calls made afterwards; returns the previous count."""
+    return _lib.load().STORM_b200_set_devices(int(n))
+
+
+def set_device_list(ids) -> None:
+    """``STORM_b200_set_device_list``: explicit ordinals (one may repeat: replicas on one device); () = the default."""
+    ids = list(ids)
+    arr = (C.c_int * max(1, len(ids)))(*ids)
+    _lib.check(_lib.load().STORM_b200_set_device_list(arr if ids else None, len(ids)), "STORM_b200_set_device_list")
+
+
+def get_devices() -> list:
+    out = (C.c_int * 64)()
+    n = _lib.load().STORM_b200_get_devices(out, 64)
+    if n < 0:
+        raise StormError(f"STORM_b200_get_devices failed ({n}): {_lib.last_error()}")
+    return [out[i] for i in range(min(n, 64))]
+
+
+def last_error() -> str:
+    return _lib.last_error()
 
 
 def device_info(dev: int = 0) -> dict:

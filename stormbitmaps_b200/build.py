@@ -58,7 +58,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if force or procs or _newer(objs, LIB):
         subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    build_tools(force)
     return LIB
+
+
+TOOLS = {"contig_api_bench": os.path.join(ROOT, "tools", "contig_api_bench.c")}
+
+
+def tool_path(name: str) -> str:
+    return os.path.join(OBJ, name)
+
+
+def build_tools(force: bool = False) -> None:
+    """C programs written against include/*.h and linked with the shared object (rpath relative to the binary, so
+    that they run from the gpurun snapshot): the struct-API end-to-end driver bench.py times."""
+    for name, src in TOOLS.items():
+        exe = tool_path(name)
+        if force or _newer([src, LIB], exe):
+            subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src,
+                                   "-L", PKG, "-lstorm_b200", "-Wl,-rpath,$ORIGIN/..", "-o", exe])
 
 
 if __name__ == "__main__":

@@ -75,6 +75,13 @@ struct DenseJob {
     // so the accumulator may hold the sum of several tiles as long as no element can overflow its exact
     // range); 0 or 1 = every segment is drained on its own.
     uint32_t chain_max;
+    // SMs the persistent UMMA kernel leaves to work running beside it (a collective of a multi-process caller); -1 = the
+    // process default (STORM_b200_set_umma_reserved_sms).  Per launch, so that no caller has to flip a global mid-query.
+    int reserved_sms;
+    // Optional clock probe (STORM_b200_set_clock_probe): per CTA {clock64 delta, %globaltimer delta in ns} around the
+    // kernel's main loop, from which the host derives the SM clock the launch actually ran at (the board's power cap
+    // lowers it below what nvidia-smi reports for long tensor launches).
+    unsigned long long* clk;
 };
 
 // Last row block of column block bj that intersects the strict upper triangle when A == B (square
@@ -164,6 +171,8 @@ TileShape popc_tile_shape();
 int launch_dense_popc(const DenseJob& job, cudaStream_t stream);
 TileShape csa_tile_shape();
 int launch_dense_csa(const DenseJob& job, cudaStream_t stream);
+TileShape b1_tile_shape();
+int launch_dense_b1(const DenseJob& job, cudaStream_t stream);   // mma.sync .b1 AND + POPC (emulated on sm_100a; for the record)
 TileShape umma_tile_shape();
 int launch_dense_umma(const DenseJob& job, cudaStream_t stream);
 // UMMA needs at least one full K step of 128 bits and 16-byte aligned rows.
@@ -171,9 +180,9 @@ bool umma_supports(const DenseJob& job);
 bool umma_fp4_supports(const DenseJob& job);          // + every pair count below 2^24 (fp32-exact)
 int launch_dense_fp4(const DenseJob& job, cudaStream_t stream);   // same kernel, kind::mxf4 form
 // int8 ops per second of the UMMA kernel's own instruction issued back to back (cta_group 1 or 2).
-int umma_peak_ops(int cg, double* ops_per_s);
+int umma_peak_ops(int cg, double* ops_per_s, double* clock64_mhz);
 int fp4_selftest_ok();                          // 1 if this device accumulates E2M1 bit products exactly (cached)
-int fp4_peak_ops(int cg, double* ops_per_s);   // tcgen05.mma kind::mxf4 issue-rate probe (fp4_probe.cu)
+int fp4_peak_ops(int cg, double* ops_per_s, double* clock64_mhz);   // tcgen05.mma kind::mxf4 issue-rate probe (fp4_probe.cu)
 
 int launch_synth_uniform(uint64_t* d_rows, uint64_t n_rows, uint64_t stride, uint32_t M,
                          uint32_t n_draws, uint64_t seed, uint64_t row0, cudaStream_t stream);

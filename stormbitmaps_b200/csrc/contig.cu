@@ -8,12 +8,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "common.cuh"
+#include "devices.h"
 #include "runtime.h"
 
 namespace storm {
@@ -21,40 +23,38 @@ namespace storm {
 namespace {
 
 constexpr uint64_t ROW_ALIGN_WORDS = 16;   // device row stride is a multiple of 128 bytes
+constexpr uint64_t BG_UPLOAD_BYTES = 8ull << 20;   // STORM_contig_add pushes finished rows to the devices in batches of this size
 
-struct ContigState {
-    int device = -1;
-    cudaStream_t stream = nullptr;
-    // device arena
-    uint64_t* d_rows = nullptr;
+// One replica of the container on one device.
+struct ContigDev {
+    DevCtx ctx;
+    uint64_t* d_rows = nullptr;        // row arena (stride words per row)
     uint64_t d_cap_rows = 0;
-    uint64_t stride = 0;               // words
-    uint64_t uploaded_rows = 0;        // rows [0, uploaded_rows) of the host mirror are on the device
-    // sparse-row position lists (host offsets + device mirrors, rebuilt lazily)
-    std::vector<uint64_t> pos_off;     // per row: offset into c->scalar (valid for sparse rows)
+    // sparse-row position lists and row classes (the *_list queries)
     uint32_t* d_pos = nullptr; uint64_t d_pos_cap = 0;
     uint64_t* d_pos_off = nullptr; uint32_t* d_is_sparse = nullptr; uint32_t* d_sparse_rows = nullptr;
-    uint32_t* d_dense_rows = nullptr; uint64_t d_meta_cap = 0;
-    uint64_t list_rows_synced = 0;     // lists of rows [0, list_rows_synced) are on the device
-    uint64_t n_sparse = 0, n_dense = 0;
-    std::vector<uint32_t> h_group_start; uint32_t* d_group_start = nullptr;   // row groups of the stream kernel (all rows sparse)
-    bool stream_ok = false;            // every row is sparse and short enough for the stream kernel
-    int last_list_route = 0;           // 1 tile kernel, 2 tile + probe kernels, 3 stream kernel
+    uint32_t* d_dense_rows = nullptr; uint32_t* d_group_start = nullptr; uint64_t d_meta_cap = 0;
+    uint64_t list_rows_synced = 0;     // list metadata of rows [0, list_rows_synced) is on this device
     uint64_t* d_gather = nullptr; uint64_t d_gather_cap = 0;   // compact arena of dense rows (list path)
-    // result + timing
-    unsigned long long* d_total = nullptr;
-    unsigned long long* h_total = nullptr;   // pinned
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    double timing[3] = {0, 0, 0};
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};           // timing (primary device)
 };
 
-struct DeviceGuard {
-    int prev = -1; bool active = false;
-    explicit DeviceGuard(int dev) {
-        if (dev < 0) return;
-        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); active = true; }
-    }
-    ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+struct ContigState {
+    int home_device = -1;              // current device of the creating thread: the default device set
+    int dev_status = 0;                // 0 = devices not set up yet, 1 = ready, -1 = setting them up failed
+    std::vector<ContigDev*> devs;      // devs[0] is the primary (rectangles, bulk ingest, set operations)
+    uint64_t stride = 0;               // words, the same on every device
+    uint64_t uploaded_rows = 0;        // rows [0, uploaded_rows) of the host mirror have been requested on every device's copy stream
+    bool data_pinned = false;          // c->data came from cudaHostAlloc (portable): uploads are direct DMA
+    // sparse-row position lists: per-row offsets into c->scalar, and the host form of the list metadata
+    std::vector<uint64_t> pos_off;
+    std::vector<uint64_t> h_off;
+    std::vector<uint32_t> h_is_sparse, h_sparse_rows, h_dense_rows, h_group_start;
+    uint64_t list_rows_built = (uint64_t)-1;
+    uint64_t n_sparse = 0, n_dense = 0;
+    bool stream_ok = false;            // every row is sparse and short enough for the stream kernel
+    int last_list_route = 0;           // 1 tile kernel, 2 tile + probe kernels, 3 stream kernel
+    double timing[3] = {0, 0, 0};
 };
 
 inline ContigState* state_of(STORM_contiguous_t* c) { return static_cast<ContigState*>(c->b200); }
@@ -68,54 +68,95 @@ uint64_t host_intersect_count(const uint64_t* a, const uint64_t* b, const size_t
     return c;
 }
 
-int ensure_device_state(ContigState* st) {
-    if (st->device >= 0 && st->d_total) return STORM_B200_OK;
-    int rc = require_device();
+bool have_device() {
+    static int state = 0;              // 0 unknown, 1 yes, 2 no
+    if (state == 0) {
+        int n = 0;
+        state = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 2;
+        if (state == 2) cudaGetLastError();
+    }
+    return state == 1;
+}
+
+// Device replicas of a container: the device set in force at its first use (devices.h), fixed for its lifetime.
+int ensure_devs(ContigState* st) {
+    if (st->dev_status == 1) return STORM_B200_OK;
+    DeviceGuard home(st->home_device);               // "current device" means the creating thread's
+    std::vector<int> ids;
+    int rc = query_devices(&ids);
     if (rc) return rc;
-    STORM_CUDA_TRY(cudaGetDevice(&st->device));
-    STORM_CUDA_TRY(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
-    STORM_CUDA_TRY(cudaMalloc(&st->d_total, sizeof(unsigned long long)));
-    STORM_CUDA_TRY(cudaMallocHost(&st->h_total, sizeof(unsigned long long)));
-    for (auto& e : st->ev) STORM_CUDA_TRY(cudaEventCreate(&e));
+    if (st->home_device < 0) st->home_device = ids[0];
+    enable_peers(ids);
+    for (int id : ids) {
+        ContigDev* d = new (std::nothrow) ContigDev();
+        if (!d) { set_error("out of host memory"); return STORM_B200_ENOMEM; }
+        st->devs.push_back(d);                       // (a half-built replica is torn down by STORM_contig_free)
+        if ((rc = d->ctx.init(id))) { st->dev_status = -1; return rc; }
+    }
+    {
+        DeviceGuard guard(st->devs[0]->ctx.device);
+        for (auto& e : st->devs[0]->ev) STORM_CUDA_TRY(cudaEventCreate(&e));
+    }
+    st->dev_status = 1;
     return STORM_B200_OK;
 }
 
-int ensure_device_rows(STORM_contiguous_t* c, ContigState* st, uint64_t rows) {
+// Device arena of one replica with room for `rows` rows (grows geometrically, like the host mirror).
+int ensure_device_rows(STORM_contiguous_t* c, ContigState* st, ContigDev* d, uint64_t rows) {
     if (st->stride == 0)
         st->stride = ((uint64_t)c->n_bitmaps_vector + ROW_ALIGN_WORDS - 1) / ROW_ALIGN_WORDS * ROW_ALIGN_WORDS;
-    if (rows <= st->d_cap_rows) return STORM_B200_OK;
-    uint64_t cap = std::max<uint64_t>(rows, st->d_cap_rows + st->d_cap_rows / 2);
+    if (rows <= d->d_cap_rows) return STORM_B200_OK;
+    DeviceGuard guard(d->ctx.device);
+    uint64_t cap = std::max<uint64_t>({rows, c->m_data, d->d_cap_rows + d->d_cap_rows / 2});
     cap = (cap + 511) / 512 * 512;
     uint64_t* fresh = nullptr;
     if (cudaMalloc(&fresh, cap * st->stride * sizeof(uint64_t)) != cudaSuccess) {
         cudaGetLastError();
-        set_error("device arena of %llu rows x %llu words does not fit", (unsigned long long)cap, (unsigned long long)st->stride);
+        set_error("device arena of %llu rows x %llu words does not fit on device %d", (unsigned long long)cap,
+                  (unsigned long long)st->stride, d->ctx.device);
         return STORM_B200_ENOMEM;
     }
-    STORM_CUDA_TRY(cudaMemsetAsync(fresh, 0, cap * st->stride * sizeof(uint64_t), st->stream));
-    if (st->d_rows && st->uploaded_rows)
-        STORM_CUDA_TRY(cudaMemcpyAsync(fresh, st->d_rows, st->uploaded_rows * st->stride * sizeof(uint64_t),
-                                       cudaMemcpyDeviceToDevice, st->stream));
-    if (st->d_rows) {
-        STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));
-        cudaFree(st->d_rows);
+    STORM_CUDA_TRY(cudaMemsetAsync(fresh, 0, cap * st->stride * sizeof(uint64_t), d->ctx.copy_stream));
+    if (d->d_rows && st->uploaded_rows)
+        STORM_CUDA_TRY(cudaMemcpyAsync(fresh, d->d_rows, st->uploaded_rows * st->stride * sizeof(uint64_t),
+                                       cudaMemcpyDeviceToDevice, d->ctx.copy_stream));
+    if (d->d_rows) {
+        STORM_CUDA_TRY(cudaStreamSynchronize(d->ctx.copy_stream));
+        STORM_CUDA_TRY(cudaStreamSynchronize(d->ctx.stream));
+        cudaFree(d->d_rows);
     }
-    st->d_rows = fresh;
-    st->d_cap_rows = cap;
+    d->d_rows = fresh;
+    d->d_cap_rows = cap;
     return STORM_B200_OK;
 }
 
-// Bring rows [uploaded_rows, n_data) of the host mirror to the device.
-int sync_rows(STORM_contiguous_t* c, ContigState* st) {
-    int rc = ensure_device_rows(c, st, std::max<uint64_t>(c->n_data, 1));
-    if (rc) return rc;
-    if (st->uploaded_rows < c->n_data) {
-        const uint64_t W = c->n_bitmaps_vector, r0 = st->uploaded_rows, n = c->n_data - r0;
-        STORM_CUDA_TRY(cudaMemcpy2DAsync(st->d_rows + r0 * st->stride, st->stride * 8, c->data + r0 * W, W * 8,
-                                         W * 8, n, cudaMemcpyHostToDevice, st->stream));
-        st->uploaded_rows = c->n_data;
+inline HostRows mirror_of(const STORM_contiguous_t* c, const ContigState* st) {
+    return HostRows{c->data, c->n_bitmaps_vector, st->data_pinned};
+}
+
+// Request rows [uploaded_rows, upto) of the host mirror on every replica (each over its own PCIe link, copy stream).
+int upload_pending(STORM_contiguous_t* c, ContigState* st, uint64_t upto) {
+    for (ContigDev* d : st->devs) {
+        int rc = ensure_device_rows(c, st, d, std::max<uint64_t>(upto, 1));
+        if (rc) return rc;
+        if (st->uploaded_rows < upto && (rc = upload_rows(&d->ctx, d->d_rows, st->stride, mirror_of(c, st), c->n_bitmaps_vector, st->uploaded_rows, upto))) return rc;
     }
+    if (st->uploaded_rows < upto) st->uploaded_rows = upto;
     return STORM_B200_OK;
+}
+
+// Kernels on `stream` launched after this see every upload requested so far on the replica's copy stream.
+int order_after_uploads(ContigDev* d) {
+    DeviceGuard guard(d->ctx.device);
+    STORM_CUDA_TRY(cudaEventRecord(d->ctx.mark, d->ctx.copy_stream));
+    STORM_CUDA_TRY(cudaStreamWaitEvent(d->ctx.stream, d->ctx.mark, 0));
+    return STORM_B200_OK;
+}
+
+// Block the host until no copy of any replica reads the host mirror any more (before it is freed).
+void wait_uploads(ContigState* st) {
+    for (ContigDev* d : st->devs)
+        if (d->ctx.copy_stream) { DeviceGuard guard(d->ctx.device); cudaStreamSynchronize(d->ctx.copy_stream); }
 }
 
 template <typename T>
@@ -123,55 +164,69 @@ int grow_device(T** p, uint64_t* cap, uint64_t need) {
     if (need <= *cap) return STORM_B200_OK;
     if (*p) cudaFree(*p);
     *p = nullptr;
-    uint64_t n = std::max<uint64_t>(need, *cap * 2);
-    if (cudaMalloc(p, n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); *cap = 0; set_error("device allocation of %llu bytes failed", (unsigned long long)(n * sizeof(T))); return STORM_B200_ENOMEM; }
+    const uint64_t n = std::max<uint64_t>(need, *cap * 2);
+    *cap = 0;
+    if (cudaMalloc(p, n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); *p = nullptr; set_error("device allocation of %llu bytes failed", (unsigned long long)(n * sizeof(T))); return STORM_B200_ENOMEM; }
     *cap = n;
     return STORM_B200_OK;
 }
 
-// Upload the sparse-row metadata used by the *_list entry points.
-int sync_lists(STORM_contiguous_t* c, ContigState* st) {
-    if (st->list_rows_synced == c->n_data && st->d_pos_off) return STORM_B200_OK;
+// Host form of the sparse-row metadata used by the *_list entry points (rebuilt when rows were added).
+void build_list_meta(STORM_contiguous_t* c, ContigState* st) {
+    if (st->list_rows_built == c->n_data) return;
     const uint64_t n = c->n_data;
-    std::vector<uint64_t> off(n + 1);
-    std::vector<uint32_t> is_sparse(n), sparse_rows, dense_rows;
+    st->h_off.assign(n + 1, 0);
+    st->h_is_sparse.assign(n, 0);
+    st->h_sparse_rows.clear(); st->h_dense_rows.clear();
     for (uint64_t r = 0; r < n; ++r) {
         const bool sp = c->n_scalar[r] < c->scalar_cutoff;
-        is_sparse[r] = sp;
-        off[r] = st->pos_off[r];
-        (sp ? sparse_rows : dense_rows).push_back((uint32_t)r);
+        st->h_is_sparse[r] = sp;
+        st->h_off[r] = st->pos_off[r];
+        (sp ? st->h_sparse_rows : st->h_dense_rows).push_back((uint32_t)r);
     }
-    off[n] = c->tot_scalar;
     // off[r+1]-off[r] must be the list length for sparse rows: dense rows store nothing,
     // so consecutive offsets already delimit each sparse row's list.
-    if (st->d_meta_cap < n + 1) {
-        for (void* p : {(void*)st->d_pos_off, (void*)st->d_is_sparse, (void*)st->d_sparse_rows, (void*)st->d_dense_rows, (void*)st->d_group_start})
-            if (p) cudaFree(p);
-        const uint64_t cap = (n + 1) * 2;
-        STORM_CUDA_TRY(cudaMalloc(&st->d_group_start, (cap + 1) * sizeof(uint32_t)));
-        STORM_CUDA_TRY(cudaMalloc(&st->d_pos_off, cap * sizeof(uint64_t)));
-        STORM_CUDA_TRY(cudaMalloc(&st->d_is_sparse, cap * sizeof(uint32_t)));
-        STORM_CUDA_TRY(cudaMalloc(&st->d_sparse_rows, cap * sizeof(uint32_t)));
-        STORM_CUDA_TRY(cudaMalloc(&st->d_dense_rows, cap * sizeof(uint32_t)));
-        st->d_meta_cap = cap;
-    }
-    int rc = grow_device(&st->d_pos, &st->d_pos_cap, std::max<uint64_t>(c->tot_scalar, 1));
-    if (rc) return rc;
-    STORM_CUDA_TRY(cudaMemcpy(st->d_pos_off, off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    STORM_CUDA_TRY(cudaMemcpy(st->d_is_sparse, is_sparse.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (!sparse_rows.empty())
-        STORM_CUDA_TRY(cudaMemcpy(st->d_sparse_rows, sparse_rows.data(), sparse_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (!dense_rows.empty())
-        STORM_CUDA_TRY(cudaMemcpy(st->d_dense_rows, dense_rows.data(), dense_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (c->tot_scalar)
-        STORM_CUDA_TRY(cudaMemcpy(st->d_pos, c->scalar, c->tot_scalar * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    st->n_sparse = sparse_rows.size();
-    st->n_dense = dense_rows.size();
+    st->h_off[n] = c->tot_scalar;
+    st->n_sparse = st->h_sparse_rows.size();
+    st->n_dense = st->h_dense_rows.size();
     // every row sparse: the lists are a complete flat form of the matrix, which the row-group stream kernel can answer from
-    st->stream_ok = dense_rows.empty() && stream_groups(c->n_scalar, n, &st->h_group_start);
+    st->stream_ok = st->h_dense_rows.empty() && stream_groups(c->n_scalar, n, &st->h_group_start);
+    st->list_rows_built = n;
+}
+
+// ... and its copy on one replica.
+int sync_lists(STORM_contiguous_t* c, ContigState* st, ContigDev* d) {
+    build_list_meta(c, st);
+    if (d->list_rows_synced == c->n_data && d->d_pos_off) return STORM_B200_OK;
+    DeviceGuard guard(d->ctx.device);
+    const uint64_t n = c->n_data;
+    if (d->d_meta_cap < n + 1) {
+        for (void* p : {(void*)d->d_pos_off, (void*)d->d_is_sparse, (void*)d->d_sparse_rows, (void*)d->d_dense_rows, (void*)d->d_group_start})
+            if (p) cudaFree(p);
+        d->d_pos_off = nullptr; d->d_is_sparse = nullptr; d->d_sparse_rows = nullptr; d->d_dense_rows = nullptr; d->d_group_start = nullptr;
+        d->d_meta_cap = 0;                           // (a failed allocation below leaves a consistent, empty state)
+        d->list_rows_synced = 0;
+        const uint64_t cap = (n + 1) * 2;
+        STORM_CUDA_TRY(cudaMalloc(&d->d_group_start, (cap + 1) * sizeof(uint32_t)));
+        STORM_CUDA_TRY(cudaMalloc(&d->d_pos_off, cap * sizeof(uint64_t)));
+        STORM_CUDA_TRY(cudaMalloc(&d->d_is_sparse, cap * sizeof(uint32_t)));
+        STORM_CUDA_TRY(cudaMalloc(&d->d_sparse_rows, cap * sizeof(uint32_t)));
+        STORM_CUDA_TRY(cudaMalloc(&d->d_dense_rows, cap * sizeof(uint32_t)));
+        d->d_meta_cap = cap;
+    }
+    int rc = grow_device(&d->d_pos, &d->d_pos_cap, std::max<uint64_t>(c->tot_scalar, 1));
+    if (rc) return rc;
+    STORM_CUDA_TRY(cudaMemcpy(d->d_pos_off, st->h_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    STORM_CUDA_TRY(cudaMemcpy(d->d_is_sparse, st->h_is_sparse.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!st->h_sparse_rows.empty())
+        STORM_CUDA_TRY(cudaMemcpy(d->d_sparse_rows, st->h_sparse_rows.data(), st->h_sparse_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!st->h_dense_rows.empty())
+        STORM_CUDA_TRY(cudaMemcpy(d->d_dense_rows, st->h_dense_rows.data(), st->h_dense_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (c->tot_scalar)
+        STORM_CUDA_TRY(cudaMemcpy(d->d_pos, c->scalar, c->tot_scalar * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (st->stream_ok)
-        STORM_CUDA_TRY(cudaMemcpy(st->d_group_start, st->h_group_start.data(), st->h_group_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    st->list_rows_synced = n;
+        STORM_CUDA_TRY(cudaMemcpy(d->d_group_start, st->h_group_start.data(), st->h_group_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    d->list_rows_synced = n;
     return STORM_B200_OK;
 }
 
@@ -263,9 +318,9 @@ int launch_gather_rows(uint64_t* dst, const uint64_t* src, uint64_t stride, cons
 namespace {
 
 enum QueryMode { QUERY_DENSE = 0, QUERY_LIST = 1 };
-int g_list_route = 0;   // STORM_b200_set_contig_list_route: 0 cost model, 1 tile kernel, 2 tile + probe kernels, 3 stream kernel
+std::atomic<int> g_list_route{0};   // STORM_b200_set_contig_list_route: 0 cost model, 1 tile kernel, 2 tile + probe kernels, 3 stream kernel
 
-// Shared body of all contiguous queries.
+// Shared body of all contiguous queries.  Replica g of G answers shard (shard * G + g) of (n_shards * G); the host adds the G totals.
 uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uint32_t n_shards, int kernel) {
     if (c == nullptr) return (uint64_t)-1;                               // storm.c:1150,1176
     ContigState* st = state_of(c);
@@ -274,23 +329,33 @@ uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uin
         if (c->n_scalar == nullptr) return (uint64_t)-3;                 // storm.c:1246
     }
     if (c->n_data < 2) return 0;
-    DeviceGuard guard(st->device);
-    if (ensure_device_state(st)) return (uint64_t)-1;
+    DeviceGuard home(st->home_device);
+    if (ensure_devs(st)) return (uint64_t)-1;
+    const int G = (int)st->devs.size();
     const auto t0 = std::chrono::steady_clock::now();
-    cudaEventRecord(st->ev[0], st->stream);
-    if (sync_rows(c, st)) return (uint64_t)-1;
-    if (cudaMemsetAsync(st->d_total, 0, sizeof(unsigned long long), st->stream) != cudaSuccess) return (uint64_t)-1;
-    cudaEventRecord(st->ev[1], st->stream);
+    ContigDev* prim = st->devs[0];
+    { DeviceGuard guard(prim->ctx.device); cudaEventRecord(prim->ev[0], prim->ctx.stream); }
+    std::vector<DevCtx*> ctxs(G);
+    std::vector<uint64_t*> arenas(G);
+    for (int g = 0; g < G; ++g) {
+        ContigDev* d = st->devs[g];
+        if (ensure_device_rows(c, st, d, c->n_data)) return (uint64_t)-1;
+        if (order_after_uploads(d)) return (uint64_t)-1;                  // rows pushed while STORM_contig_add was running
+        DeviceGuard guard(d->ctx.device);
+        if (cudaMemsetAsync(d->ctx.d_total, 0, sizeof(unsigned long long), d->ctx.stream) != cudaSuccess) return (uint64_t)-1;
+        ctxs[g] = &d->ctx; arenas[g] = d->d_rows;
+    }
+    { DeviceGuard guard(prim->ctx.device); cudaEventRecord(prim->ev[1], prim->ctx.stream); }
 
     int rc = STORM_B200_OK;
     bool hybrid = false, stream = false;
     if (mode == QUERY_LIST) {
-        if ((rc = sync_lists(c, st))) return (uint64_t)-1;
+        build_list_meta(c, st);
         // storm.c:1253-1258 switches per pair between the probe and the bitmap kernel; both give |i AND j|, so the
         // switch is a cost decision here (fitted: tile kernel 6e13 wp/s; probe kernel 0.08 ns + 1.3 ps per value
         // and pair, profiles/r01_configs_c1_c4_full.jsonl; stream kernel: stream_seconds): all rows through the
         // tile kernel, or dense x dense pairs through it and the rest probed, or -- when every row is a list --
-        // the row-group stream kernel over the lists.
+        // the row-group stream kernel over the lists.  A pure function of the container: every shard decides alike.
         const double N = (double)c->n_data, W = (double)c->n_bitmaps_vector, pairs = 0.5 * N * (N - 1.0);
         const double avg = (double)c->tot_scalar / std::max(1.0, (double)st->n_sparse);
         const double nd = (double)st->n_dense;
@@ -298,73 +363,102 @@ uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uin
         const double hybrid_s = 0.5 * nd * (nd - 1.0) * W / 6e13 + (nd >= 2 ? 3e-5 + nd * W * 8 / 2e12 : 0.0) +
                                 (pairs - 0.5 * nd * (nd - 1.0)) * (0.08e-9 + 1.3e-12 * avg) + 1e-5;
         const double stream_s = st->stream_ok ? stream_seconds(pairs, avg) : 1e30;
+        const int forced = g_list_route.load();
         if (st->n_sparse > 0) {
             stream = stream_s < tile_all_s && stream_s < hybrid_s;
             hybrid = !stream && hybrid_s < tile_all_s;
-            if (g_list_route == 1) { stream = false; hybrid = false; }
-            if (g_list_route == 2) { stream = false; hybrid = true; }
-            if (g_list_route == 3) { stream = st->stream_ok; hybrid = !stream; }
+            if (forced == 1) { stream = false; hybrid = false; }
+            if (forced == 2) { stream = false; hybrid = true; }
+            if (forced == 3) { stream = st->stream_ok; hybrid = !stream; }
         }
         st->last_list_route = stream ? 3 : hybrid ? 2 : 1;
     }
-    if (stream) {
-        rc = launch_sparse_stream(st->d_pos_off, st->d_pos, st->h_group_start, st->d_group_start, st->d_pos_off, st->d_pos,
-                                  c->tot_scalar, 0, c->n_data, 0, c->n_data, 1, shard, n_shards, st->d_total, st->stream);
-    } else if (!hybrid) {
-        rc = pairw_triangle(st->d_rows, c->n_data, c->n_bitmaps_vector, st->stride, shard, n_shards, kernel,
-                            reinterpret_cast<uint64_t*>(st->d_total), st->stream);
+    if (!stream && !hybrid) {
+        // every pair through the tile kernel: rows not yet on the devices go up band by band (1/G of a band per
+        // PCIe link, the rest from the peers) while the tiles of the bands already complete are being computed
+        rc = banded_triangle(ctxs.data(), arenas.data(), G, st->stride, mirror_of(c, st), st->uploaded_rows, c->n_data,
+                             c->n_bitmaps_vector, shard, n_shards, kernel);
+        if (!rc) st->uploaded_rows = c->n_data;
     } else {
-        // per-pair dispatch of storm.c:1253-1258: dense x dense pairs -> tile kernel on the
-        // compacted dense rows; every pair with a sparse row -> probe kernel.
-        if (st->n_dense >= 2) {
-            if (st->d_gather_cap < st->n_dense * st->stride) {
-                if (st->d_gather) cudaFree(st->d_gather);
-                st->d_gather = nullptr; st->d_gather_cap = 0;
-                if (cudaMalloc(&st->d_gather, st->n_dense * st->stride * 8) != cudaSuccess) {
-                    cudaGetLastError(); set_error("device allocation for the dense-row gather failed"); return (uint64_t)-1;
-                }
-                st->d_gather_cap = st->n_dense * st->stride;
+        if (!stream && (upload_pending(c, st, c->n_data))) return (uint64_t)-1;          // the probe kernel reads the bitmaps
+        for (int g = 0; g < G && !rc; ++g) {
+            ContigDev* d = st->devs[g];
+            const uint32_t sh = shard * (uint32_t)G + (uint32_t)g, nsh = n_shards * (uint32_t)G;
+            if ((rc = sync_lists(c, st, d))) break;
+            DeviceGuard guard(d->ctx.device);
+            if (stream) {
+                rc = launch_sparse_stream(d->d_pos_off, d->d_pos, st->h_group_start, d->d_group_start, d->d_pos_off, d->d_pos,
+                                          c->tot_scalar, 0, c->n_data, 0, c->n_data, 1, sh, nsh, d->ctx.d_total, d->ctx.stream);
+                continue;
             }
-            rc = launch_gather_rows(st->d_gather, st->d_rows, st->stride, st->d_dense_rows, st->n_dense, st->stream);
-            if (!rc) rc = pairw_triangle(st->d_gather, st->n_dense, c->n_bitmaps_vector, st->stride, shard, n_shards,
-                                         kernel, reinterpret_cast<uint64_t*>(st->d_total), st->stream);
-        }
-        if (!rc) {
-            uint64_t b, e;
-            shard_range(st->n_sparse, shard, n_shards, &b, &e);
-            rc = launch_contig_probe(st->d_rows, st->stride, c->n_data, st->d_is_sparse, st->d_sparse_rows + b, e - b,
-                                     st->d_pos, st->d_pos_off, st->d_total, st->stream);
+            if ((rc = order_after_uploads(d))) break;
+            // per-pair dispatch of storm.c:1253-1258: dense x dense pairs -> tile kernel on the
+            // compacted dense rows; every pair with a sparse row -> probe kernel.
+            if (st->n_dense >= 2) {
+                if (d->d_gather_cap < st->n_dense * st->stride) {
+                    if (d->d_gather) cudaFree(d->d_gather);
+                    d->d_gather = nullptr; d->d_gather_cap = 0;
+                    if (cudaMalloc(&d->d_gather, st->n_dense * st->stride * 8) != cudaSuccess) {
+                        cudaGetLastError(); d->d_gather = nullptr; set_error("device allocation for the dense-row gather failed"); return (uint64_t)-1;
+                    }
+                    d->d_gather_cap = st->n_dense * st->stride;
+                }
+                rc = launch_gather_rows(d->d_gather, d->d_rows, st->stride, d->d_dense_rows, st->n_dense, d->ctx.stream);
+                if (!rc) rc = pairw_triangle(d->d_gather, st->n_dense, c->n_bitmaps_vector, st->stride, sh, nsh,
+                                             kernel, reinterpret_cast<uint64_t*>(d->ctx.d_total), d->ctx.stream);
+            }
+            if (!rc) {
+                uint64_t b, e;
+                shard_range(st->n_sparse, sh, nsh, &b, &e);
+                rc = launch_contig_probe(d->d_rows, st->stride, c->n_data, d->d_is_sparse, d->d_sparse_rows + b, e - b,
+                                         d->d_pos, d->d_pos_off, d->ctx.d_total, d->ctx.stream);
+            }
         }
     }
     if (rc) return (uint64_t)-1;
-    cudaEventRecord(st->ev[2], st->stream);
-    if (cudaMemcpyAsync(st->h_total, st->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
-        cudaStreamSynchronize(st->stream) != cudaSuccess) {
-        set_error("query failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return (uint64_t)-1;
-    }
+    { DeviceGuard guard(prim->ctx.device); cudaEventRecord(prim->ev[2], prim->ctx.stream); }
+    const uint64_t total = collect_totals(ctxs.data(), G, "query");
+    if (total == (uint64_t)-1) return total;
     float up = 0, kn = 0;
-    cudaEventElapsedTime(&up, st->ev[0], st->ev[1]);
-    cudaEventElapsedTime(&kn, st->ev[1], st->ev[2]);
+    cudaEventElapsedTime(&up, prim->ev[0], prim->ev[1]);
+    cudaEventElapsedTime(&kn, prim->ev[1], prim->ev[2]);
     st->timing[0] = up * 1e-3;
     st->timing[1] = kn * 1e-3;
     st->timing[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    return *st->h_total;
+    return total;
+}
+
+// The host mirror (public field `data`): page-locked when a device is there, so that uploads are direct DMA at
+// PCIe rate and can run while STORM_contig_add is still being called; plain memory on a box without one.
+uint64_t* alloc_mirror(uint64_t bytes, bool* pinned) {
+    void* p = nullptr;
+    *pinned = false;
+    if (have_device() && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) { *pinned = true; return (uint64_t*)p; }
+    cudaGetLastError();
+    if (posix_memalign(&p, 4096, bytes)) return nullptr;
+    return (uint64_t*)p;
+}
+void free_mirror(uint64_t* p, bool pinned) {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
 }
 
 int grow_host_rows(STORM_contiguous_t* c, uint64_t need) {
     if (need <= c->m_data) return 0;
+    ContigState* st = state_of(c);
     uint64_t cap = std::max<uint64_t>({need, (uint64_t)512, c->m_data * 2});     // geometric, not +512 (storm.c:1078-1100)
     const uint64_t W = c->n_bitmaps_vector;
-    void* fresh = nullptr;
-    if (posix_memalign(&fresh, 64, std::max<uint64_t>(cap * W * 8, 64))) return -1;
+    bool pinned = false;
+    uint64_t* fresh = alloc_mirror(std::max<uint64_t>(cap * W * 8, 64), &pinned);
+    if (!fresh) return -1;
     if (c->data) memcpy(fresh, c->data, c->n_data * W * 8);
-    memset((uint64_t*)fresh + c->n_data * W, 0, (cap - c->n_data) * W * 8);
+    memset(fresh + c->n_data * W, 0, (cap - c->n_data) * W * 8);
     uint32_t* ns = (uint32_t*)realloc(c->n_scalar, cap * sizeof(uint32_t));
     STORM_contiguous_bitmap_t* bm = (STORM_contiguous_bitmap_t*)realloc(c->bitmaps, cap * sizeof(STORM_contiguous_bitmap_t));
-    if (!ns || !bm) { free(fresh); if (ns) c->n_scalar = ns; if (bm) c->bitmaps = bm; return -1; }
-    free(c->data);
-    c->data = (uint64_t*)fresh; c->n_scalar = ns; c->bitmaps = bm; c->m_data = cap;
+    if (!ns || !bm) { free_mirror(fresh, pinned); if (ns) c->n_scalar = ns; if (bm) c->bitmaps = bm; return -1; }
+    wait_uploads(st);                                                     // copies in flight still read the old mirror
+    free_mirror(c->data, st->data_pinned);
+    c->data = fresh; st->data_pinned = pinned; c->n_scalar = ns; c->bitmaps = bm; c->m_data = cap;
     for (uint64_t i = 0; i < cap; ++i) {
         c->bitmaps[i].data = c->data + i * W;
         if (i >= c->n_data) { c->bitmaps[i].scalar = nullptr; c->bitmaps[i].n_scalar = 0; }
@@ -383,142 +477,108 @@ int grow_host_scalar(STORM_contiguous_t* c, ContigState* st, uint64_t need) {
     return 0;
 }
 
-// ---- scratch arena for the raw-buffer wrappers ----------------------------------
-constexpr int MAX_UPLOAD_CHUNKS = 16;
-constexpr uint64_t MIN_UPLOAD_CHUNK_BYTES = 32ull << 20;
-struct Scratch {
-    std::mutex mu;
-    int device = -1;
+// ---- scratch arenas of the raw-buffer wrappers: one per device of the current device set ---------------------
+struct WrapDev {
+    DevCtx ctx;
     uint64_t* d_rows = nullptr; uint64_t cap_words = 0;
-    unsigned long long* d_total = nullptr; unsigned long long* h_total = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;          // uploads of a streamed query run ahead of its kernels here
-    cudaEvent_t chunk_ready[MAX_UPLOAD_CHUNKS] = {};
-    cudaEvent_t idle = nullptr;
 };
-Scratch g_scratch;
+struct WrapState {
+    std::mutex mu;
+    std::vector<int> ids;
+    std::vector<WrapDev*> devs;
+};
+WrapState g_wrap;
 
-int scratch_prepare(uint64_t words) {
-    int rc = require_device();
-    if (rc) return rc;
-    int dev = 0;
-    STORM_CUDA_TRY(cudaGetDevice(&dev));
-    Scratch& s = g_scratch;
-    if (s.device != dev) {                       // first use, or the caller switched device
-        if (s.d_rows) cudaFree(s.d_rows);
-        if (s.d_total) cudaFree(s.d_total);
-        if (s.h_total) cudaFreeHost(s.h_total);
-        if (s.stream) cudaStreamDestroy(s.stream);
-        if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
-        for (cudaEvent_t& e : s.chunk_ready) { if (e) cudaEventDestroy(e); e = nullptr; }
-        if (s.idle) cudaEventDestroy(s.idle);
-        s.d_rows = nullptr; s.cap_words = 0; s.d_total = nullptr; s.h_total = nullptr; s.stream = nullptr;
-        s.copy_stream = nullptr; s.idle = nullptr;
-        s.device = dev;
-        STORM_CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        STORM_CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
-        for (cudaEvent_t& e : s.chunk_ready) STORM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        STORM_CUDA_TRY(cudaEventCreateWithFlags(&s.idle, cudaEventDisableTiming));
-        STORM_CUDA_TRY(cudaMalloc(&s.d_total, 8));
-        STORM_CUDA_TRY(cudaMallocHost(&s.h_total, 8));
+void wrap_teardown() {
+    for (WrapDev* d : g_wrap.devs) {
+        if (d->ctx.device >= 0) { DeviceGuard guard(d->ctx.device); if (d->d_rows) cudaFree(d->d_rows); }
+        d->ctx.destroy();
+        delete d;
     }
-    if (words > s.cap_words) {
-        if (s.d_rows) cudaFree(s.d_rows);
-        s.d_rows = nullptr; s.cap_words = 0;
-        if (cudaMalloc(&s.d_rows, words * 8) != cudaSuccess) {
-            cudaGetLastError(); set_error("scratch arena of %llu bytes does not fit", (unsigned long long)(words * 8));
+    g_wrap.devs.clear();
+    g_wrap.ids.clear();
+}
+
+// Arenas of `words` words on the first n_use devices of the set (all of them for n_use <= 0).
+int wrap_prepare(uint64_t words, int n_use) {
+    std::vector<int> ids;
+    int rc = query_devices(&ids);
+    if (rc) return rc;
+    if (ids != g_wrap.ids) {                         // first use, or the device set / the caller's device changed
+        wrap_teardown();
+        enable_peers(ids);
+        for (int id : ids) {
+            WrapDev* d = new (std::nothrow) WrapDev();
+            if (!d) { set_error("out of host memory"); return STORM_B200_ENOMEM; }
+            g_wrap.devs.push_back(d);
+            if ((rc = d->ctx.init(id))) { wrap_teardown(); return rc; }
+        }
+        g_wrap.ids = ids;
+    }
+    const int n = n_use <= 0 ? (int)g_wrap.devs.size() : std::min<int>(n_use, (int)g_wrap.devs.size());
+    for (int g = 0; g < n; ++g) {
+        WrapDev* d = g_wrap.devs[g];
+        if (words <= d->cap_words) continue;
+        DeviceGuard guard(d->ctx.device);
+        if (d->d_rows) cudaFree(d->d_rows);
+        d->d_rows = nullptr; d->cap_words = 0;
+        if (cudaMalloc(&d->d_rows, words * 8) != cudaSuccess) {
+            cudaGetLastError(); d->d_rows = nullptr; set_error("scratch arena of %llu bytes does not fit on device %d", (unsigned long long)(words * 8), d->ctx.device);
             return STORM_B200_ENOMEM;
         }
-        s.cap_words = words;
+        d->cap_words = words;
     }
     return STORM_B200_OK;
 }
 
 inline uint64_t padded_stride(uint64_t n_words) { return (n_words + ROW_ALIGN_WORDS - 1) / ROW_ALIGN_WORDS * ROW_ALIGN_WORDS; }
 
-// Upload a host matrix with row pitch n_ints into the scratch arena at word offset `at`.
-int scratch_upload(const uint64_t* vals, uint64_t n_vectors, uint64_t n_ints, uint64_t stride, uint64_t at) {
-    Scratch& s = g_scratch;
-    if (stride != n_ints)    // padding columns must read as zero
-        STORM_CUDA_TRY(cudaMemsetAsync(s.d_rows + at, 0, n_vectors * stride * 8, s.stream));
-    STORM_CUDA_TRY(cudaMemcpy2DAsync(s.d_rows + at, stride * 8, vals, n_ints * 8, n_ints * 8, n_vectors,
-                                     cudaMemcpyHostToDevice, s.stream));
+// Upload a whole host matrix into the primary scratch arena at word offset `at`, ordered before later work on its stream.
+int wrap_upload_primary(const uint64_t* vals, uint64_t n_vectors, uint64_t n_ints, uint64_t stride, uint64_t at) {
+    WrapDev* d = g_wrap.devs[0];
+    int rc = upload_rows(&d->ctx, d->d_rows + at, stride, HostRows{vals, n_ints, host_pointer_is_pinned(vals)}, (uint32_t)n_ints, 0, n_vectors);
+    if (rc) return rc;
+    DeviceGuard guard(d->ctx.device);
+    STORM_CUDA_TRY(cudaEventRecord(d->ctx.mark, d->ctx.copy_stream));
+    STORM_CUDA_TRY(cudaStreamWaitEvent(d->ctx.stream, d->ctx.mark, 0));
     return STORM_B200_OK;
 }
 
-// Host-buffer query with the upload hidden behind the kernels.  The triangle raster is monotone in the
-// largest row a tile touches (common.cuh), so the matrix is uploaded in row chunks on a copy stream and
-// the tiles that only need the rows uploaded so far are launched as soon as their chunk has landed:
-// the query takes one chunk of PCIe time plus the kernel time instead of the whole upload plus the kernels.
-int streamed_triangle(const uint64_t* vals, uint64_t n_vectors, uint64_t n_ints, uint64_t stride,
-                      uint32_t shard, uint32_t n_shards, int kernel) {
-    Scratch& s = g_scratch;
-    kernel = resolve_kernel_for_rows(kernel, s.d_rows, n_vectors, (uint32_t)n_ints, stride);
-    const TileShape ts = tile_shape_for(kernel);
-    std::vector<uint64_t> prefix;
-    uint32_t nbi = 0, nbj = 0;
-    const uint64_t n_tiles = triangle_prefix(n_vectors, ts, &prefix, &nbi, &nbj);
-    uint64_t tb = 0, te = 0;
-    shard_range(n_tiles, shard, n_shards, &tb, &te);
-    const uint64_t group_rows = (uint64_t)TRI_GROUP * ts.tn;               // rows a raster group adds
-    const uint64_t n_groups = prefix.size() - 1;
-    // chunks of whole groups, at least MIN_UPLOAD_CHUNK_BYTES each, at most MAX_UPLOAD_CHUNKS of them
-    uint64_t groups_per_chunk = std::max<uint64_t>(1, (MIN_UPLOAD_CHUNK_BYTES + group_rows * n_ints * 8 - 1) / (group_rows * n_ints * 8));
-    groups_per_chunk = std::max(groups_per_chunk, (n_groups + MAX_UPLOAD_CHUNKS - 1) / MAX_UPLOAD_CHUNKS);
-    // the copy stream must not overwrite the arena while an earlier query's kernels still read it
-    STORM_CUDA_TRY(cudaEventRecord(s.idle, s.stream));
-    STORM_CUDA_TRY(cudaStreamWaitEvent(s.copy_stream, s.idle, 0));
-    int chunk = 0;
-    for (uint64_t g0 = 0; g0 < n_groups; g0 += groups_per_chunk, ++chunk) {
-        const uint64_t g1 = std::min(n_groups, g0 + groups_per_chunk);
-        const uint64_t r0 = g0 * group_rows, r1 = std::min<uint64_t>(n_vectors, g1 * group_rows);
-        if (r1 > r0) {
-            uint64_t* dst = s.d_rows + r0 * stride;
-            if (stride != n_ints) STORM_CUDA_TRY(cudaMemsetAsync(dst, 0, (r1 - r0) * stride * 8, s.copy_stream));
-            STORM_CUDA_TRY(cudaMemcpy2DAsync(dst, stride * 8, vals + r0 * n_ints, n_ints * 8, n_ints * 8, r1 - r0,
-                                             cudaMemcpyHostToDevice, s.copy_stream));
-        }
-        STORM_CUDA_TRY(cudaEventRecord(s.chunk_ready[chunk], s.copy_stream));
-        const uint64_t t0 = std::max(tb, prefix[g0]), t1 = std::min(te, prefix[g1]);
-        if (t1 > t0) {
-            STORM_CUDA_TRY(cudaStreamWaitEvent(s.stream, s.chunk_ready[chunk], 0));
-            int rc = pairw_triangle_range(s.d_rows, n_vectors, (uint32_t)n_ints, stride, t0, t1, kernel,
-                                          reinterpret_cast<uint64_t*>(s.d_total), s.stream);
-            if (rc) return rc;
-        }
-    }
-    // later queries on s.stream may reuse the arena: order them after the last upload as well
-    STORM_CUDA_TRY(cudaStreamWaitEvent(s.stream, s.chunk_ready[chunk - 1], 0));
-    return STORM_B200_OK;
-}
-
+// STORM_wrapper_diag[_blocked] (storm.c:132-150, 222-279) and its sharded / set-operation forms.  The host matrix
+// goes up band by band over every device of the set (devices.h: banded_triangle) and the tiles that only need the
+// rows already there start at once: the query costs about one band of upload plus the kernel time.
 uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_ints,
                            uint32_t shard = 0, uint32_t n_shards = 1, int kernel = STORM_B200_KERNEL_AUTO,
                            int op = STORM_B200_OP_INTERSECT) {
     if (vals == nullptr || n_ints == 0) { set_error("STORM_wrapper_diag: NULL buffer or zero width"); return (uint64_t)-1; }
     if (n_shards == 0 || shard >= n_shards) { set_error("shard %u of %u", shard, n_shards); return (uint64_t)-1; }
+    if (op < 0) return (uint64_t)-1;                                     // unrecognised per-pair function (error already set)
     if (n_vectors < 2) return 0;
-    std::lock_guard<std::mutex> lock(g_scratch.mu);
+    std::lock_guard<std::mutex> lock(g_wrap.mu);
     const uint64_t stride = padded_stride(n_ints);
-    if (scratch_prepare(n_vectors * stride)) return (uint64_t)-1;
-    Scratch& s = g_scratch;
-    if (cudaMemsetAsync(s.d_total, 0, 8, s.stream) != cudaSuccess) return (uint64_t)-1;
-    if (op == STORM_B200_OP_INTERSECT && n_vectors * n_ints * 8 >= 2 * MIN_UPLOAD_CHUNK_BYTES) {
-        if (streamed_triangle(vals, n_vectors, n_ints, stride, shard, n_shards, kernel)) return (uint64_t)-1;
-    } else if (scratch_upload(vals, n_vectors, n_ints, stride, 0)) {
-        return (uint64_t)-1;
-    } else if (op != STORM_B200_OP_INTERSECT) {
-        if (n_shards != 1) { set_error("set operations other than intersect are not sharded"); return (uint64_t)-1; }
-        if (pairw_rect_op(s.d_rows, n_vectors, stride, 0, s.d_rows, n_vectors, stride, 0, (uint32_t)n_ints, 1, op, kernel, true,
-                          nullptr, 0, reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
-    } else if (pairw_triangle(s.d_rows, n_vectors, (uint32_t)n_ints, stride, shard, n_shards, kernel,
-                              reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
-    if (cudaMemcpyAsync(s.h_total, s.d_total, 8, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
-        cudaStreamSynchronize(s.stream) != cudaSuccess) {
-        set_error("STORM_wrapper_diag failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return (uint64_t)-1;
+    const bool all = op == STORM_B200_OP_INTERSECT;
+    if (wrap_prepare(n_vectors * stride, all ? 0 : 1)) return (uint64_t)-1;
+    const int G = all ? (int)g_wrap.devs.size() : 1;
+    std::vector<DevCtx*> ctxs(G);
+    std::vector<uint64_t*> arenas(G);
+    for (int g = 0; g < G; ++g) {
+        WrapDev* d = g_wrap.devs[g];
+        DeviceGuard guard(d->ctx.device);
+        if (cudaMemsetAsync(d->ctx.d_total, 0, 8, d->ctx.stream) != cudaSuccess) return (uint64_t)-1;
+        ctxs[g] = &d->ctx; arenas[g] = d->d_rows;
     }
-    return *s.h_total;
+    if (all) {
+        if (banded_triangle(ctxs.data(), arenas.data(), G, stride, HostRows{vals, n_ints, host_pointer_is_pinned(vals)}, 0, n_vectors,
+                            (uint32_t)n_ints, shard, n_shards, kernel)) return (uint64_t)-1;
+    } else {
+        if (n_shards != 1) { set_error("set operations other than intersect are not sharded"); return (uint64_t)-1; }
+        if (wrap_upload_primary(vals, n_vectors, n_ints, stride, 0)) return (uint64_t)-1;
+        WrapDev* d = g_wrap.devs[0];
+        DeviceGuard guard(d->ctx.device);
+        if (pairw_rect_op(d->d_rows, n_vectors, stride, 0, d->d_rows, n_vectors, stride, 0, (uint32_t)n_ints, 1, op, kernel, true,
+                          nullptr, 0, reinterpret_cast<uint64_t*>(d->ctx.d_total), d->ctx.stream)) return (uint64_t)-1;
+    }
+    return collect_totals(ctxs.data(), G, "STORM_wrapper_diag");
 }
 
 }  // namespace
@@ -528,14 +588,45 @@ uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_
 // C ABI: storm.h contiguous entry points
 // =================================================================================
 extern "C" {
+uint64_t STORM_b200_host_intersect_count(const uint64_t* a, const uint64_t* b, const size_t n);
 uint64_t STORM_b200_host_union_count(const uint64_t* a, const uint64_t* b, const size_t n);
 uint64_t STORM_b200_host_diff_count(const uint64_t* a, const uint64_t* b, const size_t n);
 }
 namespace storm {
+// Which set operation a caller's per-pair kernel stands for.  The reference's raw-buffer loops apply whatever
+// STORM_compute_func they are handed (storm.c:132-150); host code cannot run on the device, so the function is
+// identified instead: this library's own three by address, anything else -- libalgebra's static kernels of the
+// caller's translation unit, a hand-written one -- by what it returns on three small probe vectors (and / or / xor
+// counts differ on each).  NULL means intersect.  A function that is none of the three gets the error sentinel:
+// answering it with an intersect total would be silently wrong.
 int op_of_compute_func(const STORM_compute_func f) {
+    if (f == nullptr || f == &STORM_b200_host_intersect_count) return STORM_B200_OP_INTERSECT;
     if (f == &STORM_b200_host_union_count) return STORM_B200_OP_UNION;
     if (f == &STORM_b200_host_diff_count) return STORM_B200_OP_DIFF;
-    return STORM_B200_OP_INTERSECT;
+    static std::mutex mu;
+    static std::vector<std::pair<STORM_compute_func, int>> seen;            // a caller passes the same pointer every time
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& e : seen) if (e.first == f) { if (e.second < 0) set_error("STORM_compute_func %p is neither an intersect, a union nor a diff count", (void*)f); return e.second; }
+    alignas(64) uint64_t a[3][72], b[3][72];
+    const size_t len[3] = {1, 7, 72};                                      // below, across and above the SIMD widths of libalgebra's kernels
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    auto next = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    bool is_and = true, is_or = true, is_xor = true;
+    for (int t = 0; t < 3; ++t) {
+        uint64_t want_and = 0, want_or = 0, want_xor = 0;
+        for (size_t k = 0; k < len[t]; ++k) {
+            a[t][k] = next() | next(); b[t][k] = next() & next();          // different densities: the three counts differ
+            want_and += (uint64_t)__builtin_popcountll(a[t][k] & b[t][k]);
+            want_or += (uint64_t)__builtin_popcountll(a[t][k] | b[t][k]);
+            want_xor += (uint64_t)__builtin_popcountll(a[t][k] ^ b[t][k]);
+        }
+        const uint64_t got = f(a[t], b[t], len[t]);
+        is_and = is_and && got == want_and; is_or = is_or && got == want_or; is_xor = is_xor && got == want_xor;
+    }
+    const int op = is_and ? STORM_B200_OP_INTERSECT : is_or ? STORM_B200_OP_UNION : is_xor ? STORM_B200_OP_DIFF : -1;
+    if (seen.size() < 64) seen.emplace_back(f, op);
+    if (op < 0) set_error("STORM_compute_func %p is neither an intersect, a union nor a diff count", (void*)f);
+    return op;
 }
 }  // namespace storm
 
@@ -554,26 +645,33 @@ STORM_contiguous_t* STORM_contig_new(size_t vector_length) {               // st
     c->alignment = 64;
     c->intsec_func = &host_intersect_count;
     c->scalar_cutoff = (uint32_t)(vector_length / 200 > 200 ? 200 : vector_length / 200);
-    int n = 0;                                   // remember the creating thread's device, if any
-    if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) cudaGetDevice(&st->device); else cudaGetLastError();
+    if (have_device()) cudaGetDevice(&st->home_device);                   // remember the creating thread's device, if any
     return c;
 }
 
 void STORM_contig_free(STORM_contiguous_t* c) {                             // storm.c:1020-1029
     if (c == nullptr) return;
     ContigState* st = state_of(c);
+    bool pinned = false;
     if (st) {
-        DeviceGuard guard(st->device);
-        if (st->stream) cudaStreamSynchronize(st->stream);
-        for (void* p : {(void*)st->d_rows, (void*)st->d_pos, (void*)st->d_pos_off, (void*)st->d_is_sparse,
-                        (void*)st->d_sparse_rows, (void*)st->d_dense_rows, (void*)st->d_group_start, (void*)st->d_gather, (void*)st->d_total})
-            if (p) cudaFree(p);
-        if (st->h_total) cudaFreeHost(st->h_total);
-        for (auto e : st->ev) if (e) cudaEventDestroy(e);
-        if (st->stream) cudaStreamDestroy(st->stream);
+        pinned = st->data_pinned;
+        for (ContigDev* d : st->devs) {
+            if (d->ctx.device >= 0) {
+                DeviceGuard guard(d->ctx.device);
+                if (d->ctx.stream) cudaStreamSynchronize(d->ctx.stream);
+                if (d->ctx.copy_stream) cudaStreamSynchronize(d->ctx.copy_stream);
+                for (void* p : {(void*)d->d_rows, (void*)d->d_pos, (void*)d->d_pos_off, (void*)d->d_is_sparse,
+                                (void*)d->d_sparse_rows, (void*)d->d_dense_rows, (void*)d->d_group_start, (void*)d->d_gather})
+                    if (p) cudaFree(p);
+                for (auto e : d->ev) if (e) cudaEventDestroy(e);
+            }
+            d->ctx.destroy();
+            delete d;
+        }
         delete st;
     }
-    free(c->data); free(c->scalar); free(c->n_scalar); free(c->bitmaps);
+    free_mirror(c->data, pinned);
+    free(c->scalar); free(c->n_scalar); free(c->bitmaps);
     free(c);
 }
 
@@ -611,6 +709,14 @@ int STORM_contig_add(STORM_contiguous_t* c, const uint32_t* values, const uint32
     c->n_scalar[c->n_data] = used;                                        // :1132-1133
     view->n_scalar = used;
     ++c->n_data;                                                          // :1134
+    // Rows are append-only and complete once this call returns, and the mirror is page-locked: every few megabytes of
+    // finished rows are handed to the copy engines right away, so that the first query finds (nearly) all rows
+    // resident instead of paying for the whole upload.  Failures here are not errors of the add: the query retries.
+    if (st->data_pinned && st->dev_status >= 0 &&
+        (c->n_data - st->uploaded_rows) * (uint64_t)c->n_bitmaps_vector * 8 >= BG_UPLOAD_BYTES) {
+        DeviceGuard home(st->home_device);
+        if (ensure_devs(st) || upload_pending(c, st, c->n_data)) { if (st->dev_status == 0) st->dev_status = -1; }
+    }
     return (int)n_values;                                                 // :1136
 }
 
@@ -622,10 +728,13 @@ int STORM_contig_clear(STORM_contiguous_t* c) {                            // st
     c->tot_scalar = 0;
     ContigState* st = state_of(c);
     st->uploaded_rows = 0;
-    st->list_rows_synced = 0;
-    if (st->d_rows) {
-        DeviceGuard guard(st->device);
-        cudaMemsetAsync(st->d_rows, 0, st->d_cap_rows * st->stride * 8, st->stream);
+    st->list_rows_built = (uint64_t)-1;
+    for (ContigDev* d : st->devs) {
+        d->list_rows_synced = 0;
+        if (d->d_rows) {                                                  // on the copy stream: ordered after any upload still in flight, before the next one
+            DeviceGuard guard(d->ctx.device);
+            cudaMemsetAsync(d->d_rows, 0, d->d_cap_rows * st->stride * 8, d->ctx.copy_stream);
+        }
     }
     return 1;
 }
@@ -642,8 +751,8 @@ uint64_t STORM_contig_pairw_intersect_cardinality_blocked(STORM_contiguous_t* c,
 }
 
 int STORM_b200_set_contig_list_route(int route) {
-    const int prev = g_list_route;
-    if (route >= 0 && route <= 3) g_list_route = route;
+    const int prev = g_list_route.load();
+    if (route >= 0 && route <= 3) g_list_route.store(route);
     return prev;
 }
 
@@ -663,13 +772,8 @@ uint64_t STORM_contig_pairw_intersect_cardinality_blocked_list(STORM_contiguous_
     return contig_query(c, QUERY_LIST, 0, 1, STORM_B200_KERNEL_AUTO);
 }
 
-// ---- raw-buffer wrappers (storm.c:132-369) ---------------------------------------
 // ---- per-pair kernel pointers (libalgebra.h:3035, 3094-3236) ----------------------------------
-// The reference's raw-buffer loops apply whatever STORM_compute_func the caller hands them.  Host code
-// cannot run on the device, but the three families libalgebra offers can be told apart by address:
-// these exported functions are what the STORM_get_*_count_func choosers of this library return, and a
-// wrapper that receives the union or diff one answers with that set operation (setops.cu).  Any other
-// pointer, including NULL and the reference's own static kernels, means intersect.
+// These exported functions are what the STORM_get_*_count_func choosers of this library return.
 uint64_t STORM_b200_host_intersect_count(const uint64_t* a, const uint64_t* b, const size_t n) {
     return host_intersect_count(a, b, n);
 }
@@ -687,6 +791,7 @@ STORM_compute_func STORM_get_intersect_count_func(const size_t n_bitmaps_vector)
 STORM_compute_func STORM_get_union_count_func(const size_t n_bitmaps_vector) { (void)n_bitmaps_vector; return &STORM_b200_host_union_count; }
 STORM_compute_func STORM_get_diff_count_func(const size_t n_bitmaps_vector) { (void)n_bitmaps_vector; return &STORM_b200_host_diff_count; }
 
+// ---- raw-buffer wrappers (storm.c:132-369) ---------------------------------------
 uint64_t STORM_wrapper_diag(const uint32_t n_vectors, const uint64_t* vals, const uint32_t n_ints, const STORM_compute_func f) {
     return wrapper_diag_impl(n_vectors, vals, n_ints, 0, 1, STORM_B200_KERNEL_AUTO, op_of_compute_func(f));
 }
@@ -701,42 +806,41 @@ uint64_t STORM_wrapper_square(const uint32_t n_vectors1, const uint64_t* STORM_R
                               const uint32_t n_vectors2, const uint64_t* STORM_RESTRICT vals2,
                               const uint32_t n_ints, const STORM_compute_func f) {
     const int op = op_of_compute_func(f);
+    if (op < 0) return (uint64_t)-1;
     if (!vals1 || !vals2 || n_ints == 0) { set_error("STORM_wrapper_square: NULL buffer or zero width"); return (uint64_t)-1; }
     if (n_vectors1 == 0 || n_vectors2 == 0) return 0;
-    std::lock_guard<std::mutex> lock(g_scratch.mu);
+    std::lock_guard<std::mutex> lock(g_wrap.mu);
     const uint64_t stride = padded_stride(n_ints);
-    if (scratch_prepare(((uint64_t)n_vectors1 + n_vectors2) * stride)) return (uint64_t)-1;
-    Scratch& s = g_scratch;
+    if (wrap_prepare(((uint64_t)n_vectors1 + n_vectors2) * stride, 1)) return (uint64_t)-1;
+    WrapDev* d = g_wrap.devs[0];
     const uint64_t at2 = (uint64_t)n_vectors1 * stride;
-    if (scratch_upload(vals1, n_vectors1, n_ints, stride, 0) || scratch_upload(vals2, n_vectors2, n_ints, stride, at2)) return (uint64_t)-1;
-    if (cudaMemsetAsync(s.d_total, 0, 8, s.stream) != cudaSuccess) return (uint64_t)-1;
-    if (pairw_rect_op(s.d_rows, n_vectors1, stride, 0, s.d_rows + at2, n_vectors2, stride, 0, n_ints, 0, op,
-                      STORM_B200_KERNEL_AUTO, false, nullptr, 0, reinterpret_cast<uint64_t*>(s.d_total), s.stream)) return (uint64_t)-1;
-    if (cudaMemcpyAsync(s.h_total, s.d_total, 8, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
-        cudaStreamSynchronize(s.stream) != cudaSuccess) {
-        set_error("STORM_wrapper_square failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return (uint64_t)-1;
-    }
-    return *s.h_total;
+    DeviceGuard guard(d->ctx.device);
+    if (cudaMemsetAsync(d->ctx.d_total, 0, 8, d->ctx.stream) != cudaSuccess) return (uint64_t)-1;
+    if (wrap_upload_primary(vals1, n_vectors1, n_ints, stride, 0) || wrap_upload_primary(vals2, n_vectors2, n_ints, stride, at2)) return (uint64_t)-1;
+    if (pairw_rect_op(d->d_rows, n_vectors1, stride, 0, d->d_rows + at2, n_vectors2, stride, 0, n_ints, 0, op,
+                      STORM_B200_KERNEL_AUTO, false, nullptr, 0, reinterpret_cast<uint64_t*>(d->ctx.d_total), d->ctx.stream)) return (uint64_t)-1;
+    DevCtx* ctx = &d->ctx;
+    return collect_totals(&ctx, 1, "STORM_wrapper_square");
 }
 
-// The list wrappers take caller-built position arrays (storm.c:173-220, 281-369).
-// They are answered from the bitmaps alone: the value is identical (the lists only
-// select a cheaper CPU code path per pair in the reference).
+// The list wrappers take caller-built position arrays (storm.c:173-220, 281-369) and switch, per pair, between
+// the bitmap kernel `f` and the list probe `fl` on n_alts < cutoff.  Both branches give |i AND j| when the lists
+// describe the bitmaps (which is the contract: the driver builds them from the same draws, benchmark.cpp:765-790),
+// so the query is answered from the bitmaps alone, through the same kernels as STORM_wrapper_diag.
 uint64_t STORM_wrapper_diag_list(const uint32_t n_vectors, const uint64_t* STORM_RESTRICT vals, const uint32_t n_ints,
                                  const uint32_t* STORM_RESTRICT n_alts, const uint32_t* STORM_RESTRICT alt_positions,
                                  const uint32_t* STORM_RESTRICT alt_offsets, const STORM_compute_func f,
                                  const STORM_compute_lfunc fl, const uint32_t cutoff) {
-    (void)n_alts; (void)alt_positions; (void)alt_offsets; (void)f; (void)fl; (void)cutoff;
-    return wrapper_diag_impl(n_vectors, vals, n_ints);
+    (void)n_alts; (void)alt_positions; (void)alt_offsets; (void)fl; (void)cutoff;
+    return wrapper_diag_impl(n_vectors, vals, n_ints, 0, 1, STORM_B200_KERNEL_AUTO, op_of_compute_func(f));
 }
 
 uint64_t STORM_wrapper_diag_list_blocked(const uint32_t n_vectors, const uint64_t* STORM_RESTRICT vals, const uint32_t n_ints,
                                          const uint32_t* STORM_RESTRICT n_alts, const uint32_t* STORM_RESTRICT alt_positions,
                                          const uint32_t* STORM_RESTRICT alt_offsets, const STORM_compute_func f,
                                          const STORM_compute_lfunc fl, const uint32_t cutoff, uint32_t block_size) {
-    (void)n_alts; (void)alt_positions; (void)alt_offsets; (void)f; (void)fl; (void)cutoff; (void)block_size;
-    return wrapper_diag_impl(n_vectors, vals, n_ints);
+    (void)n_alts; (void)alt_positions; (void)alt_offsets; (void)fl; (void)cutoff; (void)block_size;
+    return wrapper_diag_impl(n_vectors, vals, n_ints, 0, 1, STORM_B200_KERNEL_AUTO, op_of_compute_func(f));
 }
 
 uint64_t STORM_b200_wrapper_diag_shard(uint64_t n_vectors, const uint64_t* vals, uint64_t n_ints,
@@ -751,22 +855,31 @@ uint64_t STORM_b200_contig_pairw_shard(STORM_contiguous_t* c, uint32_t shard, ui
     return contig_query(c, QUERY_DENSE, shard, n_shards, kernel);
 }
 
+// Number of device replicas the container's queries run on (0 before its first use of a device).
+int STORM_b200_contig_device_count(const STORM_contiguous_t* c) {
+    if (c == nullptr || c->b200 == nullptr) return 0;
+    return (int)state_of(const_cast<STORM_contiguous_t*>(c))->devs.size();
+}
+
 int STORM_b200_contig_pairw_rect(STORM_contiguous_t* c, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, uint32_t* out) {
     if (c == nullptr || out == nullptr) { set_error("NULL argument"); return STORM_B200_EINVAL; }
     if (i0 > i1 || j0 > j1 || i1 > c->n_data || j1 > c->n_data) { set_error("rectangle outside the %llu rows", (unsigned long long)c->n_data); return STORM_B200_EINVAL; }
     if (i0 == i1 || j0 == j1) return STORM_B200_OK;
     ContigState* st = state_of(c);
-    DeviceGuard guard(st->device);
-    int rc = ensure_device_state(st);
+    DeviceGuard home(st->home_device);
+    int rc = ensure_devs(st);
     if (rc) return rc;
-    if ((rc = sync_rows(c, st))) return rc;
+    if ((rc = upload_pending(c, st, c->n_data))) return rc;
+    ContigDev* d = st->devs[0];
+    if ((rc = order_after_uploads(d))) return rc;
+    DeviceGuard guard(d->ctx.device);
     const uint64_t ni = i1 - i0, nj = j1 - j0;
     uint32_t* d_out = nullptr;
     if (cudaMalloc(&d_out, ni * nj * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); set_error("device allocation for %llu x %llu counts failed", (unsigned long long)ni, (unsigned long long)nj); return STORM_B200_ENOMEM; }
-    rc = pairw_rect(st->d_rows + i0 * st->stride, ni, st->stride, i0, st->d_rows + j0 * st->stride, nj, st->stride, j0,
-                    c->n_bitmaps_vector, 1, STORM_B200_KERNEL_AUTO, d_out, nj, nullptr, st->stream);
-    if (!rc && (cudaMemcpyAsync(out, d_out, ni * nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
-                cudaStreamSynchronize(st->stream) != cudaSuccess)) {
+    rc = pairw_rect(d->d_rows + i0 * st->stride, ni, st->stride, i0, d->d_rows + j0 * st->stride, nj, st->stride, j0,
+                    c->n_bitmaps_vector, 1, STORM_B200_KERNEL_AUTO, d_out, nj, nullptr, d->ctx.stream);
+    if (!rc && (cudaMemcpyAsync(out, d_out, ni * nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->ctx.stream) != cudaSuccess ||
+                cudaStreamSynchronize(d->ctx.stream) != cudaSuccess)) {
         set_error("rect query failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = STORM_B200_ECUDA;
     }
@@ -777,18 +890,22 @@ int STORM_b200_contig_pairw_rect(STORM_contiguous_t* c, uint64_t i0, uint64_t i1
 const uint64_t* STORM_b200_contig_device_rows(STORM_contiguous_t* c, uint64_t* row_stride_words) {
     if (c == nullptr) return nullptr;
     ContigState* st = state_of(c);
-    DeviceGuard guard(st->device);
-    if (ensure_device_state(st) || sync_rows(c, st)) return nullptr;
-    if (cudaStreamSynchronize(st->stream) != cudaSuccess) return nullptr;
+    DeviceGuard home(st->home_device);
+    if (ensure_devs(st) || upload_pending(c, st, c->n_data)) return nullptr;
+    ContigDev* d = st->devs[0];
+    DeviceGuard guard(d->ctx.device);
+    if (cudaStreamSynchronize(d->ctx.copy_stream) != cudaSuccess) return nullptr;
     if (row_stride_words) *row_stride_words = st->stride;
-    return st->d_rows;
+    return d->d_rows;
 }
 
 int STORM_b200_contig_invalidate_device(STORM_contiguous_t* c) {
     if (c == nullptr) return STORM_B200_EINVAL;
     ContigState* st = state_of(c);
+    wait_uploads(st);
     st->uploaded_rows = 0;
-    st->list_rows_synced = 0;
+    st->list_rows_built = (uint64_t)-1;
+    for (ContigDev* d : st->devs) d->list_rows_synced = 0;
     return STORM_B200_OK;
 }
 
@@ -796,8 +913,8 @@ int STORM_b200_contig_add_bulk(STORM_contiguous_t* c, const uint32_t* positions,
     if (c == nullptr || offsets == nullptr || (positions == nullptr && n_rows && offsets[n_rows] != offsets[0])) { set_error("NULL argument"); return STORM_B200_EINVAL; }
     if (n_rows == 0) return STORM_B200_OK;
     ContigState* st = state_of(c);
-    DeviceGuard guard(st->device);
-    int rc = ensure_device_state(st);
+    DeviceGuard home(st->home_device);
+    int rc = ensure_devs(st);
     if (rc) return rc;
     // host pass: validate, compact away empty rows (D7) and adjacent duplicates, record list metadata.  The checks
     // are one tight loop per row (range, adjacent duplicates); a clean row is taken over with one memcpy, and when
@@ -842,23 +959,27 @@ int STORM_b200_contig_add_bulk(STORM_contiguous_t* c, const uint32_t* positions,
     if (n_new == 0) return STORM_B200_OK;
     if (grow_host_rows(c, c->n_data + n_new)) { set_error("host arena allocation failed"); return STORM_B200_ENOMEM; }
     if (c->scalar == nullptr && grow_host_scalar(c, st, 1)) return STORM_B200_ENOMEM;
-    if ((rc = sync_rows(c, st))) return rc;                               // earlier rows first
-    if ((rc = ensure_device_rows(c, st, c->n_data + n_new))) return rc;
+    if ((rc = upload_pending(c, st, c->n_data))) return rc;               // earlier rows first, on every replica
+    ContigDev* d = st->devs[0];                                           // the bits are scattered on the primary device
+    if ((rc = ensure_device_rows(c, st, d, c->n_data + n_new))) return rc;
+    DeviceGuard guard(d->ctx.device);
+    cudaStream_t cs = d->ctx.copy_stream;                                 // the stream the arena's other writes are ordered on
 
-    uint32_t* d_pos = nullptr; uint64_t* d_off = nullptr;
-    STORM_CUDA_TRY(cudaMalloc(&d_pos, std::max<size_t>(n_pos, 1) * sizeof(uint32_t)));
-    STORM_CUDA_TRY(cudaMalloc(&d_off, off.size() * sizeof(uint64_t)));
-    STORM_CUDA_TRY(cudaMemcpyAsync(d_pos, src_pos, n_pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st->stream));
-    STORM_CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st->stream));
-    uint64_t* d_dst = st->d_rows + c->n_data * st->stride;
-    STORM_CUDA_TRY(cudaMemsetAsync(d_dst, 0, n_new * st->stride * 8, st->stream));
-    rc = launch_scatter_positions(d_dst, st->stride, d_pos, d_off, n_new, st->stream);
+    struct DeviceTemp { void* p = nullptr; ~DeviceTemp() { if (p) cudaFree(p); } } t_pos, t_off;   // released on every return path
+    STORM_CUDA_TRY(cudaMalloc(&t_pos.p, std::max<size_t>(n_pos, 1) * sizeof(uint32_t)));
+    STORM_CUDA_TRY(cudaMalloc(&t_off.p, off.size() * sizeof(uint64_t)));
+    uint32_t* d_pos = static_cast<uint32_t*>(t_pos.p);
+    uint64_t* d_off = static_cast<uint64_t*>(t_off.p);
+    STORM_CUDA_TRY(cudaMemcpyAsync(d_pos, src_pos, n_pos * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    STORM_CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+    uint64_t* d_dst = d->d_rows + c->n_data * st->stride;
+    STORM_CUDA_TRY(cudaMemsetAsync(d_dst, 0, n_new * st->stride * 8, cs));
+    rc = launch_scatter_positions(d_dst, st->stride, d_pos, d_off, n_new, cs);
     // keep the public host mirror valid: copy the scattered rows back
     const uint64_t W = c->n_bitmaps_vector;
     if (!rc && cudaMemcpy2DAsync(c->data + c->n_data * W, W * 8, d_dst, st->stride * 8, W * 8, n_new,
-                                 cudaMemcpyDeviceToHost, st->stream) != cudaSuccess) rc = STORM_B200_ECUDA;
-    if (cudaStreamSynchronize(st->stream) != cudaSuccess) rc = STORM_B200_ECUDA;
-    cudaFree(d_pos); cudaFree(d_off);
+                                 cudaMemcpyDeviceToHost, cs) != cudaSuccess) rc = STORM_B200_ECUDA;
+    if (cudaStreamSynchronize(cs) != cudaSuccess) rc = STORM_B200_ECUDA;
     if (rc) { set_error("bulk ingest failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
 
     if (st->pos_off.size() < c->n_data + n_new) st->pos_off.resize(c->n_data + n_new);
@@ -876,8 +997,14 @@ int STORM_b200_contig_add_bulk(STORM_contiguous_t* c, const uint32_t* positions,
         c->n_scalar[row] = used;
         c->bitmaps[row].n_scalar = used;
     }
+    // the other replicas take the new rows from the mirror
+    for (size_t g = 1; g < st->devs.size(); ++g) {
+        ContigDev* o = st->devs[g];
+        if ((rc = ensure_device_rows(c, st, o, c->n_data + n_new))) return rc;
+        if ((rc = upload_rows(&o->ctx, o->d_rows, st->stride, mirror_of(c, st), c->n_bitmaps_vector, c->n_data, c->n_data + n_new))) return rc;
+    }
     c->n_data += n_new;
-    st->uploaded_rows = c->n_data;            // the device already holds them
+    st->uploaded_rows = c->n_data;            // every replica holds them (or has the copy queued)
     return STORM_B200_OK;
 }
 

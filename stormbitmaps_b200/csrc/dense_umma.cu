@@ -39,8 +39,10 @@
 // memory, which halves the per-SM expansion work and shared-memory reads per MMA.
 #include <cuda.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "umma_ptx.cuh"
@@ -127,21 +129,26 @@ __device__ __forceinline__ void expand32_b_scaled(uint32_t w, uint32_t (&r)[8]) 
 // FP4 form (VAR_FP4): 32 bits -> 32 E2M1 nibbles in four registers; register j holds bit j of every
 // nibble of the word, moved to a nibble position whose E2M1 reading (0001 = 0.5, 0010 = 1, 0100 = 2)
 // multiplies to exactly 1.0 with its partner on the other side:
-//     A: 0.5, 1, 2, 2      B: 2, 1, 0.5, 0.5
-// so the A side needs one shift and the B side three (bit 3 of a nibble is the E2M1 sign and cannot be
-// used in place).  Every matching bit adds exactly 1.0f to an fp32 accumulator; integers below 2^24 are
-// exact in fp32 and the tensor core's accumulation of them was measured to be exact (fp4_probe.cu).
+//     A: 0.5, 1, 2, 1      B: 2, 1, 0.5, 1
+// Bit 3 of a nibble is the E2M1 sign and cannot be used in place, so bit 3 has to move on both sides; with
+// positions p (value 2^(p-1)) the pair (pA, pB) of a bit must satisfy pA + pB = 2, and the assignment above
+// is the one with the fewest distinct shift amounts: one on the A side (>> 2), two on the B side (<< 2 and a
+// >> 2 that serves two registers) -- 5 + 6 instructions per 32 bits.  (Round 1 used A 0.5, 1, 2, 2 x
+// B 2, 1, 0.5, 0.5: three different shifts on the B side, 5 + 7.)  Every matching bit adds exactly 1.0f to an
+// fp32 accumulator; integers below 2^24 are exact in fp32 and the tensor core's accumulation of them was
+// measured to be exact (fp4_probe.cu, which encodes its operands the same way).
 __device__ __forceinline__ void expand32_a_fp4(uint32_t w, uint32_t* r) {
     r[0] = w & 0x11111111u;
     r[1] = w & 0x22222222u;
     r[2] = w & 0x44444444u;
-    r[3] = (w >> 1) & 0x44444444u;
+    r[3] = (w >> 2) & 0x22222222u;
 }
 __device__ __forceinline__ void expand32_b_fp4(uint32_t w, uint32_t* r) {
+    const uint32_t d = w >> 2;
     r[0] = (w << 2) & 0x44444444u;
     r[1] = w & 0x22222222u;
-    r[2] = (w >> 2) & 0x11111111u;
-    r[3] = (w >> 3) & 0x11111111u;
+    r[2] = d & 0x11111111u;
+    r[3] = d & 0x22222222u;
 }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T with E2M1 operands, UE8M0 scale factors per 32 elements from tensor
@@ -258,6 +265,11 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // clock probe: the (mostly idle) TMA thread brackets the kernel's main part with clock64 / %globaltimer
+    const bool clk_thread = job.clk != nullptr && tid == (uint32_t)C::TMA_WARP * 32u;
+    long long clk0 = 0;
+    uint64_t gt0 = 0;
+    if (clk_thread) { clk0 = clock64(); gt0 = global_timer_ns(); }
 
     unsigned long long sum = 0;
     // interior tile: every row and column valid, nothing on or below the diagonal, no per-pair output
@@ -601,6 +613,10 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int w = 0; w < C::EXPANDER_WARPS; ++w) t += red[w];
         if (t) atomicAdd(job.total, t);
     }
+    if (clk_thread) {
+        job.clk[2 * blockIdx.x] = (unsigned long long)(clock64() - clk0);
+        job.clk[2 * blockIdx.x + 1] = global_timer_ns() - gt0;
+    }
     if (warp == C::MMA_WARP) tmem_free<CG>(tmem_base);
 }
 
@@ -610,12 +626,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // all, so that its rate is the ceiling the tile kernel can reach on this device at its clocks.
 // Operands are whatever the (zeroed) shared memory and tensor memory hold; results are discarded.
 template <int CG>
-__global__ void __launch_bounds__(128, 1) umma_peak_kernel(uint32_t iters) {
+__global__ void __launch_bounds__(128, 1) umma_peak_kernel(uint32_t iters, unsigned long long* cycles) {
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    constexpr uint32_t RING = 4;
+    constexpr uint32_t RING = 8;                                             // commits in flight
+    constexpr uint32_t BATCH = 8;                                            // MMAs per commit (two k-blocks of the tile kernel)
     const uint32_t bar_base = smem_base + C::STAGE_BYTES;                   // RING barriers, then the TMEM slot
     const uint32_t tmem_slot = bar_base + 8 * RING;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -633,19 +650,30 @@ __global__ void __launch_bounds__(128, 1) umma_peak_kernel(uint32_t iters) {
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    if (rank == 0 && tid == 0) {
+    // Issue loop as in the tile kernel: the whole warp walks it (waits included), one elected lane issues, so that
+    // descriptors and addresses stay in uniform registers.  (First version: one thread in a divergent branch, four
+    // MMAs per commit, ring of four -- it reached 93.8 % of the pipe where the tile kernel itself reaches 99 %.)
+    if (rank == 0 && warp == 0) {
+        const bool leader = elect_one();
         const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const long long c0 = clock64();
         for (uint32_t it = 0; it < iters; ++it) {
-            if (it >= RING) mbar_wait(bar_base + 8 * (it % RING), ((it / RING) - 1) & 1);
+            if (it >= RING) mbar_wait_t<true>(bar_base + 8 * (it % RING), ((it / RING) - 1) & 1);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint64_t b_desc = desc_hi | (uint64_t)(((smem_base + k * 32) >> 4) & 0x3FFF);
-                umma_i8_ts<CG>(tmem_base + UM_ACC_COL, tmem_base + UM_A_COL + k * 8, b_desc, C::IDESC, 1u);
+                for (int k = 0; k < (int)BATCH; ++k) {
+                    const uint64_t b_desc = desc_hi | (uint64_t)(((smem_base + (k & 3) * 32) >> 4) & 0x3FFF);
+                    umma_i8_ts<CG>(tmem_u + UM_ACC_COL, tmem_u + UM_A_COL + (k & 3) * 8, b_desc, C::IDESC, 1u);
+                }
+                umma_commit<CG>(bar_base + 8 * (it % RING));
             }
-            umma_commit<CG>(bar_base + 8 * (it % RING));
+            __syncwarp();
         }
         for (uint32_t it = iters > RING ? iters - RING : 0; it < iters; ++it)   // drain
-            mbar_wait(bar_base + 8 * (it % RING), (it / RING) & 1);
+            mbar_wait_t<true>(bar_base + 8 * (it % RING), (it / RING) & 1);
+        const long long c1 = clock64();
+        if (leader && cycles) cycles[blockIdx.x / CG] = (unsigned long long)(c1 - c0);
     }
     __syncwarp();
     tc_fence_before();
@@ -654,7 +682,7 @@ __global__ void __launch_bounds__(128, 1) umma_peak_kernel(uint32_t iters) {
 }
 
 template <int CG>
-int run_umma_peak(double* ops_per_s) {
+int run_umma_peak(double* ops_per_s, double* clock64_mhz) {
     using C = Cfg<CG>;
     int dev = 0, sms = 0;
     STORM_CUDA_TRY(cudaGetDevice(&dev));
@@ -672,22 +700,32 @@ int run_umma_peak(double* ops_per_s) {
     cudaEvent_t e0, e1;
     STORM_CUDA_TRY(cudaEventCreate(&e0));
     STORM_CUDA_TRY(cudaEventCreate(&e1));
-    const uint32_t iters = 100000;                                        // ~50 M clocks: tens of milliseconds
-    double best = 0;
+    const unsigned n_clusters = cfg.gridDim.x / CG;
+    unsigned long long* d_cyc = nullptr;
+    STORM_CUDA_TRY(cudaMalloc(&d_cyc, n_clusters * sizeof(unsigned long long)));
+    std::vector<unsigned long long> h_cyc(n_clusters);
+    const uint32_t iters = 50000;                                         // x 8 MMAs: ~50 M clocks, tens of milliseconds
+    double best = 0, best_mhz = 0;
     for (int rep = 0; rep < 4; ++rep) {                                   // rep 0 is the warm-up
         STORM_CUDA_TRY(cudaEventRecord(e0));
-        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_peak_kernel<CG>, iters));
+        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_peak_kernel<CG>, iters, d_cyc));
         STORM_CUDA_TRY(cudaEventRecord(e1));
         STORM_CUDA_TRY(cudaEventSynchronize(e1));
         count_launch();
         float ms = 0;
         STORM_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        STORM_CUDA_TRY(cudaMemcpy(h_cyc.data(), d_cyc, n_clusters * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double cyc = 0;
+        for (unsigned long long c : h_cyc) cyc += (double)c;
+        cyc /= n_clusters;
         // per SM and instruction: 128 x 256 x 32 MACs = 2 ops each
-        const double ops = (double)cfg.gridDim.x * iters * 4.0 * 128.0 * 256.0 * 32.0 * 2.0;
-        if (rep > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+        const double ops = (double)cfg.gridDim.x * iters * 8.0 * 128.0 * 256.0 * 32.0 * 2.0;
+        if (rep > 0 && ops / (ms * 1e-3) > best) { best = ops / (ms * 1e-3); best_mhz = cyc / (ms * 1e-3) / 1e6; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_cyc);
     *ops_per_s = best;
+    if (clock64_mhz) *clock64_mhz = best_mhz;                             // issue-loop clock64 ticks per second of the launch
     return STORM_B200_OK;
 }
 
@@ -742,10 +780,19 @@ int wave_counter(cudaStream_t stream, unsigned int** slot) {
     return STORM_B200_OK;
 }
 
-int g_umma_wave_sync = 1;   // STORM_b200_set_umma_wave_sync
-int g_umma_reserved_sms = 0;   // STORM_b200_set_umma_reserved_sms
-int g_umma_stream_k = 1;    // STORM_b200_set_umma_stream_k
-int g_umma_chain = 1;       // STORM_b200_set_umma_chain
+// Process-wide development / measurement knobs.  Atomics: a launch reads each of them once, so a caller on another
+// thread that flips one never tears a launch (what it cannot have is a per-object value: see DenseJob::reserved_sms
+// for the one knob a multi-process caller used to flip mid-query).
+std::atomic<int> g_umma_wave_sync{1};      // STORM_b200_set_umma_wave_sync
+std::atomic<int> g_umma_reserved_sms{0};   // STORM_b200_set_umma_reserved_sms
+std::atomic<int> g_umma_stream_k{1};       // STORM_b200_set_umma_stream_k
+std::atomic<int> g_umma_chain{1};          // STORM_b200_set_umma_chain
+std::atomic<int> g_clock_probe{0};         // STORM_b200_set_clock_probe
+
+// Clock-probe buffer of the current device (2 x u64 per CTA of the last probed launch) and the grid of that launch.
+struct ClockProbe { unsigned long long* d = nullptr; unsigned grid = 0; };
+ClockProbe g_clk[16];
+std::mutex g_clk_mu;
 
 template <int CG, int VAR>
 int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
@@ -760,7 +807,8 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     STORM_CUDA_TRY(cudaGetDevice(&dev));
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const uint64_t n_tiles = job.tile_end - job.tile_begin;
-    const int reserved = g_umma_reserved_sms < sms - 2 ? g_umma_reserved_sms : sms - 2;
+    const int want_reserved = job.reserved_sms >= 0 ? job.reserved_sms : g_umma_reserved_sms.load();
+    const int reserved = want_reserved < sms - 2 ? want_reserved : sms - 2;
     const uint64_t max_clusters = (uint64_t)((sms - reserved) / CG);                               // persistent: one per SM (pair)
     uint64_t clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
     job.wave_sync = nullptr;
@@ -768,7 +816,7 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     // Worth it when the rows do not fit in L2 anyway and a tile lasts long enough to hide the barrier: below
     // that it costs up to 10 % (32768 x 4096: 0.79 vs 0.71 ms) and there is no DRAM traffic to save.
     const uint64_t matrix_bytes = (job.nA + (job.A == job.B ? 0 : job.nB)) * (uint64_t)job.n_words * 8;
-    if (g_umma_wave_sync && n_tiles > clusters && matrix_bytes >= (96ull << 20) && job.n_words >= 512) {
+    if (g_umma_wave_sync.load() && n_tiles > clusters && matrix_bytes >= (96ull << 20) && job.n_words >= 512) {
         int rc2 = wave_counter(stream, &job.wave_sync);
         if (rc2) return rc2;
     }
@@ -777,7 +825,7 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     // with fewer tiles than clusters the idle SMs get K slices of the tiles (at least STREAMK_MIN_CHUNKS TMA
     // boxes each, so that a segment's epilogue stays small beside its MMAs).
     constexpr uint64_t STREAMK_MIN_CHUNKS = 8;
-    if (g_umma_stream_k && !job.out) {
+    if (g_umma_stream_k.load() && !job.out) {
         if (n_tiles >= max_clusters) job.stream_k = (n_tiles % max_clusters) != 0;   // (the wave barrier covers the full waves only)
         else if (!job.wave_sync) {
             const uint32_t n_kb = C::FP4_FORM ? (job.n_words + 3) / 4 : (job.n_words + 1) / 2;
@@ -793,11 +841,17 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     // exact range of the form: fp32 integers below 2^24 for kind::mxf4 (and 32 of them must still add up
     // exactly in the epilogue's float sum), s32 for kind::i8 (x 128 in the scaled form).
     job.chain_max = 1;
-    if (g_umma_chain && !job.out && job.total) {
+    if (g_umma_chain.load() && !job.out && job.total) {
         const uint64_t M = (uint64_t)job.n_words * 64;
         const uint64_t room = C::FP4_FORM ? (1ull << 24) / (M * 32)
                             : (VAR & VAR_SCALED) ? 0x7FFFFFFFull / (M * 128) : 0x7FFFFFFFull / M;
         job.chain_max = (uint32_t)(room < 1 ? 1 : room > 4096 ? 4096 : room);
+    }
+    job.clk = nullptr;
+    if (g_clock_probe.load() && dev < 16) {
+        std::lock_guard<std::mutex> lock(g_clk_mu);
+        if (!g_clk[dev].d) STORM_CUDA_TRY(cudaMalloc(&g_clk[dev].d, 2 * 512 * sizeof(unsigned long long)));
+        if (clusters * CG <= 512) { job.clk = g_clk[dev].d; g_clk[dev].grid = (unsigned)(clusters * CG); }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
@@ -816,23 +870,23 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     return STORM_B200_OK;
 }
 
-int g_umma_cg = 2;        // cta_group used by launch_dense_umma (1 or 2); see STORM_b200_set_umma_cta_group
+std::atomic<int> g_umma_cg{2};        // cta_group used by launch_dense_umma (1 or 2); see STORM_b200_set_umma_cta_group
 // FP4 form, cta_group 2: two expander warps per 32 rows (STORM_b200_set_umma_variant bit 3).  Off by default:
 // once the MMA issue loop was made warp-uniform the narrow form reached 95.8 % of the pipe on C3 and the
 // wide one 92.5 % (it only wins by a few percent below 16 Ki bits per row), profiles/r01_fp4_tune.jsonl.
-int g_umma_fp4_wide = 0;
-int g_umma_variant = 3;   // VAR_* bits (both on: 4.27 vs 3.60 POP/s on 30k x 131072); see STORM_b200_set_umma_variant
+std::atomic<int> g_umma_fp4_wide{0};
+std::atomic<int> g_umma_variant{3};   // VAR_* bits (both on: 4.27 vs 3.60 POP/s on 30k x 131072); see STORM_b200_set_umma_variant
 
 template <int CG>
 int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
-    int var = g_umma_variant & 3;
+    int var = g_umma_variant.load() & 3;
     if (fp4) {
         if (!umma_fp4_supports(job)) {
             set_error("FP4 kernel: a pair count must stay below 2^24 for exact fp32 accumulation (n_words %u)", job.n_words);
             return STORM_B200_EINVAL;
         }
         if constexpr (CG == 2) {
-            if (g_umma_fp4_wide) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_WIDE>(job, stream);
+            if (g_umma_fp4_wide.load()) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_WIDE>(job, stream);
         }
         return launch_cg<CG, VAR_FP4 | VAR_SUSPEND>(job, stream);
     }
@@ -847,7 +901,7 @@ int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
 
 }  // namespace
 
-TileShape umma_tile_shape() { return {(uint32_t)(128 * g_umma_cg), (uint32_t)UM_N}; }
+TileShape umma_tile_shape() { return {(uint32_t)(128 * g_umma_cg.load()), (uint32_t)UM_N}; }
 
 bool umma_supports(const DenseJob& job) {
     if (job.n_words == 0 || job.n_words >= (1u << 25)) return false;        // counts stay below 2^31
@@ -863,18 +917,18 @@ bool umma_fp4_supports(const DenseJob& job) {
     return umma_supports(job) && (uint64_t)job.n_words * 64 <= (1ull << 24);
 }
 
-int umma_peak_ops(int cg, double* ops_per_s) {
-    return cg == 1 ? run_umma_peak<1>(ops_per_s) : run_umma_peak<2>(ops_per_s);
+int umma_peak_ops(int cg, double* ops_per_s, double* clock64_mhz) {
+    return cg == 1 ? run_umma_peak<1>(ops_per_s, clock64_mhz) : run_umma_peak<2>(ops_per_s, clock64_mhz);
 }
 
 int launch_dense_umma(const DenseJob& job, cudaStream_t stream) {
     if (job.tile_end <= job.tile_begin) return STORM_B200_OK;
-    return g_umma_cg == 2 ? launch_var<2>(job, stream, false) : launch_var<1>(job, stream, false);
+    return g_umma_cg.load() == 2 ? launch_var<2>(job, stream, false) : launch_var<1>(job, stream, false);
 }
 
 int launch_dense_fp4(const DenseJob& job, cudaStream_t stream) {
     if (job.tile_end <= job.tile_begin) return STORM_B200_OK;
-    return g_umma_cg == 2 ? launch_var<2>(job, stream, true) : launch_var<1>(job, stream, true);
+    return g_umma_cg.load() == 2 ? launch_var<2>(job, stream, true) : launch_var<1>(job, stream, true);
 }
 
 }  // namespace storm
@@ -882,46 +936,68 @@ int launch_dense_fp4(const DenseJob& job, cudaStream_t stream) {
 // Development / measurement knob: cta_group of the UMMA kernel (1 = one CTA per 128 x 256 tile,
 // 2 = CTA pair per 256 x 256 tile).  Returns the previous value.
 extern "C" int STORM_b200_set_umma_cta_group(int cg) {
-    const int prev = storm::g_umma_cg;
-    if (cg == 1 || cg == 2) storm::g_umma_cg = cg;
+    const int prev = storm::g_umma_cg.load();
+    if (cg == 1 || cg == 2) storm::g_umma_cg.store(cg);
     return prev;
 }
 
 // Development / measurement knob: 1 (default) = the CTAs of the persistent UMMA kernel keep their tile
 // waves in step (L2 reuse of the shared row blocks), 0 = free-running.  Returns the previous value.
 extern "C" int STORM_b200_set_umma_wave_sync(int on) {
-    const int prev = storm::g_umma_wave_sync;
-    storm::g_umma_wave_sync = on ? 1 : 0;
-    return prev;
+    return storm::g_umma_wave_sync.exchange(on ? 1 : 0);
 }
 
 // SMs the persistent kernel leaves to a collective running beside it (multi-GPU host queries).  Returns the previous value.
 extern "C" int STORM_b200_set_umma_reserved_sms(int n) {
-    const int prev = storm::g_umma_reserved_sms;
-    storm::g_umma_reserved_sms = n < 0 ? 0 : n;
-    return prev;
+    return storm::g_umma_reserved_sms.exchange(n < 0 ? 0 : n);
 }
 
 // Development / measurement knob: 1 (default) = total-only jobs with few tiles per CTA split (tile, K chunk)
 // units evenly over the persistent CTAs, 0 = whole tiles only.  Returns the previous value.
 extern "C" int STORM_b200_set_umma_stream_k(int on) {
-    const int prev = storm::g_umma_stream_k;
-    storm::g_umma_stream_k = on ? 1 : 0;
-    return prev;
+    return storm::g_umma_stream_k.exchange(on ? 1 : 0);
 }
 
 // Development / measurement knob: 1 (default) = total-only jobs drain the accumulator once per run of interior
 // segments (DenseJob::chain_max), 0 = once per segment.  Returns the previous value.
 extern "C" int STORM_b200_set_umma_chain(int on) {
-    const int prev = storm::g_umma_chain;
-    storm::g_umma_chain = on ? 1 : 0;
-    return prev;
+    return storm::g_umma_chain.exchange(on ? 1 : 0);
 }
 
 // Development / measurement knob: bit 0 = hardware-suspended mbarrier waits, bit 1 = scaled expansion.
 // Returns the previous value.
 extern "C" int STORM_b200_set_umma_variant(int variant) {
-    const int prev = storm::g_umma_variant | (storm::g_umma_fp4_wide ? 8 : 0);
-    if (variant >= 0 && variant <= 15) { storm::g_umma_variant = variant & 3; storm::g_umma_fp4_wide = (variant >> 3) & 1; }
+    const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0);
+    if (variant >= 0 && variant <= 15) { storm::g_umma_variant.store(variant & 3); storm::g_umma_fp4_wide.store((variant >> 3) & 1); }
     return prev;
+}
+
+// 1: every tensor-kernel launch records, per CTA, the clock64 and %globaltimer deltas around its main loop (one thread,
+// a handful of instructions); 0 (default): off.  Returns the previous value.
+extern "C" int STORM_b200_set_clock_probe(int on) { return storm::g_clock_probe.exchange(on ? 1 : 0); }
+
+// SM clock of the most recent probed tensor-kernel launch on the current device, in clock64 ticks per microsecond
+// (= MHz if clock64 ticks once per SM cycle; STORM_b200_microbench(8) calibrates that): waits for the device to go
+// idle, then averages the per-CTA records.  *min_mhz / *max_mhz (optional): the spread over CTAs.
+extern "C" int STORM_b200_last_kernel_clock(double* mhz, double* min_mhz, double* max_mhz) {
+    using namespace storm;
+    if (!mhz) { set_error("mhz is NULL"); return STORM_B200_EINVAL; }
+    int dev = 0;
+    STORM_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 16 || !g_clk[dev].d || g_clk[dev].grid == 0) { set_error("no probed launch on device %d (STORM_b200_set_clock_probe)", dev); return STORM_B200_EINVAL; }
+    STORM_CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<unsigned long long> h(2 * g_clk[dev].grid);
+    STORM_CUDA_TRY(cudaMemcpy(h.data(), g_clk[dev].d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    double c = 0, t = 0, lo = 1e30, hi = 0;
+    for (unsigned i = 0; i < g_clk[dev].grid; ++i) {
+        const double ci = (double)h[2 * i], ti = (double)h[2 * i + 1];
+        if (ti <= 0) continue;
+        c += ci; t += ti;
+        lo = std::min(lo, ci / ti * 1e3); hi = std::max(hi, ci / ti * 1e3);
+    }
+    if (t <= 0) { set_error("clock probe holds no record"); return STORM_B200_EINVAL; }
+    *mhz = c / t * 1e3;
+    if (min_mhz) *min_mhz = lo;
+    if (max_mhz) *max_mhz = hi;
+    return STORM_B200_OK;
 }

@@ -17,6 +17,8 @@
 //   fp4_peak_kernel    the same instruction back to back on every SM: the pipe's ceiling.
 //
 // Results go to STORM_b200_fp4_probe() / STORM_b200_microbench(6|7); tools/fp4_probe.py prints them.
+#include <string.h>
+
 #include <mutex>
 #include <vector>
 
@@ -183,11 +185,12 @@ __global__ void __launch_bounds__(128, 1) fp4_exact_kernel(const Fp4Case* cases,
 }
 
 template <int CG>
-__global__ void __launch_bounds__(128, 1) fp4_peak_kernel(uint32_t iters) {
+__global__ void __launch_bounds__(128, 1) fp4_peak_kernel(uint32_t iters, unsigned long long* cycles) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    constexpr uint32_t RING = 4;
+    constexpr uint32_t RING = 8;                                             // commits in flight
+    constexpr uint32_t BATCH = 8;                                            // MMAs per commit
     constexpr uint32_t B_BYTES = (FP_N / CG) * 128;
     const uint32_t bar_base = smem_base + B_BYTES;
     const uint32_t tmem_slot = bar_base + 8 * RING;
@@ -206,20 +209,29 @@ __global__ void __launch_bounds__(128, 1) fp4_peak_kernel(uint32_t iters) {
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    if (rank == 0 && tid == 0) {
+    // warp-uniform issue loop with one elected lane, as in the tile kernel (see umma_peak_kernel)
+    if (rank == 0 && warp == 0) {
+        const bool leader = elect_one();
         const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-        const uint32_t sfa = tmem_base + FP_SF_COL, sfb = tmem_base + FP_SF_COL + 32;
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t sfa = tmem_u + FP_SF_COL, sfb = tmem_u + FP_SF_COL + 32;
+        const long long c0 = clock64();
         for (uint32_t it = 0; it < iters; ++it) {
-            if (it >= RING) mbar_wait(bar_base + 8 * (it % RING), ((it / RING) - 1) & 1);
+            if (it >= RING) mbar_wait_t<true>(bar_base + 8 * (it % RING), ((it / RING) - 1) & 1);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint64_t b_desc = desc_hi | (uint64_t)(((smem_base + k * 32) >> 4) & 0x3FFF);
-                umma_mxf4_ts<CG>(tmem_base + FP_ACC_COL, tmem_base + FP_A_COL + k * 8, b_desc, fp4_idesc<CG>(), sfa, sfb, 1u);
+                for (int k = 0; k < (int)BATCH; ++k) {
+                    const uint64_t b_desc = desc_hi | (uint64_t)(((smem_base + (k & 3) * 32) >> 4) & 0x3FFF);
+                    umma_mxf4_ts<CG>(tmem_u + FP_ACC_COL, tmem_u + FP_A_COL + (k & 3) * 8, b_desc, fp4_idesc<CG>(), sfa, sfb, 1u);
+                }
+                umma_commit<CG>(bar_base + 8 * (it % RING));
             }
-            umma_commit<CG>(bar_base + 8 * (it % RING));
+            __syncwarp();
         }
         for (uint32_t it = iters > RING ? iters - RING : 0; it < iters; ++it)
-            mbar_wait(bar_base + 8 * (it % RING), (it / RING) & 1);
+            mbar_wait_t<true>(bar_base + 8 * (it % RING), (it / RING) & 1);
+        const long long c1 = clock64();
+        if (leader && cycles) cycles[blockIdx.x / CG] = (unsigned long long)(c1 - c0);
     }
     __syncwarp();
     tc_fence_before();
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(128, 1) fp4_peak_kernel(uint32_t iters) {
 }
 
 template <int CG>
-int run_fp4_peak(double* ops_per_s) {
+int run_fp4_peak(double* ops_per_s, double* clock64_mhz) {
     int dev = 0, sms = 0;
     STORM_CUDA_TRY(cudaGetDevice(&dev));
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -245,28 +257,234 @@ int run_fp4_peak(double* ops_per_s) {
     cudaEvent_t e0, e1;
     STORM_CUDA_TRY(cudaEventCreate(&e0));
     STORM_CUDA_TRY(cudaEventCreate(&e1));
-    const uint32_t iters = 100000;
-    double best = 0;
+    const unsigned n_clusters = cfg.gridDim.x / CG;
+    unsigned long long* d_cyc = nullptr;
+    STORM_CUDA_TRY(cudaMalloc(&d_cyc, n_clusters * sizeof(unsigned long long)));
+    std::vector<unsigned long long> h_cyc(n_clusters);
+    const uint32_t iters = 50000;
+    double best = 0, best_mhz = 0;
     for (int rep = 0; rep < 4; ++rep) {                                   // rep 0 is the warm-up
         STORM_CUDA_TRY(cudaEventRecord(e0));
-        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, fp4_peak_kernel<CG>, iters));
+        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, fp4_peak_kernel<CG>, iters, d_cyc));
         STORM_CUDA_TRY(cudaEventRecord(e1));
         STORM_CUDA_TRY(cudaEventSynchronize(e1));
         count_launch();
         float ms = 0;
         STORM_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        STORM_CUDA_TRY(cudaMemcpy(h_cyc.data(), d_cyc, n_clusters * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double cyc = 0;
+        for (unsigned long long c : h_cyc) cyc += (double)c;
+        cyc /= n_clusters;
         // per SM and instruction: 128 x 256 x 64 MACs = 2 ops each
-        const double ops = (double)cfg.gridDim.x * iters * 4.0 * 128.0 * 256.0 * 64.0 * 2.0;
-        if (rep > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+        const double ops = (double)cfg.gridDim.x * iters * 8.0 * 128.0 * 256.0 * 64.0 * 2.0;
+        if (rep > 0 && ops / (ms * 1e-3) > best) { best = ops / (ms * 1e-3); best_mhz = cyc / (ms * 1e-3) / 1e6; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_cyc);
     *ops_per_s = best;
+    if (clock64_mhz) *clock64_mhz = best_mhz;
+    return STORM_B200_OK;
+}
+
+// ---- data-dependent increments, cta_group 1 and 2 ----------------------------------------------------------
+// The probe above drives every accumulator with the SAME increment per instruction (+64, then +1) on one CTA.
+// The tile kernel is cta_group::2 and its increments are whatever the data says: 0 .. 64 per instruction,
+// different for every accumulator element.  This kernel reproduces that: 4 A operands (tensor memory) x 4 B
+// operands (the four K steps of one SWIZZLE_128B line block) hold pseudo-random bit masks in the production
+// encoding (nibble codes {0.5, 1, 2, 1} x {2, 1, 0.5, 1} by register of a word, expand32_*_fp4 of dense_umma.cu),
+// with all-ones and all-zero rows mixed in; a pseudo-random sequence of n_steps (A, B) combinations is issued
+// back to back into one accumulator, and every element is compared with the integer it must hold:
+//     sum over (a, b) of times[a][b] x popcount(maskA[a][row] & maskB[b][col]).
+// Row 0 x column 0 are all ones in every operand, so that element reaches 64 x n_steps (2^24 - 64 at 262 143 steps).
+struct Fp4RandResult {
+    float max_expected, min_diff, max_diff;
+    uint32_t mismatches;
+};
+
+__host__ __device__ inline uint64_t probe_hash(uint64_t x) {               // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// 64-bit mask of operand `op` (0..3) of side (0 = A, 1 = B) for global row / column idx
+__host__ __device__ inline uint64_t probe_mask(uint32_t seed, uint32_t side, uint32_t op, uint32_t idx) {
+    const uint32_t cls = idx & 15u;
+    if (cls == 0) return ~0ull;                                            // every instruction adds 64 where two of these meet
+    if (cls == 1) return 0ull;
+    const uint64_t h1 = probe_hash(((uint64_t)seed << 32) ^ ((uint64_t)side << 28) ^ ((uint64_t)op << 24) ^ idx);
+    const uint64_t h2 = probe_hash(h1 ^ 0xD1B54A32D192ED03ull);
+    return cls < 6 ? (h1 & h2) : cls < 11 ? h1 : (h1 | h2);                 // ~25 %, 50 %, 75 % ones
+}
+// 32 mask bits -> 4 TMEM cells / shared-memory words of 8 E2M1 nibbles each, production encoding
+__device__ __forceinline__ void probe_encode(uint32_t bits, bool b_side, uint32_t (&cell)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const uint32_t k = 8u * c + n;                                 // K index within this half
+            // as the tile kernel lays a word out: cell (register) c of the four holds one code in all its nibbles
+            const uint32_t code = b_side ? (c == 0 ? 4u : c == 2 ? 1u : 2u)                  // 2, 1, 0.5, 1
+                                         : (c == 0 ? 1u : c == 2 ? 4u : 2u);                 // 0.5, 1, 2, 1
+            if ((bits >> k) & 1u) w |= code << (4 * n);
+        }
+        cell[c] = w;
+    }
+}
+__host__ __device__ inline uint32_t probe_step_combo(uint32_t seed, uint32_t t) { return (uint32_t)(probe_hash(((uint64_t)seed << 32) | t) >> 17) & 15u; }
+
+template <int CG>
+__global__ void __launch_bounds__(128, 1) fp4_random_kernel(uint32_t n_steps, uint32_t seed, Fp4RandResult* results) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    constexpr uint32_t B_ROWS = FP_N / CG;                                 // B rows (accumulator columns) held by this CTA
+    constexpr uint32_t B_BYTES = B_ROWS * 128;
+    const uint32_t bar = smem_base + B_BYTES;
+    const uint32_t tmem_slot = bar + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    uint32_t* times = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot + 8 - smem_base));     // [16]
+    uint32_t* red = times + 16;                                                                  // [4][4]
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+
+    if (warp == 0) tmem_alloc<CG>(tmem_slot);
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (tid < 16) times[tid] = 0;
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t my_lanes = tmem_base + ((warp * 32u) << 16);
+    const uint32_t row = rank * 128u + tid;                                // global accumulator row of this thread (= its TMEM lane)
+
+    {   // scale factors x 1.0; A operands: operand a occupies columns [FP_A_COL + 8 a, + 8)
+        uint32_t sf[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sf[j] = 0x7F7F7F7Fu;
+        for (int c = 0; c < 64; c += 8) tmem_st8(my_lanes + FP_SF_COL + c, sf);
+        for (uint32_t a = 0; a < 4; ++a) {
+            const uint64_t m = probe_mask(seed, 0, a, row);
+            uint32_t lo[4], hi[4], cells[8];
+            probe_encode((uint32_t)m, false, lo);
+            probe_encode((uint32_t)(m >> 32), false, hi);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { cells[c] = lo[c]; cells[4 + c] = hi[c]; }
+            tmem_st8(my_lanes + FP_A_COL + 8 * a, cells);
+        }
+        tc_wait_st();
+    }
+    // B operands: K step b (32 bytes) of the 128-byte line of B row r holds operand b of global column rank * B_ROWS + r
+    for (uint32_t r = tid; r < B_ROWS; r += 128) {
+        const uint32_t line = smem_base + (r >> 3) * 1024u + (r & 7u) * 128u;
+        for (uint32_t b = 0; b < 4; ++b) {
+            const uint64_t m = probe_mask(seed, 1, b, rank * B_ROWS + r);
+            uint32_t lo[4], hi[4];
+            probe_encode((uint32_t)m, true, lo);
+            probe_encode((uint32_t)(m >> 32), true, hi);
+            st_shared_v4(line + (((2 * b) ^ (r & 7u)) << 4), lo[0], lo[1], lo[2], lo[3]);
+            st_shared_v4(line + (((2 * b + 1) ^ (r & 7u)) << 4), hi[0], hi[1], hi[2], hi[3]);
+        }
+    }
+    fence_proxy_async_smem();
+    if (tid == 0) for (uint32_t t = 0; t < n_steps; ++t) times[probe_step_combo(seed, t)] += 1;   // both CTAs: the same sequence
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+
+    if (rank == 0 && tid == 0) {
+        const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+        const uint32_t sfa = tmem_base + FP_SF_COL, sfb = tmem_base + FP_SF_COL + 32;
+        for (uint32_t t = 0; t < n_steps; ++t) {
+            const uint32_t combo = probe_step_combo(seed, t), a = combo >> 2, b = combo & 3u;
+            const uint64_t b_desc = desc_hi | (uint64_t)(((smem_base + b * 32) >> 4) & 0x3FFF);
+            umma_mxf4_ts<CG>(tmem_base + FP_ACC_COL, tmem_base + FP_A_COL + 8 * a, b_desc, fp4_idesc<CG>(), sfa, sfb, t ? 1u : 0u);
+        }
+        umma_commit<CG>(bar);
+    }
+    mbar_wait_t<true>(bar, 0);
+    tc_fence_after();
+
+    uint64_t ma[4];
+    for (uint32_t a = 0; a < 4; ++a) ma[a] = probe_mask(seed, 0, a, row);
+    float mn = 3.0e38f, mx = -3.0e38f, top = 0.0f;
+    uint32_t bad = 0;
+    for (uint32_t c0 = 0; c0 < (uint32_t)FP_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(my_lanes + FP_ACC_COL + c0, v);
+        tc_wait_ld();
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            uint64_t expect = 0;
+            for (uint32_t b = 0; b < 4; ++b) {
+                const uint64_t mb = probe_mask(seed, 1, b, c0 + k);
+                for (uint32_t a = 0; a < 4; ++a) expect += (uint64_t)times[a * 4 + b] * (uint64_t)__popcll(ma[a] & mb);
+            }
+            const float want = (float)expect, got = __uint_as_float(v[k]);  // expect < 2^24: exact as a float
+            mn = fminf(mn, got - want); mx = fmaxf(mx, got - want); top = fmaxf(top, want);
+            bad += (got != want) || expect >= (1ull << 24);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) { red[warp * 4] = __float_as_uint(mn); red[warp * 4 + 1] = __float_as_uint(mx); red[warp * 4 + 2] = __float_as_uint(top); red[warp * 4 + 3] = bad; }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        Fp4RandResult r{0.0f, 3.0e38f, -3.0e38f, 0};
+        for (int w = 0; w < 4; ++w) {
+            r.min_diff = fminf(r.min_diff, __uint_as_float(red[w * 4]));
+            r.max_diff = fmaxf(r.max_diff, __uint_as_float(red[w * 4 + 1]));
+            r.max_expected = fmaxf(r.max_expected, __uint_as_float(red[w * 4 + 2]));
+            r.mismatches += red[w * 4 + 3];
+        }
+        results[rank] = r;
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 0) tmem_free<CG>(tmem_base);
+}
+
+template <int CG>
+int run_fp4_random(uint32_t n_steps, uint32_t seed, Fp4RandResult* out) {
+    Fp4RandResult* d_res = nullptr;
+    STORM_CUDA_TRY(cudaMalloc(&d_res, 2 * sizeof(Fp4RandResult)));
+    struct Release { void* p; ~Release() { cudaFree(p); } } release{d_res};
+    const int smem_bytes = 1024 + (FP_N / CG) * 128 + 512;
+    STORM_CUDA_TRY(cudaFuncSetAttribute(fp4_random_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CG);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, fp4_random_kernel<CG>, n_steps, seed, d_res));
+    count_launch();
+    Fp4RandResult h[2];
+    STORM_CUDA_TRY(cudaMemcpy(h, d_res, CG * sizeof(Fp4RandResult), cudaMemcpyDeviceToHost));
+    *out = h[0];
+    if (CG == 2) {
+        out->max_expected = fmaxf(h[0].max_expected, h[1].max_expected);
+        out->min_diff = fminf(h[0].min_diff, h[1].min_diff);
+        out->max_diff = fmaxf(h[0].max_diff, h[1].max_diff);
+        out->mismatches = h[0].mismatches + h[1].mismatches;
+    }
     return STORM_B200_OK;
 }
 
 }  // namespace
 
-int fp4_peak_ops(int cg, double* ops_per_s) { return cg == 1 ? run_fp4_peak<1>(ops_per_s) : run_fp4_peak<2>(ops_per_s); }
+int fp4_peak_ops(int cg, double* ops_per_s, double* clock64_mhz) {
+    return cg == 1 ? run_fp4_peak<1>(ops_per_s, clock64_mhz) : run_fp4_peak<2>(ops_per_s, clock64_mhz);
+}
 
 static int run_fp4_cases(const Fp4Case* cases, uint32_t n_cases, Fp4Result* results) {
     Fp4Case* d_cases = nullptr; Fp4Result* d_res = nullptr;
@@ -305,6 +523,12 @@ int fp4_selftest_ok() {
         std::vector<Fp4Result> res(cases.size());
         bool ok = run_fp4_cases(cases.data(), (uint32_t)cases.size(), res.data()) == STORM_B200_OK;
         for (const Fp4Result& r : res) ok = ok && r.mismatches == 0;
+        // data-dependent increments (0 .. 64 per instruction and element), both cta_group forms, up to 2^24 - 64
+        for (uint32_t steps : {1000u, 262143u}) {
+            Fp4RandResult r1{}, r2{};
+            ok = ok && run_fp4_random<1>(steps, 17u + steps, &r1) == STORM_B200_OK && r1.mismatches == 0 && r1.max_expected == 64.0f * (float)steps;
+            ok = ok && run_fp4_random<2>(steps, 29u + steps, &r2) == STORM_B200_OK && r2.mismatches == 0 && r2.max_expected == 64.0f * (float)steps;
+        }
         state[dev] = ok ? 1 : 2;
     }
     return state[dev] == 1;
@@ -320,6 +544,22 @@ extern "C" int STORM_b200_fp4_probe(const uint32_t* cases, uint32_t n_cases, flo
     if (!cases || !results || n_cases == 0) { set_error("fp4 probe: bad arguments"); return STORM_B200_EINVAL; }
     static_assert(sizeof(Fp4Case) == 12 && sizeof(Fp4Result) == 16, "C-ABI layout of the probe records");
     return run_fp4_cases(reinterpret_cast<const Fp4Case*>(cases), n_cases, reinterpret_cast<Fp4Result*>(results));
+}
+
+// Data-dependent increments (see fp4_random_kernel): n_steps instructions (at most 262 143: the all-ones element then holds
+// 2^24 - 64) at cta_group cg (1 or 2).  results: {largest expected element, smallest and largest (got - expected)} as floats
+// and the number of elements that differ (u32 bits).
+extern "C" int STORM_b200_fp4_probe_random(int cg, uint32_t n_steps, uint32_t seed, float* results) {
+    using namespace storm;
+    int rc = require_device();
+    if (rc) return rc;
+    if (!results || n_steps == 0 || n_steps > 262143u || (cg != 1 && cg != 2)) { set_error("fp4 random probe: bad arguments"); return STORM_B200_EINVAL; }
+    static_assert(sizeof(Fp4RandResult) == 16, "C-ABI layout of the probe record");
+    Fp4RandResult r{};
+    rc = cg == 1 ? run_fp4_random<1>(n_steps, seed, &r) : run_fp4_random<2>(n_steps, seed, &r);
+    if (rc) return rc;
+    memcpy(results, &r, sizeof(r));
+    return STORM_B200_OK;
 }
 
 extern "C" int STORM_b200_fp4_selftest(void) {

@@ -5,6 +5,8 @@
 // so their roofline denominators are measured here on the device itself
 // (SURVEY.md section 7.3 item 1).  Each kernel runs 8 independent dependency
 // chains per thread, 16 warps per SM, long enough to amortise the launch.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace storm {
@@ -80,6 +82,39 @@ int run_kind(double* rate, double* mhz, double ops_per_inner) {
     return STORM_B200_OK;
 }
 
+// How fast does clock64() tick?  Every per-clock figure of this library divides by a clock64 delta, and the first
+// round's table was off by a factor of two against nvidia-smi's SM clock.  One thread per SM spins for 250 ms of
+// %globaltimer and reports its clock64 delta: ticks per nanosecond, to be read beside `nvidia-smi clocks.sm`
+// sampled during the spin (the part idles at its maximum clock here: nothing else runs).
+__global__ void clock_calibration_kernel(unsigned long long spin_ns, unsigned long long* out) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < spin_ns);
+    const long long c1 = clock64();
+    out[2 * blockIdx.x] = (unsigned long long)(c1 - c0);
+    out[2 * blockIdx.x + 1] = t1 - t0;
+}
+
+int run_clock_calibration(double* ticks_per_s, double* mhz) {
+    int dev = 0, sms = 0;
+    STORM_CUDA_TRY(cudaGetDevice(&dev));
+    STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    unsigned long long* d = nullptr;
+    STORM_CUDA_TRY(cudaMalloc(&d, 2 * sms * sizeof(unsigned long long)));
+    clock_calibration_kernel<<<sms, 1>>>(250000000ull, d);
+    count_launch();
+    unsigned long long h[2 * 256] = {};
+    const cudaError_t e = cudaMemcpy(h, d, 2 * std::min(sms, 256) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    STORM_CUDA_TRY(e);
+    double c = 0, t = 0;
+    for (int i = 0; i < std::min(sms, 256); ++i) { c += (double)h[2 * i]; t += (double)h[2 * i + 1]; }
+    *ticks_per_s = c / t * 1e9;
+    if (mhz) *mhz = c / t * 1e3;
+    return STORM_B200_OK;
+}
+
 }  // namespace
 }  // namespace storm
 
@@ -91,10 +126,11 @@ extern "C" int STORM_b200_microbench(int kind, double* rate, double* sm_mhz) {
         case 1: return run_kind<1>(rate, sm_mhz, 8.0);
         case 2: return run_kind<2>(rate, sm_mhz, 8.0);
         case 3: return run_kind<3>(rate, sm_mhz, 6.0);   // 2 POPC + 4 LOP3 per inner step
-        case 4: if (sm_mhz) *sm_mhz = 0; return umma_peak_ops(1, rate);   // tcgen05.mma kind::i8, cta_group::1
-        case 5: if (sm_mhz) *sm_mhz = 0; return umma_peak_ops(2, rate);   // tcgen05.mma kind::i8, cta_group::2
-        case 6: if (sm_mhz) *sm_mhz = 0; return fp4_peak_ops(1, rate);    // tcgen05.mma kind::mxf4 (E2M1, K 64), cta_group::1
-        case 7: if (sm_mhz) *sm_mhz = 0; return fp4_peak_ops(2, rate);    // tcgen05.mma kind::mxf4, cta_group::2
+        case 4: return umma_peak_ops(1, rate, sm_mhz);   // tcgen05.mma kind::i8, cta_group::1
+        case 5: return umma_peak_ops(2, rate, sm_mhz);   // tcgen05.mma kind::i8, cta_group::2
+        case 6: return fp4_peak_ops(1, rate, sm_mhz);    // tcgen05.mma kind::mxf4 (E2M1, K 64), cta_group::1
+        case 7: return fp4_peak_ops(2, rate, sm_mhz);    // tcgen05.mma kind::mxf4, cta_group::2
+        case 8: return run_clock_calibration(rate, sm_mhz);   // clock64 ticks per second (and per 1e6) over a 250 ms spin
         default: set_error("unknown microbench kind %d", kind); return STORM_B200_EINVAL;
     }
 }

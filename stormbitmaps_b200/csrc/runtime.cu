@@ -51,6 +51,7 @@ TileShape tile_shape_for(int kernel) {
         case STORM_B200_KERNEL_UMMA:
         case STORM_B200_KERNEL_FP4:  return umma_tile_shape();
         case STORM_B200_KERNEL_CSA:  return csa_tile_shape();
+        case STORM_B200_KERNEL_B1:   return b1_tile_shape();
         default:                     return popc_tile_shape();
     }
 }
@@ -124,6 +125,7 @@ int launch_dense(int kernel, const DenseJob& job, cudaStream_t stream) {
     switch (kernel) {
         case STORM_B200_KERNEL_POPC: return launch_dense_popc(job, stream);
         case STORM_B200_KERNEL_CSA:  return launch_dense_csa(job, stream);
+        case STORM_B200_KERNEL_B1:   return launch_dense_b1(job, stream);
         case STORM_B200_KERNEL_UMMA:
             if (!umma_supports(job)) {
                 set_error("UMMA kernel needs n_words >= 2, 16-byte aligned rows and an even row stride");
@@ -142,7 +144,7 @@ int launch_dense(int kernel, const DenseJob& job, cudaStream_t stream) {
     }
 }
 
-static int check_rows(const uint64_t* d_rows, uint64_t stride, uint32_t n_words) {
+int check_rows(const uint64_t* d_rows, uint64_t stride, uint32_t n_words) {
     if (!d_rows) { set_error("d_rows is NULL"); return STORM_B200_EINVAL; }
     if (((uintptr_t)d_rows & 15) || (stride & 1)) {
         set_error("rows must be 16-byte aligned with an even word stride (got %p, stride %llu)", (const void*)d_rows,
@@ -163,6 +165,7 @@ static DenseJob triangle_job(const uint64_t* d_rows, uint64_t n_rows, uint32_t n
     job.strict_upper = 1;
     job.triangle = 1;
     job.total = reinterpret_cast<unsigned long long*>(d_total);
+    job.reserved_sms = -1;
     return job;
 }
 
@@ -173,13 +176,14 @@ int resolve_kernel_for_rows(int kernel, const uint64_t* d_rows, uint64_t n_rows,
 // shard < n_shards: that shard's range of the raster; n_shards == 0: the explicit range [tile_begin, tile_end)
 static int pairw_triangle_impl(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
                                uint32_t shard, uint32_t n_shards, uint64_t tile_begin, uint64_t tile_end,
-                               int kernel, uint64_t* d_total, cudaStream_t stream) {
+                               int kernel, uint64_t* d_total, cudaStream_t stream, int reserved_sms = -1) {
     int rc = require_device();
     if (rc) return rc;
     if (!d_total) { set_error("d_total is NULL"); return STORM_B200_EINVAL; }
     if (n_rows < 2) return STORM_B200_OK;
     if ((rc = check_rows(d_rows, stride, n_words))) return rc;
     DenseJob job = triangle_job(d_rows, n_rows, n_words, stride, d_total);
+    job.reserved_sms = reserved_sms;
     kernel = resolve_kernel(kernel, job);
     const TileShape ts = tile_shape_for(kernel);
     uint64_t n_tiles = 0;
@@ -199,8 +203,8 @@ int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, ui
 }
 
 int pairw_triangle_range(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
-                         uint64_t tile_begin, uint64_t tile_end, int kernel, uint64_t* d_total, cudaStream_t stream) {
-    return pairw_triangle_impl(d_rows, n_rows, n_words, stride, 0, 0, tile_begin, tile_end, kernel, d_total, stream);
+                         uint64_t tile_begin, uint64_t tile_end, int kernel, uint64_t* d_total, cudaStream_t stream, int reserved_sms) {
+    return pairw_triangle_impl(d_rows, n_rows, n_words, stride, 0, 0, tile_begin, tile_end, kernel, d_total, stream, reserved_sms);
 }
 
 int pairw_rect(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off,
@@ -222,6 +226,7 @@ int pairw_rect(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off
     job.triangle = 0;
     job.out = d_out; job.ld = ld;
     job.total = reinterpret_cast<unsigned long long*>(d_total);
+    job.reserved_sms = -1;
     kernel = resolve_kernel(kernel, job);
     const TileShape ts = tile_shape_for(kernel);
     job.n_bi = (uint32_t)((nA + ts.tm - 1) / ts.tm);
@@ -292,6 +297,7 @@ int STORM_b200_square_device(const uint64_t* d_rows1, uint64_t n1, uint64_t stri
 
 int STORM_b200_resolve_kernel(int kernel, uint32_t n_words) {
     DenseJob job{};
+    job.reserved_sms = -1;
     job.n_words = n_words;
     job.strideA = job.strideB = (n_words + 15) / 16 * 16;
     return resolve_kernel(kernel, job);
@@ -333,6 +339,14 @@ int STORM_b200_pairw_tiles_device(const uint64_t* d_rows, uint64_t n_rows, uint3
     if (tile_begin == tile_end) return STORM_B200_OK;
     return pairw_triangle_range(d_rows, n_rows, n_words, row_stride_words, tile_begin, tile_end, kernel, d_total,
                                 (cudaStream_t)stream);
+}
+
+int STORM_b200_pairw_tiles_device_ex(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words,
+                                     uint64_t row_stride_words, uint64_t tile_begin, uint64_t tile_end,
+                                     int kernel, int reserved_sms, uint64_t* d_total, void* stream) {
+    if (tile_begin == tile_end) return STORM_B200_OK;
+    return pairw_triangle_range(d_rows, n_rows, n_words, row_stride_words, tile_begin, tile_end, kernel, d_total,
+                                (cudaStream_t)stream, reserved_sms < 0 ? -1 : reserved_sms);
 }
 
 int STORM_b200_tile_rect(uint64_t n_rows, int kernel, uint64_t tile, uint64_t* i0, uint64_t* i1, uint64_t* j0, uint64_t* j1) {

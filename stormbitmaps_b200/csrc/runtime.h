@@ -14,6 +14,8 @@ TileShape tile_shape_for(int kernel);
 uint64_t triangle_prefix(uint64_t n_rows, TileShape ts, std::vector<uint64_t>* prefix, uint32_t* n_bi, uint32_t* n_bj);
 void shard_range(uint64_t n_tiles, uint32_t shard, uint32_t n_shards, uint64_t* begin, uint64_t* end);
 int resolve_kernel(int kernel, const DenseJob& job);
+// Alignment / stride / width checks every dense entry point applies to a device matrix before any launch.
+int check_rows(const uint64_t* d_rows, uint64_t stride, uint32_t n_words);
 int launch_dense(int kernel, const DenseJob& job, cudaStream_t stream);
 
 // Upper-triangle total of a device matrix (shard of the tile raster), accumulated into *d_total.
@@ -21,7 +23,8 @@ int pairw_triangle(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, ui
                    uint32_t shard, uint32_t n_shards, int kernel, uint64_t* d_total, cudaStream_t stream);
 // The same over an explicit range [tile_begin, tile_end) of the triangle raster.
 int pairw_triangle_range(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride,
-                         uint64_t tile_begin, uint64_t tile_end, int kernel, uint64_t* d_total, cudaStream_t stream);
+                         uint64_t tile_begin, uint64_t tile_end, int kernel, uint64_t* d_total, cudaStream_t stream,
+                         int reserved_sms = -1);
 // Kernel id AUTO resolves to for square-matrix rows of this geometry on the current device.
 int resolve_kernel_for_rows(int kernel, const uint64_t* d_rows, uint64_t n_rows, uint32_t n_words, uint64_t stride);
 // All pairs of A rows x B rows (optionally only global j > i), counts and/or total.

@@ -112,12 +112,14 @@ int pairw_rect_op(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_
     int rc = require_device();
     if (rc) return rc;
     if (nA == 0 || nB == 0) return STORM_B200_OK;
+    if ((rc = check_rows(dA, strideA, n_words)) || (rc = check_rows(dB, strideB, n_words))) return rc;   // before any launch: the popcount kernel loads 16 bytes at a time
     const unsigned long long k = op == STORM_B200_OP_UNION ? 1 : 2;
     const bool same = dA == dB && nA == nB && strideA == strideB;
-    uint32_t* counts = nullptr;
-    unsigned long long* scal = nullptr;                                     // [0] popcount term, [1] intersections
-    STORM_CUDA_TRY(cudaMallocAsync(&counts, (nA + (same ? 0 : nB)) * sizeof(uint32_t), stream));
-    STORM_CUDA_TRY(cudaMallocAsync(&scal, 2 * sizeof(unsigned long long), stream));
+    // one stream-ordered allocation: [2 x u64: popcount term, intersections][row popcounts of A (and B)]
+    unsigned long long* scal = nullptr;
+    STORM_CUDA_TRY(cudaMallocAsync(&scal, 2 * sizeof(unsigned long long) + (nA + (same ? 0 : nB)) * sizeof(uint32_t), stream));
+    struct Release { void* p; cudaStream_t s; ~Release() { cudaFreeAsync(p, s); } } release{scal, stream};   // every return path
+    uint32_t* counts = reinterpret_cast<uint32_t*>(scal + 2);
     STORM_CUDA_TRY(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), stream));
     uint32_t* ca = counts;
     uint32_t* cb = same ? counts : counts + nA;
@@ -145,8 +147,6 @@ int pairw_rect_op(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_
             if (cudaGetLastError() != cudaSuccess) rc = STORM_B200_ECUDA;
         }
     }
-    cudaFreeAsync(counts, stream);
-    cudaFreeAsync(scal, stream);
     return rc;
 }
 

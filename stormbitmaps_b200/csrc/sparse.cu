@@ -36,6 +36,7 @@ constexpr uint32_t BLOCK_BITS = STORM_DEFAULT_BLOCK_SIZE;          // 65536
 constexpr uint32_t BLOCK_WORDS = BLOCK_BITS / 64;                  // 1024
 constexpr uint32_t LIST_THRESHOLD = STORM_DEFAULT_SCALAR_THRESHOLD;  // 4096
 constexpr uint32_t BITMAP_FLAG = 0x80000000u;
+constexpr uint32_t ROW_HAS_BITMAP = 0x80000000u;                   // device copy of row_nnz: the row holds a bitmap block
 
 // Threads per CTA: the kernel is latency-bound (dependent global loads of the merge, random probes), so it
 // wants every warp it can get next to one CTA's shared bitmaps: 1024 threads when the shared-memory slots
@@ -52,7 +53,7 @@ constexpr uint32_t SP_PROBE_I_MAX = 256;   // i-list probes into a j-bitmap up t
 // Flattened device view of one STORM_t.
 struct SparseView {
     const uint32_t* row_ptr;   // n_rows + 1: first block of each row
-    const uint32_t* row_nnz;   // values handed to the builder per row
+    const uint32_t* row_nnz;   // values per row; ROW_HAS_BITMAP set if any of the row's blocks is a bitmap block
     const uint32_t* blk_id;    // block index (value / 65536), ascending within a row
     const uint32_t* blk_len;   // number of values; BITMAP_FLAG set for bitmap blocks
     const uint64_t* blk_off;   // list: element offset into `lists`; bitmap: word offset into `words`
@@ -121,6 +122,9 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_pairs_kernel(const S
     const SparseView& B = job.B;
     const uint32_t rb = A.row_ptr[i], nbi = A.row_ptr[i + 1] - rb;
     if (nbi == 0) return;                                          // empty row: all counts 0 (out is pre-zeroed)
+    // tiny rows are never expanded into shared memory: every block must be a list.  (A block built from >= 4096
+    // values with duplicates is a bitmap block holding few bits -- storm.c:745-748 decides on the values handed in,
+    // not on the bits set -- and carries ROW_HAS_BITMAP, so the compare below is false for its row.)
     const bool tiny = A.row_nnz[i] <= SP_TINY_NNZ;
 
     unsigned long long cta_lane_total = 0;
@@ -575,7 +579,11 @@ int sync_mirror(const STORM_t* s, StormState* st) {
     stream_groups(row_nnz.data(), s->n_conts, &gs);
     if ((rc = upload(&st->d_group_start, gs, st->stream))) return rc;
     st->max_row_nnz = max_row_nnz;
-    if ((rc = upload(&st->d_row_ptr, row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, row_nnz, st->stream)) ||
+    std::vector<uint32_t> row_nnz_dev(row_nnz);                    // device copy: + the "holds a bitmap block" flag
+    for (uint32_t r = 0; r < s->n_conts; ++r)
+        for (uint32_t b = row_ptr[r]; b < row_ptr[r + 1]; ++b)
+            if (blk_len[b] & BITMAP_FLAG) { row_nnz_dev[r] |= ROW_HAS_BITMAP; break; }
+    if ((rc = upload(&st->d_row_ptr, row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, row_nnz_dev, st->stream)) ||
         (rc = upload(&st->d_blk_id, blk_id, st->stream)) || (rc = upload(&st->d_blk_len, blk_len, st->stream)) ||
         (rc = upload(&st->d_blk_off, blk_off, st->stream)) || (rc = upload(&st->d_lists, lists, st->stream)) ||
         (rc = upload(&st->d_words, words, st->stream)))
@@ -765,23 +773,32 @@ void storm_route_model(uint64_t n_rows, uint64_t W, double avg_nnz, double avg_b
     if (stream_applies) *sparse_s = std::min(*sparse_s, stream_seconds(pairs, avg_nnz));          // row-group stream kernel
 }
 
+// Which route a whole-container query takes.  A PURE function of the container (rows, width, values, blocks) and
+// of the process-wide route knobs -- never of free memory, of the self-test of the device at hand or of what happens
+// to be resident: the shards of one query run on different devices and partition the pair set differently per
+// route (tile raster / row groups / rows), so every shard has to arrive at the same answer.  Whether the chosen
+// route can run here (memory) is checked afterwards: an unsharded query may then fall back, a sharded one fails.
 bool choose_dense_route(const StormState* st, uint64_t n_rows) {
     if (g_storm_route == 1) return false;
     const uint64_t W = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
     if (W >= (1u << 25)) return false;                                   // per-pair counts must stay below 2^31
-    const uint64_t need = n_rows * W * 8;
-    if (need > st->dense_cap_words * 8) {                                // (cudaMemGetInfo costs ~0.1 ms: only when the arena must grow)
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
-        const uint64_t have = free_b + (st->d_dense ? st->dense_cap_words * 8 : 0);
-        if (need > have / 10 * 8) return false;                          // keep 20 % of the free memory
-    }
     if (g_storm_route == 2) return true;
     double dense_s = 0, sparse_s = 0;
     storm_route_model(n_rows, W, (double)st->total_nnz / (double)n_rows, (double)st->total_blocks / (double)n_rows,
                       g_sparse_flat && g_sparse_stream && st->n_bitmap_blocks == 0 && st->max_row_nnz <= STREAM_ENTRIES,
-                      W * 64 <= (1ull << 24) && fp4_selftest_ok(), st->dense_valid, &dense_s, &sparse_s);
+                      W * 64 <= (1ull << 24), false, &dense_s, &sparse_s);
     return dense_s < sparse_s;
+}
+
+// Does the dense form of the rows fit on this device (keeping 20 % of the free memory)?
+bool dense_fits(const StormState* st, uint64_t n_rows) {
+    const uint64_t W = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
+    const uint64_t need = n_rows * W * 8;
+    if (need <= st->dense_cap_words * 8) return true;                    // (cudaMemGetInfo costs ~0.1 ms: only when the arena must grow)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+    const uint64_t have = free_b + (st->d_dense ? st->dense_cap_words * 8 : 0);
+    return need <= have / 10 * 8;
 }
 
 int ensure_dense(StormState* st, uint64_t n_rows, uint64_t* stride_out) {
@@ -815,13 +832,22 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     if (sync_mirror(s, st)) return (uint64_t)-1;
     if (cudaMemsetAsync(st->d_total, 0, 8, st->stream) != cudaSuccess) return (uint64_t)-1;
     uint64_t stride = 0;
-    if (choose_dense_route(st, s->n_conts) && ensure_dense(st, s->n_conts, &stride) == STORM_B200_OK) {
+    bool dense = choose_dense_route(st, s->n_conts);
+    if (dense && (!dense_fits(st, s->n_conts) || ensure_dense(st, s->n_conts, &stride) != STORM_B200_OK)) {
+        // the dense form does not fit on this device: an unsharded query answers through the sparse kernels instead;
+        // a shard must not (the other shards partition the pairs by the tile raster)
+        if (n_shards > 1) { set_error("shard %u of %u: the dense form of the rows does not fit on this device and a shard cannot switch route", shard, n_shards); return (uint64_t)-1; }
+        dense = false;
+    }
+    if (dense) {
         st->last_route = 2;
         if (pairw_triangle(st->d_dense, s->n_conts, (uint32_t)stride, stride, shard, n_shards, STORM_B200_KERNEL_AUTO,
                            reinterpret_cast<uint64_t*>(st->d_total), st->stream)) return (uint64_t)-1;
     } else {
         st->last_route = 1;
         if (ensure_flat(st)) return (uint64_t)-1;
+        // (same rule inside the sparse route: the stream kernel shards row groups, the other two rows)
+        if (n_shards > 1 && flat_eligible(st) && !st->flat_valid) { set_error("shard %u of %u: no room for the flat position mirror and a shard cannot switch kernel", shard, n_shards); return (uint64_t)-1; }
         if (stream_eligible(st, st)) {
             if (launch_stream(st, st, 0, s->n_conts, 0, s->n_conts, 1, shard, n_shards, st->d_total, st->stream)) return (uint64_t)-1;
         } else {

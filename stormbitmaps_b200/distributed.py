@@ -177,18 +177,14 @@ def pairw_total_from_host(host_rows, kernel=api.KERNEL_AUTO, group=None, arena=N
         st.comm.wait_stream(cur)                  # an earlier query's kernels may still be reading the arena
         reserve = STREAM_RESERVED_SMS if reserved_sms is None else reserved_sms
         rows_view = arena[:n_rows]
-        prev = api.set_umma_reserved_sms(reserve)
-        try:
-            for b, (r0, r1, t0, t1) in enumerate(plan):
-                with torch.cuda.stream(st.comm):
-                    gather_band(host_rows, arena, r0, r1, rank, world, group)
-                    st.events[b].record(st.comm)
-                cur.wait_event(st.events[b])
-                if b == len(plan) - 1:
-                    api.set_umma_reserved_sms(0)  # nothing left in flight: the last (largest) launch takes every SM
-                tb, te = rank_tiles(t0, t1, rank, world)
-                api.pairw_tiles_device(rows_view, tb, te, n_words=n_words, kernel=kid, total=total)
-        finally:
-            api.set_umma_reserved_sms(prev)
+        for b, (r0, r1, t0, t1) in enumerate(plan):
+            with torch.cuda.stream(st.comm):
+                gather_band(host_rows, arena, r0, r1, rank, world, group)
+                st.events[b].record(st.comm)
+            cur.wait_event(st.events[b])
+            tb, te = rank_tiles(t0, t1, rank, world)
+            # per launch, not a process-wide knob: the last (largest) launch has nothing left in flight beside it and takes every SM
+            api.pairw_tiles_device(rows_view, tb, te, n_words=n_words, kernel=kid, total=total,
+                                   reserved_sms=0 if b == len(plan) - 1 else reserve)
     dist.all_reduce(total, group=group)
     return int(total.item())                                  # D2H of the result

@@ -229,3 +229,108 @@ def test_route_model_decisions_on_the_measured_cases(lib):
     assert sb.storm_route_model(10000, 8192, 104, 8, 150, n_bitmap_blocks=3)["route"] == "dense"   # bitmap blocks: block kernel only
     # without the FP4 form the tile kernel is half as fast and the crossover moves up
     assert sb.storm_route_model(10000, 8192, 800, 8, 900, fp4=False)["route"] == "sparse"
+
+
+def test_header_declares_every_reference_prototype():
+    """Drop-in means every function the reference's storm.h declares is declared (and exported) here.  The name list
+    is a committed fixture (minted with: grep -oE '\\bSTORM_[a-zA-Z0-9_]+ *\\(' /root/reference/storm.h | tr -d ' (' | sort -u, minus the STORM_ALIGN macro);
+    where the reference tree is present the fixture itself is checked against it."""
+    want = set(open(os.path.join(ROOT, "tests", "golden", "reference_storm_h_prototypes.txt")).read().split())
+    assert len(want) == 42
+    ours = _declared_functions("storm.h")
+    assert not (want - ours), f"reference prototypes missing from include/storm.h: {sorted(want - ours)}"
+    ref_header = "/root/reference/storm.h"
+    if os.path.isfile(ref_header):
+        text = re.sub(r"/\*.*?\*/", "", open(ref_header).read(), flags=re.S)
+        live = set(re.findall(r"\b(STORM_[A-Za-z0-9_]+)\s*\(", text)) - {"STORM_ALIGN"}
+        assert live == want, (sorted(live - want), sorted(want - live))
+
+
+def test_per_pair_host_helpers(lib, orc):
+    """storm.h:56-61, 207-210, 220-221: the reference's CPU helpers for ONE pair, restated on the host
+    (host_pairs.cu).  Exact set semantics, checked against numpy and the oracle's u16 restatement."""
+    u16p, u32p, u64p = C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    rng = np.random.default_rng(7)
+    for na, nb in [(0, 5), (1, 1), (7, 9), (8, 8), (64, 4000), (4095, 4095), (3, 4095), (500, 17)]:
+        a = np.unique(rng.integers(0, 65536, na)).astype(np.uint16)
+        b = np.unique(rng.integers(0, 65536, nb)).astype(np.uint16)
+        if len(a) and len(b):
+            b[0] = a[0] = min(a[0], b[0]); a.sort(); b.sort(); a = np.unique(a); b = np.unique(b)
+        want = len(np.intersect1d(a, b))
+        got = lib.STORM_intersect_vector16_cardinality(a.ctypes.data_as(u16p), b.ctypes.data_as(u16p), len(a), len(b))
+        assert got == want == (orc.intersect_u16(a, b) if len(a) and len(b) else want), (na, nb)
+    a = np.array([1, 4, 9, 16, 25, 36], dtype=np.uint32); b = np.array([0, 4, 5, 16, 36, 99], dtype=np.uint32)
+    out = np.zeros(12, dtype=np.uint32)
+    n = lib.STORM_intersect_vector32_unsafe(a.ctypes.data_as(u32p), b.ctypes.data_as(u32p), 6, 6, out.ctypes.data_as(u32p))
+    assert n == 6 and out[:6].tolist() == [1, 1, 3, 3, 5, 4]              # (index in a, index in b) pairs
+    assert lib.STORM_intersect_vector32_unsafe(a.ctypes.data_as(u32p), b.ctypes.data_as(u32p), 6, 6, None) == 0
+    # list probe: the shorter list goes into the other row's bitmap (storm.c:108-129)
+    M = 4096
+    l1 = np.array([3, 64, 700, 4095], dtype=np.uint32); l2 = np.array([3, 5, 64, 65, 700, 701], dtype=np.uint32)
+    b1 = np.zeros(M // 64, dtype=np.uint64); b2 = np.zeros(M // 64, dtype=np.uint64)
+    for v in l1: b1[v >> 6] |= np.uint64(1) << np.uint64(v & 63)
+    for v in l2: b2[v >> 6] |= np.uint64(1) << np.uint64(v & 63)
+    for (x1, x2, y1, y2) in [(b1, b2, l1, l2), (b2, b1, l2, l1)]:
+        assert lib.STORM_intersect_bitmaps_scalar_list(x1.ctypes.data_as(u64p), x2.ctypes.data_as(u64p), y1.ctypes.data_as(u32p),
+                                                       y2.ctypes.data_as(u32p), len(y1), len(y2)) == 3
+    # blocks and rows: every (list | bitmap) x (list | bitmap) combination, exact (D1 not reproduced)
+    def row(values):
+        h = lib.STORM_bitmap_cont_new()
+        v = np.asarray(values, dtype=np.uint32)
+        assert lib.STORM_bitmap_cont_add(h, v.ctypes.data_as(u32p), len(v)) == 1
+        return h
+    dense = np.sort(rng.choice(3 * 65536, 40000, replace=False)).astype(np.uint32)       # bitmap blocks
+    sparse = np.sort(rng.choice(3 * 65536, 900, replace=False)).astype(np.uint32)        # list blocks
+    sparse2 = np.unique(np.concatenate([sparse[::3], dense[::50]])).astype(np.uint32)
+    rows = {"dense": dense, "sparse": sparse, "sparse2": sparse2, "dense2": dense[5000:35000]}
+    handles = {k: row(v) for k, v in rows.items()}
+    scratch = np.zeros(64, dtype=np.uint32)
+    f = C.cast(lib.STORM_get_intersect_count_func(1024), C.c_void_p)
+    for ka in rows:
+        for kb in rows:
+            want = len(np.intersect1d(rows[ka], rows[kb]))
+            assert lib.STORM_bitmap_cont_intersect_cardinality(handles[ka], handles[kb]) == want, (ka, kb)
+            assert lib.STORM_bitmap_cont_intersect_cardinality_premade(handles[ka], handles[kb], f, scratch.ctypes.data_as(u32p)) == want
+    for h in handles.values():
+        lib.STORM_bitmap_cont_free(h)
+    # one block built with bits + list (storm.c:467-519): duplicates enter the list once
+    blk = lib.STORM_bitmap_new()
+    v = np.array([5, 5, 9, 70, 9, 65535], dtype=np.uint32)
+    assert lib.STORM_bitmap_add_with_scalar(blk, v.ctypes.data_as(u32p), len(v)) == 6
+    blk2 = lib.STORM_bitmap_new()
+    w = np.array([9, 65535, 100], dtype=np.uint32)
+    assert lib.STORM_bitmap_add_scalar_only(blk2, w.ctypes.data_as(u32p), 3) == 3
+    assert lib.STORM_bitmap_intersect_cardinality(blk, blk2) == 2 == lib.STORM_bitmap_intersect_cardinality_func(blk, blk2, f)
+    assert lib.STORM_bitmap_intersect_cardinality(blk, None) == 0
+    lib.STORM_bitmap_free(blk); lib.STORM_bitmap_free(blk2)
+
+
+def test_foreign_compute_func_is_classified_not_assumed(lib):
+    """storm.c:132-150 applies whatever per-pair function it is handed.  A foreign function is identified by its
+    values on probe vectors: a union / diff / intersect count selects that operation, anything else is an error --
+    never a silent intersect total."""
+    import stormbitmaps_b200 as sb
+    proto = C.CFUNCTYPE(C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t)
+    bogus = proto(lambda a, b, n: 42)
+    vals = np.ones((4, 4), dtype=np.uint64)
+    rc = lib.STORM_wrapper_diag(4, vals.ctypes.data_as(C.POINTER(C.c_uint64)), 4, C.cast(bogus, C.c_void_p))
+    assert rc == 2**64 - 1 and "neither" in sb.last_error()
+    xor_count = proto(lambda a, b, n: sum(bin(a[k] ^ b[k]).count("1") for k in range(n)))
+    rc = lib.STORM_wrapper_diag(4, vals.ctypes.data_as(C.POINTER(C.c_uint64)), 4, C.cast(xor_count, C.c_void_p))
+    if lib.STORM_b200_device_count() == 0:
+        assert rc == 2**64 - 1 and "neither" not in sb.last_error()      # classified; then fails for want of a device
+    else:
+        assert rc == 0                                                    # four identical rows: every xor count is 0
+
+
+def test_device_set_api_without_gpu(lib):
+    import stormbitmaps_b200 as sb
+    prev = lib.STORM_b200_set_devices(2)
+    assert prev >= 0
+    assert lib.STORM_b200_set_devices(prev if prev > 1 else 1) == 2
+    ids = (C.c_int * 2)(0, 0)
+    assert lib.STORM_b200_set_device_list(ids, 2) == 0
+    assert lib.STORM_b200_set_device_list(None, 0) == 0                   # back to the default: the current device
+    if lib.STORM_b200_device_count() == 0:
+        got = (C.c_int * 4)()
+        assert lib.STORM_b200_get_devices(got, 4) < 0 and "no CUDA device" in sb.last_error()

@@ -16,7 +16,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = os.environ.get("STORM_TEST_KERNELS", "popc,csa,umma,fp4").split(",")
+KERNELS = os.environ.get("STORM_TEST_KERNELS", "popc,csa,umma,fp4,b1").split(",")
 
 
 def _sha(a):
@@ -561,3 +561,234 @@ def test_c_caller_linked_with_the_library_prints_the_reference_totals(sb):
             got = run_dropin_driver(exe, args)
             for k in HOST_FIELDS + QUERY_FIELDS:
                 assert got[k] == want[k], (args, k, got[k], want[k])
+
+
+# --------------------------------------------------------------------------- #
+# round 2: FP4 exactness at the top of the range, through the production kernel
+# --------------------------------------------------------------------------- #
+def test_fp4_random_increment_probe_both_cta_groups(sb):
+    """Data-dependent increments (0 .. 64 per instruction and element, production nibble encoding) at cta_group 1
+    and 2, driven to 2^24 - 64: every one of the 128 (256) x 256 accumulators must hold the exact integer."""
+    import ctypes as C
+    lib = sb.load()
+    for cg in (1, 2):
+        for steps, seed in [(1, 1), (7, 2), (4097, 3), (100000, 4), (262143, 5), (262143, 6)]:
+            res = np.zeros(4, dtype=np.float32)
+            rc = lib.STORM_b200_fp4_probe_random(cg, steps, seed, res.ctypes.data_as(C.POINTER(C.c_float)))
+            assert rc == 0, sb.last_error()
+            assert res[0] == 64.0 * steps, (cg, steps, res)
+            assert res[1] == 0.0 and res[2] == 0.0 and res[3:4].view(np.uint32)[0] == 0, (cg, steps, res)
+
+
+def _random_density_rows(N, W, seed):
+    """Rows of W words on the GPU with per-row densities ~25 / 50 / 75 / 94 / 3 % (torch generators; the oracle
+    gets a host copy), rows 0 and 1 all ones."""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    def rnd(n):
+        return torch.randint(-2**63, 2**63 - 1, (n, W), dtype=torch.int64, device="cuda", generator=g)
+    rows = torch.empty((N, (W + 15) // 16 * 16), dtype=torch.int64, device="cuda")
+    rows.zero_()
+    k = N // 5
+    rows[:k, :W] = rnd(k) & rnd(k)
+    rows[k:2 * k, :W] = rnd(k)
+    rows[2 * k:3 * k, :W] = rnd(k) | rnd(k)
+    rows[3 * k:4 * k, :W] = rnd(k) | rnd(k) | rnd(k) | rnd(k)
+    n5 = N - 4 * k
+    rows[4 * k:, :W] = rnd(n5) & rnd(n5) & rnd(n5) & rnd(n5) & rnd(n5)
+    rows[0, :W] = -1
+    rows[1, :W] = -1
+    return rows
+
+
+@pytest.mark.parametrize("N,M", [(300, 1 << 23), (272, (1 << 24) - 64)])
+def test_fp4_production_kernel_at_the_top_of_its_range(sb, orc, N, M):
+    """dense_umma_kernel<2, FP4> (the AUTO default) on random-density rows of 2^23 and 2^24 - 64 bits: totals, shard
+    sums and every per-pair count against the oracle.  Pair counts run up to M itself (the all-ones pair), i.e. the
+    fp32 accumulators are driven by data-dependent increments to the top of their exact range."""
+    import torch
+    W = M // 64
+    rows = _random_density_rows(N, W, 1234 + N)
+    host = np.ascontiguousarray(rows[:, :W].cpu().numpy().view(np.uint64))
+    want = orc.rect_counts(host, 0, N, 0, N)
+    assert int(want.max()) == M
+    exact = int(want.sum(dtype=np.uint64))
+    assert sb.resolved_kernel_name("auto", W) == "fp4"
+    for kernel in ("fp4", "auto", "umma"):
+        assert int(sb.pairw_device(rows, n_words=W, kernel=kernel).item()) == exact, kernel
+    assert sum(int(sb.pairw_device(rows, n_words=W, shard=k, n_shards=3, kernel="fp4").item()) for k in range(3)) == exact
+    counts, total = sb.pairw_rect_device(rows, 0, N, 0, N, n_words=W, kernel="fp4")
+    assert (counts.cpu().numpy().view(np.uint32) == want).all()
+    assert int(total.item()) == exact
+
+
+def test_fp4_chained_accumulators_at_the_top_of_their_range(sb, orc):
+    """Total-only queries keep several interior tiles in one accumulator (chain_max = 2^24 / (32 M)): with M = 2^18 a
+    run is two tiles long, an element reaches 2 M = 2^19 and the epilogue's 32-column float sum 2^24 exactly when the
+    rows are all ones.  Random-density rows against the closed form and the oracle on sampled tiles, then all ones."""
+    import torch
+    N, M = 4700, 1 << 18
+    W = M // 64
+    rows = _random_density_rows(N, W, 99)
+    closed = _colcount_total_torch(rows, W)
+    for chain in (True, False):
+        prev = sb.set_umma_chain(chain)
+        try:
+            assert int(sb.pairw_device(rows, n_words=W, kernel="fp4").item()) == closed, chain
+            parts = [int(sb.pairw_device(rows, n_words=W, shard=r, n_shards=2, kernel="fp4").item()) for r in range(2)]
+            assert sum(parts) == closed, (chain, parts)
+        finally:
+            sb.set_umma_chain(bool(prev))
+    for (i0, i1, j0, j1) in [(0, 24, 0, 24), (900, 930, 4670, 4700), (2800, 2816, 2800, 2830)]:
+        sub = np.ascontiguousarray(torch.cat([rows[i0:i1, :W], rows[j0:j1, :W]]).cpu().numpy().view(np.uint64))
+        ni, nj = i1 - i0, j1 - j0
+        want = orc.rect_counts(sub, 0, ni, ni, ni + nj)
+        got, _ = sb.pairw_rect_device(rows, i0, i1, j0, j1, n_words=W, kernel="fp4", strict_upper=False)
+        assert (got.cpu().numpy().view(np.uint32) == want).all(), (i0, j0)
+    rows[:, :W] = -1
+    assert int(sb.pairw_device(rows, n_words=W, kernel="fp4").item()) == N * (N - 1) // 2 * M
+
+
+# --------------------------------------------------------------------------- #
+# round 2: raw-buffer list wrappers, foreign per-pair functions
+# --------------------------------------------------------------------------- #
+def test_wrapper_diag_list_and_blocked(sb, orc):
+    """STORM_wrapper_diag_list[_blocked] (storm.c:173-220, 281-369): host matrix + caller-built position arrays, any
+    cutoff / block size; equal to the dense wrapper and to the exact value on sparse, mixed and dense rows."""
+    M = 8192
+    for draws in ([3, 20, 150, 40], [5, 600, 4000, 90, 2500], [3000, 6000]):
+        pos = [orc.gen_row_positions(19, i, draws[i % len(draws)], M) for i in range(333)]
+        vals = O.positions_to_dense(pos, M)
+        exact = orc.wrapper_diag(vals)
+        assert sb.wrapper_diag(vals) == exact
+        for cutoff in (0, 40, 200, 10**6):
+            assert sb.wrapper_diag_list(vals, pos, cutoff) == exact, (draws, cutoff)
+            assert sb.wrapper_diag_list(vals, pos, cutoff, bsize=15) == exact, (draws, cutoff)
+    assert sb.wrapper_diag_list(vals[:1], pos[:1], 40) == 0
+
+
+def test_wrappers_identify_a_foreign_compute_func(sb, orc):
+    """A per-pair function that is not this library's own (here: ctypes callbacks standing in for libalgebra's static
+    kernels in the caller's translation unit) selects the set operation it computes; an unrecognisable one is an error."""
+    import ctypes as C
+    lib = sb.load()
+    proto = C.CFUNCTYPE(C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t)
+    fns = {0: proto(lambda a, b, n: sum(bin(a[k] & b[k]).count("1") for k in range(n))),
+           1: proto(lambda a, b, n: sum(bin(a[k] | b[k]).count("1") for k in range(n))),
+           2: proto(lambda a, b, n: sum(bin(a[k] ^ b[k]).count("1") for k in range(n)))}
+    vals = orc.gen_dense_uniform(5, 90, 700, 4096)
+    p = vals.ctypes.data_as(C.POINTER(C.c_uint64))
+    for op, f in fns.items():
+        assert lib.STORM_wrapper_diag(90, p, 64, C.cast(f, C.c_void_p)) == orc.wrapper_diag_op(vals, op), op
+        assert lib.STORM_wrapper_diag_blocked(90, p, 64, C.cast(f, C.c_void_p), 7) == orc.wrapper_diag_op(vals, op), op
+    bogus = proto(lambda a, b, n: 7)
+    assert lib.STORM_wrapper_diag(90, p, 64, C.cast(bogus, C.c_void_p)) == 2**64 - 1
+    assert "neither" in sb.last_error()
+
+
+# --------------------------------------------------------------------------- #
+# round 2: device sets behind storm.h (replicas; several on one device when the box has one GPU)
+# --------------------------------------------------------------------------- #
+def _device_lists(sb):
+    n = sb.load().STORM_b200_device_count()
+    lists = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        lists += [list(range(n)), [1, 0]]
+    return lists
+
+
+def test_multi_device_contig_queries_equal_single_device(sb, orc):
+    """STORM_B200_DEVICES / STORM_b200_set_device_list: every query entry point of the dense model and the raw-buffer
+    wrappers return the single-device value when the tile raster is sharded over G replicas (G real GPUs where the
+    box has them; replicas on one GPU otherwise -- the same host logic: band slices, peer pulls, per-replica
+    shards, host-side sum)."""
+    M = 65536
+    draws = [5, 150, 4000, 30000, 90, 250, 20000]
+    rows = [orc.gen_row_positions(71, i, draws[i % len(draws)], M) for i in range(1500)]
+    vals = O.positions_to_dense(rows, M)
+    exact = orc.wrapper_diag(vals)
+    sparse_rows = [orc.gen_row_positions(72, i, [1, 5, 60, 150, 199, 3][i % 6], M) for i in range(900)]
+    sparse_exact = orc.wrapper_diag(O.positions_to_dense(sparse_rows, M))
+    for ids in _device_lists(sb):
+        sb.set_device_list(ids)
+        try:
+            assert sb.get_devices() == ids
+            with sb.StormContiguous(M) as c:
+                for r in rows[:700]:
+                    c.add(r)
+                assert c.pairw_intersect_cardinality_blocked(31) == orc.wrapper_diag(vals[:700])   # first query: banded upload
+                assert c.device_count() == len(ids)
+                for r in rows[700:]:
+                    c.add(r)                                                                   # rows added after a query
+                assert c.pairw_intersect_cardinality() == exact
+                assert c.pairw_intersect_cardinality_blocked(5) == exact                           # steady state
+                for route in ("auto", "tile", "probe"):
+                    prev = sb.set_contig_list_route(route)
+                    try:
+                        assert c.pairw_intersect_cardinality_list() == exact, (ids, route)
+                    finally:
+                        sb.set_contig_list_route(prev)
+                assert sum(c.pairw_shard(k, 3) for k in range(3)) == exact                       # external shards x replicas
+                n = vals.shape[0]
+                assert (c.pairw_rect(10, 90, 40, 300) == orc.rect_counts(vals, 10, 90, 40, 300)).all()
+                c.clear()
+                for r in sparse_rows:
+                    c.add(r)
+                for route in ("auto", "stream", "probe", "tile"):
+                    prev = sb.set_contig_list_route(route)
+                    try:
+                        assert c.pairw_intersect_cardinality_blocked_list(9) == sparse_exact, (ids, route)
+                    finally:
+                        sb.set_contig_list_route(prev)
+            assert sb.wrapper_diag(vals) == exact
+            assert sb.wrapper_diag(vals[:3]) == orc.wrapper_diag(vals[:3])
+            big = orc.gen_dense_uniform(3, 5000, 3000, 131072)          # 82 MB: several bands
+            assert sb.wrapper_diag(big) == orc.colcount_total(big)
+            assert sb.wrapper_diag(vals, op="union") == orc.wrapper_diag_op(vals, 1)
+        finally:
+            sb.set_device_list(())
+    assert len(sb.get_devices()) == 1
+
+
+def test_bulk_ingest_on_replicas(sb, orc):
+    M, N = 65536, 600
+    rows = [orc.gen_row_positions(77, i, [3, 150, 4000, 0, 30000][i % 5], M) for i in range(N)]
+    offs = np.zeros(N + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in rows])
+    flat = np.concatenate(rows).astype(np.uint32)
+    exact = orc.wrapper_diag(O.positions_to_dense([r for r in rows if len(r)], M))
+    sb.set_device_list([0, 0])
+    try:
+        with sb.StormContiguous(M) as c:
+            c.add_bulk(flat[: offs[200]], offs[:201])
+            for r in rows[200:300]:
+                c.add(r)
+            c.add_bulk(flat[offs[300]:], offs[300:] - offs[300])
+            assert c.pairw_intersect_cardinality() == exact
+            assert c.pairw_intersect_cardinality_list() == exact
+    finally:
+        sb.set_device_list(())
+
+
+def test_rows_are_uploaded_while_they_are_added(sb, orc):
+    """The host mirror is page-locked and finished rows go to the device in the background (every 8 MB), so the
+    first query after row-by-row ingest pays (almost) no upload; results do not depend on where the batches fall,
+    on growth of the mirror in between, on clear + reuse, or on a pageable source (the raw-buffer wrapper)."""
+    M, N = 131072, 3000                                  # 16 KiB rows: 512 rows per batch, mirror grows 512 -> 4096
+    vals = orc.gen_dense_uniform(8, N, 9000, M)
+    exact = orc.colcount_total(vals)
+    pos = [np.flatnonzero(np.unpackbits(vals[i].view(np.uint8), bitorder="little")).astype(np.uint32) for i in range(N)]
+    with sb.StormContiguous(M) as c:
+        for p in pos:
+            c.add(p)
+        assert c.pairw_intersect_cardinality_blocked(15) == exact
+        first = c.last_timing()
+        assert c.pairw_intersect_cardinality_blocked(15) == exact
+        steady = c.last_timing()
+        assert first["total_s"] < 20 * steady["total_s"] + 0.05, (first, steady)
+        c.clear()
+        for p in pos[:700]:
+            c.add(p)
+        assert c.pairw_intersect_cardinality() == orc.colcount_total(vals[:700])
+    assert sb.wrapper_diag(vals) == exact                # numpy memory: pageable, goes through the staging ring
