@@ -89,6 +89,12 @@ int STORM_b200_pairw_device(const uint64_t* d_rows, uint64_t n_rows, uint32_t n_
                             uint64_t row_stride_words, uint32_t shard, uint32_t n_shards,
                             int kernel, uint64_t* d_total, void* stream);
 
+/* The same total over a matrix that is ALREADY resident on several devices (d_rows[g] on device device_ids[g]; same
+ * n_rows, n_words and row stride everywhere): device g computes shard g of n_devices, the host adds the totals.  One
+ * host thread, one launch per device, no collective.  UINT64_MAX on error. */
+uint64_t STORM_b200_pairw_devices(const uint64_t* const* d_rows, const int* device_ids, int n_devices, uint64_t n_rows,
+                                  uint32_t n_words, uint64_t row_stride_words, int kernel);
+
 /* Per-pair counts of the rectangle rows [i0,i1) x [j0,j1): d_out[(i-i0)*ld + (j-j0)]
  * = popcount(row_i & row_j); with strict_upper != 0 entries with j <= i are
  * written as 0 and excluded from the total.  d_total may be NULL.  d_out may be
@@ -186,6 +192,12 @@ int STORM_b200_contig_invalidate_device(STORM_contiguous_t* bitmap);
  * (rows with zero positions are skipped, D7). */
 int STORM_b200_contig_add_bulk(STORM_contiguous_t* bitmap, const uint32_t* positions,
                                const uint64_t* offsets, uint64_t n_rows);
+/* Rows handed over as bitmaps (n_rows x n_bitmaps_vector words at `pitch_words`; bit v of a row = word[v/64] >> (v%64) & 1,
+ * storm.c:1114) instead of position lists: same row semantics as STORM_contig_add on the row's sorted positions (an
+ * all-zero row appends nothing; rows below the cutoff also get their position list).  Bits >= vector_length must be 0. */
+int STORM_b200_contig_add_dense(STORM_contiguous_t* bitmap, const uint64_t* rows, uint64_t n_rows, uint64_t pitch_words);
+/* Move the container's device replicas to the device set in force now; they are rebuilt from the host mirror lazily. */
+int STORM_b200_contig_rehome(STORM_contiguous_t* bitmap);
 /* Seconds spent in the last query of this object: [0] upload (H2D), [1] kernels, [2] total. */
 int STORM_b200_contig_last_timing(STORM_contiguous_t* bitmap, double out_seconds[3]);
 

@@ -123,6 +123,9 @@ SIGNATURES = {
     "STORM_b200_set_device_list": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "STORM_b200_get_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "STORM_b200_contig_device_count": (C.c_int, [C.c_void_p]),
+    "STORM_b200_contig_add_dense": (C.c_int, [C.c_void_p, u64p, C.c_uint64, C.c_uint64]),
+    "STORM_b200_contig_rehome": (C.c_int, [C.c_void_p]),
+    "STORM_b200_pairw_devices": (C.c_uint64, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]),
     # ---- storm.h: per-pair host helpers
     "STORM_bitmap_add_with_scalar": (C.c_int, [C.c_void_p, u32p, C.c_uint32]),
     "STORM_intersect_vector16_cardinality": (C.c_uint64, [C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_uint32, C.c_uint32]),

@@ -88,6 +88,19 @@ class StormContiguous:
                    "STORM_b200_contig_pairw_rect")
         return out
 
+    def add_dense(self, rows: np.ndarray) -> None:
+        """``STORM_b200_contig_add_dense``: rows given as bitmaps (2-D uint64, one row per line)."""
+        v = np.ascontiguousarray(rows, dtype=np.uint64)
+        _lib.check(self._L.STORM_b200_contig_add_dense(self._h, v.ctypes.data_as(u64p), v.shape[0], v.shape[1]),
+                   "STORM_b200_contig_add_dense")
+
+    def add_dense_ptr(self, ptr: int, n_rows: int, pitch_words: int) -> None:
+        _lib.check(self._L.STORM_b200_contig_add_dense(self._h, C.cast(ptr, u64p), n_rows, pitch_words), "STORM_b200_contig_add_dense")
+
+    def rehome(self) -> None:
+        """``STORM_b200_contig_rehome``: rebuild the device replicas on the device set in force now."""
+        _lib.check(self._L.STORM_b200_contig_rehome(self._h), "STORM_b200_contig_rehome")
+
     def device_count(self) -> int:
         """Device replicas this container's queries run on (0 before its first use of a device)."""
         return int(self._L.STORM_b200_contig_device_count(self._h))
@@ -519,6 +532,18 @@ def set_umma_stream_k(on: bool) -> int:
 def set_umma_chain(on: bool) -> int:
     """Accumulator chaining of total-only UMMA queries (one drain per run of interior tiles, default on); returns the previous value."""
     return _lib.load().STORM_b200_set_umma_chain(int(bool(on)))
+
+
+def pairw_devices(rows_per_device, n_words: Optional[int] = None, kernel=KERNEL_AUTO) -> int:
+    """``STORM_b200_pairw_devices``: the same matrix resident on several devices (one CUDA tensor per device), tile raster
+    sharded over them behind one C call, totals added on the host."""
+    L = _lib.load()
+    n = len(rows_per_device)
+    ptrs = (C.c_void_p * n)(*[r.data_ptr() for r in rows_per_device])
+    ids = (C.c_int * n)(*[r.device.index for r in rows_per_device])
+    _, n_rows, stride = _rows_args(rows_per_device[0])
+    return _query(L.STORM_b200_pairw_devices(ptrs, ids, n, n_rows, n_words or rows_per_device[0].shape[1], stride, _kernel_id(kernel)),
+                  "STORM_b200_pairw_devices")
 
 
 def set_clock_probe(on: bool) -> int:

@@ -101,6 +101,12 @@ int ensure_devs(ContigState* st) {
     return STORM_B200_OK;
 }
 
+// One-time work a device's first dense query would otherwise pay (the FP4 accumulation self-test behind KERNEL_AUTO,
+// ~0.1 s per device and process): done when the background uploads start, i.e. while the caller is still adding rows.
+void warm_up_devices(ContigState* st) {
+    for (ContigDev* d : st->devs) { DeviceGuard guard(d->ctx.device); (void)fp4_selftest_ok(); }
+}
+
 // Device arena of one replica with room for `rows` rows (grows geometrically, like the host mirror).
 int ensure_device_rows(STORM_contiguous_t* c, ContigState* st, ContigDev* d, uint64_t rows) {
     if (st->stride == 0)
@@ -680,17 +686,26 @@ int STORM_contig_add(STORM_contiguous_t* c, const uint32_t* values, const uint32
     if (values == nullptr) return -2;
     if (n_values == 0) return 0;                                          // no row appended (D7)
     ContigState* st = state_of(c);
-    for (uint32_t i = 0; i < n_values; ++i)
-        if (values[i] >= c->vector_length) { set_error("position %u >= vector_length %llu", values[i], (unsigned long long)c->vector_length); return -3; }
+    uint32_t top = 0;                                                     // (one vectorisable pass; the reference writes out of bounds instead)
+    for (uint32_t i = 0; i < n_values; ++i) top = values[i] > top ? values[i] : top;
+    if (top >= c->vector_length) { set_error("position %u >= vector_length %llu", top, (unsigned long long)c->vector_length); return -3; }
     if (grow_host_rows(c, c->n_data + 1)) return -3;
     if (c->scalar == nullptr && grow_host_scalar(c, st, 1)) return -3;    // reference allocates it on first add (:1037-1041)
 
+    // :1103-1115.  The bits of one word are collected in a register and stored when the word index changes: a dense
+    // sorted row sets ~16 bits per word, and a read-modify-write of memory per bit serialises on store forwarding.
     uint64_t* row = c->data + c->n_data * c->n_bitmaps_vector;
-    uint32_t used = n_values;
-    for (uint32_t i = 0; i < n_values; ++i) {                             // :1103-1115
-        if (i != 0 && values[i] == values[i - 1]) { --used; continue; }
-        row[values[i] >> 6] |= 1ull << (values[i] & 63);
+    uint32_t dups = 0, prev = ~values[0];
+    uint64_t word = values[0] >> 6, bits = 0;
+    for (uint32_t i = 0; i < n_values; ++i) {
+        const uint32_t v = values[i];
+        dups += (v == prev);                                              // adjacent duplicates are skipped (:1106-1108)
+        prev = v;
+        if ((v >> 6) != word) { row[word] |= bits; bits = 0; word = v >> 6; }
+        bits |= 1ull << (v & 63);
     }
+    row[word] |= bits;
+    const uint32_t used = n_values - dups;
     if (st->pos_off.size() <= c->n_data) st->pos_off.resize(std::max<size_t>(c->n_data + 1, st->pos_off.size() * 2));
     st->pos_off[c->n_data] = c->tot_scalar;
     STORM_contiguous_bitmap_t* view = &c->bitmaps[c->n_data];
@@ -715,7 +730,9 @@ int STORM_contig_add(STORM_contiguous_t* c, const uint32_t* values, const uint32
     if (st->data_pinned && st->dev_status >= 0 &&
         (c->n_data - st->uploaded_rows) * (uint64_t)c->n_bitmaps_vector * 8 >= BG_UPLOAD_BYTES) {
         DeviceGuard home(st->home_device);
+        const bool first = st->dev_status == 0;
         if (ensure_devs(st) || upload_pending(c, st, c->n_data)) { if (st->dev_status == 0) st->dev_status = -1; }
+        else if (first) warm_up_devices(st);
     }
     return (int)n_values;                                                 // :1136
 }
@@ -1006,6 +1023,113 @@ int STORM_b200_contig_add_bulk(STORM_contiguous_t* c, const uint32_t* positions,
     c->n_data += n_new;
     st->uploaded_rows = c->n_data;            // every replica holds them (or has the copy queued)
     return STORM_B200_OK;
+}
+
+// Rows handed over as bitmaps (the container's own layout: n_rows x W words at `pitch_words`, bit v of a row =
+// word[v / 64] >> (v % 64) & 1; storm.c:1114).  Same row semantics as STORM_contig_add on the row's sorted positions: an
+// all-zero row appends nothing (D7), rows below the cutoff also get their position list.  Bits at or above
+// vector_length must be zero.
+int STORM_b200_contig_add_dense(STORM_contiguous_t* c, const uint64_t* rows, uint64_t n_rows, uint64_t pitch_words) {
+    if (c == nullptr || (rows == nullptr && n_rows)) { set_error("NULL argument"); return STORM_B200_EINVAL; }
+    const uint64_t W = c->n_bitmaps_vector;
+    if (pitch_words < W) { set_error("pitch of %llu words < %llu words per row", (unsigned long long)pitch_words, (unsigned long long)W); return STORM_B200_EINVAL; }
+    if (n_rows == 0) return STORM_B200_OK;
+    ContigState* st = state_of(c);
+    const uint32_t tail_bits = (uint32_t)(c->vector_length & 63);
+    const uint64_t tail_mask = tail_bits ? ~((1ull << tail_bits) - 1) : 0ull;     // bits of the last word that must be clear
+    if (tail_mask)
+        for (uint64_t r = 0; r < n_rows; ++r)
+            if (rows[r * pitch_words + W - 1] & tail_mask) { set_error("row %llu has bits set at or above vector_length", (unsigned long long)r); return STORM_B200_EINVAL; }
+    if (grow_host_rows(c, c->n_data + n_rows)) { set_error("host arena allocation failed"); return STORM_B200_ENOMEM; }
+    if (c->scalar == nullptr && grow_host_scalar(c, st, 1)) return STORM_B200_ENOMEM;
+    if (st->pos_off.size() < c->n_data + n_rows) st->pos_off.resize(c->n_data + n_rows);
+    for (uint64_t r = 0; r < n_rows; ++r) {
+        const uint64_t* src = rows + r * pitch_words;
+        uint64_t used = 0;
+        for (uint64_t k = 0; k < W; ++k) used += (uint64_t)__builtin_popcountll(src[k]);
+        if (used == 0) continue;
+        const uint64_t row = c->n_data;
+        memcpy(c->data + row * W, src, W * 8);
+        st->pos_off[row] = c->tot_scalar;
+        c->bitmaps[row].scalar = nullptr;
+        if (used < c->scalar_cutoff) {
+            if (grow_host_scalar(c, st, c->tot_scalar + used)) return STORM_B200_ENOMEM;
+            uint32_t* dst = c->scalar + c->tot_scalar;
+            for (uint64_t k = 0; k < W; ++k)
+                for (uint64_t w = src[k]; w; w &= w - 1) *dst++ = (uint32_t)(k * 64 + (uint64_t)__builtin_ctzll(w));
+            c->bitmaps[row].scalar = c->scalar + c->tot_scalar;
+            c->tot_scalar += used;
+        }
+        c->n_scalar[row] = (uint32_t)used;
+        c->bitmaps[row].n_scalar = (uint32_t)used;
+        ++c->n_data;
+    }
+    if (st->data_pinned && st->dev_status >= 0) {                          // hand the new rows to the copy engines right away
+        DeviceGuard home(st->home_device);
+        const bool first = st->dev_status == 0;
+        if (ensure_devs(st) || upload_pending(c, st, c->n_data)) { if (st->dev_status == 0) st->dev_status = -1; }
+        else if (first) warm_up_devices(st);
+    }
+    return STORM_B200_OK;
+}
+
+// Move the container's device replicas to the device set in force now (STORM_b200_set_devices / the calling thread's
+// current device): the replicas are dropped and rebuilt from the host mirror at the next query or add.
+int STORM_b200_contig_rehome(STORM_contiguous_t* c) {
+    if (c == nullptr) return STORM_B200_EINVAL;
+    ContigState* st = state_of(c);
+    for (ContigDev* d : st->devs) {
+        if (d->ctx.device >= 0) {
+            DeviceGuard guard(d->ctx.device);
+            if (d->ctx.stream) cudaStreamSynchronize(d->ctx.stream);
+            if (d->ctx.copy_stream) cudaStreamSynchronize(d->ctx.copy_stream);
+            for (void* p : {(void*)d->d_rows, (void*)d->d_pos, (void*)d->d_pos_off, (void*)d->d_is_sparse,
+                            (void*)d->d_sparse_rows, (void*)d->d_dense_rows, (void*)d->d_group_start, (void*)d->d_gather})
+                if (p) cudaFree(p);
+            for (auto e : d->ev) if (e) cudaEventDestroy(e);
+        }
+        d->ctx.destroy();
+        delete d;
+    }
+    st->devs.clear();
+    st->dev_status = 0;
+    st->uploaded_rows = 0;
+    st->home_device = -1;
+    if (have_device()) cudaGetDevice(&st->home_device);
+    return STORM_B200_OK;
+}
+
+// Upper-triangle total of a matrix that is ALREADY resident on several devices (d_rows[g] on device device_ids[g],
+// same n_rows / n_words / row stride everywhere): device g computes shard g of the tile raster, the host adds the
+// totals.  The steady-state query of the multi-device mode without a container; UINT64_MAX on error.
+uint64_t STORM_b200_pairw_devices(const uint64_t* const* d_rows, const int* device_ids, int n_devices, uint64_t n_rows,
+                                  uint32_t n_words, uint64_t row_stride_words, int kernel) {
+    if (d_rows == nullptr || device_ids == nullptr || n_devices < 1 || n_devices > 64) { set_error("bad device list"); return (uint64_t)-1; }
+    if (n_rows < 2) return 0;
+    static std::mutex mu;
+    static std::vector<DevCtx*> cache;                                    // one context per device ordinal, kept for the process
+    std::lock_guard<std::mutex> lock(mu);
+    std::vector<DevCtx*> ctxs(n_devices);
+    std::vector<uint64_t*> arenas(n_devices);
+    std::vector<int> ids(device_ids, device_ids + n_devices);
+    for (int g = 0; g < n_devices; ++g) {
+        const int id = ids[g];
+        if (id < 0 || id >= 64 || d_rows[g] == nullptr) { set_error("device %d / NULL rows", id); return (uint64_t)-1; }
+        if ((int)cache.size() <= id) cache.resize(id + 1, nullptr);
+        if (!cache[id]) {
+            DevCtx* fresh = new (std::nothrow) DevCtx();
+            if (!fresh || fresh->init(id)) { if (fresh) { fresh->destroy(); delete fresh; } return (uint64_t)-1; }
+            cache[id] = fresh;
+        }
+        for (int o = 0; o < g; ++o) if (ids[o] == id) { set_error("device %d listed twice", id); return (uint64_t)-1; }
+        ctxs[g] = cache[id];
+        arenas[g] = const_cast<uint64_t*>(d_rows[g]);
+        DeviceGuard guard(id);
+        if (check_rows(d_rows[g], row_stride_words, n_words)) return (uint64_t)-1;
+        if (cudaMemsetAsync(ctxs[g]->d_total, 0, 8, ctxs[g]->stream) != cudaSuccess) return (uint64_t)-1;
+    }
+    if (banded_triangle(ctxs.data(), arenas.data(), n_devices, row_stride_words, HostRows{}, n_rows, n_rows, n_words, 0, 1, kernel)) return (uint64_t)-1;
+    return collect_totals(ctxs.data(), n_devices, "STORM_b200_pairw_devices");
 }
 
 int STORM_b200_contig_last_timing(STORM_contiguous_t* c, double out_seconds[3]) {

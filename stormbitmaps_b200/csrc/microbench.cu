@@ -4,7 +4,10 @@
 // kernels are bound by the POPC (and, for the carry-save variant, the ALU) pipe,
 // so their roofline denominators are measured here on the device itself
 // (SURVEY.md section 7.3 item 1).  Each kernel runs 8 independent dependency
-// chains per thread, 16 warps per SM, long enough to amortise the launch.
+// chains per thread, ONE CTA of 16 warps per SM, long enough to amortise the launch.
+// (Round 1 launched two CTAs of 8 warps per SM and divided by the clock64 delta of CTA 0, which only
+// spans its own half of the kernel: every per-clock figure came out 2x too high.  One clock64 tick is one
+// SM cycle -- kind 8 below measures 1964.4 ticks per microsecond at nvidia-smi's 1965 MHz.)
 #include <algorithm>
 
 #include "common.cuh"
@@ -12,7 +15,7 @@
 namespace storm {
 namespace {
 
-constexpr int MB_THREADS = 256;
+constexpr int MB_THREADS = 512;
 constexpr int MB_UNROLL = 16;
 
 template <int KIND>
@@ -59,7 +62,7 @@ int run_kind(double* rate, double* mhz, double ops_per_inner) {
     cudaEvent_t e0, e1;
     STORM_CUDA_TRY(cudaEventCreate(&e0));
     STORM_CUDA_TRY(cudaEventCreate(&e1));
-    const int grid = sms * 2, iters = 4096;
+    const int grid = sms, iters = 4096;
     double best = 0, best_mhz = 0;
     for (int rep = 0; rep < 4; ++rep) {                // rep 0 is the warm-up
         STORM_CUDA_TRY(cudaEventRecord(e0));

@@ -334,3 +334,36 @@ def test_device_set_api_without_gpu(lib):
     if lib.STORM_b200_device_count() == 0:
         got = (C.c_int * 4)()
         assert lib.STORM_b200_get_devices(got, 4) < 0 and "no CUDA device" in sb.last_error()
+
+
+def test_add_dense_builds_the_same_container_as_add(lib, orc):
+    """STORM_b200_contig_add_dense (rows as bitmaps) leaves the public fields exactly as STORM_contig_add on the rows'
+    sorted positions does: mirror words, per-row counts, position lists of the rows below the cutoff, skipped empty rows."""
+    import stormbitmaps_b200 as sb
+    from oracle import oracle as O
+    M = 5000                                              # not a multiple of 64: the tail bits are checked
+    draws = [0, 1, 3, 24, 25, 26, 400, 3000]
+    rows = [orc.gen_row_positions(9, i, draws[i % len(draws)], M) for i in range(64)]
+    vals = O.positions_to_dense(rows, M)
+
+    class Contig(C.Structure):
+        _fields_ = [("data", C.POINTER(C.c_uint64)), ("scalar", C.POINTER(C.c_uint32)), ("n_scalar", C.POINTER(C.c_uint32)), ("bitmaps", C.c_void_p),
+                    ("n_data", C.c_uint64), ("m_data", C.c_uint64), ("tot_scalar", C.c_uint64), ("m_scalar", C.c_uint64),
+                    ("vector_length", C.c_uint64), ("n_bitmaps_vector", C.c_uint32), ("intsec_func", C.c_void_p),
+                    ("alignment", C.c_uint32), ("scalar_cutoff", C.c_uint32)]
+    a, b = sb.StormContiguous(M), sb.StormContiguous(M)
+    for r in rows:
+        a.add(r)
+    b.add_dense(vals[:40])
+    b.add_dense(vals[40:])
+    sa, sb_ = Contig.from_address(a._h), Contig.from_address(b._h)
+    assert sa.n_data == sb_.n_data == sum(1 for r in rows if len(r)) and sa.tot_scalar == sb_.tot_scalar
+    W = sa.n_bitmaps_vector
+    assert [sa.data[i] for i in range(sa.n_data * W)] == [sb_.data[i] for i in range(sa.n_data * W)]
+    assert [sa.n_scalar[i] for i in range(sa.n_data)] == [sb_.n_scalar[i] for i in range(sa.n_data)]
+    assert [sa.scalar[i] for i in range(sa.tot_scalar)] == [sb_.scalar[i] for i in range(sa.tot_scalar)]
+    bad = vals[:1].copy()
+    bad[0, -1] |= np.uint64(1) << np.uint64(63)           # bit 5055 >= vector_length
+    with pytest.raises(sb.StormError, match="vector_length"):
+        b.add_dense(bad)
+    a.free(); b.free()

@@ -792,3 +792,36 @@ def test_rows_are_uploaded_while_they_are_added(sb, orc):
             c.add(p)
         assert c.pairw_intersect_cardinality() == orc.colcount_total(vals[:700])
     assert sb.wrapper_diag(vals) == exact                # numpy memory: pageable, goes through the staging ring
+
+
+def test_dense_ingest_rehome_and_resident_multi_device_query(sb, orc):
+    """STORM_b200_contig_add_dense (rows as bitmaps), STORM_b200_contig_rehome (same container, another device set) and
+    STORM_b200_pairw_devices (matrix already resident on every device of a list) against the oracle."""
+    import torch
+    M, N = 65536, 1300
+    vals = orc.gen_dense_uniform(61, N, 20000, M)
+    exact = orc.wrapper_diag(vals)
+    with sb.StormContiguous(M) as c:
+        c.add_dense(vals[:500])
+        assert c.pairw_intersect_cardinality() == orc.wrapper_diag(vals[:500])
+        c.add_dense(vals[500:])
+        assert c.pairw_intersect_cardinality_blocked(31) == exact and c.device_count() == 1
+        for ids in _device_lists(sb):
+            sb.set_device_list(ids)
+            try:
+                c.rehome()
+                assert c.pairw_intersect_cardinality_blocked(31) == exact and c.device_count() == len(ids)
+                assert c.pairw_intersect_cardinality_list() == exact
+            finally:
+                sb.set_device_list(())
+        c.rehome()
+        assert c.pairw_intersect_cardinality() == exact and c.device_count() == 1
+    n_dev = torch.cuda.device_count()
+    copies = []
+    for d in range(n_dev):
+        rows, W = sb.alloc_rows(N, M, device=f"cuda:{d}")
+        rows[:, :W] = torch.from_numpy(vals.view(np.int64)).to(f"cuda:{d}")
+        copies.append(rows)
+    for k in sorted({1, n_dev, max(1, n_dev // 2)}):
+        assert sb.pairw_devices(copies[:k], n_words=vals.shape[1]) == exact, k
+    torch.cuda.set_device(0)
