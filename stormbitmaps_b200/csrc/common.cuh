@@ -174,6 +174,7 @@ int launch_dense_csa(const DenseJob& job, cudaStream_t stream);
 TileShape b1_tile_shape();
 int launch_dense_b1(const DenseJob& job, cudaStream_t stream);   // mma.sync .b1 AND + POPC (emulated on sm_100a; for the record)
 TileShape umma_tile_shape();
+TileShape umma_pairs_tile_shape();   // ... of a job with per-pair output (the tensor kernels' two-accumulator form)
 int launch_dense_umma(const DenseJob& job, cudaStream_t stream);
 // UMMA needs at least one full K step of 128 bits and 16-byte aligned rows.
 bool umma_supports(const DenseJob& job);

@@ -67,17 +67,31 @@ constexpr int UM_CHUNK_KB_FP4 = 4;
 // XW = expander warps per 32 rows: 1 = a thread expands its row's whole k-block (4 K steps), 2 = two
 // threads of different warps expand K steps {0, 1} and {2, 3} of it, which halves the time from "stage free"
 // to "stage full" (the FP4 form expands twice the bits per MMA and fell 15 % short of the pipe with XW = 1).
-template <int CG, int XW = 1, bool FP4 = false>
+//
+// PAIRS = the per-pair output form (DenseJob::out set: every tile is drained, nothing can be chained or split
+// along K).  With one 256-column accumulator the drain of a tile is dead time for the tensor pipe (the MMA warp
+// cannot start the next tile before the epilogue has read the accumulator, and the epilogue ran on the expander
+// warps, which meanwhile staged nothing): 27 % of a 4096-bit tile, 6.5 % of a 131072-bit one.  The PAIRS form
+// therefore works on tiles of 128 B rows with TWO 128-column accumulators used alternately, and hands the drain to
+// four dedicated epilogue warps: while they read accumulator t & 1 and store its counts, the expanders and the MMA
+// warp are already on tile t + 1 in the other one.  The price is one A expansion per 128 instead of 256 B rows
+// (1.5 x the expander work per pair; the ALU pipe was 46 % busy).
+template <int CG, int XW = 1, bool FP4 = false, bool PAIRS = false>
 struct Cfg {
     static constexpr bool FP4_FORM = FP4;
+    static constexpr int TN = PAIRS ? 128 : UM_N;            // B rows (accumulator columns) per tile
+    static constexpr int ACCS = PAIRS ? 2 : 1;               // accumulators of TN columns: columns [0, 256) either way
     static constexpr int A_ROW_WARPS = 4;                    // 128 A rows = TMEM lanes
-    static constexpr int B_ROWS = UM_N / CG;                 // B rows expanded by this CTA
+    static constexpr int B_ROWS = TN / CG;                   // B rows expanded by this CTA
     static constexpr int B_ROW_WARPS = B_ROWS / 32;
     static constexpr int A_WARPS = A_ROW_WARPS * XW;
     static constexpr int B_WARPS = B_ROW_WARPS * XW;
     static constexpr int MMA_WARP = A_WARPS + B_WARPS;
     static constexpr int TMA_WARP = MMA_WARP + 1;
-    static constexpr int THREADS = (A_WARPS + B_WARPS + 2) * 32;
+    static constexpr int EPI_WARP0 = (TMA_WARP + 1 + 3) / 4 * 4;   // dedicated epilogue warps (PAIRS): warp % 4 = TMEM lane quarter
+    static constexpr int EPI_WARPS = PAIRS ? 4 : 0;
+    static constexpr int N_WARPS = PAIRS ? EPI_WARP0 + EPI_WARPS : A_WARPS + B_WARPS + 2;
+    static constexpr int THREADS = N_WARPS * 32;
     // expanded k-blocks in flight between the expanders and the MMA thread (A: 32 TMEM columns each,
     // next to the 256 accumulator columns and, in the FP4 form, 32 scale-factor columns)
     static constexpr int STAGES = CG == 2 ? (FP4 ? 7 : 6) : 3;
@@ -85,24 +99,27 @@ struct Cfg {
     static constexpr int RAW_A_BYTES = 128 * 128;            // one box of packed A rows
     static constexpr int RAW_B_BYTES = B_ROWS * 128;
     static constexpr int RAW_BYTES = RAW_A_BYTES + RAW_B_BYTES;
-    static constexpr int TM = 128 * CG, TN = UM_N;
+    static constexpr int TM = 128 * CG;
     static constexpr int EXPANDER_WARPS = A_WARPS + B_WARPS;
-    static constexpr uint32_t OFF_RAW = STAGES * STAGE_BYTES;
+    static constexpr uint32_t OFF_RAW = (STAGES * STAGE_BYTES + 1023) / 1024 * 1024;
     // packed-row boxes in flight between the TMA thread and the expanders (how far the loads run ahead of the
     // expansion: one box = 4 (FP4) or 8 k-blocks); three fit beside the stages of the CTA-pair form
     static constexpr int RAW_BUFS = CG == 2 ? STORM_RAW_BUFS : 2;
     static constexpr uint32_t OFF_BAR = OFF_RAW + RAW_BUFS * RAW_BYTES;
     static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 512;
     static_assert(SMEM_BYTES <= 232448, "shared memory of one CTA");
+    static_assert(TN * ACCS <= UM_A_COL, "accumulators overflow their tensor-memory columns");
     static_assert(UM_A_COL + 32 * STAGES <= (FP4 ? UM_SF_COL : 512), "A stages overflow tensor memory");
     static_assert(XW == 1 || XW == 2, "one or two expander warps per 32 rows");
+    static_assert(!(PAIRS && XW == 2), "the per-pair form uses one expander warp per 32 rows");
+    static_assert(N_WARPS <= 24, "per-warp reduction slots");
     // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor bit layout):
     //   [4,6) c_format = 2 (S32); [7,10) a_format = 0 (u8); [10,13) b_format = 0 (u8);
     //   [15] a_major = 0 (K); [16] b_major = 0 (K); [17,23) N >> 3; [24,29) M >> 4
-    static constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(UM_N >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+    static constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
     // kind::mxf4 block-scaled descriptor (cute::UMMA::InstrDescriptorBlockScaled): [7,10) a_format = 1 (E2M1);
     //   [10,13) b_format = 1; K-major; [17,23) N >> 3; [23] scale format 1 (UE8M0); [24,29) M >> 4; [31] 0 = K 64
-    static constexpr uint32_t IDESC_FP4 = (1u << 7) | (1u << 10) | ((uint32_t)(UM_N >> 3) << 17) | (1u << 23) |
+    static constexpr uint32_t IDESC_FP4 = (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | (1u << 23) |
                                           ((uint32_t)((128 * CG) >> 4) << 24);
 };
 
@@ -208,12 +225,14 @@ constexpr int VAR_SUSPEND = 1;          // hardware-suspended mbarrier waits
 constexpr int VAR_SCALED = 2;           // scaled expansion (counts accumulate x128); kind::i8 only
 constexpr int VAR_FP4 = 4;              // bits -> E2M1 nibbles, tcgen05.mma kind::mxf4, fp32 accumulators
 constexpr int VAR_WIDE = 8;             // two expander warps per 32 rows (Cfg::XW = 2)
+constexpr int VAR_PAIRS = 16;           // per-pair output form: 128-column tiles, two accumulators, epilogue warps (Cfg::PAIRS)
 
 template <int CG, int VAR>
-__global__ void __launch_bounds__((Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0>::THREADS), 1)
+__global__ void __launch_bounds__((Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0, (VAR & VAR_PAIRS) != 0>::THREADS), 1)
 dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DenseJob job) {
-    using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0>;
+    using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0, (VAR & VAR_PAIRS) != 0>;
     constexpr int XW = (VAR & VAR_WIDE) ? 2 : 1;
+    constexpr bool PAIRS = (VAR & VAR_PAIRS) != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
@@ -223,12 +242,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t empty_bar = full_bar + 8 * C::STAGES;
     const uint32_t raw_full_bar = empty_bar + 8 * C::STAGES;                // RAW_BUFS x 8 B
     const uint32_t raw_empty_bar = raw_full_bar + 8 * C::RAW_BUFS;          // RAW_BUFS x 8 B
-    const uint32_t acc_full_bar = raw_empty_bar + 8 * C::RAW_BUFS;
-    const uint32_t acc_empty_bar = acc_full_bar + 8;
-    const uint32_t tmem_slot = acc_empty_bar + 8;
+    const uint32_t acc_full_bar = raw_empty_bar + 8 * C::RAW_BUFS;          // ACCS x 8 B
+    const uint32_t acc_empty_bar = acc_full_bar + 8 * C::ACCS;              // ACCS x 8 B
+    const uint32_t tmem_slot = acc_empty_bar + 8 * C::ACCS;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + (tmem_slot + 8 - smem_base));
-    const uint32_t run_ring = tmem_slot + 8 + 8 * 16;                       // RUN_RING x 4 B: run flags, expanders -> MMA warp
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + (tmem_slot + 8 - smem_base));   // one slot per warp (<= 24)
+    const uint32_t run_ring = tmem_slot + 8 + 8 * 24;                       // RUN_RING x 4 B: run flags, expanders -> MMA warp
+    static_assert(8 * (2 * C::STAGES + 2 * C::RAW_BUFS + 2 * C::ACCS) + 8 + 8 * 24 + 4 * RUN_RING <= 512, "barrier block");
 
     auto wait = [](uint32_t bar, uint32_t parity) { mbar_wait_t<(VAR & VAR_SUSPEND) != 0>(bar, parity); };
     constexpr bool FP4 = (VAR & VAR_FP4) != 0;
@@ -253,8 +273,10 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_init(raw_full_bar + 8 * b, 1);                            // expect_tx arrive + TMA bytes
             mbar_init(raw_empty_bar + 8 * b, C::EXPANDER_WARPS);
         }
-        mbar_init(acc_full_bar, 1);                                        // tcgen05.commit
-        mbar_init(acc_empty_bar, CG * C::EXPANDER_WARPS);                  // every epilogue warp of the pair
+        for (int a = 0; a < C::ACCS; ++a) {
+            mbar_init(acc_full_bar + 8 * a, 1);                            // tcgen05.commit
+            mbar_init(acc_empty_bar + 8 * a, CG * (PAIRS ? C::EPI_WARPS : C::EXPANDER_WARPS));   // every epilogue warp of the pair
+        }
         fence_mbar_init();
     }
     if (warp == C::TMA_WARP && lane == 0) {
@@ -277,6 +299,94 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint64_t a0 = (uint64_t)bi_ * C::TM, b0 = (uint64_t)bj_ * C::TN;
         return job.out == nullptr && a0 + C::TM <= job.nA && b0 + C::TN <= job.nB &&
                (!job.strict_upper || job.j_off + b0 >= job.i_off + a0 + C::TM);
+    };
+
+    // ---- epilogue of one run: TMEM -> registers -> masked sum / per-pair store ----------------------------------
+    // Warp w may read TMEM lanes 32 (w % 4) .. +31 (`quarter`); the `n_sharers` warps of a quarter split the accumulator's
+    // columns between them in 32-column chunks dealt round-robin (`sharer` = this warp's turn).  Total-only form: every
+    // expander warp takes part (the A warp and the B warp(s) of a quarter), so the drain takes half (a third) as long.
+    // Per-pair form: the four dedicated epilogue warps, one per quarter, on the accumulator half `acc_col`.
+    auto drain = [&](uint32_t acc_col, uint32_t quarter, uint32_t sharer, uint32_t n_sharers, uint32_t bi, uint32_t bj,
+                     bool interior, bool fp4_sum_exact) {
+        const uint64_t rowA0 = (uint64_t)bi * C::TM, rowB0 = (uint64_t)bj * C::TN;
+        const uint64_t li = rowA0 + rank * 128u + quarter * 32u + lane;      // accumulator row of this thread (= its TMEM lane)
+        const uint64_t gi = job.i_off + li;
+        const bool row_ok = li < job.nA;
+        const uint32_t acc_lane = tmem_base + ((quarter * 32u) << 16) + UM_ACC_COL + acc_col;
+        const bool out_vec = ((reinterpret_cast<uintptr_t>(job.out) | (job.ld * 4)) & 31) == 0;   // 32-byte stores possible
+#pragma unroll 1
+        for (uint32_t c0 = sharer * 32u; c0 < (uint32_t)C::TN; c0 += 32u * n_sharers) {
+            uint32_t v[32];
+            tmem_ld32(acc_lane + c0, v);
+            tc_wait_ld();
+            if (!PAIRS && interior) {
+                if constexpr (FP4) {
+                    // fp32 accumulators holding exact integers.  While 32 counts cannot exceed 2^24 their
+                    // float sum is exact too (one conversion per 32 columns); otherwise convert one by one.
+                    if (fp4_sum_exact) {
+                        float part = 0.0f;
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) part += __uint_as_float(v[cc]);
+                        sum += __float2uint_rn(part);
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) sum += __float2uint_rn(__uint_as_float(v[cc]));
+                    }
+                } else if (SCALED) {                               // 32 counts of at most 2^24 each fit 32 bits
+                    uint32_t part = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 32; ++cc) part += v[cc] >> 7;
+                    sum += part;
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < 32; ++cc) sum += v[cc];
+                }
+            } else if (!PAIRS || job.out == nullptr) {
+                // Edge or diagonal tile, total only: the columns of this 32-column chunk that count are
+                // [lo, lo + span) -- those below nB and right of the diagonal for this row (one range
+                // compare per column instead of 64-bit index arithmetic: stream-K can hand a run of
+                // diagonal tiles to one CTA, and the slow path made that CTA the last to finish).
+                const long long cb = (long long)(rowB0 + c0);
+                const long long h = (long long)job.nB - cb;
+                const int hi = row_ok ? (h < 0 ? 0 : h > 32 ? 32 : (int)h) : 0;
+                int lo = 0;
+                if (job.strict_upper) {
+                    const long long l = (long long)gi - (long long)job.j_off - cb + 1;
+                    lo = l < 0 ? 0 : l > 32 ? 32 : (int)l;
+                }
+                const uint32_t span = (uint32_t)(hi > lo ? hi - lo : 0);
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc) {
+                    const uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
+                    sum += ((uint32_t)(cc - lo) < span) ? x : 0u;
+                }
+            } else if (row_ok && out_vec && rowB0 + c0 + 32 <= job.nB &&
+                       (!job.strict_upper || job.j_off + rowB0 + c0 > gi)) {
+                // Per-pair output, all 32 columns of the chunk valid and right of the diagonal: this thread's
+                // 128 consecutive bytes of its output row go out as four 32-byte stores (whole sectors; the
+                // scalar form below issues 32 stores that each touch 32 different lines across the warp
+                // and held the tensor pipe up for a third of a 2048-word tile).
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc) {
+                    v[cc] = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
+                    sum += v[cc];
+                }
+                uint32_t* dst = job.out + li * job.ld + (rowB0 + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st_global_v8(dst + 8 * q, &v[8 * q]);
+            } else if (row_ok) {
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc) {
+                    const uint64_t lj = rowB0 + c0 + cc;
+                    if (lj < job.nB) {
+                        uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
+                        if (job.strict_upper && job.j_off + lj <= gi) x = 0;
+                        sum += x;
+                        job.out[li * job.ld + lj] = x;
+                    }
+                }
+            }
+        }
     };
 
     if (FP4 && warp < C::A_ROW_WARPS) {
@@ -384,7 +494,11 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 wait(full_s, phase);
                 const uint32_t flags = ld_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)));
                 const bool run_first = __any_sync(0xffffffffu, (flags & RUN_FIRST) != 0);      // (warp-uniform anyway)
-                if (run_first) wait(acc_empty_bar, (run_iter & 1) ^ 1);    // epilogue of the previous run drained TMEM
+                // accumulator of this run: the only one, or (per-pair form) the two 128-column halves in turn
+                const uint32_t acc_sel = C::ACCS == 2 ? (run_iter & 1u) : 0u;
+                const uint32_t acc_use = C::ACCS == 2 ? (run_iter >> 1) : run_iter;      // how often this accumulator has been used
+                const uint32_t acc_col = tmem_u + UM_ACC_COL + acc_sel * (uint32_t)C::TN;
+                if (run_first) wait(acc_empty_bar + 8 * acc_sel, (acc_use & 1) ^ 1);     // the epilogue of its previous run has drained it
                 tc_fence_after();
                 uint32_t fresh = run_first ? 0u : 1u;                      // accumulate flag of the segment's first MMA
                 for (uint32_t kb = kb0; kb < kb1; ++kb) {
@@ -396,10 +510,10 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             const uint64_t b_desc = (desc_hi & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + 2 * k);
                             const uint32_t accumulate = k == 0 ? fresh : 1u;
                             if (FP4)
-                                umma_mxf4_ts<CG>(tmem_u + UM_ACC_COL, a_col + k * 8, b_desc, C::IDESC_FP4,
+                                umma_mxf4_ts<CG>(acc_col, a_col + k * 8, b_desc, C::IDESC_FP4,
                                                  tmem_u + UM_SF_COL, tmem_u + UM_SF_COL + UM_SF_COLS / 2, accumulate);
                             else
-                                umma_i8_ts<CG>(tmem_u + UM_ACC_COL, a_col + k * 8, b_desc, C::IDESC, accumulate);
+                                umma_i8_ts<CG>(acc_col, a_col + k * 8, b_desc, C::IDESC, accumulate);
                         }
                         umma_commit<CG>(empty_s);                          // frees the stage when these MMAs are done
                     }
@@ -413,13 +527,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                 }
                 if (flags & RUN_LAST) {
-                    if (leader) umma_commit<CG>(acc_full_bar);             // accumulator of this run complete
+                    if (leader) umma_commit<CG>(acc_full_bar + 8 * acc_sel);   // accumulator of this run complete
                     ++run_iter;
                 }
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp < (uint32_t)C::EXPANDER_WARPS) {
         // ===== expanders (A: warps 0-3 -> TMEM, B: warps 4.. -> shared memory) ==========
         // warp -> (side, K half, 32-row group): A warps [0, 4 XW), then B warps; within a side the row group
         // varies fastest, so that an A warp's TMEM lane quarter (warp % 4) is its row group
@@ -497,105 +611,38 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
                 if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
             }
-            if (flags & RUN_LAST) {
+            if (!PAIRS && (flags & RUN_LAST)) {
                 // a run of several segments is interior by construction; a run of one may be a diagonal or edge tile
                 uint32_t bi = 0, bj = 0;
                 bool interior = true;
                 if (flags & RUN_FIRST) { cursor.coords(job, seg.tile, C::TM, C::TN, bi, bj); interior = is_interior(bi, bj); }
                 const uint64_t run_cap = job.chain_max > 1 ? job.chain_max : 1;    // an accumulator element is at most run_cap x M
                 const bool fp4_sum_exact = (uint64_t)job.n_words * 64 * 32 * run_cap <= (1ull << 24);
-                // ---- epilogue of this tile: TMEM -> registers -> masked sum / per-pair store ----
-                // Every expander warp takes part: warp w may read TMEM lanes 32 (w % 4) .. +31, so the
-                // A warp and the B warp(s) of one lane quarter split the 256 accumulator columns between
-                // them (32-column chunks dealt round-robin) and the drain takes half (a third) as long.
-                const uint32_t quarter = warp & 3u, sharer = warp >> 2;
-                constexpr uint32_t N_SHARERS = C::EXPANDER_WARPS / 4;
-                const uint64_t rowA0 = (uint64_t)bi * C::TM, rowB0 = (uint64_t)bj * C::TN;
-                const uint64_t li = rowA0 + rank * 128u + quarter * 32u + lane;  // accumulator row of this thread (= its TMEM lane)
-                const uint64_t gi = job.i_off + li;
-                const bool row_ok = li < job.nA;
-                const uint32_t acc_lane = tmem_base + ((quarter * 32u) << 16) + UM_ACC_COL;
-                const bool out_vec = ((reinterpret_cast<uintptr_t>(job.out) | (job.ld * 4)) & 31) == 0;   // 32-byte stores possible
                 wait(acc_full_bar, run_iter & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (uint32_t c0 = sharer * 32u; c0 < (uint32_t)UM_N; c0 += 32u * N_SHARERS) {
-                    uint32_t v[32];
-                    tmem_ld32(acc_lane + c0, v);
-                    tc_wait_ld();
-                    if (interior) {
-                        if constexpr (FP4) {
-                            // fp32 accumulators holding exact integers.  While 32 counts cannot exceed 2^24 their
-                            // float sum is exact too (one conversion per 32 columns); otherwise convert one by one.
-                            if (fp4_sum_exact) {
-                                float part = 0.0f;
-#pragma unroll
-                                for (int cc = 0; cc < 32; ++cc) part += __uint_as_float(v[cc]);
-                                sum += __float2uint_rn(part);
-                            } else {
-#pragma unroll
-                                for (int cc = 0; cc < 32; ++cc) sum += __float2uint_rn(__uint_as_float(v[cc]));
-                            }
-                        } else if (SCALED) {                               // 32 counts of at most 2^24 each fit 32 bits
-                            uint32_t part = 0;
-#pragma unroll
-                            for (int cc = 0; cc < 32; ++cc) part += v[cc] >> 7;
-                            sum += part;
-                        } else {
-#pragma unroll
-                            for (int cc = 0; cc < 32; ++cc) sum += v[cc];
-                        }
-                    } else if (job.out == nullptr) {
-                        // Edge or diagonal tile, total only: the columns of this 32-column chunk that count are
-                        // [lo, lo + span) -- those below nB and right of the diagonal for this row (one range
-                        // compare per column instead of 64-bit index arithmetic: stream-K can hand a run of
-                        // diagonal tiles to one CTA, and the slow path made that CTA the last to finish).
-                        const long long cb = (long long)(rowB0 + c0);
-                        const long long h = (long long)job.nB - cb;
-                        const int hi = row_ok ? (h < 0 ? 0 : h > 32 ? 32 : (int)h) : 0;
-                        int lo = 0;
-                        if (job.strict_upper) {
-                            const long long l = (long long)gi - (long long)job.j_off - cb + 1;
-                            lo = l < 0 ? 0 : l > 32 ? 32 : (int)l;
-                        }
-                        const uint32_t span = (uint32_t)(hi > lo ? hi - lo : 0);
-#pragma unroll
-                        for (int cc = 0; cc < 32; ++cc) {
-                            const uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
-                            sum += ((uint32_t)(cc - lo) < span) ? x : 0u;
-                        }
-                    } else if (row_ok && out_vec && rowB0 + c0 + 32 <= job.nB &&
-                               (!job.strict_upper || job.j_off + rowB0 + c0 > gi)) {
-                        // Per-pair output, all 32 columns of the chunk valid and right of the diagonal: this thread's
-                        // 128 consecutive bytes of its output row go out as four 32-byte stores (whole sectors; the
-                        // scalar form below issues 32 stores that each touch 32 different lines across the warp
-                        // and held the tensor pipe up for a third of a 2048-word tile).
-#pragma unroll
-                        for (int cc = 0; cc < 32; ++cc) {
-                            v[cc] = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
-                            sum += v[cc];
-                        }
-                        uint32_t* dst = job.out + li * job.ld + (rowB0 + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) st_global_v8(dst + 8 * q, &v[8 * q]);
-                    } else if (row_ok) {
-#pragma unroll
-                        for (int cc = 0; cc < 32; ++cc) {
-                            const uint64_t lj = rowB0 + c0 + cc;
-                            if (lj < job.nB) {
-                                uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
-                                if (job.strict_upper && job.j_off + lj <= gi) x = 0;
-                                sum += x;
-                                job.out[li * job.ld + lj] = x;
-                            }
-                        }
-                    }
-                }
+                drain(0u, warp & 3u, warp >> 2, (uint32_t)(C::EXPANDER_WARPS / 4), bi, bj, interior, fp4_sum_exact);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
                 ++run_iter;
             }
+        }
+    } else if (PAIRS && warp >= (uint32_t)C::EPI_WARP0) {
+        // ===== epilogue warps (per-pair form): drain accumulator t & 1 while tile t + 1 fills the other one =====
+        // Every segment of a per-pair job is a whole tile and a run of its own (nothing is chained or split along K).
+        SegWalk walk(job, cluster_id, n_clusters, n_chunks);
+        TileCursor cursor;
+        Seg seg;
+        for (uint32_t t_iter = 0; walk.next(seg); ++t_iter) {
+            uint32_t bi = 0, bj = 0;
+            cursor.coords(job, seg.tile, C::TM, C::TN, bi, bj);
+            const uint32_t acc_sel = t_iter & 1u, acc_use = t_iter >> 1;
+            wait(acc_full_bar + 8 * acc_sel, acc_use & 1);
+            tc_fence_after();
+            drain(acc_sel * (uint32_t)C::TN, warp & 3u, 0u, 1u, bi, bj, false, false);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar + 8 * acc_sel);
         }
     }
     __syncwarp();                                                          // re-converge (aligned ops follow)
@@ -603,14 +650,14 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ---- one atomic per CTA, then teardown --------------------------------------------
     if (job.total) {
         sum = warp_sum(sum);
-        if (lane == 0 && warp < C::EXPANDER_WARPS) red[warp] = sum;
+        if (lane == 0) red[warp] = sum;                                    // (zero for the roles that drain nothing)
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();                 // everyone is done with TMEM / smem
     if (job.total && tid == 0) {
         unsigned long long t = 0;
 #pragma unroll
-        for (int w = 0; w < C::EXPANDER_WARPS; ++w) t += red[w];
+        for (int w = 0; w < C::N_WARPS; ++w) t += red[w];
         if (t) atomicAdd(job.total, t);
     }
     if (clk_thread) {
@@ -796,7 +843,7 @@ std::mutex g_clk_mu;
 
 template <int CG, int VAR>
 int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
-    using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0>;
+    using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0, (VAR & VAR_PAIRS) != 0>;
     DenseJob job = job_in;
     alignas(64) CUtensorMap map_a, map_b;
     int rc = make_row_map(&map_a, job.A, job.nA, job.strideA, job.n_words, 128);
@@ -880,17 +927,21 @@ std::atomic<int> g_umma_variant{3};   // VAR_* bits (both on: 4.27 vs 3.60 POP/s
 template <int CG>
 int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
     int var = g_umma_variant.load() & 3;
+    const bool pairs = job.out != nullptr;                                  // per-pair output: the two-accumulator form
     if (fp4) {
         if (!umma_fp4_supports(job)) {
             set_error("FP4 kernel: a pair count must stay below 2^24 for exact fp32 accumulation (n_words %u)", job.n_words);
             return STORM_B200_EINVAL;
         }
+        if (pairs) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_PAIRS>(job, stream);
         if constexpr (CG == 2) {
             if (g_umma_fp4_wide.load()) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_WIDE>(job, stream);
         }
         return launch_cg<CG, VAR_FP4 | VAR_SUSPEND>(job, stream);
     }
     if ((uint64_t)job.n_words * 64 * 128 >= (1ull << 31)) var &= ~VAR_SCALED;   // x128 counts must stay below 2^31
+    if (pairs) return (var & VAR_SCALED) ? launch_cg<CG, VAR_SUSPEND | VAR_SCALED | VAR_PAIRS>(job, stream)
+                                         : launch_cg<CG, VAR_SUSPEND | VAR_PAIRS>(job, stream);
     switch (var) {
         case 0: return launch_cg<CG, 0>(job, stream);
         case 1: return launch_cg<CG, 1>(job, stream);
@@ -902,6 +953,8 @@ int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
 }  // namespace
 
 TileShape umma_tile_shape() { return {(uint32_t)(128 * g_umma_cg.load()), (uint32_t)UM_N}; }
+// Tiles of a per-pair job (DenseJob::out set): 128 B rows, two accumulators (Cfg::PAIRS).
+TileShape umma_pairs_tile_shape() { return {(uint32_t)(128 * g_umma_cg.load()), 128u}; }
 
 bool umma_supports(const DenseJob& job) {
     if (job.n_words == 0 || job.n_words >= (1u << 25)) return false;        // counts stay below 2^31

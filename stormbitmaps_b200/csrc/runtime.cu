@@ -228,7 +228,8 @@ int pairw_rect(const uint64_t* dA, uint64_t nA, uint64_t strideA, uint64_t i_off
     job.total = reinterpret_cast<unsigned long long*>(d_total);
     job.reserved_sms = -1;
     kernel = resolve_kernel(kernel, job);
-    const TileShape ts = tile_shape_for(kernel);
+    TileShape ts = tile_shape_for(kernel);
+    if (d_out && (kernel == STORM_B200_KERNEL_UMMA || kernel == STORM_B200_KERNEL_FP4)) ts = umma_pairs_tile_shape();
     job.n_bi = (uint32_t)((nA + ts.tm - 1) / ts.tm);
     job.n_bj = (uint32_t)((nB + ts.tn - 1) / ts.tn);
     job.tile_begin = 0;
