@@ -183,7 +183,7 @@ int launch_dense_fp4(const DenseJob& job, cudaStream_t stream);   // same kernel
 // int8 ops per second of the UMMA kernel's own instruction issued back to back (cta_group 1 or 2).
 int umma_peak_ops(int cg, double* ops_per_s, double* clock64_mhz);
 int fp4_selftest_ok();                          // 1 if this device accumulates E2M1 bit products exactly (cached)
-int fp4_peak_ops(int cg, double* ops_per_s, double* clock64_mhz);   // tcgen05.mma kind::mxf4 issue-rate probe (fp4_probe.cu)
+int fp4_peak_ops(int cg, double* ops_per_s, double* clock64_mhz, int n = 256);   // tcgen05.mma kind::mxf4 issue-rate probe (fp4_probe.cu)
 
 int launch_synth_uniform(uint64_t* d_rows, uint64_t n_rows, uint64_t stride, uint32_t M,
                          uint32_t n_draws, uint64_t seed, uint64_t row0, cudaStream_t stream);

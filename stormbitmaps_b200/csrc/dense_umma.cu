@@ -111,7 +111,6 @@ struct Cfg {
     static_assert(TN * ACCS <= UM_A_COL, "accumulators overflow their tensor-memory columns");
     static_assert(UM_A_COL + 32 * STAGES <= (FP4 ? UM_SF_COL : 512), "A stages overflow tensor memory");
     static_assert(XW == 1 || XW == 2, "one or two expander warps per 32 rows");
-    static_assert(!(PAIRS && XW == 2), "the per-pair form uses one expander warp per 32 rows");
     static_assert(N_WARPS <= 24, "per-warp reduction slots");
     // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor bit layout):
     //   [4,6) c_format = 2 (S32); [7,10) a_format = 0 (u8); [10,13) b_format = 0 (u8);
@@ -233,6 +232,13 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0, (VAR & VAR_PAIRS) != 0>;
     constexpr int XW = (VAR & VAR_WIDE) ? 2 : 1;
     constexpr bool PAIRS = (VAR & VAR_PAIRS) != 0;
+    // Per-pair form with two expander warps per 32 rows: the two warps do not split a k-block along K (as the wide
+    // total-only form does) but ALTERNATE -- one takes the even k-blocks, the other the odd ones.  What bounds an
+    // expander at 128-column tiles is not ALU work but the fixed latency of its serial chain per k-block (box read,
+    // empty-barrier wait, tcgen05.st, wait::st, fence, arrive: ~450 clocks against 256 clocks of MMA work; splitting
+    // along K left that chain as long as it was: 7.9 ms against 8.1 ms for 12288^2 counts at 131072 bits).  Alternating
+    // gives every warp 512 clocks per k-block of its own, the regime in which the total-only form keeps the pipe 99 % busy.
+    constexpr bool ALT = PAIRS && XW == 2;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
@@ -266,7 +272,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == C::MMA_WARP) tmem_alloc<CG>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(full_bar + 8 * s, CG * C::EXPANDER_WARPS);           // every expander warp of the pair
+            mbar_init(full_bar + 8 * s, CG * C::EXPANDER_WARPS / (ALT ? 2 : 1));   // every expander warp of the pair (that works on this k-block)
             mbar_init(empty_bar + 8 * s, 1);                               // tcgen05.commit
         }
         for (int b = 0; b < C::RAW_BUFS; ++b) {
@@ -549,6 +555,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint32_t s = 0, phase = 0, t_iter = 0;                             // stage ring position and its parity
         uint32_t buf = 0, buf_phase = 0;                                   // ring of packed-row boxes and its parity
         uint32_t run_iter = 0;                                             // runs drained
+        uint32_t kb_count = 0;                                             // k-blocks seen so far (ALT: this warp expands those of its parity)
         SegWalk walk(job, cluster_id, n_clusters, n_chunks);
         TileCursor cursor;
         Seg seg;
@@ -560,13 +567,18 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q) {
+                    if (ALT && ((kb_count++ & 1u) != half)) {              // the other warp of this row group has this k-block
+                        if (++s == (uint32_t)C::STAGES) { s = 0; phase ^= 1; }
+                        continue;
+                    }
                     // the packed bits of this row that this thread expands: the whole k-block (16 B in the i8 form,
-                    // 32 B in the FP4 form) or, with two warps per row group, the half that feeds its two K steps
-                    constexpr int NW = (FP4 ? 8 : 4) / XW;                 // 32-bit words per thread and k-block
-                    constexpr int KS = 4 / XW;                             // K steps (MMAs) per thread and k-block
+                    // 32 B in the FP4 form) or, with two warps per row group that split it, the half that feeds its two K steps
+                    constexpr int SPLIT = ALT ? 1 : XW;
+                    constexpr int NW = (FP4 ? 8 : 4) / SPLIT;              // 32-bit words per thread and k-block
+                    constexpr int KS = 4 / SPLIT;                          // K steps (MMAs) per thread and k-block
                     static_assert(!(XW == 2 && !FP4), "two expander warps per row group: FP4 form only");
                     uint32_t ws[NW];
-                    if constexpr (FP4 && XW == 1) {
+                    if constexpr (FP4 && SPLIT == 1) {
                         const uint4 w0 = ld_shared_v4(src + (((2 * q) ^ sw) << 4));
                         const uint4 w1 = ld_shared_v4(src + (((2 * q + 1) ^ sw) << 4));
                         ws[0] = w0.x; ws[1] = w0.y; ws[2] = w0.z; ws[3] = w0.w;
@@ -578,7 +590,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     wait(empty_bar + 8 * s, phase ^ 1);
                     uint32_t e[8];
-                    const uint32_t k0 = half * KS;                         // first K step of this thread
+                    const uint32_t k0 = ALT ? 0u : half * KS;              // first K step of this thread
                     if (is_a) {
                         tc_fence_after();
                         const uint32_t t = a_lane + UM_A_COL + s * 32;
@@ -922,6 +934,7 @@ std::atomic<int> g_umma_cg{2};        // cta_group used by launch_dense_umma (1 
 // once the MMA issue loop was made warp-uniform the narrow form reached 95.8 % of the pipe on C3 and the
 // wide one 92.5 % (it only wins by a few percent below 16 Ki bits per row), profiles/r01_fp4_tune.jsonl.
 std::atomic<int> g_umma_fp4_wide{0};
+std::atomic<int> g_umma_pairs_wide{1};   // per-pair FP4 form: two expander warps per 32 rows (STORM_b200_set_umma_variant bit 4)
 std::atomic<int> g_umma_variant{3};   // VAR_* bits (both on: 4.27 vs 3.60 POP/s on 30k x 131072); see STORM_b200_set_umma_variant
 
 template <int CG>
@@ -933,7 +946,15 @@ int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
             set_error("FP4 kernel: a pair count must stay below 2^24 for exact fp32 accumulation (n_words %u)", job.n_words);
             return STORM_B200_EINVAL;
         }
-        if (pairs) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_PAIRS>(job, stream);
+        if (pairs) {
+            // 128-column tiles leave an expander half the time per k-block (256 clocks): two warps per 32 rows taking the
+            // k-blocks in turn keep the stages full where one warp's load -> expand -> tcgen05.st -> wait chain does not
+            // (one warp per 32 rows: 8.13 ms for 12288^2 counts at 131072 bits against 4.46 ms total-only)
+            if constexpr (CG == 2) {
+                if (g_umma_pairs_wide.load()) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_PAIRS | VAR_WIDE>(job, stream);
+            }
+            return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_PAIRS>(job, stream);
+        }
         if constexpr (CG == 2) {
             if (g_umma_fp4_wide.load()) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_WIDE>(job, stream);
         }
@@ -1020,8 +1041,10 @@ extern "C" int STORM_b200_set_umma_chain(int on) {
 // Development / measurement knob: bit 0 = hardware-suspended mbarrier waits, bit 1 = scaled expansion.
 // Returns the previous value.
 extern "C" int STORM_b200_set_umma_variant(int variant) {
-    const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0);
-    if (variant >= 0 && variant <= 15) { storm::g_umma_variant.store(variant & 3); storm::g_umma_fp4_wide.store((variant >> 3) & 1); }
+    const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0) | (storm::g_umma_pairs_wide.load() ? 16 : 0);
+    if (variant >= 0 && variant <= 31) {
+        storm::g_umma_variant.store(variant & 3); storm::g_umma_fp4_wide.store((variant >> 3) & 1); storm::g_umma_pairs_wide.store((variant >> 4) & 1);
+    }
     return prev;
 }
 

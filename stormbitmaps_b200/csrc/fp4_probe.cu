@@ -37,9 +37,9 @@ constexpr int FP_SF_COL = 384;           // 64 columns of 0x7F7F7F7F (every layo
 // Block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled): [7,10) a_format = 1
 // (E2M1), [10,13) b_format = 1, [15]/[16] K-major, [17,23) N >> 3, [23] scale format 1 = UE8M0,
 // [24,29) M >> 4, [31] k_size 0 = K 64.
-template <int CG>
+template <int CG, int N = FP_N>
 __host__ __device__ constexpr uint32_t fp4_idesc() {
-    return (1u << 7) | (1u << 10) | ((uint32_t)(FP_N >> 3) << 17) | (1u << 23) | ((uint32_t)((128 * CG) >> 4) << 24);
+    return (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)((128 * CG) >> 4) << 24);
 }
 
 template <int CG>
@@ -184,14 +184,14 @@ __global__ void __launch_bounds__(128, 1) fp4_exact_kernel(const Fp4Case* cases,
     if (warp == 0) tmem_free<1>(tmem_base);
 }
 
-template <int CG>
+template <int CG, int N>
 __global__ void __launch_bounds__(128, 1) fp4_peak_kernel(uint32_t iters, unsigned long long* cycles) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     constexpr uint32_t RING = 8;                                             // commits in flight
     constexpr uint32_t BATCH = 8;                                            // MMAs per commit
-    constexpr uint32_t B_BYTES = (FP_N / CG) * 128;
+    constexpr uint32_t B_BYTES = (N / CG) * 128;
     const uint32_t bar_base = smem_base + B_BYTES;
     const uint32_t tmem_slot = bar_base + 8 * RING;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128, 1) fp4_peak_kernel(uint32_t iters, unsign
 #pragma unroll
                 for (int k = 0; k < (int)BATCH; ++k) {
                     const uint64_t b_desc = desc_hi | (uint64_t)(((smem_base + (k & 3) * 32) >> 4) & 0x3FFF);
-                    umma_mxf4_ts<CG>(tmem_u + FP_ACC_COL, tmem_u + FP_A_COL + (k & 3) * 8, b_desc, fp4_idesc<CG>(), sfa, sfb, 1u);
+                    umma_mxf4_ts<CG>(tmem_u + FP_ACC_COL, tmem_u + FP_A_COL + (k & 3) * 8, b_desc, fp4_idesc<CG, N>(), sfa, sfb, 1u);
                 }
                 umma_commit<CG>(bar_base + 8 * (it % RING));
             }
@@ -239,13 +239,13 @@ __global__ void __launch_bounds__(128, 1) fp4_peak_kernel(uint32_t iters, unsign
     if (warp == 0) tmem_free<CG>(tmem_base);
 }
 
-template <int CG>
+template <int CG, int N>
 int run_fp4_peak(double* ops_per_s, double* clock64_mhz) {
     int dev = 0, sms = 0;
     STORM_CUDA_TRY(cudaGetDevice(&dev));
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int smem_bytes = 1024 + (FP_N / CG) * 128 + 256;
-    STORM_CUDA_TRY(cudaFuncSetAttribute(fp4_peak_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int smem_bytes = 1024 + (N / CG) * 128 + 256;
+    STORM_CUDA_TRY(cudaFuncSetAttribute(fp4_peak_kernel<CG, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(sms / CG * CG));
     cfg.blockDim = dim3(128);
@@ -265,7 +265,7 @@ int run_fp4_peak(double* ops_per_s, double* clock64_mhz) {
     double best = 0, best_mhz = 0;
     for (int rep = 0; rep < 4; ++rep) {                                   // rep 0 is the warm-up
         STORM_CUDA_TRY(cudaEventRecord(e0));
-        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, fp4_peak_kernel<CG>, iters, d_cyc));
+        STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, fp4_peak_kernel<CG, N>, iters, d_cyc));
         STORM_CUDA_TRY(cudaEventRecord(e1));
         STORM_CUDA_TRY(cudaEventSynchronize(e1));
         count_launch();
@@ -275,8 +275,8 @@ int run_fp4_peak(double* ops_per_s, double* clock64_mhz) {
         double cyc = 0;
         for (unsigned long long c : h_cyc) cyc += (double)c;
         cyc /= n_clusters;
-        // per SM and instruction: 128 x 256 x 64 MACs = 2 ops each
-        const double ops = (double)cfg.gridDim.x * iters * 8.0 * 128.0 * 256.0 * 64.0 * 2.0;
+        // per SM and instruction: 128 x N x 64 MACs = 2 ops each
+        const double ops = (double)cfg.gridDim.x * iters * 8.0 * 128.0 * (double)N * 64.0 * 2.0;
         if (rep > 0 && ops / (ms * 1e-3) > best) { best = ops / (ms * 1e-3); best_mhz = cyc / (ms * 1e-3) / 1e6; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -482,8 +482,9 @@ int run_fp4_random(uint32_t n_steps, uint32_t seed, Fp4RandResult* out) {
 
 }  // namespace
 
-int fp4_peak_ops(int cg, double* ops_per_s, double* clock64_mhz) {
-    return cg == 1 ? run_fp4_peak<1>(ops_per_s, clock64_mhz) : run_fp4_peak<2>(ops_per_s, clock64_mhz);
+int fp4_peak_ops(int cg, double* ops_per_s, double* clock64_mhz, int n) {
+    if (n == 128) return cg == 1 ? run_fp4_peak<1, 128>(ops_per_s, clock64_mhz) : run_fp4_peak<2, 128>(ops_per_s, clock64_mhz);
+    return cg == 1 ? run_fp4_peak<1, FP_N>(ops_per_s, clock64_mhz) : run_fp4_peak<2, FP_N>(ops_per_s, clock64_mhz);
 }
 
 static int run_fp4_cases(const Fp4Case* cases, uint32_t n_cases, Fp4Result* results) {

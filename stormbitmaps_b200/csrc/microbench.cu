@@ -133,6 +133,7 @@ extern "C" int STORM_b200_microbench(int kind, double* rate, double* sm_mhz) {
         case 5: return umma_peak_ops(2, rate, sm_mhz);   // tcgen05.mma kind::i8, cta_group::2
         case 6: return fp4_peak_ops(1, rate, sm_mhz);    // tcgen05.mma kind::mxf4 (E2M1, K 64), cta_group::1
         case 7: return fp4_peak_ops(2, rate, sm_mhz);    // tcgen05.mma kind::mxf4, cta_group::2
+        case 9: return fp4_peak_ops(2, rate, sm_mhz, 128);   // kind::mxf4, cta_group::2, N = 128 (the per-pair form's instruction)
         case 8: return run_clock_calibration(rate, sm_mhz);   // clock64 ticks per second (and per 1e6) over a 250 ms spin
         default: set_error("unknown microbench kind %d", kind); return STORM_B200_EINVAL;
     }
