@@ -82,6 +82,9 @@ struct DenseJob {
     // kernel's main loop, from which the host derives the SM clock the launch actually ran at (the board's power cap
     // lowers it below what nvidia-smi reports for long tensor launches).
     unsigned long long* clk;
+    // Set by the UMMA launcher for per-pair jobs whose output matrix a tensor map can describe (16-byte aligned base, ld a
+    // multiple of 4): the counts leave through TMA stores instead of per-thread stores.
+    int out_tma;
 };
 
 // Last row block of column block bj that intersects the strict upper triangle when A == B (square

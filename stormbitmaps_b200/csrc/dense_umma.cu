@@ -68,19 +68,22 @@ constexpr int UM_CHUNK_KB_FP4 = 4;
 // threads of different warps expand K steps {0, 1} and {2, 3} of it, which halves the time from "stage free"
 // to "stage full" (the FP4 form expands twice the bits per MMA and fell 15 % short of the pipe with XW = 1).
 //
-// PAIRS = the per-pair output form (DenseJob::out set: every tile is drained, nothing can be chained or split
-// along K).  With one 256-column accumulator the drain of a tile is dead time for the tensor pipe (the MMA warp
-// cannot start the next tile before the epilogue has read the accumulator, and the epilogue ran on the expander
-// warps, which meanwhile staged nothing): 27 % of a 4096-bit tile, 6.5 % of a 131072-bit one.  The PAIRS form
-// therefore works on tiles of 128 B rows with TWO 128-column accumulators used alternately, and hands the drain to
-// four dedicated epilogue warps: while they read accumulator t & 1 and store its counts, the expanders and the MMA
-// warp are already on tile t + 1 in the other one.  The price is one A expansion per 128 instead of 256 B rows
-// (1.5 x the expander work per pair; the ALU pipe was 46 % busy).
+// PAIRS = the per-pair output form (DenseJob::out set: every tile is drained, nothing can be chained or split along K),
+// a separate instantiation so that the total-only kernel carries none of its code.  Its drain does not store from
+// registers (a thread owns one accumulator ROW, so a warp-wide store touched 32 different lines -- the drain of a tile
+// was bound by the LSU at ~2 clocks per 32-byte sector, ~9000 clocks per 256 x 256 tile): each 32 x 32 chunk of counts
+// goes through the shared-memory slices of the B stages -- idle while a tile is drained, and already laid out in
+// SWIZZLE_128B atoms of 8 rows x 128 bytes -- and leaves as ONE cp.async.bulk.tensor store of a 32 x 32 box, clipped
+// by the TMA unit at the edges of the output matrix.
+// (Tried first, profiles/r02_rect_output_n128_*.jsonl: 128-column tiles with two accumulators and dedicated epilogue
+// warps, so that the drain overlaps the next tile.  The drain did vanish, but an expander has only 256 clocks per
+// k-block then and its serial chain -- box read, barrier wait, tcgen05.st, wait::st, fence, arrive -- takes ~600: the
+// tensor pipe ran 64 % busy, 7.0 ms for 12288^2 counts at 131072 bits where this form takes 4.6 ms.)
 template <int CG, int XW = 1, bool FP4 = false, bool PAIRS = false>
 struct Cfg {
     static constexpr bool FP4_FORM = FP4;
-    static constexpr int TN = PAIRS ? 128 : UM_N;            // B rows (accumulator columns) per tile
-    static constexpr int ACCS = PAIRS ? 2 : 1;               // accumulators of TN columns: columns [0, 256) either way
+    static constexpr int TN = UM_N;                          // B rows (accumulator columns) per tile
+    static constexpr int ACCS = 1;                           // accumulators of TN columns
     static constexpr int A_ROW_WARPS = 4;                    // 128 A rows = TMEM lanes
     static constexpr int B_ROWS = TN / CG;                   // B rows expanded by this CTA
     static constexpr int B_ROW_WARPS = B_ROWS / 32;
@@ -88,14 +91,16 @@ struct Cfg {
     static constexpr int B_WARPS = B_ROW_WARPS * XW;
     static constexpr int MMA_WARP = A_WARPS + B_WARPS;
     static constexpr int TMA_WARP = MMA_WARP + 1;
-    static constexpr int EPI_WARP0 = (TMA_WARP + 1 + 3) / 4 * 4;   // dedicated epilogue warps (PAIRS): warp % 4 = TMEM lane quarter
-    static constexpr int EPI_WARPS = PAIRS ? 4 : 0;
-    static constexpr int N_WARPS = PAIRS ? EPI_WARP0 + EPI_WARPS : A_WARPS + B_WARPS + 2;
+    static constexpr int N_WARPS = A_WARPS + B_WARPS + 2;
     static constexpr int THREADS = N_WARPS * 32;
     // expanded k-blocks in flight between the expanders and the MMA thread (A: 32 TMEM columns each,
     // next to the 256 accumulator columns and, in the FP4 form, 32 scale-factor columns)
     static constexpr int STAGES = CG == 2 ? (FP4 ? 7 : 6) : 3;
     static constexpr int STAGE_BYTES = B_ROWS * 128;         // expanded B rows of one k-block
+    // per-pair form: counts leave through TMA stores when each TMEM lane quarter has an A warp and a B warp to share
+    // the B-stage slices of that quarter (the default cta_group::2 form with one expander warp per 32 rows)
+    static constexpr bool TMA_DRAIN = PAIRS && CG == 2 && XW == 1 && STAGES >= 6;
+
     static constexpr int RAW_A_BYTES = 128 * 128;            // one box of packed A rows
     static constexpr int RAW_B_BYTES = B_ROWS * 128;
     static constexpr int RAW_BYTES = RAW_A_BYTES + RAW_B_BYTES;
@@ -228,17 +233,11 @@ constexpr int VAR_PAIRS = 16;           // per-pair output form: 128-column tile
 
 template <int CG, int VAR>
 __global__ void __launch_bounds__((Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0, (VAR & VAR_PAIRS) != 0>::THREADS), 1)
-dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DenseJob job) {
+dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_out, const DenseJob job) {
     using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0, (VAR & VAR_PAIRS) != 0>;
     constexpr int XW = (VAR & VAR_WIDE) ? 2 : 1;
     constexpr bool PAIRS = (VAR & VAR_PAIRS) != 0;
-    // Per-pair form with two expander warps per 32 rows: the two warps do not split a k-block along K (as the wide
-    // total-only form does) but ALTERNATE -- one takes the even k-blocks, the other the odd ones.  What bounds an
-    // expander at 128-column tiles is not ALU work but the fixed latency of its serial chain per k-block (box read,
-    // empty-barrier wait, tcgen05.st, wait::st, fence, arrive: ~450 clocks against 256 clocks of MMA work; splitting
-    // along K left that chain as long as it was: 7.9 ms against 8.1 ms for 12288^2 counts at 131072 bits).  Alternating
-    // gives every warp 512 clocks per k-block of its own, the regime in which the total-only form keeps the pipe 99 % busy.
-    constexpr bool ALT = PAIRS && XW == 2;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
@@ -272,7 +271,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == C::MMA_WARP) tmem_alloc<CG>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(full_bar + 8 * s, CG * C::EXPANDER_WARPS / (ALT ? 2 : 1));   // every expander warp of the pair (that works on this k-block)
+            mbar_init(full_bar + 8 * s, CG * C::EXPANDER_WARPS);           // every expander warp of the pair
             mbar_init(empty_bar + 8 * s, 1);                               // tcgen05.commit
         }
         for (int b = 0; b < C::RAW_BUFS; ++b) {
@@ -281,13 +280,14 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         for (int a = 0; a < C::ACCS; ++a) {
             mbar_init(acc_full_bar + 8 * a, 1);                            // tcgen05.commit
-            mbar_init(acc_empty_bar + 8 * a, CG * (PAIRS ? C::EPI_WARPS : C::EXPANDER_WARPS));   // every epilogue warp of the pair
+            mbar_init(acc_empty_bar + 8 * a, CG * C::EXPANDER_WARPS);      // every epilogue warp of the pair
         }
         fence_mbar_init();
     }
     if (warp == C::TMA_WARP && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (C::TMA_DRAIN && job.out_tma) tma_prefetch_desc(&map_out);
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -325,6 +325,67 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t v[32];
             tmem_ld32(acc_lane + c0, v);
             tc_wait_ld();
+            if constexpr (C::TMA_DRAIN) {
+                if (job.out_tma) {
+                    // Per-pair output through the TMA unit.  The columns of this chunk that count for this row are
+                    // [lo, lo + span) (below nB, right of the diagonal); everything else is stored as 0.  The warp's
+                    // 32 rows x 32 counts go into one 4 KiB slice of the B stages -- the stages are empty while a tile is
+                    // drained, and quarter q's rows of a stage are exactly such a slice: 32 lines of 128 bytes in
+                    // SWIZZLE_128B atoms.  The A warp of a quarter takes the slices of stages 0-3 (one per chunk), the B
+                    // warp those of stages 4.. in turn; one lane then issues a single 32 x 32 box store.
+                    const long long cb = (long long)(rowB0 + c0);
+                    const long long h = (long long)job.nB - cb;
+                    const int hi = row_ok ? (h < 0 ? 0 : h > 32 ? 32 : (int)h) : 0;
+                    int lo = 0;
+                    if (job.strict_upper) {
+                        const long long l = (long long)gi - (long long)job.j_off - cb + 1;
+                        lo = l < 0 ? 0 : l > 32 ? 32 : (int)l;
+                    }
+                    const uint32_t span = (uint32_t)(hi > lo ? hi - lo : 0);
+                    // With the stores out of the way the conversions showed (F2I runs at 16 per clock and SM: 2048 clocks
+                    // per tile; 64-bit adds and per-element masks as much again, profiles/r02_pairs_tma_4096_ncu.md): an
+                    // fp32 accumulator holding an integer below 2^23 is converted by one FADD with 2^23 and one integer
+                    // subtract (the integer sits in the mantissa); chunks that lie wholly inside the matrix and right of
+                    // the diagonal -- all but the edge chunks -- skip the masks; a chunk's 32 counts are summed in 32 bits.
+                    const bool whole = __all_sync(0xffffffffu, lo == 0 && span == 32u);
+                    const bool magic = FP4 && job.n_words < (1u << 17);            // every count below 2^23
+                    uint32_t part = 0;
+                    if (whole && magic) {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) {
+                            v[cc] = __float_as_uint(__uint_as_float(v[cc]) + 8388608.0f) - 0x4B000000u;
+                            part += v[cc];
+                        }
+                        sum += part;
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) {
+                            const uint32_t x = FP4 ? __float2uint_rn(__uint_as_float(v[cc])) : SCALED ? (v[cc] >> 7) : v[cc];
+                            v[cc] = ((uint32_t)(cc - lo) < span) ? x : 0u;
+                            if (FP4) part += v[cc]; else sum += v[cc];
+                        }
+                        sum += part;
+                    }
+                    constexpr uint32_t B_RING = (uint32_t)C::STAGES - 4u;            // slices the B warp of a quarter rotates through
+                    const uint32_t n_chunk = c0 / (32u * n_sharers);                 // this warp's n-th chunk of the tile
+                    const uint32_t st = sharer == 0 ? n_chunk : 4u + n_chunk % B_RING;
+                    if (sharer != 0 && n_chunk >= B_RING) {                          // the store that last read this slice must be done with it
+                        if (lane == 0) bulk_wait_read<(int)B_RING - 1>();
+                        __syncwarp();
+                    }
+                    const uint32_t slice = smem_base + st * (uint32_t)C::STAGE_BYTES + quarter * 4096u;
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j)
+                        st_shared_v4(slice + lane * 128u + ((j ^ (lane & 7u)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_proxy_async_smem();                              // generic writes -> visible to the TMA unit (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_out, slice, (uint32_t)(rowB0 + c0), (uint32_t)(rowA0 + rank * 128u + quarter * 32u));
+                        bulk_commit();
+                    }
+                    continue;
+                }
+            }
             if (!PAIRS && interior) {
                 if constexpr (FP4) {
                     // fp32 accumulators holding exact integers.  While 32 counts cannot exceed 2^24 their
@@ -391,6 +452,17 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         job.out[li * job.ld + lj] = x;
                     }
                 }
+            }
+        }
+        if constexpr (C::TMA_DRAIN) {
+            if (job.out_tma) {
+                // The B warp of this quarter writes the slices again as soon as it expands the next tile: both warps of the
+                // quarter wait until their stores have read them, then meet (named barrier 1 + quarter, 64 threads).
+                // (Handing the accumulator back before that and checking per stage in the expander loop, and keeping the
+                // tensor-memory load of the next chunk in flight, changed nothing measurable: profiles/r02_rect_output_tma_store_v3*, _v4*.)
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                asm volatile("bar.sync %0, 64;" ::"r"(1u + quarter) : "memory");
             }
         }
     };
@@ -555,7 +627,6 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint32_t s = 0, phase = 0, t_iter = 0;                             // stage ring position and its parity
         uint32_t buf = 0, buf_phase = 0;                                   // ring of packed-row boxes and its parity
         uint32_t run_iter = 0;                                             // runs drained
-        uint32_t kb_count = 0;                                             // k-blocks seen so far (ALT: this warp expands those of its parity)
         SegWalk walk(job, cluster_id, n_clusters, n_chunks);
         TileCursor cursor;
         Seg seg;
@@ -567,13 +638,9 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t src = raw_base + buf * C::RAW_BYTES + raw_row;
                 const uint32_t nq = min(CHUNK_KB, n_kb - c * CHUNK_KB);
                 for (uint32_t q = 0; q < nq; ++q) {
-                    if (ALT && ((kb_count++ & 1u) != half)) {              // the other warp of this row group has this k-block
-                        if (++s == (uint32_t)C::STAGES) { s = 0; phase ^= 1; }
-                        continue;
-                    }
                     // the packed bits of this row that this thread expands: the whole k-block (16 B in the i8 form,
                     // 32 B in the FP4 form) or, with two warps per row group that split it, the half that feeds its two K steps
-                    constexpr int SPLIT = ALT ? 1 : XW;
+                    constexpr int SPLIT = XW;
                     constexpr int NW = (FP4 ? 8 : 4) / SPLIT;              // 32-bit words per thread and k-block
                     constexpr int KS = 4 / SPLIT;                          // K steps (MMAs) per thread and k-block
                     static_assert(!(XW == 2 && !FP4), "two expander warps per row group: FP4 form only");
@@ -590,7 +657,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     wait(empty_bar + 8 * s, phase ^ 1);
                     uint32_t e[8];
-                    const uint32_t k0 = ALT ? 0u : half * KS;              // first K step of this thread
+                    const uint32_t k0 = half * KS;                         // first K step of this thread
                     if (is_a) {
                         tc_fence_after();
                         const uint32_t t = a_lane + UM_A_COL + s * 32;
@@ -623,7 +690,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
                 if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
             }
-            if (!PAIRS && (flags & RUN_LAST)) {
+            if (flags & RUN_LAST) {
                 // a run of several segments is interior by construction; a run of one may be a diagonal or edge tile
                 uint32_t bi = 0, bj = 0;
                 bool interior = true;
@@ -638,23 +705,6 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
                 ++run_iter;
             }
-        }
-    } else if (PAIRS && warp >= (uint32_t)C::EPI_WARP0) {
-        // ===== epilogue warps (per-pair form): drain accumulator t & 1 while tile t + 1 fills the other one =====
-        // Every segment of a per-pair job is a whole tile and a run of its own (nothing is chained or split along K).
-        SegWalk walk(job, cluster_id, n_clusters, n_chunks);
-        TileCursor cursor;
-        Seg seg;
-        for (uint32_t t_iter = 0; walk.next(seg); ++t_iter) {
-            uint32_t bi = 0, bj = 0;
-            cursor.coords(job, seg.tile, C::TM, C::TN, bi, bj);
-            const uint32_t acc_sel = t_iter & 1u, acc_use = t_iter >> 1;
-            wait(acc_full_bar + 8 * acc_sel, acc_use & 1);
-            tc_fence_after();
-            drain(acc_sel * (uint32_t)C::TN, warp & 3u, 0u, 1u, bi, bj, false, false);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar + 8 * acc_sel);
         }
     }
     __syncwarp();                                                          // re-converge (aligned ops follow)
@@ -671,6 +721,9 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
         for (int w = 0; w < C::N_WARPS; ++w) t += red[w];
         if (t) atomicAdd(job.total, t);
+    }
+    if constexpr (C::TMA_DRAIN) {
+        if (job.out_tma && lane == 0 && warp < (uint32_t)C::EXPANDER_WARPS) bulk_wait_all();   // (the stores were issued before the sync above)
     }
     if (clk_thread) {
         job.clk[2 * blockIdx.x] = (unsigned long long)(clock64() - clk0);
@@ -821,6 +874,22 @@ int make_row_map(CUtensorMap* map, const uint64_t* base, uint64_t n_rows, uint64
     return STORM_B200_OK;
 }
 
+// Per-pair counts as a 2-D uint32 tensor: inner = the nB valid columns, outer = the nA rows, pitch ld; box = 32 x 32
+// (128 bytes x 32 rows, SWIZZLE_128B: what a warp of the epilogue stages in one 4 KiB slice).
+int make_out_map(CUtensorMap* map, uint32_t* out, uint64_t nA, uint64_t nB, uint64_t ld) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return STORM_B200_ECUDA; }
+    const cuuint64_t dims[2] = {(cuuint64_t)nB, (cuuint64_t)nA};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, out, dims, strides, box, elem,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r); return STORM_B200_ECUDA; }
+    return STORM_B200_OK;
+}
+
 // Wave counters: a small ring per device, one slot per launch, zeroed on the launch's stream.
 int wave_counter(cudaStream_t stream, unsigned int** slot) {
     constexpr int MAX_DEV = 16, RING = 256;
@@ -847,6 +916,7 @@ std::atomic<int> g_umma_reserved_sms{0};   // STORM_b200_set_umma_reserved_sms
 std::atomic<int> g_umma_stream_k{1};       // STORM_b200_set_umma_stream_k
 std::atomic<int> g_umma_chain{1};          // STORM_b200_set_umma_chain
 std::atomic<int> g_clock_probe{0};         // STORM_b200_set_clock_probe
+std::atomic<int> g_umma_out_tma{1};        // STORM_b200_set_umma_variant bit 4: per-pair counts leave through TMA stores
 
 // Clock-probe buffer of the current device (2 x u64 per CTA of the last probed launch) and the grid of that launch.
 struct ClockProbe { unsigned long long* d = nullptr; unsigned grid = 0; };
@@ -857,10 +927,17 @@ template <int CG, int VAR>
 int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     using C = Cfg<CG, (VAR & VAR_WIDE) ? 2 : 1, (VAR & VAR_FP4) != 0, (VAR & VAR_PAIRS) != 0>;
     DenseJob job = job_in;
-    alignas(64) CUtensorMap map_a, map_b;
+    alignas(64) CUtensorMap map_a, map_b, map_out;
     int rc = make_row_map(&map_a, job.A, job.nA, job.strideA, job.n_words, 128);
     if (!rc) rc = make_row_map(&map_b, job.B, job.nB, job.strideB, job.n_words, C::B_ROWS);
     if (rc) return rc;
+    map_out = map_a;                                                         // (a valid descriptor when none is needed)
+    job.out_tma = 0;
+    if (C::TMA_DRAIN && job.out && g_umma_out_tma.load() && ((reinterpret_cast<uintptr_t>(job.out) & 15) == 0) && (job.ld % 4 == 0) &&
+        job.nA < (1ull << 32) && job.nB < (1ull << 32) && job.ld < (1ull << 38)) {
+        if ((rc = make_out_map(&map_out, job.out, job.nA, job.nB, job.ld))) return rc;
+        job.out_tma = 1;
+    }
     STORM_CUDA_TRY(cudaFuncSetAttribute(dense_umma_kernel<CG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     int dev = 0, sms = 0;
     STORM_CUDA_TRY(cudaGetDevice(&dev));
@@ -924,7 +1001,7 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_umma_kernel<CG, VAR>, map_a, map_b, job));
+    STORM_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_umma_kernel<CG, VAR>, map_a, map_b, map_out, job));
     count_launch();
     return STORM_B200_OK;
 }
@@ -934,7 +1011,6 @@ std::atomic<int> g_umma_cg{2};        // cta_group used by launch_dense_umma (1 
 // once the MMA issue loop was made warp-uniform the narrow form reached 95.8 % of the pipe on C3 and the
 // wide one 92.5 % (it only wins by a few percent below 16 Ki bits per row), profiles/r01_fp4_tune.jsonl.
 std::atomic<int> g_umma_fp4_wide{0};
-std::atomic<int> g_umma_pairs_wide{1};   // per-pair FP4 form: two expander warps per 32 rows (STORM_b200_set_umma_variant bit 4)
 std::atomic<int> g_umma_variant{3};   // VAR_* bits (both on: 4.27 vs 3.60 POP/s on 30k x 131072); see STORM_b200_set_umma_variant
 
 template <int CG>
@@ -946,15 +1022,7 @@ int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
             set_error("FP4 kernel: a pair count must stay below 2^24 for exact fp32 accumulation (n_words %u)", job.n_words);
             return STORM_B200_EINVAL;
         }
-        if (pairs) {
-            // 128-column tiles leave an expander half the time per k-block (256 clocks): two warps per 32 rows taking the
-            // k-blocks in turn keep the stages full where one warp's load -> expand -> tcgen05.st -> wait chain does not
-            // (one warp per 32 rows: 8.13 ms for 12288^2 counts at 131072 bits against 4.46 ms total-only)
-            if constexpr (CG == 2) {
-                if (g_umma_pairs_wide.load()) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_PAIRS | VAR_WIDE>(job, stream);
-            }
-            return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_PAIRS>(job, stream);
-        }
+        if (pairs) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_PAIRS>(job, stream);
         if constexpr (CG == 2) {
             if (g_umma_fp4_wide.load()) return launch_cg<CG, VAR_FP4 | VAR_SUSPEND | VAR_WIDE>(job, stream);
         }
@@ -974,8 +1042,8 @@ int launch_var(const DenseJob& job, cudaStream_t stream, bool fp4) {
 }  // namespace
 
 TileShape umma_tile_shape() { return {(uint32_t)(128 * g_umma_cg.load()), (uint32_t)UM_N}; }
-// Tiles of a per-pair job (DenseJob::out set): 128 B rows, two accumulators (Cfg::PAIRS).
-TileShape umma_pairs_tile_shape() { return {(uint32_t)(128 * g_umma_cg.load()), 128u}; }
+// Tiles of a per-pair job (DenseJob::out set): the same as the total-only form's.
+TileShape umma_pairs_tile_shape() { return umma_tile_shape(); }
 
 bool umma_supports(const DenseJob& job) {
     if (job.n_words == 0 || job.n_words >= (1u << 25)) return false;        // counts stay below 2^31
@@ -1041,9 +1109,9 @@ extern "C" int STORM_b200_set_umma_chain(int on) {
 // Development / measurement knob: bit 0 = hardware-suspended mbarrier waits, bit 1 = scaled expansion.
 // Returns the previous value.
 extern "C" int STORM_b200_set_umma_variant(int variant) {
-    const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0) | (storm::g_umma_pairs_wide.load() ? 16 : 0);
+    const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0) | (storm::g_umma_out_tma.load() ? 16 : 0);
     if (variant >= 0 && variant <= 31) {
-        storm::g_umma_variant.store(variant & 3); storm::g_umma_fp4_wide.store((variant >> 3) & 1); storm::g_umma_pairs_wide.store((variant >> 4) & 1);
+        storm::g_umma_variant.store(variant & 3); storm::g_umma_fp4_wide.store((variant >> 3) & 1); storm::g_umma_out_tma.store((variant >> 4) & 1);
     }
     return prev;
 }
