@@ -215,7 +215,11 @@ uint64_t STORM_b200_storm_pairw_shard(STORM_t* bitmap, uint32_t shard, uint32_t 
  * 1 if the dense form does not fit in device memory).  Results are identical.  Returns the
  * previous value; STORM_b200_storm_last_route tells which one the last query of `bitmap` took. */
 int STORM_b200_set_storm_route(int route);
-int STORM_b200_storm_last_route(const STORM_t* bitmap);
+int STORM_b200_storm_last_route(const STORM_t* bitmap);   /* 1 sparse kernels, 2 densified rows + tile kernel, 3 the same in row bands */
+/* A container whose dense form exceeds 48 GiB is densified in row bands of 12 GiB (two arenas; triangle of a band, then its
+ * rectangles with the later bands) instead of falling back to the block merge/probe kernel.  This knob forces the banded
+ * form with bands of `rows` rows for any size (0 = the size rule again); results are identical.  Returns the previous value. */
+uint64_t STORM_b200_set_storm_band_rows(uint64_t rows);
 /* The route cost model as a function (pure arithmetic, no device): expected seconds of a whole-container query of
  * n_rows rows of n_words 64-bit words holding avg_nnz values in avg_blocks blocks each, out[0] through the
  * densified rows + tile kernel, out[1] through the sparse kernels.  The query takes the smaller one. */

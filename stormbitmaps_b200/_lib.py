@@ -97,6 +97,7 @@ SIGNATURES = {
     "STORM_b200_storm_pairw_shard": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "STORM_b200_set_storm_route": (C.c_int, [C.c_int]),
     "STORM_b200_set_sparse_flat": (C.c_int, [C.c_int]),
+    "STORM_b200_set_storm_band_rows": (C.c_uint64, [C.c_uint64]),
     "STORM_b200_storm_route_model": (C.c_int, [C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_uint64, C.c_int, C.c_int,
                                               C.POINTER(C.c_double)]),
     "STORM_b200_set_contig_list_route": (C.c_int, [C.c_int]),

@@ -166,7 +166,7 @@ class Storm:
 
     def last_route(self) -> str:
         """Which kernel family answered the last whole-container query: 'sparse' or 'dense'."""
-        return {0: "none", 1: "sparse", 2: "dense"}[self._L.STORM_b200_storm_last_route(self._h)]
+        return {0: "none", 1: "sparse", 2: "dense", 3: "dense"}[self._L.STORM_b200_storm_last_route(self._h)]
 
     def pairw_shard(self, shard: int, n_shards: int) -> int:
         return _query(self._L.STORM_b200_storm_pairw_shard(self._h, shard, n_shards), "STORM_b200_storm_pairw_shard")
@@ -500,6 +500,11 @@ def storm_route_model(n_rows: int, n_words: int, avg_nnz: float, avg_blocks: flo
     _lib.check(_lib.load().STORM_b200_storm_route_model(n_rows, n_words, avg_nnz, avg_blocks, max_row_nnz, n_bitmap_blocks,
                                                         int(fp4), int(dense_resident), out), "STORM_b200_storm_route_model")
     return {"dense_s": out[0], "sparse_s": out[1], "route": "dense" if out[0] < out[1] else "sparse"}
+
+
+def set_storm_band_rows(rows: int) -> int:
+    """``STORM_b200_set_storm_band_rows``: force the banded dense form of STORM_t queries (0 = size rule)."""
+    return int(_lib.load().STORM_b200_set_storm_band_rows(int(rows)))
 
 
 def set_sparse_flat(mode) -> int:

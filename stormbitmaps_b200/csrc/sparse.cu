@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -447,9 +448,9 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_stream_kernel(const 
 // layout of the contiguous model (bit v -> word v/64, bit v%64; storm.c:1114), after which
 // the query is the dense tile kernel's.  A bitmap block is a 8 KiB copy; a list block sets
 // its bits with 64-bit atomic ORs (two values of a list may share a word).
-__global__ void __launch_bounds__(256) densify_rows_kernel(const SparseView v, uint64_t* dense, uint64_t stride) {
-    const uint32_t row = blockIdx.x;
-    unsigned long long* out = reinterpret_cast<unsigned long long*>(dense + (uint64_t)row * stride);
+__global__ void __launch_bounds__(256) densify_rows_kernel(const SparseView v, uint64_t* dense, uint64_t stride, uint32_t row0) {
+    const uint32_t row = row0 + blockIdx.x;                      // dense row blockIdx.x = container row row0 + blockIdx.x
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(dense + (uint64_t)blockIdx.x * stride);
     for (uint32_t b = v.row_ptr[row]; b < v.row_ptr[row + 1]; ++b) {
         const uint32_t len = v.blk_len[b];
         unsigned long long* blk = out + (uint64_t)v.blk_id[b] * BLOCK_WORDS;
@@ -817,12 +818,67 @@ int ensure_dense(StormState* st, uint64_t n_rows, uint64_t* stride_out) {
         st->dense_cap_words = words;
     }
     STORM_CUDA_TRY(cudaMemsetAsync(st->d_dense, 0, words * 8, st->stream));
-    densify_rows_kernel<<<(unsigned)n_rows, 256, 0, st->stream>>>(view_of(st), st->d_dense, stride);
+    densify_rows_kernel<<<(unsigned)n_rows, 256, 0, st->stream>>>(view_of(st), st->d_dense, stride, 0u);
     STORM_CUDA_TRY(cudaGetLastError());
     count_launch();
     st->dense_valid = true;
     return STORM_B200_OK;
 }
+
+// Dense route for containers whose dense form is too large to keep whole (N x W x 8 bytes above DENSE_WHOLE_MAX): the
+// rows are densified one band of DENSE_BAND_BYTES at a time into two arenas and the triangle is walked band pair by
+// band pair -- the triangle of a band, then its rectangle with every later band -- through the same tile kernels.  The
+// merge/probe block kernel (10-70 x slower on such rows) is no longer what a large container falls back to.  Band size
+// and the whole / banded decision are fixed byte counts, not functions of free memory: every shard of a sharded query
+// cuts the same bands, and shard s takes the band pairs k with k mod n_shards == s.
+constexpr uint64_t DENSE_WHOLE_MAX = 48ull << 30;
+constexpr uint64_t DENSE_BAND_BYTES = 12ull << 30;
+
+int dense_banded(StormState* st, uint64_t n_rows, uint32_t shard, uint32_t n_shards, uint64_t band_rows_override = 0) {
+    const uint64_t stride = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
+    uint64_t R = band_rows_override ? band_rows_override : std::max<uint64_t>(256, DENSE_BAND_BYTES / (stride * 8) / 256 * 256);
+    R = std::min(R, n_rows);
+    uint64_t* arena[2] = {nullptr, nullptr};
+    struct Release { uint64_t** a; ~Release() { cudaFree(a[0]); cudaFree(a[1]); } } release{arena};
+    for (auto& a : arena)
+        if (cudaMalloc(&a, R * stride * 8) != cudaSuccess) {
+            cudaGetLastError(); a = nullptr;
+            set_error("two dense bands of %llu rows x %llu words do not fit on this device", (unsigned long long)R, (unsigned long long)stride);
+            return STORM_B200_ENOMEM;
+        }
+    auto densify = [&](uint64_t* dst, uint64_t r0, uint64_t n) -> int {
+        STORM_CUDA_TRY(cudaMemsetAsync(dst, 0, n * stride * 8, st->stream));
+        densify_rows_kernel<<<(unsigned)n, 256, 0, st->stream>>>(view_of(st), dst, stride, (uint32_t)r0);
+        STORM_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return STORM_B200_OK;
+    };
+    const uint64_t n_bands = (n_rows + R - 1) / R;
+    uint64_t k = 0;                                                        // running band-pair index (I <= J, I-major)
+    for (uint64_t I = 0; I < n_bands; ++I) {
+        const uint64_t i0 = I * R, ni = std::min(R, n_rows - i0);
+        bool have_i = false;
+        for (uint64_t J = I; J < n_bands; ++J, ++k) {
+            if (k % n_shards != shard) continue;
+            int rc = STORM_B200_OK;
+            if (!have_i) { if ((rc = densify(arena[0], i0, ni))) return rc; have_i = true; }
+            if (J == I) {
+                rc = pairw_triangle(arena[0], ni, (uint32_t)stride, stride, 0, 1, STORM_B200_KERNEL_AUTO,
+                                    reinterpret_cast<uint64_t*>(st->d_total), st->stream);
+            } else {
+                const uint64_t j0 = J * R, nj = std::min(R, n_rows - j0);
+                if ((rc = densify(arena[1], j0, nj))) return rc;
+                rc = pairw_rect(arena[0], ni, stride, i0, arena[1], nj, stride, j0, (uint32_t)stride, 0, STORM_B200_KERNEL_AUTO,
+                                nullptr, 0, reinterpret_cast<uint64_t*>(st->d_total), st->stream);
+            }
+            if (rc) return rc;
+        }
+    }
+    STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));                     // the arenas are freed on return
+    return STORM_B200_OK;
+}
+
+std::atomic<uint64_t> g_dense_band_rows{0};   // STORM_b200_set_storm_band_rows: force the banded form with this band height (tests)
 
 uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     if (s == nullptr) return (uint64_t)-1;                          // storm.c:878,898
@@ -833,6 +889,17 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     if (cudaMemsetAsync(st->d_total, 0, 8, st->stream) != cudaSuccess) return (uint64_t)-1;
     uint64_t stride = 0;
     bool dense = choose_dense_route(st, s->n_conts);
+    const uint64_t forced_band = g_dense_band_rows.load();
+    if (dense && (forced_band || (uint64_t)s->n_conts * (((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS) * 8 > DENSE_WHOLE_MAX)) {
+        st->last_route = 3;                                              // dense, banded
+        if (dense_banded(st, s->n_conts, shard, n_shards, forced_band)) return (uint64_t)-1;
+        if (cudaMemcpyAsync(st->h_total, st->d_total, 8, cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
+            cudaStreamSynchronize(st->stream) != cudaSuccess) {
+            set_error("STORM_t query failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return (uint64_t)-1;
+        }
+        return *st->h_total;
+    }
     if (dense && (!dense_fits(st, s->n_conts) || ensure_dense(st, s->n_conts, &stride) != STORM_B200_OK)) {
         // the dense form does not fit on this device: an unsharded query answers through the sparse kernels instead;
         // a shard must not (the other shards partition the pairs by the tile raster)
@@ -1144,6 +1211,9 @@ int STORM_b200_set_sparse_flat(int mode) {
     return prev;
 }
 
+// Tests / measurements: force the banded dense form with bands of `rows` rows (0 = back to the size rule).  Returns the previous value.
+uint64_t STORM_b200_set_storm_band_rows(uint64_t rows) { return g_dense_band_rows.exchange(rows); }
+
 int STORM_b200_storm_last_route(const STORM_t* s) {
     if (s == nullptr || s->b200 == nullptr) return 0;
     return state_of(s)->last_route;
@@ -1160,6 +1230,33 @@ int STORM_b200_storm_pairw_rect(STORM_t* s, uint64_t i0, uint64_t i1, uint64_t j
     const uint64_t ni = i1 - i0, nj = j1 - j0;
     uint32_t* d_out = nullptr;
     if (cudaMalloc(&d_out, ni * nj * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); set_error("device allocation for %llu x %llu counts failed", (unsigned long long)ni, (unsigned long long)nj); return STORM_B200_ENOMEM; }
+    // Containers with bitmap blocks: the two row ranges are densified and the rectangle goes through the tile kernel
+    // (per-pair form) -- the block merge/probe kernel is 10-70 x slower on such rows.  Containers of list blocks keep
+    // the flat probe kernel below.
+    const uint64_t dense_stride = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
+    if (st->n_bitmap_blocks > 0 && g_storm_route != 1 && dense_stride < (1u << 25) && (ni + nj) * dense_stride * 8 <= DENSE_WHOLE_MAX / 2) {
+        uint64_t* d_rows = nullptr;
+        if (cudaMalloc(&d_rows, (ni + nj) * dense_stride * 8) == cudaSuccess) {
+            rc = STORM_B200_OK;
+            if (cudaMemsetAsync(d_rows, 0, (ni + nj) * dense_stride * 8, st->stream) != cudaSuccess) rc = STORM_B200_ECUDA;
+            if (!rc) {
+                densify_rows_kernel<<<(unsigned)ni, 256, 0, st->stream>>>(view_of(st), d_rows, dense_stride, (uint32_t)i0);
+                densify_rows_kernel<<<(unsigned)nj, 256, 0, st->stream>>>(view_of(st), d_rows + ni * dense_stride, dense_stride, (uint32_t)j0);
+                count_launch(2);
+                if (cudaGetLastError() != cudaSuccess) rc = STORM_B200_ECUDA;
+            }
+            if (!rc) rc = pairw_rect(d_rows, ni, dense_stride, i0, d_rows + ni * dense_stride, nj, dense_stride, j0, (uint32_t)dense_stride, 1,
+                                     STORM_B200_KERNEL_AUTO, d_out, nj, nullptr, st->stream);
+            if (!rc && (cudaMemcpyAsync(out, d_out, ni * nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(st->stream) != cudaSuccess)) {
+                set_error("STORM_t rect query failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = STORM_B200_ECUDA;
+            }
+            cudaFree(d_rows); cudaFree(d_out);
+            return rc;
+        }
+        cudaGetLastError();                                              // no room for the dense rows: the block kernel answers
+    }
     if ((rc = ensure_flat(st))) { cudaFree(d_out); return rc; }
     SparseJob job{};
     job.A = job.B = view_of(st);

@@ -825,3 +825,37 @@ def test_dense_ingest_rehome_and_resident_multi_device_query(sb, orc):
     for k in sorted({1, n_dev, max(1, n_dev // 2)}):
         assert sb.pairw_devices(copies[:k], n_words=vals.shape[1]) == exact, k
     torch.cuda.set_device(0)
+
+
+def test_storm_t_banded_dense_route_and_densified_rectangles(sb, orc):
+    """Containers whose dense form is too large to keep whole are densified in row bands (forced here with small
+    bands): triangle of a band + rectangles with the later bands = the exact total, shards included; per-pair
+    rectangles of containers with bitmap blocks go through densified row ranges and the tile kernel."""
+    M = 3 * 65536 + 1000
+    draws = [1, 5, 40, 300, 3000, 9000, 20000, 60000, 150000, 0, 64, 65]
+    rows = [orc.gen_row_positions(58, i, draws[i % len(draws)], M) for i in range(700)]
+    vals = O.positions_to_dense(rows, M)
+    exact = orc.wrapper_diag(vals)
+    prev_route = sb.set_storm_route("dense")
+    try:
+        with sb.Storm() as s:
+            for p in rows:
+                s.add(p)
+            assert s.pairw_intersect_cardinality() == exact
+            for band in (256, 300, 512, 10000):
+                prev = sb.set_storm_band_rows(band)
+                try:
+                    assert s.pairw_intersect_cardinality() == exact, band
+                    assert s.pairw_intersect_cardinality_blocked(0) == exact, band
+                    assert sum(s.pairw_shard(r, 3) for r in range(3)) == exact, band
+                finally:
+                    sb.set_storm_band_rows(prev)
+            assert s.pairw_intersect_cardinality() == exact
+    finally:
+        sb.set_storm_route(prev_route)
+    with sb.Storm() as s:                                   # AUTO: rectangles through densified rows (bitmap blocks present)
+        for p in rows:
+            s.add(p)
+        assert (s.pairw_rect(0, 700, 0, 700) == orc.rect_counts(vals, 0, 700, 0, 700)).all()
+        assert (s.pairw_rect(20, 290, 150, 671) == orc.rect_counts(vals, 20, 290, 150, 671)).all()
+        assert (s.pairw_rect(500, 700, 3, 130) == orc.rect_counts(vals, 500, 700, 3, 130)).all()
