@@ -65,7 +65,8 @@ int  STORM_b200_set_default_kernel(int kernel);
  *   STORM_b200_set_device_list(ids, n): explicit ordinals (one may repeat: several replicas on one device, which
  *     is how the multi-device logic is tested on a one-GPU box); n = 0 restores the default
  * Default: the calling thread's current device alone (what a multi-process caller with one rank per GPU wants).
- * STORM_t queries and per-pair rectangles use the first device of the set. */
+ * Whole-container STORM_t queries run on the set as well (the block mirror is uploaded to every device, each densifies or
+ * probes its own copy and answers its shard); per-pair rectangles and XY^T totals use the first device of the set. */
 int STORM_b200_set_devices(int n);
 int STORM_b200_set_device_list(const int* ids, int n);
 /* The devices a query made now would use: fills ids[0 .. min(cap, count)), returns the count (negative on error). */

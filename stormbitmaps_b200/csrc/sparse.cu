@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "devices.h"
 #include "runtime.h"
 
 namespace storm {
@@ -487,15 +488,11 @@ struct StormState {
     uint32_t max_row_nnz = 0;
     std::vector<uint32_t> h_group_start; // row groups of the stream kernel (<= 32 rows, <= STREAM_ENTRIES values)
     uint32_t* d_group_start = nullptr;
-};
-
-struct DeviceGuard {
-    int prev = -1; bool active = false;
-    explicit DeviceGuard(int dev) {
-        if (dev < 0) return;
-        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); active = true; }
-    }
-    ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+    // Whole-container queries run on the device set (devices.h): this state is the replica on the set's first device
+    // and owns the replicas on the others (resolved at the first query; rectangles and XY^T stay on this one).
+    std::vector<StormState*> replicas;
+    bool set_resolved = false;
+    uint64_t* d_band[2] = {nullptr, nullptr}; uint64_t band_cap_words = 0;   // arenas of the banded dense route
 };
 
 inline StormState* state_of(const STORM_t* s) { return static_cast<StormState*>(s->b200); }
@@ -524,80 +521,127 @@ int ensure_state(StormState* st) {
     if (st->device >= 0 && st->d_total) return STORM_B200_OK;
     int rc = require_device();
     if (rc) return rc;
-    STORM_CUDA_TRY(cudaGetDevice(&st->device));
+    STORM_CUDA_TRY(cudaGetDevice(&st->device));                     // (callers made the state's device current, if it has one)
     STORM_CUDA_TRY(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
     STORM_CUDA_TRY(cudaMalloc(&st->d_total, 8));
     STORM_CUDA_TRY(cudaMallocHost(&st->h_total, 8));
     return STORM_B200_OK;
 }
 
-// Flatten the host containers and upload them (whole-container rebuild on change).
-int sync_mirror(const STORM_t* s, StormState* st) {
-    int rc = ensure_state(st);
-    if (rc) return rc;
-    if (!st->dirty && st->n_rows == s->n_conts) return STORM_B200_OK;
-    free_mirror(st);
-    std::vector<uint32_t> row_ptr(s->n_conts + 1, 0), row_nnz(s->n_conts, 0), blk_id, blk_len;
-    std::vector<uint64_t> blk_off, words;
+// The host containers flattened (CSR of blocks + one u16 pool + one bitmap pool): built once per change of the
+// container and uploaded to every replica.
+struct HostMirror {
+    std::vector<uint32_t> row_ptr, row_nnz, row_nnz_dev, blk_id, blk_len, group_start;
+    std::vector<uint64_t> blk_off, words, pos_off;
     std::vector<uint16_t> lists;
-    uint32_t max_blocks = 0, max_blk_id = 0;
-    uint64_t n_bitmap_blocks = 0;
+    uint32_t max_blocks = 0, max_blk_id = 0, max_row_nnz = 0;
+    uint64_t n_bitmap_blocks = 0, total_nnz = 0;
+};
+
+void build_host_mirror(const STORM_t* s, HostMirror* h) {
+    h->row_ptr.assign(s->n_conts + 1, 0);
+    h->row_nnz.assign(s->n_conts, 0);
     for (uint32_t r = 0; r < s->n_conts; ++r) {
         const STORM_bitmap_cont_t* row = &s->conts[r];
-        row_ptr[r] = (uint32_t)blk_id.size();
-        max_blocks = std::max(max_blocks, row->n_bitmaps);
+        h->row_ptr[r] = (uint32_t)h->blk_id.size();
+        h->max_blocks = std::max(h->max_blocks, row->n_bitmaps);
         for (uint32_t b = 0; b < row->n_bitmaps; ++b) {
             const STORM_bitmap_t* k = &row->bitmaps[b];
-            blk_id.push_back(k->id);
-            max_blk_id = std::max(max_blk_id, k->id);
+            h->blk_id.push_back(k->id);
+            h->max_blk_id = std::max(h->max_blk_id, k->id);
             if (k->n_bitmap) {
-                ++n_bitmap_blocks;
-                blk_len.push_back(k->n_bits_set | BITMAP_FLAG);
-                blk_off.push_back(words.size());
-                words.insert(words.end(), k->data, k->data + BLOCK_WORDS);
-                row_nnz[r] += k->n_bits_set;
+                ++h->n_bitmap_blocks;
+                h->blk_len.push_back(k->n_bits_set | BITMAP_FLAG);
+                h->blk_off.push_back(h->words.size());
+                h->words.insert(h->words.end(), k->data, k->data + BLOCK_WORDS);
+                h->row_nnz[r] += k->n_bits_set;
             } else {
-                while (lists.size() % 8) lists.push_back(0);       // 16-byte aligned lists
-                blk_off.push_back(lists.size());
+                while (h->lists.size() % 8) h->lists.push_back(0);       // 16-byte aligned lists
+                h->blk_off.push_back(h->lists.size());
                 // set semantics on the device: adjacent duplicates (which the reference's list
                 // builder keeps, storm.c:548-556) collapse, as they do in a bitmap block
                 uint32_t kept = 0;
                 for (uint32_t v = 0; v < k->n_scalar; ++v)
-                    if (v == 0 || k->scalar[v] != k->scalar[v - 1]) { lists.push_back(k->scalar[v]); ++kept; }
-                blk_len.push_back(kept);
-                row_nnz[r] += kept;
+                    if (v == 0 || k->scalar[v] != k->scalar[v - 1]) { h->lists.push_back(k->scalar[v]); ++kept; }
+                h->blk_len.push_back(kept);
+                h->row_nnz[r] += kept;
             }
         }
     }
-    row_ptr[s->n_conts] = (uint32_t)blk_id.size();
-    while (lists.size() % 8) lists.push_back(0);                   // 16-byte loads of the last list stay inside the pool
-    std::vector<uint64_t> pos_off(s->n_conts + 1, 0);              // CSR offsets of the flat form (built on demand)
-    for (uint32_t r = 0; r < s->n_conts; ++r) pos_off[r + 1] = pos_off[r] + row_nnz[r];
-    if ((rc = upload(&st->d_pos_off, pos_off, st->stream))) return rc;
-    uint32_t max_row_nnz = 0;
-    for (uint32_t v : row_nnz) max_row_nnz = std::max(max_row_nnz, v);
-    std::vector<uint32_t>& gs = st->h_group_start;
-    stream_groups(row_nnz.data(), s->n_conts, &gs);
-    if ((rc = upload(&st->d_group_start, gs, st->stream))) return rc;
-    st->max_row_nnz = max_row_nnz;
-    std::vector<uint32_t> row_nnz_dev(row_nnz);                    // device copy: + the "holds a bitmap block" flag
+    h->row_ptr[s->n_conts] = (uint32_t)h->blk_id.size();
+    while (h->lists.size() % 8) h->lists.push_back(0);             // 16-byte loads of the last list stay inside the pool
+    h->pos_off.assign(s->n_conts + 1, 0);                          // CSR offsets of the flat form (built on demand)
+    for (uint32_t r = 0; r < s->n_conts; ++r) h->pos_off[r + 1] = h->pos_off[r] + h->row_nnz[r];
+    for (uint32_t v : h->row_nnz) { h->max_row_nnz = std::max(h->max_row_nnz, v); h->total_nnz += v; }
+    stream_groups(h->row_nnz.data(), s->n_conts, &h->group_start);
+    h->row_nnz_dev = h->row_nnz;                                   // device copy: + the "holds a bitmap block" flag
     for (uint32_t r = 0; r < s->n_conts; ++r)
-        for (uint32_t b = row_ptr[r]; b < row_ptr[r + 1]; ++b)
-            if (blk_len[b] & BITMAP_FLAG) { row_nnz_dev[r] |= ROW_HAS_BITMAP; break; }
-    if ((rc = upload(&st->d_row_ptr, row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, row_nnz_dev, st->stream)) ||
-        (rc = upload(&st->d_blk_id, blk_id, st->stream)) || (rc = upload(&st->d_blk_len, blk_len, st->stream)) ||
-        (rc = upload(&st->d_blk_off, blk_off, st->stream)) || (rc = upload(&st->d_lists, lists, st->stream)) ||
-        (rc = upload(&st->d_words, words, st->stream)))
+        for (uint32_t b = h->row_ptr[r]; b < h->row_ptr[r + 1]; ++b)
+            if (h->blk_len[b] & BITMAP_FLAG) { h->row_nnz_dev[r] |= ROW_HAS_BITMAP; break; }
+}
+
+// One replica's copy of the mirror (on the current device = the replica's).
+int upload_mirror(StormState* st, const HostMirror& h, uint32_t n_conts) {
+    int rc = ensure_state(st);
+    if (rc) return rc;
+    free_mirror(st);
+    st->h_group_start = h.group_start;
+    if ((rc = upload(&st->d_pos_off, h.pos_off, st->stream)) || (rc = upload(&st->d_group_start, h.group_start, st->stream)) ||
+        (rc = upload(&st->d_row_ptr, h.row_ptr, st->stream)) || (rc = upload(&st->d_row_nnz, h.row_nnz_dev, st->stream)) ||
+        (rc = upload(&st->d_blk_id, h.blk_id, st->stream)) || (rc = upload(&st->d_blk_len, h.blk_len, st->stream)) ||
+        (rc = upload(&st->d_blk_off, h.blk_off, st->stream)) || (rc = upload(&st->d_lists, h.lists, st->stream)) ||
+        (rc = upload(&st->d_words, h.words, st->stream)))
         return rc;
-    STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));              // host vectors die here
-    st->n_rows = s->n_conts;
-    st->max_blocks = max_blocks;
-    st->max_blk_id = max_blk_id;
-    st->total_nnz = 0;
-    st->total_blocks = blk_id.size();
-    st->n_bitmap_blocks = n_bitmap_blocks;
-    for (uint32_t v : row_nnz) st->total_nnz += v;
+    STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));              // (the host vectors may die after this)
+    st->n_rows = n_conts;
+    st->max_blocks = h.max_blocks;
+    st->max_blk_id = h.max_blk_id;
+    st->max_row_nnz = h.max_row_nnz;
+    st->total_nnz = h.total_nnz;
+    st->total_blocks = h.blk_id.size();
+    st->n_bitmap_blocks = h.n_bitmap_blocks;
     st->dirty = false;
+    return STORM_B200_OK;
+}
+
+// The replicas of a container: the device set in force at its first query, first device = this state's.
+int resolve_replicas(StormState* st) {
+    if (st->set_resolved) return STORM_B200_OK;
+    std::vector<int> ids;
+    int rc = query_devices(&ids);
+    if (rc) return rc;
+    if (!st->d_total) st->device = ids[0];                           // (not initialised yet: adopt the set's first device)
+    size_t own = 0;                                                  // the entry of the set this state stands for
+    for (size_t k = 0; k < ids.size(); ++k) if (ids[k] == st->device) { own = k; break; }
+    for (size_t k = 0; k < ids.size(); ++k) {
+        if (k == own) continue;
+        StormState* rep = new (std::nothrow) StormState();
+        if (!rep) { set_error("out of host memory"); return STORM_B200_ENOMEM; }
+        rep->device = ids[k];
+        rep->set_resolved = true;
+        st->replicas.push_back(rep);
+    }
+    st->set_resolved = true;
+    return STORM_B200_OK;
+}
+
+// Flatten the host containers and bring every replica up to date (whole-container rebuild on change).
+// `all` = false: this state only (rectangles, XY^T).
+int sync_mirror(const STORM_t* s, StormState* st, bool all = false) {
+    if (all) { int rc = resolve_replicas(st); if (rc) return rc; }
+    std::vector<StormState*> targets{st};
+    if (all) targets.insert(targets.end(), st->replicas.begin(), st->replicas.end());
+    bool need = false;
+    for (StormState* t : targets) need = need || t->dirty || !t->d_total || t->n_rows != s->n_conts;
+    if (!need) return STORM_B200_OK;
+    HostMirror h;
+    build_host_mirror(s, &h);
+    for (StormState* t : targets) {
+        if (!(t->dirty || !t->d_total || t->n_rows != s->n_conts)) continue;
+        DeviceGuard guard(t->device);
+        int rc = upload_mirror(t, h, s->n_conts);
+        if (rc) return rc;
+    }
     return STORM_B200_OK;
 }
 
@@ -838,14 +882,18 @@ int dense_banded(StormState* st, uint64_t n_rows, uint32_t shard, uint32_t n_sha
     const uint64_t stride = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
     uint64_t R = band_rows_override ? band_rows_override : std::max<uint64_t>(256, DENSE_BAND_BYTES / (stride * 8) / 256 * 256);
     R = std::min(R, n_rows);
-    uint64_t* arena[2] = {nullptr, nullptr};
-    struct Release { uint64_t** a; ~Release() { cudaFree(a[0]); cudaFree(a[1]); } } release{arena};
-    for (auto& a : arena)
-        if (cudaMalloc(&a, R * stride * 8) != cudaSuccess) {
-            cudaGetLastError(); a = nullptr;
-            set_error("two dense bands of %llu rows x %llu words do not fit on this device", (unsigned long long)R, (unsigned long long)stride);
-            return STORM_B200_ENOMEM;
-        }
+    if (R * stride > st->band_cap_words) {
+        for (auto& a : st->d_band) { if (a) cudaFree(a); a = nullptr; }
+        st->band_cap_words = 0;
+        for (auto& a : st->d_band)
+            if (cudaMalloc(&a, R * stride * 8) != cudaSuccess) {
+                cudaGetLastError(); a = nullptr;
+                set_error("two dense bands of %llu rows x %llu words do not fit on device %d", (unsigned long long)R, (unsigned long long)stride, st->device);
+                return STORM_B200_ENOMEM;
+            }
+        st->band_cap_words = R * stride;
+    }
+    uint64_t* const* arena = st->d_band;                                  // (kept for the next query: everything here is asynchronous)
     auto densify = [&](uint64_t* dst, uint64_t r0, uint64_t n) -> int {
         STORM_CUDA_TRY(cudaMemsetAsync(dst, 0, n * stride * 8, st->stream));
         densify_rows_kernel<<<(unsigned)n, 256, 0, st->stream>>>(view_of(st), dst, stride, (uint32_t)r0);
@@ -874,68 +922,94 @@ int dense_banded(StormState* st, uint64_t n_rows, uint32_t shard, uint32_t n_sha
             if (rc) return rc;
         }
     }
-    STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));                     // the arenas are freed on return
     return STORM_B200_OK;
 }
 
 std::atomic<uint64_t> g_dense_band_rows{0};   // STORM_b200_set_storm_band_rows: force the banded form with this band height (tests)
 
-uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
-    if (s == nullptr) return (uint64_t)-1;                          // storm.c:878,898
-    if (s->n_conts < 2) return 0;
-    StormState* st = state_of(s);
-    DeviceGuard guard(st->device);
-    if (sync_mirror(s, st)) return (uint64_t)-1;
-    if (cudaMemsetAsync(st->d_total, 0, 8, st->stream) != cudaSuccess) return (uint64_t)-1;
+// One replica's share of a whole-container query (asynchronous on its stream, accumulated into its d_total).
+int storm_query_on(StormState* st, uint32_t n_conts, bool dense, uint32_t shard, uint32_t n_shards) {
+    if (cudaMemsetAsync(st->d_total, 0, 8, st->stream) != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(cudaGetLastError())); return STORM_B200_ECUDA; }
     uint64_t stride = 0;
-    bool dense = choose_dense_route(st, s->n_conts);
     const uint64_t forced_band = g_dense_band_rows.load();
-    if (dense && (forced_band || (uint64_t)s->n_conts * (((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS) * 8 > DENSE_WHOLE_MAX)) {
+    if (dense && (forced_band || (uint64_t)n_conts * (((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS) * 8 > DENSE_WHOLE_MAX)) {
         st->last_route = 3;                                              // dense, banded
-        if (dense_banded(st, s->n_conts, shard, n_shards, forced_band)) return (uint64_t)-1;
-        if (cudaMemcpyAsync(st->h_total, st->d_total, 8, cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
-            cudaStreamSynchronize(st->stream) != cudaSuccess) {
-            set_error("STORM_t query failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return (uint64_t)-1;
-        }
-        return *st->h_total;
+        return dense_banded(st, n_conts, shard, n_shards, forced_band);
     }
-    if (dense && (!dense_fits(st, s->n_conts) || ensure_dense(st, s->n_conts, &stride) != STORM_B200_OK)) {
+    if (dense && (!dense_fits(st, n_conts) || ensure_dense(st, n_conts, &stride) != STORM_B200_OK)) {
         // the dense form does not fit on this device: an unsharded query answers through the sparse kernels instead;
         // a shard must not (the other shards partition the pairs by the tile raster)
-        if (n_shards > 1) { set_error("shard %u of %u: the dense form of the rows does not fit on this device and a shard cannot switch route", shard, n_shards); return (uint64_t)-1; }
+        if (n_shards > 1) { set_error("shard %u of %u: the dense form of the rows does not fit on device %d and a shard cannot switch route", shard, n_shards, st->device); return STORM_B200_ENOMEM; }
         dense = false;
     }
     if (dense) {
         st->last_route = 2;
-        if (pairw_triangle(st->d_dense, s->n_conts, (uint32_t)stride, stride, shard, n_shards, STORM_B200_KERNEL_AUTO,
-                           reinterpret_cast<uint64_t*>(st->d_total), st->stream)) return (uint64_t)-1;
-    } else {
-        st->last_route = 1;
-        if (ensure_flat(st)) return (uint64_t)-1;
-        // (same rule inside the sparse route: the stream kernel shards row groups, the other two rows)
-        if (n_shards > 1 && flat_eligible(st) && !st->flat_valid) { set_error("shard %u of %u: no room for the flat position mirror and a shard cannot switch kernel", shard, n_shards); return (uint64_t)-1; }
-        if (stream_eligible(st, st)) {
-            if (launch_stream(st, st, 0, s->n_conts, 0, s->n_conts, 1, shard, n_shards, st->d_total, st->stream)) return (uint64_t)-1;
-        } else {
-            SparseJob job{};
-            job.A = job.B = view_of(st);
-            job.i0 = 0; job.i1 = s->n_conts; job.j0 = 0; job.j1 = s->n_conts;
-            job.strict_upper = 1;
-            job.shard = shard; job.n_shards = n_shards;
-            job.total = st->d_total;
-            if (launch_sparse(job, st->max_blocks, st->stream)) return (uint64_t)-1;
-        }
+        return pairw_triangle(st->d_dense, n_conts, (uint32_t)stride, stride, shard, n_shards, STORM_B200_KERNEL_AUTO,
+                              reinterpret_cast<uint64_t*>(st->d_total), st->stream);
     }
-    if (cudaMemcpyAsync(st->h_total, st->d_total, 8, cudaMemcpyDeviceToHost, st->stream) != cudaSuccess ||
-        cudaStreamSynchronize(st->stream) != cudaSuccess) {
-        set_error("STORM_t query failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return (uint64_t)-1;
-    }
-    return *st->h_total;
+    st->last_route = 1;
+    int rc = ensure_flat(st);
+    if (rc) return rc;
+    // (same rule inside the sparse route: the stream kernel shards row groups, the other two rows)
+    if (n_shards > 1 && flat_eligible(st) && !st->flat_valid) { set_error("shard %u of %u: no room for the flat position mirror and a shard cannot switch kernel", shard, n_shards); return STORM_B200_ENOMEM; }
+    if (stream_eligible(st, st)) return launch_stream(st, st, 0, n_conts, 0, n_conts, 1, shard, n_shards, st->d_total, st->stream);
+    SparseJob job{};
+    job.A = job.B = view_of(st);
+    job.i0 = 0; job.i1 = n_conts; job.j0 = 0; job.j1 = n_conts;
+    job.strict_upper = 1;
+    job.shard = shard; job.n_shards = n_shards;
+    job.total = st->d_total;
+    return launch_sparse(job, st->max_blocks, st->stream);
 }
 
-void mark_dirty(STORM_t* s) { if (s && s->b200) state_of(s)->dirty = true; }
+// Whole-container query: replica g of G (the device set, devices.h) answers shard (shard * G + g) of (n_shards * G)
+// on its own device and stream; the host adds the G totals.  The route is a pure function of the container, so every
+// replica -- and every shard of a multi-process caller -- takes the same one.
+uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
+    if (s == nullptr) return (uint64_t)-1;                          // storm.c:878,898
+    if (s->n_conts < 2) return 0;
+    StormState* st = state_of(s);
+    DeviceGuard home(st->device);
+    if (sync_mirror(s, st, true)) return (uint64_t)-1;
+    std::vector<StormState*> reps{st};
+    reps.insert(reps.end(), st->replicas.begin(), st->replicas.end());
+    const uint32_t G = (uint32_t)reps.size();
+    const bool dense = choose_dense_route(st, s->n_conts);
+    for (uint32_t g = 0; g < G; ++g) {
+        DeviceGuard guard(reps[g]->device);
+        if (storm_query_on(reps[g], s->n_conts, dense, shard * G + g, n_shards * G)) return (uint64_t)-1;
+        if (cudaMemcpyAsync(reps[g]->h_total, reps[g]->d_total, 8, cudaMemcpyDeviceToHost, reps[g]->stream) != cudaSuccess) return (uint64_t)-1;
+    }
+    uint64_t total = 0;
+    bool ok = true;
+    for (uint32_t g = 0; g < G; ++g) {
+        DeviceGuard guard(reps[g]->device);
+        if (cudaStreamSynchronize(reps[g]->stream) != cudaSuccess) {
+            set_error("STORM_t query failed on device %d: %s", reps[g]->device, cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+        }
+        total += *reps[g]->h_total;
+    }
+    return ok ? total : (uint64_t)-1;
+}
+
+void mark_dirty(STORM_t* s) {
+    if (!s || !s->b200) return;
+    StormState* st = state_of(s);
+    st->dirty = true;
+    for (StormState* r : st->replicas) r->dirty = true;
+}
+
+void release_state(StormState* st) {
+    DeviceGuard guard(st->device);
+    if (st->stream) cudaStreamSynchronize(st->stream);
+    free_mirror(st);
+    for (auto& a : st->d_band) if (a) cudaFree(a);
+    if (st->d_dense) cudaFree(st->d_dense);
+    if (st->d_total) cudaFree(st->d_total);
+    if (st->h_total) cudaFreeHost(st->h_total);
+    if (st->stream) cudaStreamDestroy(st->stream);
+}
 
 }  // namespace
 }  // namespace storm
@@ -1131,13 +1205,8 @@ void STORM_free(STORM_t* s) {                                               // s
     if (s == nullptr) return;
     StormState* st = state_of(s);
     if (st) {
-        DeviceGuard guard(st->device);
-        if (st->stream) cudaStreamSynchronize(st->stream);
-        free_mirror(st);
-        if (st->d_dense) cudaFree(st->d_dense);
-        if (st->d_total) cudaFree(st->d_total);
-        if (st->h_total) cudaFreeHost(st->h_total);
-        if (st->stream) cudaStreamDestroy(st->stream);
+        for (StormState* r : st->replicas) { release_state(r); delete r; }
+        release_state(st);
         delete st;
     }
     for (uint32_t i = 0; i < s->m_conts; ++i) cont_release(&s->conts[i]);

@@ -859,3 +859,43 @@ def test_storm_t_banded_dense_route_and_densified_rectangles(sb, orc):
         assert (s.pairw_rect(0, 700, 0, 700) == orc.rect_counts(vals, 0, 700, 0, 700)).all()
         assert (s.pairw_rect(20, 290, 150, 671) == orc.rect_counts(vals, 20, 290, 150, 671)).all()
         assert (s.pairw_rect(500, 700, 3, 130) == orc.rect_counts(vals, 500, 700, 3, 130)).all()
+
+
+def test_multi_device_storm_t_queries_equal_single_device(sb, orc):
+    """Whole-container STORM_t queries on a device set: the block mirror goes to every replica, each answers its
+    shard through the route every replica agrees on (sparse kernels, densified rows, densified in bands); totals,
+    external shards x replicas, mutation after a query, clear + reuse."""
+    M = 4 * 65536
+    for name, draws in (("lists", [1, 5, 60, 150, 700, 3, 0]), ("mixed", [5, 150, 4000, 30000, 90, 70000, 250]), ("bitmaps", [20000, 50000, 90000])):
+        rows = [orc.gen_row_positions(83, i, draws[i % len(draws)], M) for i in range(420)]
+        vals = O.positions_to_dense(rows, M)
+        exact = orc.wrapper_diag(vals)
+        for ids in _device_lists(sb):
+            sb.set_device_list(ids)
+            try:
+                for route in ("auto", "sparse", "dense"):
+                    prev = sb.set_storm_route(route)
+                    try:
+                        with sb.Storm() as s:
+                            for p in rows[:300]:
+                                s.add(p)
+                            assert s.pairw_intersect_cardinality() == orc.wrapper_diag(vals[:300]), (name, ids, route)
+                            for p in rows[300:]:
+                                s.add(p)
+                            assert s.pairw_intersect_cardinality_blocked(0) == exact, (name, ids, route)
+                            assert sum(s.pairw_shard(k, 2) for k in range(2)) == exact, (name, ids, route)
+                            if route == "dense":
+                                was = sb.set_storm_band_rows(256)
+                                try:
+                                    assert s.pairw_intersect_cardinality() == exact, (name, ids, "banded")
+                                finally:
+                                    sb.set_storm_band_rows(was)
+                            assert (s.pairw_rect(5, 60, 30, 200) == orc.rect_counts(vals, 5, 60, 30, 200)).all()
+                            s.clear()
+                            for p in rows[100:250]:
+                                s.add(p)
+                            assert s.pairw_intersect_cardinality() == orc.wrapper_diag(vals[100:250]), (name, ids, route)
+                    finally:
+                        sb.set_storm_route(prev)
+            finally:
+                sb.set_device_list(())
