@@ -347,8 +347,7 @@ uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uin
         ContigDev* d = st->devs[g];
         if (ensure_device_rows(c, st, d, c->n_data)) return (uint64_t)-1;
         if (order_after_uploads(d)) return (uint64_t)-1;                  // rows pushed while STORM_contig_add was running
-        DeviceGuard guard(d->ctx.device);
-        if (cudaMemsetAsync(d->ctx.d_total, 0, sizeof(unsigned long long), d->ctx.stream) != cudaSuccess) return (uint64_t)-1;
+        if (d->ctx.zero_total()) return (uint64_t)-1;
         ctxs[g] = &d->ctx; arenas[g] = d->d_rows;
     }
     { DeviceGuard guard(prim->ctx.device); cudaEventRecord(prim->ev[1], prim->ctx.stream); }
@@ -569,8 +568,7 @@ uint64_t wrapper_diag_impl(uint64_t n_vectors, const uint64_t* vals, uint64_t n_
     std::vector<uint64_t*> arenas(G);
     for (int g = 0; g < G; ++g) {
         WrapDev* d = g_wrap.devs[g];
-        DeviceGuard guard(d->ctx.device);
-        if (cudaMemsetAsync(d->ctx.d_total, 0, 8, d->ctx.stream) != cudaSuccess) return (uint64_t)-1;
+        if (d->ctx.zero_total()) return (uint64_t)-1;
         ctxs[g] = &d->ctx; arenas[g] = d->d_rows;
     }
     if (all) {
@@ -832,7 +830,7 @@ uint64_t STORM_wrapper_square(const uint32_t n_vectors1, const uint64_t* STORM_R
     WrapDev* d = g_wrap.devs[0];
     const uint64_t at2 = (uint64_t)n_vectors1 * stride;
     DeviceGuard guard(d->ctx.device);
-    if (cudaMemsetAsync(d->ctx.d_total, 0, 8, d->ctx.stream) != cudaSuccess) return (uint64_t)-1;
+    if (d->ctx.zero_total()) return (uint64_t)-1;
     if (wrap_upload_primary(vals1, n_vectors1, n_ints, stride, 0) || wrap_upload_primary(vals2, n_vectors2, n_ints, stride, at2)) return (uint64_t)-1;
     if (pairw_rect_op(d->d_rows, n_vectors1, stride, 0, d->d_rows + at2, n_vectors2, stride, 0, n_ints, 0, op,
                       STORM_B200_KERNEL_AUTO, false, nullptr, 0, reinterpret_cast<uint64_t*>(d->ctx.d_total), d->ctx.stream)) return (uint64_t)-1;
@@ -1124,9 +1122,8 @@ uint64_t STORM_b200_pairw_devices(const uint64_t* const* d_rows, const int* devi
         for (int o = 0; o < g; ++o) if (ids[o] == id) { set_error("device %d listed twice", id); return (uint64_t)-1; }
         ctxs[g] = cache[id];
         arenas[g] = const_cast<uint64_t*>(d_rows[g]);
-        DeviceGuard guard(id);
         if (check_rows(d_rows[g], row_stride_words, n_words)) return (uint64_t)-1;
-        if (cudaMemsetAsync(ctxs[g]->d_total, 0, 8, ctxs[g]->stream) != cudaSuccess) return (uint64_t)-1;
+        if (ctxs[g]->zero_total()) return (uint64_t)-1;
     }
     if (banded_triangle(ctxs.data(), arenas.data(), n_devices, row_stride_words, HostRows{}, n_rows, n_rows, n_words, 0, 1, kernel)) return (uint64_t)-1;
     return collect_totals(ctxs.data(), n_devices, "STORM_b200_pairw_devices");

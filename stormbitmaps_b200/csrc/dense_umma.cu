@@ -860,7 +860,17 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // Packed rows as a 2-D byte tensor: inner = n_words * 8 bytes, outer = rows; box = 128 bytes x box_rows.
+// Encoding is a pure function of the arguments and costs a driver call; a query on a resident matrix asks for the same
+// map again and again (and for A and B of a triangle job twice per launch), so the last few are kept per host thread.
 int make_row_map(CUtensorMap* map, const uint64_t* base, uint64_t n_rows, uint64_t stride_words, uint32_t n_words, uint32_t box_rows) {
+    struct Entry { const uint64_t* base; uint64_t n_rows, stride; uint32_t n_words, box_rows; CUtensorMap map; };
+    constexpr int SLOTS = 16;
+    thread_local Entry cache[SLOTS];
+    thread_local int used = 0, next = 0;
+    for (int k = 0; k < used; ++k) {
+        const Entry& e = cache[k];
+        if (e.base == base && e.n_rows == n_rows && e.stride == stride_words && e.n_words == n_words && e.box_rows == box_rows) { *map = e.map; return STORM_B200_OK; }
+    }
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return STORM_B200_ECUDA; }
     const cuuint64_t dims[2] = {(cuuint64_t)n_words * 8, (cuuint64_t)n_rows};
@@ -871,6 +881,10 @@ int make_row_map(CUtensorMap* map, const uint64_t* base, uint64_t n_rows, uint64
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return STORM_B200_ECUDA; }
+    Entry& slot = cache[next];
+    slot = Entry{base, n_rows, stride_words, n_words, box_rows, *map};
+    next = (next + 1) % SLOTS;
+    if (used < SLOTS) ++used;
     return STORM_B200_OK;
 }
 
@@ -938,10 +952,16 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
         if ((rc = make_out_map(&map_out, job.out, job.nA, job.nB, job.ld))) return rc;
         job.out_tma = 1;
     }
-    STORM_CUDA_TRY(cudaFuncSetAttribute(dense_umma_kernel<CG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    int dev = 0, sms = 0;
+    int dev = 0;
     STORM_CUDA_TRY(cudaGetDevice(&dev));
-    STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // once per device and instantiation: the shared-memory opt-in of this kernel, the SM count
+    static std::atomic<int> sms_of[64];
+    int sms = dev < 64 ? sms_of[dev].load(std::memory_order_relaxed) : 0;
+    if (sms == 0) {
+        STORM_CUDA_TRY(cudaFuncSetAttribute(dense_umma_kernel<CG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        STORM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev < 64) sms_of[dev].store(sms, std::memory_order_relaxed);
+    }
     const uint64_t n_tiles = job.tile_end - job.tile_begin;
     const int want_reserved = job.reserved_sms >= 0 ? job.reserved_sms : g_umma_reserved_sms.load();
     const int reserved = want_reserved < sms - 2 ? want_reserved : sms - 2;

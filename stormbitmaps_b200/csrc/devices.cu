@@ -96,6 +96,15 @@ int DevCtx::init(int dev) {
     return STORM_B200_OK;
 }
 
+// d_total is accumulated into by one atomic per CTA and must start at zero.  collect_totals re-zeroes it right after
+// reading it back -- while the host is still waiting for the other devices -- so that the next query of a resident
+// matrix does not spend a memset call per device before its launches.
+int DevCtx::zero_total() {
+    if (!total_zero) { DeviceGuard guard(device); STORM_CUDA_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), stream)); }
+    total_zero = false;                              // (the launches that follow dirty it)
+    return STORM_B200_OK;
+}
+
 void DevCtx::destroy() {
     if (device < 0) return;
     DeviceGuard guard(device);
@@ -274,6 +283,7 @@ uint64_t collect_totals(DevCtx* const* devs, int G, const char* what) {
     for (int g = 0; g < G; ++g) {
         DeviceGuard guard(devs[g]->device);
         ok = ok && cudaMemcpyAsync(devs[g]->h_total, devs[g]->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, devs[g]->stream) == cudaSuccess;
+        devs[g]->total_zero = cudaMemsetAsync(devs[g]->d_total, 0, sizeof(unsigned long long), devs[g]->stream) == cudaSuccess;   // for the next query
     }
     uint64_t total = 0;
     for (int g = 0; g < G; ++g) {

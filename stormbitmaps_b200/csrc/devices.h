@@ -39,7 +39,9 @@ struct DevCtx {
     cudaEvent_t band_ready[MAX_BANDS] = {};          // copy_stream: every row of band k is on this device
     cudaEvent_t stage_done[STAGE_SLOTS] = {};        // copy_stream: the H2D out of staging slot s has finished
     cudaEvent_t mark = nullptr;                      // scratch event (stream <-> copy_stream ordering)
+    bool total_zero = false;                         // d_total was zeroed on `stream` after the last read-back
     int init(int dev);
+    int zero_total();                                // make d_total zero on `stream` (a no-op right after collect_totals)
     void destroy();
 };
 

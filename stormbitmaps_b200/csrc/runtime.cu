@@ -28,13 +28,17 @@ void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxe
 int default_kernel() { return g_default_kernel.load(); }
 
 int require_device() {
+    static std::atomic<int> known[64];                 // per device ordinal: 1 = an sm_100 device (checked once)
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && known[dev].load(std::memory_order_relaxed) == 1) return STORM_B200_OK;
+    cudaGetLastError();
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
         set_error("no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
         return STORM_B200_ENODEV;
     }
-    int dev = 0;
     STORM_CUDA_TRY(cudaGetDevice(&dev));
     int major = 0;
     STORM_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -42,6 +46,7 @@ int require_device() {
         set_error("device %d has compute capability %d.x; libstorm_b200 is built for sm_100a only", dev, major);
         return STORM_B200_ENODEV;
     }
+    if (dev < 64) known[dev].store(1, std::memory_order_relaxed);
     return STORM_B200_OK;
 }
 

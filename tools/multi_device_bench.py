@@ -116,7 +116,34 @@ def run_grid():
             torch.cuda.empty_cache()
 
 
+def run_storm():
+    """C2-shaped STORM_t containers (10 000 x 524 288) on device sets: one level the cost model sends to the sparse
+    kernels, one it densifies.  A container takes its device set at its first query, so each G gets its own."""
+    from oracle import oracle as O
+    orc = O.Oracle()
+    M, n = 524288, 10000
+    for draws in (104, 5242):
+        rows = [orc.gen_row_positions(77, i, draws, M) for i in range(n)]
+        base, ref_total = None, None
+        for G in devs:
+            sb.set_devices(G)
+            try:
+                with sb.Storm() as s:
+                    for p in rows:
+                        s.add(p)
+                    t0 = time.perf_counter()
+                    first = s.pairw_intersect_cardinality_blocked(0)
+                    first_s = time.perf_counter() - t0
+                    sec, tot = best_wall(lambda: s.pairw_intersect_cardinality_blocked(0))
+                    ref_total = first if ref_total is None else ref_total
+                    base = base or sec
+                    emit(config="c2", mode="storm_t", draws=draws, devices=G, route=s.last_route(), first_query_s=first_s, seconds=sec,
+                         speedup=base / sec, bitmap_space_wp_per_s=n * (n - 1) / 2 * (M // 64) / sec, match=tot == ref_total and first == ref_total)
+            finally:
+                sb.set_device_list(())
+
+
 if __name__ == "__main__":
     emit(devices_visible=n_vis, devices_tested=devs, device=sb.device_info(0))
     for w in (args or ["c3"]):
-        {"c3": run_c3, "grid": run_grid}[w]()
+        {"c3": run_c3, "grid": run_grid, "storm": run_storm}[w]()
