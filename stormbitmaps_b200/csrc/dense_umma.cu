@@ -95,7 +95,7 @@ struct Cfg {
     static constexpr int THREADS = N_WARPS * 32;
     // expanded k-blocks in flight between the expanders and the MMA thread (A: 32 TMEM columns each,
     // next to the 256 accumulator columns and, in the FP4 form, 32 scale-factor columns)
-    static constexpr int STAGES = CG == 2 ? (FP4 ? 7 : 6) : 3;
+    static constexpr int STAGES = CG == 2 ? (FP4 && !PAIRS ? 7 : 6) : 3;   // (the per-pair form gives one stage's memory to its staging slices)
     static constexpr int STAGE_BYTES = B_ROWS * 128;         // expanded B rows of one k-block
     // per-pair form: counts leave through TMA stores when each TMEM lane quarter has an A warp and a B warp to share
     // the B-stage slices of that quarter (the default cta_group::2 form with one expander warp per 32 rows)
@@ -109,8 +109,12 @@ struct Cfg {
     static constexpr uint32_t OFF_RAW = (STAGES * STAGE_BYTES + 1023) / 1024 * 1024;
     // packed-row boxes in flight between the TMA thread and the expanders (how far the loads run ahead of the
     // expansion: one box = 4 (FP4) or 8 k-blocks); three fit beside the stages of the CTA-pair form
-    static constexpr int RAW_BUFS = CG == 2 ? STORM_RAW_BUFS : 2;
-    static constexpr uint32_t OFF_BAR = OFF_RAW + RAW_BUFS * RAW_BYTES;
+    static constexpr int RAW_BUFS = CG == 2 ? (TMA_DRAIN ? 2 : STORM_RAW_BUFS) : 2;
+    // per-pair form: two 4 KiB staging slices per expander warp for the counts on their way to a TMA store (the third
+    // packed-row box and the seventh stage make room: the box is worth < 2 %, profiles/r01_ab_raw_box_ring.jsonl)
+    static constexpr uint32_t OFF_STG = OFF_RAW + RAW_BUFS * RAW_BYTES;
+    static constexpr uint32_t STG_BYTES = TMA_DRAIN ? (uint32_t)EXPANDER_WARPS * 2u * 4096u : 0u;   // two slices per warp
+    static constexpr uint32_t OFF_BAR = OFF_STG + STG_BYTES;
     static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 512;
     static_assert(SMEM_BYTES <= 232448, "shared memory of one CTA");
     static_assert(TN * ACCS <= UM_A_COL, "accumulators overflow their tensor-memory columns");
@@ -329,10 +333,8 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (job.out_tma) {
                     // Per-pair output through the TMA unit.  The columns of this chunk that count for this row are
                     // [lo, lo + span) (below nB, right of the diagonal); everything else is stored as 0.  The warp's
-                    // 32 rows x 32 counts go into one 4 KiB slice of the B stages -- the stages are empty while a tile is
-                    // drained, and quarter q's rows of a stage are exactly such a slice: 32 lines of 128 bytes in
-                    // SWIZZLE_128B atoms.  The A warp of a quarter takes the slices of stages 0-3 (one per chunk), the B
-                    // warp those of stages 4.. in turn; one lane then issues a single 32 x 32 box store.
+                    // 32 rows x 32 counts go into its 4 KiB staging slice -- 32 lines of 128 bytes in SWIZZLE_128B atoms --
+                    // and one lane issues a single 32 x 32 box store.
                     const long long cb = (long long)(rowB0 + c0);
                     const long long h = (long long)job.nB - cb;
                     const int hi = row_ok ? (h < 0 ? 0 : h > 32 ? 32 : (int)h) : 0;
@@ -366,14 +368,11 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         }
                         sum += part;
                     }
-                    constexpr uint32_t B_RING = (uint32_t)C::STAGES - 4u;            // slices the B warp of a quarter rotates through
-                    const uint32_t n_chunk = c0 / (32u * n_sharers);                 // this warp's n-th chunk of the tile
-                    const uint32_t st = sharer == 0 ? n_chunk : 4u + n_chunk % B_RING;
-                    if (sharer != 0 && n_chunk >= B_RING) {                          // the store that last read this slice must be done with it
-                        if (lane == 0) bulk_wait_read<(int)B_RING - 1>();
-                        __syncwarp();
-                    }
-                    const uint32_t slice = smem_base + st * (uint32_t)C::STAGE_BYTES + quarter * 4096u;
+                    // this warp's two staging slices in turn: free again once the store before the last has read it (with
+                    // one slice every chunk waited ~400 clocks for the TMA unit, profiles/r02_pairs_ahead_4096_ncu.md)
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+                    const uint32_t slice = smem_base + C::OFF_STG + (warp * 2u + ((c0 / (32u * n_sharers)) & 1u)) * 4096u;
 #pragma unroll
                     for (uint32_t j = 0; j < 8; ++j)
                         st_shared_v4(slice + lane * 128u + ((j ^ (lane & 7u)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -452,17 +451,6 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         job.out[li * job.ld + lj] = x;
                     }
                 }
-            }
-        }
-        if constexpr (C::TMA_DRAIN) {
-            if (job.out_tma) {
-                // The B warp of this quarter writes the slices again as soon as it expands the next tile: both warps of the
-                // quarter wait until their stores have read them, then meet (named barrier 1 + quarter, 64 threads).
-                // (Handing the accumulator back before that and checking per stage in the expander loop, and keeping the
-                // tensor-memory load of the next chunk in flight, changed nothing measurable: profiles/r02_rect_output_tma_store_v3*, _v4*.)
-                if (lane == 0) bulk_wait_read<0>();
-                __syncwarp();
-                asm volatile("bar.sync %0, 64;" ::"r"(1u + quarter) : "memory");
             }
         }
     };
@@ -630,8 +618,29 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         SegWalk walk(job, cluster_id, n_clusters, n_chunks);
         TileCursor cursor;
         Seg seg;
+        // Per-pair form (TMA drain): the drain of a tile is postponed until the first K_AHEAD k-blocks of the NEXT tile
+        // are expanded.  An expander is done with a tile ~STAGES k-blocks before the MMA warp is (the stages it filled are
+        // still queued); instead of idling until the accumulator is complete and only then restarting the pipeline from
+        // empty stages, it refills the stages as the last MMAs free them and drains afterwards: when the accumulator is
+        // handed back, the next tile's MMAs find their operands waiting.  The MMA warp's order is unchanged (it waits
+        // for `acc_empty` of the tile before), the stages it needs to finish that tile are all filled before any of this.
+        constexpr uint32_t K_AHEAD = C::TMA_DRAIN ? (uint32_t)C::STAGES - 2u : 0u;
+        bool drain_pending = false;
+        uint64_t pending_tile = 0;
+        auto drain_tile = [&](uint64_t tile) {                             // every tile of a per-pair job is a run of its own
+            uint32_t bi = 0, bj = 0;
+            cursor.coords(job, tile, C::TM, C::TN, bi, bj);
+            wait(acc_full_bar, run_iter & 1);
+            tc_fence_after();
+            drain(0u, warp & 3u, warp >> 2, (uint32_t)(C::EXPANDER_WARPS / 4), bi, bj, false, false);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);          // the MMA thread may overwrite the accumulator
+            ++run_iter;
+        };
         for (; walk.next(seg); ++t_iter) {
             uint32_t flags = RUN_FIRST | RUN_LAST;
+            uint32_t kb_done = 0;                                          // k-blocks of this tile expanded so far
             for (uint32_t c = seg.c0; c < seg.c1; ++c) {
                 wait(raw_full_bar + 8 * buf, buf_phase);
                 if (c == seg.c0) flags = ld_shared_u32(run_ring + 4 * (t_iter & (RUN_RING - 1)));   // written before this box was requested
@@ -685,10 +694,21 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader<CG>(full_bar + 8 * s);
                     if (++s == (uint32_t)C::STAGES) { s = 0; phase ^= 1; }
+                    if constexpr (C::TMA_DRAIN) {
+                        if (drain_pending && ++kb_done == K_AHEAD) { drain_tile(pending_tile); drain_pending = false; }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(raw_empty_bar + 8 * buf); // this warp is done with the box
                 if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
+            }
+            if constexpr (C::TMA_DRAIN) {
+                if (job.out_tma) {
+                    if (drain_pending) drain_tile(pending_tile);           // (a tile shorter than K_AHEAD k-blocks)
+                    drain_pending = true;
+                    pending_tile = seg.tile;
+                    continue;
+                }
             }
             if (flags & RUN_LAST) {
                 // a run of several segments is interior by construction; a run of one may be a diagonal or edge tile
@@ -705,6 +725,9 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive_leader<CG>(acc_empty_bar);      // the MMA thread may overwrite the accumulator
                 ++run_iter;
             }
+        }
+        if constexpr (C::TMA_DRAIN) {
+            if (drain_pending) drain_tile(pending_tile);                   // the last tile
         }
     }
     __syncwarp();                                                          // re-converge (aligned ops follow)
