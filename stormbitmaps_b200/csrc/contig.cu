@@ -487,21 +487,28 @@ struct WrapDev {
     DevCtx ctx;
     uint64_t* d_rows = nullptr; uint64_t cap_words = 0;
 };
-struct WrapState {
-    std::mutex mu;
+// One set of scratch arenas per device set that has been used (a caller that alternates between devices, or between
+// one device and all of them, keeps its arenas; at most four sets are kept, the least recently used one goes).
+struct WrapSet {
     std::vector<int> ids;
     std::vector<WrapDev*> devs;
+    uint64_t last_use = 0;
+};
+struct WrapState {
+    std::mutex mu;
+    std::vector<WrapSet> sets;
+    uint64_t clock = 0;
+    std::vector<WrapDev*> devs;                      // = the arenas of the set in use by the current call
 };
 WrapState g_wrap;
 
-void wrap_teardown() {
-    for (WrapDev* d : g_wrap.devs) {
+void wrap_free_set(WrapSet* ws) {
+    for (WrapDev* d : ws->devs) {
         if (d->ctx.device >= 0) { DeviceGuard guard(d->ctx.device); if (d->d_rows) cudaFree(d->d_rows); }
         d->ctx.destroy();
         delete d;
     }
-    g_wrap.devs.clear();
-    g_wrap.ids.clear();
+    ws->devs.clear();
 }
 
 // Arenas of `words` words on the first n_use devices of the set (all of them for n_use <= 0).
@@ -509,17 +516,28 @@ int wrap_prepare(uint64_t words, int n_use) {
     std::vector<int> ids;
     int rc = query_devices(&ids);
     if (rc) return rc;
-    if (ids != g_wrap.ids) {                         // first use, or the device set / the caller's device changed
-        wrap_teardown();
+    WrapSet* use = nullptr;
+    for (WrapSet& ws : g_wrap.sets) if (ws.ids == ids) use = &ws;
+    if (!use) {
+        if (g_wrap.sets.size() >= 4) {                                    // drop the least recently used set
+            size_t victim = 0;
+            for (size_t k = 1; k < g_wrap.sets.size(); ++k) if (g_wrap.sets[k].last_use < g_wrap.sets[victim].last_use) victim = k;
+            wrap_free_set(&g_wrap.sets[victim]);
+            g_wrap.sets.erase(g_wrap.sets.begin() + (long)victim);
+        }
+        g_wrap.sets.emplace_back();
+        use = &g_wrap.sets.back();
+        use->ids = ids;
         enable_peers(ids);
         for (int id : ids) {
             WrapDev* d = new (std::nothrow) WrapDev();
             if (!d) { set_error("out of host memory"); return STORM_B200_ENOMEM; }
-            g_wrap.devs.push_back(d);
-            if ((rc = d->ctx.init(id))) { wrap_teardown(); return rc; }
+            use->devs.push_back(d);
+            if ((rc = d->ctx.init(id))) { wrap_free_set(use); g_wrap.sets.pop_back(); return rc; }
         }
-        g_wrap.ids = ids;
     }
+    use->last_use = ++g_wrap.clock;
+    g_wrap.devs = use->devs;
     const int n = n_use <= 0 ? (int)g_wrap.devs.size() : std::min<int>(n_use, (int)g_wrap.devs.size());
     for (int g = 0; g < n; ++g) {
         WrapDev* d = g_wrap.devs[g];
