@@ -300,6 +300,10 @@ int STORM_b200_set_umma_chain(int on);
  * all-gather with the tile kernel sets this to a small number so that the collective's CTAs find a place
  * to run beside it.  Clamped to [0, SM count - 2].  Returns the previous value. */
 int STORM_b200_set_umma_reserved_sms(int n);
+/* L2 eviction hints on the packed-row TMA loads of triangle queries whose rows do not fit in L2 (the 8 column blocks of a
+ * raster group are shared by every wave of the group, the row blocks change from wave to wave): 0 none, 1 column blocks
+ * evict_last (default), 2 + row blocks evict_first.  Results are identical.  Returns the previous value. */
+int STORM_b200_set_umma_l2_hints(int mode);
 /* Clock probe of the tensor kernels: with it on, every launch records per CTA the clock64 and %globaltimer deltas around
  * its main loop; STORM_b200_last_kernel_clock waits for the device and returns the clock the last probed launch on the
  * current device ran at, in clock64 ticks per microsecond (mean over CTAs; optional min / max).  STORM_b200_microbench(8)

@@ -117,6 +117,7 @@ SIGNATURES = {
     "STORM_b200_set_umma_chain": (C.c_int, [C.c_int]),
     "STORM_b200_set_umma_reserved_sms": (C.c_int, [C.c_int]),
     "STORM_b200_launch_count": (C.c_uint64, []),
+    "STORM_b200_set_umma_l2_hints": (C.c_int, [C.c_int]),
     "STORM_b200_set_clock_probe": (C.c_int, [C.c_int]),
     "STORM_b200_last_kernel_clock": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "STORM_b200_pairw_tiles_device_ex": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

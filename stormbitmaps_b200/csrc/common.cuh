@@ -85,6 +85,10 @@ struct DenseJob {
     // Set by the UMMA launcher for per-pair jobs whose output matrix a tensor map can describe (16-byte aligned base, ld a
     // multiple of 4): the counts leave through TMA stores instead of per-thread stores.
     int out_tma;
+    // Set by the UMMA launcher for triangle jobs: packed-row boxes of the column blocks (B side: the 8 blocks of a raster
+    // group are shared by every wave of the group) are loaded with an L2 evict_last hint, those of the row blocks
+    // (A side: new ones every wave) with evict_first, so that the former stay resident across waves.
+    int l2_hints;
 };
 
 // Last row block of column block bj that intersects the strict upper triangle when A == B (square

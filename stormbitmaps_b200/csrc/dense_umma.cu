@@ -473,6 +473,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== TMA producer: packed rows -> shared memory ==============================
         if (lane == 0) {
             uint32_t buf = 0, buf_phase = 0;                               // ring of packed-row boxes and its parity
+            const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
             uint32_t t_iter = 0, run_pos = 0;                              // segments done; segments already in the open run
             bool in_step = job.wave_sync != nullptr;
             SegWalk walk(job, cluster_id, n_clusters, n_chunks);
@@ -513,8 +514,14 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         wait(raw_empty_bar + 8 * buf, buf_phase ^ 1);
                         mbar_expect_tx(raw_full_bar + 8 * buf, C::RAW_BYTES);
                         const uint32_t dst = raw_base + buf * C::RAW_BYTES;
-                        tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
-                        tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
+                        if (job.l2_hints) {
+                            if (job.l2_hints > 1) tma_load_2d_hint(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf, pol_a);
+                            else tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
+                            tma_load_2d_hint(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf, pol_b);
+                        } else {
+                            tma_load_2d(dst, &map_a, c * 128u, ya, raw_full_bar + 8 * buf);
+                            tma_load_2d(dst + C::RAW_A_BYTES, &map_b, c * 128u, yb, raw_full_bar + 8 * buf);
+                        }
                         if (++buf == (uint32_t)C::RAW_BUFS) { buf = 0; buf_phase ^= 1; }
                     }
                     if (job.wave_sync && !seg.tail) atomicAdd(job.wave_sync, 1u);   // this CTA's loads of the wave are in flight
@@ -953,6 +960,7 @@ std::atomic<int> g_umma_reserved_sms{0};   // STORM_b200_set_umma_reserved_sms
 std::atomic<int> g_umma_stream_k{1};       // STORM_b200_set_umma_stream_k
 std::atomic<int> g_umma_chain{1};          // STORM_b200_set_umma_chain
 std::atomic<int> g_clock_probe{0};         // STORM_b200_set_clock_probe
+std::atomic<int> g_umma_l2_hints{1};       // STORM_b200_set_umma_variant bit 5: L2 eviction hints on the packed-row loads of triangle jobs
 std::atomic<int> g_umma_out_tma{1};        // STORM_b200_set_umma_variant bit 4: per-pair counts leave through TMA stores
 
 // Clock-probe buffer of the current device (2 x u64 per CTA of the last probed launch) and the grid of that launch.
@@ -992,9 +1000,12 @@ int launch_cg(const DenseJob& job_in, cudaStream_t stream) {
     uint64_t clusters = n_tiles < max_clusters ? n_tiles : max_clusters;
     job.wave_sync = nullptr;
     job.stream_k = 0;
+    // (worth it where the rows do not fit in L2 anyway: the same condition as the wave barrier below)
+    job.l2_hints = 0;
     // Worth it when the rows do not fit in L2 anyway and a tile lasts long enough to hide the barrier: below
     // that it costs up to 10 % (32768 x 4096: 0.79 vs 0.71 ms) and there is no DRAM traffic to save.
     const uint64_t matrix_bytes = (job.nA + (job.A == job.B ? 0 : job.nB)) * (uint64_t)job.n_words * 8;
+    if (g_umma_l2_hints.load() && job.triangle && n_tiles > clusters && matrix_bytes >= (96ull << 20)) job.l2_hints = g_umma_l2_hints.load();
     if (g_umma_wave_sync.load() && n_tiles > clusters && matrix_bytes >= (96ull << 20) && job.n_words >= 512) {
         int rc2 = wave_counter(stream, &job.wave_sync);
         if (rc2) return rc2;
@@ -1152,12 +1163,18 @@ extern "C" int STORM_b200_set_umma_chain(int on) {
 // Development / measurement knob: bit 0 = hardware-suspended mbarrier waits, bit 1 = scaled expansion.
 // Returns the previous value.
 extern "C" int STORM_b200_set_umma_variant(int variant) {
-    const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0) | (storm::g_umma_out_tma.load() ? 16 : 0);
-    if (variant >= 0 && variant <= 31) {
+    const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0) | (storm::g_umma_out_tma.load() ? 16 : 0) |
+                     (storm::g_umma_l2_hints.load() ? 32 : 0);
+    if (variant >= 0 && variant <= 63) {
         storm::g_umma_variant.store(variant & 3); storm::g_umma_fp4_wide.store((variant >> 3) & 1); storm::g_umma_out_tma.store((variant >> 4) & 1);
+        storm::g_umma_l2_hints.store((variant >> 5) & 1);   // (STORM_b200_set_umma_l2_hints picks between its two forms)
     }
     return prev;
 }
+
+// L2 eviction hints on the packed-row loads of triangle jobs that do not fit in L2: 0 none, 1 column blocks evict_last,
+// 2 column blocks evict_last + row blocks evict_first.  Results are identical.  Returns the previous value.
+extern "C" int STORM_b200_set_umma_l2_hints(int mode) { return storm::g_umma_l2_hints.exchange(mode < 0 ? 0 : mode > 2 ? 2 : mode); }
 
 // 1: every tensor-kernel launch records, per CTA, the clock64 and %globaltimer deltas around its main loop (one thread,
 // a handful of instructions); 0 (default): off.  Returns the previous value.

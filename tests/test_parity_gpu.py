@@ -899,3 +899,41 @@ def test_multi_device_storm_t_queries_equal_single_device(sb, orc):
                         sb.set_storm_route(prev)
             finally:
                 sb.set_device_list(())
+
+
+def test_two_host_threads_with_their_own_objects(sb, orc):
+    """The reference's threading contract is one host thread per object (storm.c has no locks).  Two threads, each with
+    its own containers and its own raw-buffer calls, run concurrently (ctypes releases the GIL) and get exact results:
+    the process-wide pieces they share -- prefix cache, wave counters, staging ring, wrapper scratch arenas, FP4
+    self-test, per-thread tensor-map cache -- are locked or thread-local."""
+    import threading
+    M = 65536
+    jobs = []
+    for t in range(2):
+        rows = [orc.gen_row_positions(200 + t, i, [5, 150, 4000, 30000, 90][i % 5], M) for i in range(900 + 100 * t)]
+        vals = O.positions_to_dense(rows, M)
+        jobs.append((rows, vals, orc.wrapper_diag(vals)))
+    errors = []
+
+    def work(t):
+        rows, vals, exact = jobs[t]
+        try:
+            for rep in range(3):
+                with sb.StormContiguous(M) as c, sb.Storm() as s:
+                    for p in rows:
+                        c.add(p)
+                        s.add(p)
+                    assert c.pairw_intersect_cardinality_blocked(31) == exact
+                    assert c.pairw_intersect_cardinality_list() == exact
+                    assert s.pairw_intersect_cardinality() == exact
+                    assert (c.pairw_rect(3, 200, 100, 700) == orc.rect_counts(vals, 3, 200, 100, 700)).all()
+                assert sb.wrapper_diag(vals) == exact
+        except Exception as e:                                # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

@@ -100,6 +100,28 @@ for route in ("sparse", "dense"):
         sb.set_sparse_flat(was)
     sb.set_storm_route(prev)
 
+# STORM_t on replicas, banded dense route, rectangles through densified rows
+for ids in ((0, 0),):
+    sb.set_device_list(ids)
+    for route in ("sparse", "dense"):
+        prev = sb.set_storm_route(route)
+        with sb.Storm() as s:
+            for p in srows:
+                s.add(p)
+            check(f"storm_t replicas route={route}", s.pairw_intersect_cardinality(), sexact)
+        sb.set_storm_route(prev)
+    sb.set_device_list(())
+prev = sb.set_storm_route("dense")
+was = sb.set_storm_band_rows(256)
+with sb.Storm() as s:
+    for p in (srows * 6)[:600]:
+        s.add(p)
+    vals6 = O.positions_to_dense((srows * 6)[:600], M)
+    check("storm_t banded dense", s.pairw_intersect_cardinality(), orc.wrapper_diag(vals6))
+    check("storm_t rect via densified rows", s.pairw_rect(7, 130, 60, 420), orc.rect_counts(vals6, 7, 130, 60, 420))
+sb.set_storm_band_rows(was)
+sb.set_storm_route(prev)
+
 torch.cuda.synchronize()
 print("sanitize_smoke:", "ALL OK" if ok else "MISMATCH")
 sys.exit(0 if ok else 1)
