@@ -44,7 +44,10 @@ void count_launch(uint64_t n = 1);
 // (g + 1) * TRI_GROUP * TN, which is what lets a host-buffer query start computing while the
 // rest of the matrix is still being uploaded (contig.cu: wrapper_diag_impl).
 // `group_prefix[g]` is the number of tiles in groups < g (n_groups + 1 entries, device).
-constexpr uint32_t TRI_GROUP = 8;
+#ifndef STORM_TRI_GROUP
+#define STORM_TRI_GROUP 8
+#endif
+constexpr uint32_t TRI_GROUP = STORM_TRI_GROUP;
 
 struct DenseJob {
     const uint64_t* A;

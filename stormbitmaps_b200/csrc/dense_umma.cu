@@ -960,7 +960,7 @@ std::atomic<int> g_umma_reserved_sms{0};   // STORM_b200_set_umma_reserved_sms
 std::atomic<int> g_umma_stream_k{1};       // STORM_b200_set_umma_stream_k
 std::atomic<int> g_umma_chain{1};          // STORM_b200_set_umma_chain
 std::atomic<int> g_clock_probe{0};         // STORM_b200_set_clock_probe
-std::atomic<int> g_umma_l2_hints{1};       // STORM_b200_set_umma_variant bit 5: L2 eviction hints on the packed-row loads of triangle jobs
+std::atomic<int> g_umma_l2_hints{2};       // STORM_b200_set_umma_variant bit 5: L2 eviction hints on the packed-row loads of triangle jobs
 std::atomic<int> g_umma_out_tma{1};        // STORM_b200_set_umma_variant bit 4: per-pair counts leave through TMA stores
 
 // Clock-probe buffer of the current device (2 x u64 per CTA of the last probed launch) and the grid of that launch.
