@@ -39,13 +39,17 @@ void count_launch(uint64_t n = 1);
 // walk is row-block-major (bi outer, bj inner).  Consecutive tile indices -- which is
 // what the CTAs of one wave hold, and what a shard is a range of -- then share their B rows
 // with the whole group and their A rows with TRI_GROUP - 1 neighbours, so a wave of 74 tiles
-// touches ~17 distinct row blocks instead of 75.  Tile indices are
+// touches ~18 distinct row blocks instead of 75.  Tile indices are
 // also monotone in the largest row they touch: tiles of groups <= g only read rows below
 // (g + 1) * TRI_GROUP * TN, which is what lets a host-buffer query start computing while the
 // rest of the matrix is still being uploaded (contig.cu: wrapper_diag_impl).
 // `group_prefix[g]` is the number of tiles in groups < g (n_groups + 1 entries, device).
+// 12 column blocks per group: with the L2 hints of the tensor kernel (column blocks evict_last, row blocks evict_first)
+// the column blocks of a group stay in L2 from wave to wave as long as they fit beside the streaming row blocks --
+// 12 x 256 rows x 16 KiB = 50 MB on C3.  Same-box A/B (profiles/r02_ab_raster_group.jsonl): 8 -> 12 -> 16 blocks:
+// C3 614.4 / 609.4 / 628.8 ms, 30 000 x 131 072 14.08 / 13.85 / 14.01 ms, 65 536 x 16 384 8.15 / 7.99 / 8.13 ms.
 #ifndef STORM_TRI_GROUP
-#define STORM_TRI_GROUP 8
+#define STORM_TRI_GROUP 12
 #endif
 constexpr uint32_t TRI_GROUP = STORM_TRI_GROUP;
 

@@ -136,18 +136,21 @@ def test_two_ranks_gather_row_slices(n_rows, n_words):
 
 
 def test_raster_is_monotone_in_rows():
-    """Tiles of raster groups <= g only touch rows below (g + 1) * 8 * tile_cols: what the streamed
-    host-buffer query relies on to start computing before the upload has finished."""
+    """Tiles of raster groups <= g only touch rows below (g + 1) * group_rows (group_rows = the raster's column-block
+    group x tile_cols, as STORM_b200_tiles_below_row reports it): what the streamed host-buffer query relies on to
+    start computing before the upload has finished."""
     import stormbitmaps_b200 as sb
     for kernel, n_rows in (("umma", 5000), ("popc", 3000), ("umma", 2049)):
         n_tiles, tm, tn = sb.tile_count(n_rows, kernel)
+        group_rows = sb.tiles_below_row(n_rows, 0, kernel)[1]
+        assert group_rows % tn == 0 and group_rows >= tn
         last_group = 0
         for t in range(n_tiles):
             i0, i1, j0, j1 = sb.tile_rect(n_rows, t, kernel)
-            g = j0 // (8 * tn)
+            g = j0 // group_rows
             assert g >= last_group, (kernel, t)
             last_group = g
-            assert i1 <= min(n_rows, (g + 1) * 8 * tn) and j1 <= min(n_rows, (g + 1) * 8 * tn)
+            assert i1 <= min(n_rows, (g + 1) * group_rows) and j1 <= min(n_rows, (g + 1) * group_rows)
 
 
 # ---- pipelined host query (distributed.pairw_total_from_host, N > 1) ---------------------------------
