@@ -375,7 +375,9 @@ def test_c1_full_size_total_and_sampled_tiles(sb, orc):
         assert int(total.item()) == closed, kernel
         parts = [int(sb.pairw_device(rows, n_words=W, shard=k, n_shards=8, kernel=kernel).item()) for k in range(8)]
         assert sum(parts) == closed, kernel
-        assert min(parts) > 0.8 * max(parts), "shards are balanced"
+        # shards hold equal numbers of TILES (the unit of kernel time); their pair totals differ where a shard collects the
+        # diagonal tiles and the ragged last column block (16 of 256 rows on C1), so this is a loose check only
+        assert min(parts) > 0.65 * max(parts), "shards are balanced"
     # sampled tiles (diagonal, interior, last ragged) against the reference kernel restated in the oracle
     host = rows[:, :W].cpu().numpy().view(np.uint64)
     for (i0, i1, j0, j1) in [(0, 40, 0, 40), (4990, 5030, 9960, 10000), (9970, 10000, 9970, 10000), (100, 130, 7000, 7040)]:
