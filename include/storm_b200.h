@@ -212,11 +212,18 @@ int STORM_b200_contig_last_list_route(const STORM_contiguous_t* bitmap);
 
 uint64_t STORM_b200_storm_pairw_shard(STORM_t* bitmap, uint32_t shard, uint32_t n_shards);
 /* How whole-container STORM_t queries are answered: 0 = cost model (default), 1 = the sparse
- * merge/probe kernel, 2 = rows densified on the device + the dense tile kernel (falls back to
- * 1 if the dense form does not fit in device memory).  Results are identical.  Returns the
- * previous value; STORM_b200_storm_last_route tells which one the last query of `bitmap` took. */
+ * merge/probe kernels, 2 = rows densified on the device + the dense tile kernel (falls back to
+ * 1 if the dense form does not fit in device memory), 3 = the split route where it applies (containers that hold
+ * heavy rows -- a bitmap block, or more than 8 192 values -- among light ones: the light rows among themselves through
+ * the row-group stream kernel, every pair with a heavy row through the block merge/probe kernel; else 1).  Results are
+ * identical.  Returns the previous value; STORM_b200_storm_last_route tells which one the last query of `bitmap` took. */
 int STORM_b200_set_storm_route(int route);
-int STORM_b200_storm_last_route(const STORM_t* bitmap);   /* 1 sparse kernels, 2 densified rows + tile kernel, 3 the same in row bands */
+int STORM_b200_storm_last_route(const STORM_t* bitmap);   /* 1 sparse kernels, 2 densified rows + tile kernel, 3 the same in row bands, 4 split */
+/* The split route's side of the cost model (pure arithmetic): seconds for n_rows rows of which n_heavy are heavy, the
+ * light ones holding light_nnz values together, all rows total_nnz, at most max_blocks blocks per row, n_bitmap_blocks
+ * bitmap blocks in the container.  Negative on a bad argument. */
+double STORM_b200_storm_split_model(uint64_t n_rows, uint64_t n_heavy, double light_nnz, double total_nnz, double max_blocks,
+                                    double n_bitmap_blocks);
 /* A container whose dense form exceeds 48 GiB is densified in row bands of 12 GiB (two arenas; triangle of a band, then its
  * rectangles with the later bands) instead of falling back to the block merge/probe kernel.  This knob forces the banded
  * form with bands of `rows` rows for any size (0 = the size rule again); results are identical.  Returns the previous value. */

@@ -96,6 +96,7 @@ SIGNATURES = {
     "STORM_b200_contig_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "STORM_b200_storm_pairw_shard": (C.c_uint64, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "STORM_b200_set_storm_route": (C.c_int, [C.c_int]),
+    "STORM_b200_storm_split_model": (C.c_double, [C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]),
     "STORM_b200_set_sparse_flat": (C.c_int, [C.c_int]),
     "STORM_b200_set_storm_band_rows": (C.c_uint64, [C.c_uint64]),
     "STORM_b200_storm_route_model": (C.c_int, [C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_uint64, C.c_int, C.c_int,

@@ -165,8 +165,8 @@ class Storm:
                       "STORM_pairw_intersect_cardinality_blocked")
 
     def last_route(self) -> str:
-        """Which kernel family answered the last whole-container query: 'sparse' or 'dense'."""
-        return {0: "none", 1: "sparse", 2: "dense", 3: "dense"}[self._L.STORM_b200_storm_last_route(self._h)]
+        """Which kernel family answered the last whole-container query: 'sparse', 'dense' or 'split'."""
+        return {0: "none", 1: "sparse", 2: "dense", 3: "dense", 4: "split"}[self._L.STORM_b200_storm_last_route(self._h)]
 
     def pairw_shard(self, shard: int, n_shards: int) -> int:
         return _query(self._L.STORM_b200_storm_pairw_shard(self._h, shard, n_shards), "STORM_b200_storm_pairw_shard")
@@ -479,9 +479,14 @@ def set_umma_cta_group(cg: int) -> int:
 
 
 def set_storm_route(route) -> int:
-    """``STORM_b200_set_storm_route``: 'auto' | 'sparse' | 'dense' for whole-container STORM_t queries."""
-    r = {"auto": 0, "sparse": 1, "dense": 2}[route] if isinstance(route, str) else int(route)
+    """``STORM_b200_set_storm_route``: 'auto' | 'sparse' | 'dense' | 'split' for whole-container STORM_t queries."""
+    r = {"auto": 0, "sparse": 1, "dense": 2, "split": 3}[route] if isinstance(route, str) else int(route)
     return _lib.load().STORM_b200_set_storm_route(r)
+
+
+def storm_split_model(n_rows: int, n_heavy: int, light_nnz: float, total_nnz: float, max_blocks: float, n_bitmap_blocks: float) -> float:
+    """``STORM_b200_storm_split_model``: expected seconds of the split route (no device needed)."""
+    return _lib.load().STORM_b200_storm_split_model(n_rows, n_heavy, light_nnz, total_nnz, max_blocks, n_bitmap_blocks)
 
 
 LIST_ROUTES = {"auto": 0, "tile": 1, "probe": 2, "stream": 3}

@@ -39,6 +39,7 @@ constexpr uint32_t BLOCK_WORDS = BLOCK_BITS / 64;                  // 1024
 constexpr uint32_t LIST_THRESHOLD = STORM_DEFAULT_SCALAR_THRESHOLD;  // 4096
 constexpr uint32_t BITMAP_FLAG = 0x80000000u;
 constexpr uint32_t ROW_HAS_BITMAP = 0x80000000u;                   // device copy of row_nnz: the row holds a bitmap block
+constexpr uint32_t ROW_HEAVY = 0x40000000u;                        // ... the row is a heavy row of the split route (below)
 
 // Threads per CTA: the kernel is latency-bound (dependent global loads of the merge, random probes), so it
 // wants every warp it can get next to one CTA's shared bitmaps: 1024 threads when the shared-memory slots
@@ -55,7 +56,8 @@ constexpr uint32_t SP_PROBE_I_MAX = 256;   // i-list probes into a j-bitmap up t
 // Flattened device view of one STORM_t.
 struct SparseView {
     const uint32_t* row_ptr;   // n_rows + 1: first block of each row
-    const uint32_t* row_nnz;   // values per row; ROW_HAS_BITMAP set if any of the row's blocks is a bitmap block
+    const uint32_t* row_nnz;   // values per row; ROW_HAS_BITMAP set if any of the row's blocks is a bitmap block, ROW_HEAVY
+                               // if it has one or holds more values than a row group of the stream kernel may
     const uint32_t* blk_id;    // block index (value / 65536), ascending within a row
     const uint32_t* blk_len;   // number of values; BITMAP_FLAG set for bitmap blocks
     const uint64_t* blk_off;   // list: element offset into `lists`; bitmap: word offset into `words`
@@ -75,6 +77,10 @@ struct SparseJob {
     int strict_upper;          // same container: only pairs with j > i
     uint32_t shard, n_shards;  // rows i are dealt round-robin to shards
     uint32_t maxb;             // shared-memory slots (<= SP_MAXB_CAP)
+    uint32_t slice;            // partner rows per CTA (SP_SLICE; fewer when there are few rows i)
+    // split route: rows i are i_list[i0 .. i1) (the heavy rows of the container, ascending), the partner rows all of
+    // [j0, j1), and pair (i, j) counts iff j is a light row or j > i -- every pair with a heavy row exactly once
+    const uint32_t* i_list;
     uint32_t* out; uint64_t ld;
     unsigned long long* total;
 };
@@ -112,13 +118,15 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_pairs_kernel(const S
     const uint32_t SP_THREADS = blockDim.x, SP_WARPS = blockDim.x >> 5;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t i = job.i0 + job.shard + (uint64_t)blockIdx.x * job.n_shards;
+    uint64_t i = job.i0 + job.shard + (uint64_t)blockIdx.x * job.n_shards;
     if (i >= job.i1) return;
+    const bool heavy_rows = job.i_list != nullptr;
+    if (heavy_rows) i = job.i_list[i];
     uint64_t jbeg = job.j0;
     if (job.strict_upper && jbeg < i + 1) jbeg = i + 1;
-    const uint64_t js0 = jbeg + (uint64_t)blockIdx.y * SP_SLICE;
+    const uint64_t js0 = jbeg + (uint64_t)blockIdx.y * job.slice;
     if (js0 >= job.j1) return;
-    const uint64_t js1 = min(js0 + (uint64_t)SP_SLICE, job.j1);
+    const uint64_t js1 = min(js0 + (uint64_t)job.slice, job.j1);
 
     const SparseView& A = job.A;
     const SparseView& B = job.B;
@@ -162,6 +170,7 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_pairs_kernel(const S
         }
 
         for (uint64_t j = js0 + warp; j < js1; j += SP_WARPS) {
+            if (heavy_rows && (j == i || (j < i && (B.row_nnz[j] & ROW_HEAVY)))) continue;   // (warp-uniform)
             uint32_t c = 0;
             uint32_t y = B.row_ptr[j];
             const uint32_t ye = B.row_ptr[j + 1];
@@ -242,12 +251,14 @@ __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_pairs_kernel(const S
 constexpr size_t FLAT_MAX_SMEM = 160 * 1024;     // whole-row bitmap: rows up to 1 310 720 bits
 constexpr uint32_t FLAT_SLICE = 4096;            // partner rows per CTA
 
-__global__ void __launch_bounds__(256) flatten_rows_kernel(const SparseView v, const uint64_t* pos_off, uint32_t* pos) {
-    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= v.n_rows) return;
-    uint64_t o = pos_off[row];
+// Flat row k = container row rows[k] (rows == NULL: row k), n of them.
+__global__ void __launch_bounds__(256) flatten_rows_kernel(const SparseView v, const uint32_t* rows, uint32_t n, const uint64_t* pos_off, uint32_t* pos) {
+    const uint32_t k_row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k_row >= n) return;
+    const uint32_t row = rows ? rows[k_row] : k_row;
+    uint64_t o = pos_off[k_row];
     for (uint32_t b = v.row_ptr[row]; b < v.row_ptr[row + 1]; ++b) {
-        const uint32_t len = v.blk_len[b];                        // (no bitmap blocks: flat_eligible)
+        const uint32_t len = v.blk_len[b];                        // (no bitmap blocks: flat_eligible / light rows)
         const uint32_t base = v.blk_id[b] << 16;
         const uint16_t* src = v.lists + v.blk_off[b];
         for (uint32_t k = lane; k < len; k += 32) pos[o + k] = base | src[k];
@@ -488,6 +499,12 @@ struct StormState {
     uint32_t max_row_nnz = 0;
     std::vector<uint32_t> h_group_start; // row groups of the stream kernel (<= 32 rows, <= STREAM_ENTRIES values)
     uint32_t* d_group_start = nullptr;
+    // Split route (containers that hold heavy rows -- a bitmap block, or more values than a row group may -- among
+    // light ones): the light rows' own flat form and row groups, and the list of heavy rows.
+    uint32_t n_light = 0, n_heavy = 0; uint64_t light_nnz = 0;
+    uint32_t *d_light_rows = nullptr, *d_heavy_rows = nullptr, *d_lgroup_start = nullptr, *d_lpos = nullptr;
+    uint64_t* d_lpos_off = nullptr; bool lflat_valid = false;
+    std::vector<uint32_t> h_lgroup_start;
     // Whole-container queries run on the device set (devices.h): this state is the replica on the set's first device
     // and owns the replicas on the others (resolved at the first query; rectangles and XY^T stay on this one).
     std::vector<StormState*> replicas;
@@ -500,8 +517,11 @@ inline StormState* state_of(const STORM_t* s) { return static_cast<StormState*>(
 void free_mirror(StormState* st) {
     for (void* p : {(void*)st->d_row_ptr, (void*)st->d_row_nnz, (void*)st->d_blk_id, (void*)st->d_blk_len,
                     (void*)st->d_blk_off, (void*)st->d_lists, (void*)st->d_words, (void*)st->d_pos_off, (void*)st->d_pos,
-                    (void*)st->d_group_start})
+                    (void*)st->d_group_start, (void*)st->d_light_rows, (void*)st->d_heavy_rows, (void*)st->d_lgroup_start,
+                    (void*)st->d_lpos, (void*)st->d_lpos_off})
         if (p) cudaFree(p);
+    st->d_light_rows = st->d_heavy_rows = st->d_lgroup_start = st->d_lpos = nullptr; st->d_lpos_off = nullptr;
+    st->lflat_valid = false; st->h_lgroup_start.clear();
     st->d_row_ptr = st->d_row_nnz = st->d_blk_id = st->d_blk_len = nullptr;
     st->d_blk_off = nullptr; st->d_lists = nullptr; st->d_words = nullptr;
     st->d_pos_off = nullptr; st->d_pos = nullptr; st->flat_valid = false;
@@ -532,7 +552,9 @@ int ensure_state(StormState* st) {
 // container and uploaded to every replica.
 struct HostMirror {
     std::vector<uint32_t> row_ptr, row_nnz, row_nnz_dev, blk_id, blk_len, group_start;
-    std::vector<uint64_t> blk_off, words, pos_off;
+    std::vector<uint32_t> light_rows, heavy_rows, lgroup_start;       // split route (filled only if there are heavy rows)
+    std::vector<uint64_t> blk_off, words, pos_off, lpos_off;
+    uint64_t light_nnz = 0;
     std::vector<uint16_t> lists;
     uint32_t max_blocks = 0, max_blk_id = 0, max_row_nnz = 0;
     uint64_t n_bitmap_blocks = 0, total_nnz = 0;
@@ -578,6 +600,21 @@ void build_host_mirror(const STORM_t* s, HostMirror* h) {
     for (uint32_t r = 0; r < s->n_conts; ++r)
         for (uint32_t b = h->row_ptr[r]; b < h->row_ptr[r + 1]; ++b)
             if (h->blk_len[b] & BITMAP_FLAG) { h->row_nnz_dev[r] |= ROW_HAS_BITMAP; break; }
+    // heavy rows: a bitmap block, or too many values for a row group of the stream kernel
+    for (uint32_t r = 0; r < s->n_conts; ++r)
+        if ((h->row_nnz_dev[r] & ROW_HAS_BITMAP) || h->row_nnz[r] > STREAM_ENTRIES) { h->row_nnz_dev[r] |= ROW_HEAVY; h->heavy_rows.push_back(r); }
+    if (!h->heavy_rows.empty()) {
+        std::vector<uint32_t> lnnz;
+        h->lpos_off.assign(1, 0);
+        for (uint32_t r = 0; r < s->n_conts; ++r)
+            if (!(h->row_nnz_dev[r] & ROW_HEAVY)) {
+                h->light_rows.push_back(r);
+                lnnz.push_back(h->row_nnz[r]);
+                h->lpos_off.push_back(h->lpos_off.back() + h->row_nnz[r]);
+            }
+        h->light_nnz = h->lpos_off.back();
+        stream_groups(lnnz.data(), lnnz.size(), &h->lgroup_start);
+    }
 }
 
 // One replica's copy of the mirror (on the current device = the replica's).
@@ -592,6 +629,15 @@ int upload_mirror(StormState* st, const HostMirror& h, uint32_t n_conts) {
         (rc = upload(&st->d_blk_off, h.blk_off, st->stream)) || (rc = upload(&st->d_lists, h.lists, st->stream)) ||
         (rc = upload(&st->d_words, h.words, st->stream)))
         return rc;
+    st->n_heavy = (uint32_t)h.heavy_rows.size();
+    st->n_light = st->n_heavy ? (uint32_t)h.light_rows.size() : n_conts;
+    st->light_nnz = st->n_heavy ? h.light_nnz : h.total_nnz;
+    if (st->n_heavy) {
+        st->h_lgroup_start = h.lgroup_start;
+        if ((rc = upload(&st->d_light_rows, h.light_rows, st->stream)) || (rc = upload(&st->d_heavy_rows, h.heavy_rows, st->stream)) ||
+            (rc = upload(&st->d_lgroup_start, h.lgroup_start, st->stream)) || (rc = upload(&st->d_lpos_off, h.lpos_off, st->stream)))
+            return rc;
+    }
     STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));              // (the host vectors may die after this)
     st->n_rows = n_conts;
     st->max_blocks = h.max_blocks;
@@ -668,10 +714,26 @@ int ensure_flat(StormState* st) {
             return STORM_B200_OK;                                  // no room: the block kernel answers
         }
     }
-    flatten_rows_kernel<<<(st->n_rows + 7) / 8, 256, 0, st->stream>>>(view_of(st), st->d_pos_off, st->d_pos);
+    flatten_rows_kernel<<<(st->n_rows + 7) / 8, 256, 0, st->stream>>>(view_of(st), nullptr, st->n_rows, st->d_pos_off, st->d_pos);
     STORM_CUDA_TRY(cudaGetLastError());
     count_launch();
     st->flat_valid = true;
+    return STORM_B200_OK;
+}
+
+// The light rows' flat form (split route).  Returns false if there is no room for it.
+int ensure_light_flat(StormState* st, bool* ok) {
+    *ok = true;
+    if (st->lflat_valid) return STORM_B200_OK;
+    if (!st->d_lpos && cudaMalloc(&st->d_lpos, std::max<uint64_t>(st->light_nnz, 1) * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        st->d_lpos = nullptr; *ok = false;
+        return STORM_B200_OK;
+    }
+    flatten_rows_kernel<<<(st->n_light + 7) / 8, 256, 0, st->stream>>>(view_of(st), st->d_light_rows, st->n_light, st->d_lpos_off, st->d_lpos);
+    STORM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    st->lflat_valid = true;
     return STORM_B200_OK;
 }
 
@@ -780,14 +842,17 @@ int launch_stream(const StormState* a, const StormState* b, uint64_t i0, uint64_
 int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t stream) {
     SparseJob job = job_in;
     if (job.i1 <= job.i0 || job.j1 <= job.j0) return STORM_B200_OK;
-    if (g_sparse_flat && job.A.pos && job.B.pos &&
+    if (g_sparse_flat && job.A.pos && job.B.pos && !job.i_list &&
         (uint64_t)std::max(job.A.n_blk_span, job.B.n_blk_span) * 8192 <= FLAT_MAX_SMEM) return launch_flat(job, stream);
     job.maxb = std::max<uint32_t>(1, std::min<uint32_t>(max_blocks, SP_MAXB_CAP));
     const size_t smem = (size_t)job.maxb * 8192;
     STORM_CUDA_TRY(cudaFuncSetAttribute(sparse_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SP_MAXB_CAP * 8192)));
     const uint64_t rows_i = (job.i1 - job.i0 + job.n_shards - 1 - job.shard) / job.n_shards;   // rows of this shard
     if (rows_i == 0) return STORM_B200_OK;
-    const uint64_t slices = (job.j1 - job.j0 + SP_SLICE - 1) / SP_SLICE;
+    // few rows i (the heavy rows of the split route): thinner slices, so that the launch still covers the SMs
+    job.slice = SP_SLICE;
+    while (job.slice > 64 && rows_i * ((job.j1 - job.j0 + job.slice - 1) / job.slice) < 4ull * 148) job.slice /= 2;
+    const uint64_t slices = (job.j1 - job.j0 + job.slice - 1) / job.slice;
     if (slices > 65535) { set_error("too many partner rows for one launch (%llu)", (unsigned long long)(job.j1 - job.j0)); return STORM_B200_EINVAL; }
     dim3 grid((unsigned)rows_i, (unsigned)slices);
     sparse_pairs_kernel<<<grid, smem > SP_ONE_CTA_SMEM ? SP_MAX_THREADS : SP_MAX_THREADS / 2, smem, stream>>>(job);
@@ -804,7 +869,7 @@ int launch_sparse(const SparseJob& job_in, uint32_t max_blocks, cudaStream_t str
 // 3 000 x 1 048 576 at 10 486 (profiles/r01_sparse_timing.jsonl).  Containers without bitmap blocks take the
 // row-group stream kernel instead (stream_seconds), which wins up to several hundred values per row: at 10 000 x
 // 524 288 the crossover with the tensor kernel is near 700 values per row (0.13 % density).
-int g_storm_route = 0;   // 0 auto, 1 sparse kernel, 2 densify + dense tile kernel (STORM_b200_set_storm_route)
+int g_storm_route = 0;   // 0 auto, 1 sparse kernels, 2 densify + dense tile kernel, 3 split (STORM_b200_set_storm_route)
 
 // The model itself (pure arithmetic: tests/test_abi.py pins its decisions on the measured cases without a GPU).
 //   dense  = N(N-1)/2 x W / tensor rate (6e13 wp/s FP4 form, 3.5e13 int8 form) + launch + the densify pass
@@ -818,21 +883,42 @@ void storm_route_model(uint64_t n_rows, uint64_t W, double avg_nnz, double avg_b
     if (stream_applies) *sparse_s = std::min(*sparse_s, stream_seconds(pairs, avg_nnz));          // row-group stream kernel
 }
 
-// Which route a whole-container query takes.  A PURE function of the container (rows, width, values, blocks) and
+// Split route: the light rows among themselves through the stream kernel, every pair with a heavy row through the
+// block merge/probe kernel (rows i = the heavy rows).  Heavy x heavy pairs meet in bitmap blocks: 8 KiB per shared
+// block from L2, ~2 ns.
+double split_seconds(uint64_t n_rows, uint64_t n_heavy, double light_nnz, double total_nnz, double max_blocks, double n_bitmap_blocks) {
+    const double nl = (double)(n_rows - n_heavy), nh = (double)n_heavy;
+    const double hh_pairs = 0.5 * nh * (nh - 1.0), h_pairs = nh * nl + hh_pairs;
+    double t = 2e-5 + h_pairs * 1e-9 * (0.08 + 0.16 * max_blocks + 0.0003 * total_nnz / (double)n_rows);
+    if (n_heavy) t += hh_pairs * (n_bitmap_blocks / nh) * 2e-9;
+    if (nl >= 2.0) t += stream_seconds(0.5 * nl * (nl - 1.0), light_nnz / nl);
+    return t;
+}
+
+// Which route a whole-container query takes: 1 sparse kernels, 2 densified rows + tile kernel, 4 split.  A PURE function
+// of the container (rows, width, values, blocks) and
 // of the process-wide route knobs -- never of free memory, of the self-test of the device at hand or of what happens
 // to be resident: the shards of one query run on different devices and partition the pair set differently per
 // route (tile raster / row groups / rows), so every shard has to arrive at the same answer.  Whether the chosen
 // route can run here (memory) is checked afterwards: an unsharded query may then fall back, a sharded one fails.
-bool choose_dense_route(const StormState* st, uint64_t n_rows) {
-    if (g_storm_route == 1) return false;
+int choose_route(const StormState* st, uint64_t n_rows) {
+    const bool split_applies = g_sparse_flat && g_sparse_stream && st->n_heavy > 0 && st->n_light >= 2;
+    if (g_storm_route == 1) return 1;
+    if (g_storm_route == 3) return split_applies ? 4 : 1;
     const uint64_t W = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
-    if (W >= (1u << 25)) return false;                                   // per-pair counts must stay below 2^31
-    if (g_storm_route == 2) return true;
+    const bool dense_applies = W < (1u << 25);                           // per-pair counts must stay below 2^31
+    if (g_storm_route == 2 && dense_applies) return 2;
     double dense_s = 0, sparse_s = 0;
     storm_route_model(n_rows, W, (double)st->total_nnz / (double)n_rows, (double)st->total_blocks / (double)n_rows,
                       g_sparse_flat && g_sparse_stream && st->n_bitmap_blocks == 0 && st->max_row_nnz <= STREAM_ENTRIES,
                       W * 64 <= (1ull << 24), false, &dense_s, &sparse_s);
-    return dense_s < sparse_s;
+    int route = dense_applies && dense_s < sparse_s ? 2 : 1;
+    if (split_applies) {
+        const double split_s = split_seconds(n_rows, st->n_heavy, (double)st->light_nnz, (double)st->total_nnz, (double)st->max_blocks,
+                                             (double)st->n_bitmap_blocks);
+        if (split_s < (route == 2 ? dense_s : sparse_s)) route = 4;
+    }
+    return route;
 }
 
 // Does the dense form of the rows fit on this device (keeping 20 % of the free memory)?
@@ -928,7 +1014,8 @@ int dense_banded(StormState* st, uint64_t n_rows, uint32_t shard, uint32_t n_sha
 std::atomic<uint64_t> g_dense_band_rows{0};   // STORM_b200_set_storm_band_rows: force the banded form with this band height (tests)
 
 // One replica's share of a whole-container query (asynchronous on its stream, accumulated into its d_total).
-int storm_query_on(StormState* st, uint32_t n_conts, bool dense, uint32_t shard, uint32_t n_shards) {
+int storm_query_on(StormState* st, uint32_t n_conts, int route, uint32_t shard, uint32_t n_shards) {
+    bool dense = route == 2;
     if (cudaMemsetAsync(st->d_total, 0, 8, st->stream) != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(cudaGetLastError())); return STORM_B200_ECUDA; }
     uint64_t stride = 0;
     const uint64_t forced_band = g_dense_band_rows.load();
@@ -947,9 +1034,27 @@ int storm_query_on(StormState* st, uint32_t n_conts, bool dense, uint32_t shard,
         return pairw_triangle(st->d_dense, n_conts, (uint32_t)stride, stride, shard, n_shards, STORM_B200_KERNEL_AUTO,
                               reinterpret_cast<uint64_t*>(st->d_total), st->stream);
     }
+    int rc = STORM_B200_OK;
+    if (route == 4) {
+        bool ok = false;
+        if ((rc = ensure_light_flat(st, &ok))) return rc;
+        if (ok) {
+            st->last_route = 4;
+            if ((rc = launch_sparse_stream(st->d_lpos_off, st->d_lpos, st->h_lgroup_start, st->d_lgroup_start, st->d_lpos_off, st->d_lpos,
+                                           st->light_nnz, 0, st->n_light, 0, st->n_light, 1, shard, n_shards, st->d_total, st->stream)))
+                return rc;
+            SparseJob job{};
+            job.A = job.B = view_of(st);
+            job.i_list = st->d_heavy_rows;
+            job.i0 = 0; job.i1 = st->n_heavy; job.j0 = 0; job.j1 = n_conts;
+            job.shard = shard; job.n_shards = n_shards;
+            job.total = st->d_total;
+            return launch_sparse(job, st->max_blocks, st->stream);
+        }
+        if (n_shards > 1) { set_error("shard %u of %u: no room for the light rows' position mirror and a shard cannot switch kernel", shard, n_shards); return STORM_B200_ENOMEM; }
+    }
     st->last_route = 1;
-    int rc = ensure_flat(st);
-    if (rc) return rc;
+    if ((rc = ensure_flat(st))) return rc;
     // (same rule inside the sparse route: the stream kernel shards row groups, the other two rows)
     if (n_shards > 1 && flat_eligible(st) && !st->flat_valid) { set_error("shard %u of %u: no room for the flat position mirror and a shard cannot switch kernel", shard, n_shards); return STORM_B200_ENOMEM; }
     if (stream_eligible(st, st)) return launch_stream(st, st, 0, n_conts, 0, n_conts, 1, shard, n_shards, st->d_total, st->stream);
@@ -974,10 +1079,10 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     std::vector<StormState*> reps{st};
     reps.insert(reps.end(), st->replicas.begin(), st->replicas.end());
     const uint32_t G = (uint32_t)reps.size();
-    const bool dense = choose_dense_route(st, s->n_conts);
+    const int route = choose_route(st, s->n_conts);
     for (uint32_t g = 0; g < G; ++g) {
         DeviceGuard guard(reps[g]->device);
-        if (storm_query_on(reps[g], s->n_conts, dense, shard * G + g, n_shards * G)) return (uint64_t)-1;
+        if (storm_query_on(reps[g], s->n_conts, route, shard * G + g, n_shards * G)) return (uint64_t)-1;
         if (cudaMemcpyAsync(reps[g]->h_total, reps[g]->d_total, 8, cudaMemcpyDeviceToHost, reps[g]->stream) != cudaSuccess) return (uint64_t)-1;
     }
     uint64_t total = 0;
@@ -1260,7 +1365,7 @@ uint64_t STORM_b200_storm_pairw_shard(STORM_t* s, uint32_t shard, uint32_t n_sha
 
 int STORM_b200_set_storm_route(int route) {
     const int prev = g_storm_route;
-    if (route >= 0 && route <= 2) g_storm_route = route;
+    if (route >= 0 && route <= 3) g_storm_route = route;
     return prev;
 }
 
@@ -1272,6 +1377,13 @@ int STORM_b200_storm_route_model(uint64_t n_rows, uint32_t n_words, double avg_n
     storm_route_model(n_rows, n_words, avg_nnz, avg_blocks, n_bitmap_blocks == 0 && max_row_nnz <= STREAM_ENTRIES, fp4 != 0,
                       dense_resident != 0, &out_seconds[0], &out_seconds[1]);
     return STORM_B200_OK;
+}
+
+// Seconds the model expects for the split route (light rows: stream kernel; pairs with a heavy row: block kernel).
+double STORM_b200_storm_split_model(uint64_t n_rows, uint64_t n_heavy, double light_nnz, double total_nnz, double max_blocks,
+                                    double n_bitmap_blocks) {
+    if (n_rows < 2 || n_heavy > n_rows) return -1.0;
+    return split_seconds(n_rows, n_heavy, light_nnz, total_nnz, max_blocks, n_bitmap_blocks);
 }
 
 int STORM_b200_set_sparse_flat(int mode) {

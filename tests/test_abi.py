@@ -231,6 +231,23 @@ def test_route_model_decisions_on_the_measured_cases(lib):
     assert sb.storm_route_model(10000, 8192, 800, 8, 900, fp4=False)["route"] == "sparse"
 
 
+def test_split_route_model(lib):
+    """The split route's estimate (pure arithmetic): a few heavy rows among light ones cost little more than the light
+    rows alone through the stream kernel and far less than densifying everything; with a quarter of the rows heavy
+    (C2's log-uniform mixed level) the densified route stays cheaper."""
+    import stormbitmaps_b200 as sb
+    light = sb.storm_route_model(10000, 8192, 300, 8, 340)                          # no heavy rows: 1.19 ms measured
+    few = sb.storm_split_model(10000, 10, 9990 * 300.0, 9990 * 300.0 + 10 * 100000.0, 8, 80)
+    assert light["sparse_s"] < few < light["sparse_s"] + 0.5e-3, (light, few)
+    assert few < light["dense_s"] / 3
+    # 16 Mbit rows: dense costs N^2 W / 2 / rate = 0.2 s, the split route still milliseconds
+    wide = sb.storm_route_model(10000, 262144, 310, 8, 200000, n_bitmap_blocks=80)
+    assert sb.storm_split_model(10000, 10, 9990 * 300.0, 9990 * 300.0 + 10 * 100000.0, 256, 80) < wide["dense_s"] / 20
+    mixed = sb.storm_split_model(10000, 2800, 7200 * 900.0, 7200 * 900.0 + 2800 * 75000.0, 8, 2800 * 6.0)
+    assert mixed > 5 * sb.storm_route_model(10000, 8192, 21000, 8, 262144, n_bitmap_blocks=16800)["dense_s"]
+    assert sb.storm_split_model(1, 0, 0, 0, 1, 0) < 0
+
+
 def test_header_declares_every_reference_prototype():
     """Drop-in means every function the reference's storm.h declares is declared (and exported) here.  The name list
     is a committed fixture (minted with: grep -oE '\\bSTORM_[a-zA-Z0-9_]+ *\\(' /root/reference/storm.h | tr -d ' (' | sort -u, minus the STORM_ALIGN macro);

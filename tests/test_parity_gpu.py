@@ -314,6 +314,50 @@ def test_storm_t_routes_agree(sb, orc, route):
         sb.set_storm_route(prev)
 
 
+@pytest.mark.parametrize("M", [524288, 40 * 65536 + 77])
+def test_storm_t_split_route(sb, orc, M):
+    """Containers that hold a few heavy rows (bitmap blocks, or more values than a row group of the stream kernel takes)
+    among light ones: the split route -- light rows among themselves through the stream kernel, every pair with a heavy
+    row through the block merge/probe kernel with the heavy rows as rows i -- gives the oracle's total, alone, in
+    shards and after a mutation, on every route.  Heavy rows first, last, adjacent, and with bitmap blocks built
+    from duplicates (few bits)."""
+    draws = [3, 40, 700, 0, 1, 2500, 64, 300]
+    rows = [orc.gen_row_positions(123, i, draws[i % len(draws)], M) for i in range(300)]
+    heavy = {0: 150000, 1: 9000, 77: 60000, 78: 12000, 150: 200000, 299: 30000}
+    for r, d in heavy.items():
+        rows[r] = orc.gen_row_positions(124, r, d, M)
+    rows[200] = np.concatenate([np.full(5000, 9, dtype=np.uint32), np.array([10, 65536 + 4], dtype=np.uint32)])   # bitmap block, 2 bits
+    vals = O.positions_to_dense(rows, M)
+    exact = orc.wrapper_diag(vals)
+    for route in ("split", "auto", "sparse", "dense"):
+        prev = sb.set_storm_route(route)
+        try:
+            with sb.Storm() as s:
+                for p in rows:
+                    s.add(p)
+                assert s.pairw_intersect_cardinality() == exact, (M, route)
+                if route != "auto":
+                    assert s.last_route() == route, (route, s.last_route())
+                assert sum(s.pairw_shard(r, 5) for r in range(5)) == exact, (M, route)
+                s.add(rows[150])                                  # one more heavy row: both halves of the mirror rebuilt
+                s.add(rows[2])
+                more = np.concatenate([vals, vals[150:151], vals[2:3]])
+                assert s.pairw_intersect_cardinality() == orc.wrapper_diag(more), (M, route)
+        finally:
+            sb.set_storm_route(prev)
+    # only heavy rows / only light rows: the split route does not apply and the sparse kernels answer
+    prev = sb.set_storm_route("split")
+    try:
+        for sel in ([rows[r] for r in heavy], rows[2:60]):
+            with sb.Storm() as s:
+                for p in sel:
+                    s.add(p)
+                assert s.pairw_intersect_cardinality() == orc.wrapper_diag(O.positions_to_dense(sel, M))
+                assert s.last_route() == "sparse"
+    finally:
+        sb.set_storm_route(prev)
+
+
 @pytest.mark.parametrize("M", [2 * 65536, 1048576, 20 * 65536, 21 * 65536 + 5])
 def test_storm_t_flat_probe_kernel_equals_block_kernel(sb, orc, M):
     """Sparse route on containers without bitmap blocks: the row-group stream kernel (totals), the flat probe kernel

@@ -3,7 +3,10 @@
 kernel, densified rows + tensor kernel, and what AUTO picks.  JSON lines (run on the GPU box); the timings are what
 the route cost model in sparse.cu (choose_dense_route) is fitted to.
 
-    python tools/sparse_routes.py [rows:bits:draws ...]
+    python tools/sparse_routes.py [rows:bits:draws[:n_heavy:heavy_draws] ...]
+
+With n_heavy > 0 that many rows, spread evenly, are drawn with heavy_draws values instead (rows with bitmap blocks among
+light ones: what the split route is for).
 """
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,18 +31,27 @@ def timed(s, min_s=0.2):
     return best, got
 
 
-for rows, bits, draws in cases:
+for case in cases:
+    rows, bits, draws = case[:3]
+    n_heavy, heavy_draws = (case[3], case[4]) if len(case) >= 5 else (0, 0)
     pos = [orc.gen_row_positions(2, i, draws, bits) for i in range(rows)]
+    for k in range(n_heavy):
+        r = (2 * k + 1) * rows // (2 * n_heavy)
+        pos[r] = orc.gen_row_positions(3, r, heavy_draws, bits)
     cnt = np.zeros(bits, dtype=np.int64)
     for p in pos:
         cnt[p] += 1
     exact = int((cnt * (cnt - 1) // 2).sum())
     nnz = int(sum(len(p) for p in pos))
-    rec = {"rows": rows, "bits": bits, "draws": draws, "avg_nnz": nnz / rows, "routes": {}}
+    rec = {"rows": rows, "bits": bits, "draws": draws, "n_heavy": n_heavy, "heavy_draws": heavy_draws, "avg_nnz": nnz / rows, "routes": {}}
     with sb.Storm() as s:
         for p in pos:
             s.add(p)
-        for name, route, flat in (("stream", "sparse", 2), ("flat", "sparse", 1), ("block", "sparse", 0), ("dense", "dense", 2), ("auto", "auto", 2)):
+        for name, route, flat in (("stream", "sparse", 2), ("flat", "sparse", 1), ("block", "sparse", 0), ("split", "split", 2), ("dense", "dense", 2), ("auto", "auto", 2)):
+            if n_heavy and name in ("flat", "block"):
+                continue                                           # (with heavy rows "stream" already is the block kernel)
+            if bits > (1 << 22) and name == "dense" and rows * rows * (bits / 64) / 2 > 3e14:
+                continue
             if (name == "block" and rows * (rows - 1) / 2 * (1 + nnz / rows / 100) > 2e8) or (name == "flat" and rows * (rows - 1) / 2 * nnz / rows > 3e10):
                 continue                                           # seconds on the block kernel
             sb.set_storm_route(route)
