@@ -71,6 +71,11 @@ int STORM_b200_set_devices(int n);
 int STORM_b200_set_device_list(const int* ids, int n);
 /* The devices a query made now would use: fills ids[0 .. min(cap, count)), returns the count (negative on error). */
 int STORM_b200_get_devices(int* ids, int cap);
+/* A query on G devices makes ~12 us of driver calls per device (launch, read-back, waits).  By default they go out from
+ * G host threads at once -- the caller takes the first device, G - 1 worker threads created at the first multi-device
+ * query take the others -- which is what lets 0.3 ms queries scale over 8 devices.  0 = issue everything from the
+ * calling thread.  Returns the previous value. */
+int STORM_b200_set_device_threads(int on);
 
 /* ---- dense path on device-resident rows ----------------------------------
  *

@@ -589,6 +589,11 @@ def get_devices() -> list:
     return [out[i] for i in range(min(n, 64))]
 
 
+def set_device_threads(on: bool) -> bool:
+    """``STORM_b200_set_device_threads``: per-device calls of a multi-device query from one host thread per device (default) or from the caller alone."""
+    return bool(_lib.load().STORM_b200_set_device_threads(int(bool(on))))
+
+
 def last_error() -> str:
     return _lib.last_error()
 

@@ -222,16 +222,16 @@ int sync_lists(STORM_contiguous_t* c, ContigState* st, ContigDev* d) {
     }
     int rc = grow_device(&d->d_pos, &d->d_pos_cap, std::max<uint64_t>(c->tot_scalar, 1));
     if (rc) return rc;
-    STORM_CUDA_TRY(cudaMemcpy(d->d_pos_off, st->h_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    STORM_CUDA_TRY(cudaMemcpy(d->d_is_sparse, st->h_is_sparse.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    { int crc = copy_to_device_now(d->d_pos_off, st->h_off.data(), (n + 1) * sizeof(uint64_t)); if (crc) return crc; }
+    { int crc = copy_to_device_now(d->d_is_sparse, st->h_is_sparse.data(), n * sizeof(uint32_t)); if (crc) return crc; }
     if (!st->h_sparse_rows.empty())
-        STORM_CUDA_TRY(cudaMemcpy(d->d_sparse_rows, st->h_sparse_rows.data(), st->h_sparse_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        { int crc = copy_to_device_now(d->d_sparse_rows, st->h_sparse_rows.data(), st->h_sparse_rows.size() * sizeof(uint32_t)); if (crc) return crc; }
     if (!st->h_dense_rows.empty())
-        STORM_CUDA_TRY(cudaMemcpy(d->d_dense_rows, st->h_dense_rows.data(), st->h_dense_rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        { int crc = copy_to_device_now(d->d_dense_rows, st->h_dense_rows.data(), st->h_dense_rows.size() * sizeof(uint32_t)); if (crc) return crc; }
     if (c->tot_scalar)
-        STORM_CUDA_TRY(cudaMemcpy(d->d_pos, c->scalar, c->tot_scalar * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        { int crc = copy_to_device_now(d->d_pos, c->scalar, c->tot_scalar * sizeof(uint32_t)); if (crc) return crc; }
     if (st->stream_ok)
-        STORM_CUDA_TRY(cudaMemcpy(d->d_group_start, st->h_group_start.data(), st->h_group_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        { int crc = copy_to_device_now(d->d_group_start, st->h_group_start.data(), st->h_group_start.size() * sizeof(uint32_t)); if (crc) return crc; }
     d->list_rows_synced = n;
     return STORM_B200_OK;
 }

@@ -4,6 +4,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -80,7 +84,112 @@ void copy_rows_parallel(uint8_t* dst, const uint8_t* src, size_t src_pitch, size
     for (unsigned t = 1; t < n_thr; ++t) th[t - 1].join();
 }
 
+// ---- one host thread per additional device ----------------------------------------------------------------------
+// A query on G devices issues, per device, a kernel launch, a read-back and two stream waits: ~12 us of driver time
+// each.  From one host thread that is ~90 us at G = 8 -- a third of a 0.26 ms query.  The calls to different devices
+// are independent, so they go out from G threads at once: the caller takes device 0, G - 1 workers (created at the
+// first multi-device query, kept for the process) the others.  A worker that has just finished a job polls for the
+// next one for a few tens of microseconds before it sleeps, so the two dispatches of one query (launch, collect) and
+// back-to-back queries do not pay a futex wake each.
+class DevicePool {
+    struct Worker {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv, cv_done;
+        std::atomic<uint32_t> posted{0}, done{0};
+        const std::function<int(int)>* fn = nullptr;
+        int arg = 0, rc = 0;
+        char err[512] = {};
+        bool quit = false;
+    };
+    std::vector<std::unique_ptr<Worker>> workers_;
+    std::mutex run_mu_;                              // one dispatch at a time (two host threads may query at once)
+
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    static void loop(Worker* w) {
+        uint32_t seen = 0;
+        for (;;) {
+            const auto t0 = std::chrono::steady_clock::now();
+            bool got = false;
+            for (int it = 0;; ++it) {
+                if (w->posted.load(std::memory_order_acquire) != seen) { got = true; break; }
+                if ((it & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(60)) break;
+                cpu_relax();
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(w->mu);
+                w->cv.wait(lk, [&] { return w->quit || w->posted.load(std::memory_order_acquire) != seen; });
+                if (w->quit) return;
+            }
+            seen = w->posted.load(std::memory_order_acquire);
+            w->err[0] = 0;
+            w->rc = (*w->fn)(w->arg);
+            if (w->rc) { strncpy(w->err, get_error(), sizeof(w->err) - 1); w->err[sizeof(w->err) - 1] = 0; }
+            { std::lock_guard<std::mutex> lk(w->mu); w->done.store(seen, std::memory_order_release); }
+            w->cv_done.notify_one();
+        }
+    }
+
+public:
+    // fn(0) on the calling thread, fn(1) .. fn(n - 1) on the workers, all at once; returns the first failure (its
+    // message becomes the caller's last error).
+    int run(int n, const std::function<int(int)>& fn) {
+        if (n <= 1) return n == 1 ? fn(0) : STORM_B200_OK;
+        std::lock_guard<std::mutex> lock(run_mu_);
+        while ((int)workers_.size() < n - 1) {
+            std::unique_ptr<Worker> w(new Worker());
+            Worker* raw = w.get();
+            raw->th = std::thread(loop, raw);
+            workers_.push_back(std::move(w));
+        }
+        for (int k = 1; k < n; ++k) {
+            Worker* w = workers_[k - 1].get();
+            w->fn = &fn; w->arg = k;
+            { std::lock_guard<std::mutex> lk(w->mu); w->posted.fetch_add(1, std::memory_order_release); }
+            w->cv.notify_one();
+        }
+        int rc = fn(0);
+        for (int k = 1; k < n; ++k) {
+            Worker* w = workers_[k - 1].get();
+            const uint32_t want = w->posted.load(std::memory_order_relaxed);
+            const auto t0 = std::chrono::steady_clock::now();
+            bool got = false;
+            for (int it = 0;; ++it) {
+                if (w->done.load(std::memory_order_acquire) == want) { got = true; break; }
+                if ((it & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(60)) break;
+                cpu_relax();
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(w->mu);
+                w->cv_done.wait(lk, [&] { return w->done.load(std::memory_order_acquire) == want; });
+            }
+            if (w->rc && !rc) { rc = w->rc; set_error("%s", w->err); }
+        }
+        return rc;
+    }
+    ~DevicePool() {
+        for (auto& w : workers_) {
+            { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+            w->cv.notify_one();
+            if (w->th.joinable()) w->th.join();
+        }
+    }
+};
+DevicePool g_pool;
+std::atomic<int> g_device_threads{1};               // STORM_b200_set_device_threads(0): one host thread issues everything
+
 }  // namespace
+
+int for_each_device(int n, const std::function<int(int)>& fn) {
+    if (n > 1 && g_device_threads.load(std::memory_order_relaxed)) return g_pool.run(n, fn);
+    int rc = STORM_B200_OK;
+    for (int g = 0; g < n; ++g) { const int r = fn(g); if (r && !rc) rc = r; }
+    return rc;
+}
 
 int DevCtx::init(int dev) {
     device = dev;
@@ -238,7 +347,7 @@ int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_
     // tiles of the raster groups whose rows are all resident already: one launch per device, no waiting
     if (resident > n_rows) resident = n_rows;
     const uint64_t g_res = resident >= n_rows ? n_groups : resident / group_rows;
-    for (int g = 0; g < G; ++g) { int rc = launch(g, 0, prefix[g_res]); if (rc) return rc; }
+    { int rc = for_each_device(G, [&](int g) { return launch(g, 0, prefix[g_res]); }); if (rc) return rc; }
     if (g_res == n_groups) return STORM_B200_OK;
 
     // the rest: bands of whole groups, at least MIN_BAND_BYTES each, at most MAX_BANDS of them
@@ -273,32 +382,32 @@ int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_
             STORM_CUDA_TRY(cudaEventRecord(devs[g]->band_ready[band], devs[g]->copy_stream));
             STORM_CUDA_TRY(cudaStreamWaitEvent(devs[g]->stream, devs[g]->band_ready[band], 0));
         }
-        for (int g = 0; g < G; ++g) { int rc = launch(g, prefix[g0], prefix[g1]); if (rc) return rc; }
+        { int rc = for_each_device(G, [&](int g) { return launch(g, prefix[g0], prefix[g1]); }); if (rc) return rc; }
     }
     return STORM_B200_OK;
 }
 
 uint64_t collect_totals(DevCtx* const* devs, int G, const char* what) {
-    bool ok = true;
-    for (int g = 0; g < G; ++g) {
-        DeviceGuard guard(devs[g]->device);
-        ok = ok && cudaMemcpyAsync(devs[g]->h_total, devs[g]->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, devs[g]->stream) == cudaSuccess;
-        devs[g]->total_zero = cudaMemsetAsync(devs[g]->d_total, 0, sizeof(unsigned long long), devs[g]->stream) == cudaSuccess;   // for the next query
-    }
-    uint64_t total = 0;
-    for (int g = 0; g < G; ++g) {
-        DeviceGuard guard(devs[g]->device);
-        // (the copy stream too: a peer may still be pulling slices out of this device's arena, and the caller may reuse it)
-        const cudaError_t e1 = cudaStreamSynchronize(devs[g]->stream), e2 = cudaStreamSynchronize(devs[g]->copy_stream);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            if (ok) set_error("%s failed on device %d: %s", what, devs[g]->device, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    // per device (each from its own host thread, for_each_device): read the total back, re-zero it for the next query
+    // while the host still waits, and wait for both streams (the copy stream too: a peer may still be pulling slices
+    // out of this device's arena, and the caller may reuse it)
+    const int rc = for_each_device(G, [&](int g) -> int {
+        DevCtx* d = devs[g];
+        DeviceGuard guard(d->device);
+        const cudaError_t e0 = cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream);
+        d->total_zero = cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), d->stream) == cudaSuccess;
+        const cudaError_t e1 = cudaStreamSynchronize(d->stream), e2 = cudaStreamSynchronize(d->copy_stream);
+        if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("%s failed on device %d: %s", what, d->device, cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2));
             cudaGetLastError();
-            ok = false;
+            return STORM_B200_ECUDA;
         }
-        total += *devs[g]->h_total;
-    }
-    if (!ok && *get_error() == 0) set_error("%s failed: %s", what, cudaGetErrorString(cudaGetLastError()));
-    return ok ? total : (uint64_t)-1;
+        return STORM_B200_OK;
+    });
+    if (rc) return (uint64_t)-1;
+    uint64_t total = 0;
+    for (int g = 0; g < G; ++g) total += *devs[g]->h_total;
+    return total;
 }
 
 }  // namespace storm
@@ -330,6 +439,10 @@ int STORM_b200_set_device_list(const int* ids, int n) {
     g_dev_list.assign(ids, ids + n);
     return STORM_B200_OK;
 }
+
+// 1 (default): the per-device calls of a multi-device query go out from one host thread per device; 0: from the
+// calling thread alone.  Returns the previous value.
+int STORM_b200_set_device_threads(int on) { return g_device_threads.exchange(on != 0); }
 
 // The devices a query made now would use: fills ids[0 .. min(cap, count)) and returns the count (negative on error).
 int STORM_b200_get_devices(int* ids, int cap) {

@@ -9,6 +9,7 @@
 // reads (common.cuh) a device starts on the tiles of a band as soon as that band is complete on it.
 #pragma once
 
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -23,7 +24,11 @@ struct DeviceGuard {
     int prev = -1; bool active = false;
     explicit DeviceGuard(int dev) {
         if (dev < 0) return;
-        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); active = true; }
+        // A thread that has never called cudaSetDevice has no context current: runtime calls bind one lazily, driver
+        // calls (cuTensorMapEncodeTiled) do not -- so the first guard of a thread binds even when the device "is" current.
+        static thread_local bool bound = false;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev != dev || !bound) { cudaSetDevice(dev); bound = true; active = prev != dev; }
     }
     ~DeviceGuard() { if (active) cudaSetDevice(prev); }
 };
@@ -52,6 +57,12 @@ int query_devices(std::vector<int>* ids);
 void enable_peers(const std::vector<int>& ids);
 // True if the driver can DMA from this host pointer directly (cudaHostAlloc / cudaHostRegister memory).
 bool host_pointer_is_pinned(const void* p);
+
+// fn(g) for g = 0 .. n-1, each on its own host thread (the caller takes 0; workers kept for the process): the driver
+// calls a query makes per device are independent and ~12 us each, which at 8 devices is a third of a 0.26 ms query when
+// one thread issues them all.  fn must make its device current itself (DeviceGuard).  Returns the first failure; its
+// message becomes the caller's last error.  STORM_b200_set_device_threads(0) runs the loop on the caller instead.
+int for_each_device(int n, const std::function<int(int)>& fn);
 
 struct HostRows {
     const uint64_t* base = nullptr;                  // row r at base + r * pitch_words

@@ -491,7 +491,7 @@ static int run_fp4_cases(const Fp4Case* cases, uint32_t n_cases, Fp4Result* resu
     Fp4Case* d_cases = nullptr; Fp4Result* d_res = nullptr;
     STORM_CUDA_TRY(cudaMalloc(&d_cases, n_cases * sizeof(Fp4Case)));
     STORM_CUDA_TRY(cudaMalloc(&d_res, n_cases * sizeof(Fp4Result)));
-    STORM_CUDA_TRY(cudaMemcpy(d_cases, cases, n_cases * sizeof(Fp4Case), cudaMemcpyHostToDevice));
+    { int crc = copy_to_device_now(d_cases, cases, n_cases * sizeof(Fp4Case)); if (crc) return crc; }
     const int smem_bytes = 1024 + 2 * FP_N * 128 + 256;
     STORM_CUDA_TRY(cudaFuncSetAttribute(fp4_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     fp4_exact_kernel<<<1, 128, smem_bytes>>>(d_cases, d_res, n_cases);

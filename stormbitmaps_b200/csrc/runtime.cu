@@ -79,6 +79,16 @@ uint64_t triangle_prefix(uint64_t n_rows, TileShape ts, std::vector<uint64_t>* p
 
 // A tiny per-thread cache of device prefix arrays keyed by (n_rows, tm, tn, device).
 struct PrefixEntry { uint64_t n_rows; uint32_t tm, tn; int dev; uint64_t* d_prefix; uint64_t n_tiles; uint32_t nbi, nbj; };
+// Host -> device copy that is COMPLETE on return.  cudaMemcpy from pageable memory returns once the source has been
+// staged, not once the DMA has reached the device; the kernels that read these tables run on non-blocking streams
+// (no implicit ordering with the legacy stream the copy used) and possibly from another host thread, so wait for it.
+int copy_to_device_now(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return STORM_B200_OK;
+    STORM_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    STORM_CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+    return STORM_B200_OK;
+}
+
 static std::mutex g_prefix_mu;
 static std::vector<PrefixEntry> g_prefix_cache;
 
@@ -96,8 +106,8 @@ int get_triangle_prefix(uint64_t n_rows, TileShape ts, cudaStream_t stream, cons
     PrefixEntry e{n_rows, ts.tm, ts.tn, dev, nullptr, 0, 0, 0};
     e.n_tiles = triangle_prefix(n_rows, ts, &h, &e.nbi, &e.nbj);
     STORM_CUDA_TRY(cudaMalloc(&e.d_prefix, h.size() * sizeof(uint64_t)));
-    // synchronous copy: the host vector dies at scope exit
-    STORM_CUDA_TRY(cudaMemcpy(e.d_prefix, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    // complete before the entry is published: other threads launch on other streams right after a cache hit
+    { int rc = copy_to_device_now(e.d_prefix, h.data(), h.size() * sizeof(uint64_t)); if (rc) { cudaFree(e.d_prefix); return rc; } }
     (void)stream;
     if (g_prefix_cache.size() >= 64) {              // bounded: drop the oldest
         cudaFree(g_prefix_cache.front().d_prefix);

@@ -9,6 +9,9 @@ namespace storm {
 
 int require_device();
 int default_kernel();
+// cudaMemcpy host -> device that has reached the device on return (pageable sources are only staged when cudaMemcpy
+// returns; the readers run on non-blocking streams, possibly from other host threads).
+int copy_to_device_now(void* dst, const void* src, size_t bytes);
 
 TileShape tile_shape_for(int kernel);
 uint64_t triangle_prefix(uint64_t n_rows, TileShape ts, std::vector<uint64_t>* prefix, uint32_t* n_bi, uint32_t* n_bj);

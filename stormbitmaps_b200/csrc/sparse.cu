@@ -1080,22 +1080,23 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     reps.insert(reps.end(), st->replicas.begin(), st->replicas.end());
     const uint32_t G = (uint32_t)reps.size();
     const int route = choose_route(st, s->n_conts);
-    for (uint32_t g = 0; g < G; ++g) {
-        DeviceGuard guard(reps[g]->device);
-        if (storm_query_on(reps[g], s->n_conts, route, shard * G + g, n_shards * G)) return (uint64_t)-1;
-        if (cudaMemcpyAsync(reps[g]->h_total, reps[g]->d_total, 8, cudaMemcpyDeviceToHost, reps[g]->stream) != cudaSuccess) return (uint64_t)-1;
-    }
-    uint64_t total = 0;
-    bool ok = true;
-    for (uint32_t g = 0; g < G; ++g) {
-        DeviceGuard guard(reps[g]->device);
-        if (cudaStreamSynchronize(reps[g]->stream) != cudaSuccess) {
-            set_error("STORM_t query failed on device %d: %s", reps[g]->device, cudaGetErrorString(cudaGetLastError()));
-            ok = false;
+    // one host thread per replica (devices.h: for_each_device): launch its share, read its total back, wait
+    const int rc = for_each_device((int)G, [&](int g) -> int {
+        StormState* r = reps[g];
+        DeviceGuard guard(r->device);
+        int qrc = storm_query_on(r, s->n_conts, route, shard * G + (uint32_t)g, n_shards * G);
+        if (qrc) return qrc;
+        if (cudaMemcpyAsync(r->h_total, r->d_total, 8, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess ||
+            cudaStreamSynchronize(r->stream) != cudaSuccess) {
+            set_error("STORM_t query failed on device %d: %s", r->device, cudaGetErrorString(cudaGetLastError()));
+            return STORM_B200_ECUDA;
         }
-        total += *reps[g]->h_total;
-    }
-    return ok ? total : (uint64_t)-1;
+        return STORM_B200_OK;
+    });
+    if (rc) return (uint64_t)-1;
+    uint64_t total = 0;
+    for (uint32_t g = 0; g < G; ++g) total += *reps[g]->h_total;
+    return total;
 }
 
 void mark_dirty(STORM_t* s) {

@@ -797,6 +797,40 @@ def test_multi_device_contig_queries_equal_single_device(sb, orc):
     assert len(sb.get_devices()) == 1
 
 
+def test_device_threads_on_and_off_agree(sb, orc):
+    """STORM_b200_set_device_threads: the per-device calls of a multi-device query go out from one host thread per
+    device (default) or from the caller alone; same totals either way, for the dense model, the raw-buffer wrapper,
+    STORM_t on both routes, and for many short queries back to back (workers polling, then asleep)."""
+    import time
+    M = 32768
+    rows = [orc.gen_row_positions(81, i, [40, 3000, 9000, 7][i % 4], M) for i in range(1300)]
+    vals = O.positions_to_dense(rows, M)
+    exact = orc.wrapper_diag(vals)
+    ids = _device_lists(sb)[-2] if len(_device_lists(sb)) > 2 else [0, 0, 0]
+    sb.set_device_list(ids)
+    try:
+        for on in (True, False, True):
+            sb.set_device_threads(on)
+            with sb.StormContiguous(M) as c, sb.Storm() as s:
+                for r in rows:
+                    c.add(r)
+                    s.add(r)
+                for k in range(40):
+                    assert c.pairw_intersect_cardinality() == exact, (on, k)
+                    if k == 20:
+                        time.sleep(0.05)                                   # the workers have gone to sleep
+                assert sb.wrapper_diag(vals) == exact
+                for route in ("dense", "sparse"):
+                    prev = sb.set_storm_route(route)
+                    try:
+                        assert s.pairw_intersect_cardinality() == exact, (on, route)
+                    finally:
+                        sb.set_storm_route(prev)
+    finally:
+        sb.set_device_threads(True)
+        sb.set_device_list(())
+
+
 def test_bulk_ingest_on_replicas(sb, orc):
     M, N = 65536, 600
     rows = [orc.gen_row_positions(77, i, [3, 150, 4000, 0, 30000][i % 5], M) for i in range(N)]

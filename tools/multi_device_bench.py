@@ -13,6 +13,7 @@ c3    BASELINE config C3 (200 000 x 131 072, genotype-like) for G in --devices:
 grid  the 25 cells of BASELINE config 5 (N 16k .. 256k rows x M 4k .. 1M bits) through STORM_b200_pairw_devices for
       every G: seconds (wall clock of the blocking C call, best of 3), speed-up over G = 1 on the same box, totals equal
       to the single-device total (which tools/bench_configs.py checks against the closed form on every cell).
+small the ten shortest cells of that grid with the per-device host threads on and off.
 """
 import json
 import os
@@ -116,6 +117,29 @@ def run_grid():
             torch.cuda.empty_cache()
 
 
+def run_small():
+    """The short cells of the C5 grid (0.2 .. 8 ms on one device) on every G with the per-device host threads on and
+    off (STORM_b200_set_device_threads): where the host's ~12 us of driver calls per device decide the scaling."""
+    for n, M in ((16384, 4096), (16384, 16384), (32768, 4096), (16384, 65536), (32768, 16384), (65536, 4096), (16384, 262144),
+                 (32768, 65536), (65536, 16384), (131072, 4096)):
+        copies, W = resident_copies(n, M, lambda rows: sb.synth_geno_device(rows, M, 5))
+        wp = n * (n - 1) / 2 * W
+        ref_total = int(sb.pairw_device(copies[0], n_words=W).item())
+        rec = {"config": "c5_small", "rows": n, "bits": M, "total": ref_total}
+        t1 = None
+        for G in devs:
+            for threads in ((True,) if G == 1 else (False, True)):
+                sb.set_device_threads(threads)
+                sb.pairw_devices(copies[:G], n_words=W)
+                s, tot = best_wall(lambda: sb.pairw_devices(copies[:G], n_words=W), reps=30)
+                t1 = t1 or s
+                rec[f"devices{G}" + ("" if threads else "_one_thread")] = {"seconds": s, "speedup": t1 / s, "match": tot == ref_total}
+        sb.set_device_threads(True)
+        emit(**rec)
+        del copies
+        torch.cuda.empty_cache()
+
+
 def run_storm():
     """C2-shaped STORM_t containers (10 000 x 524 288) on device sets: one level the cost model sends to the sparse
     kernels, one it densifies.  A container takes its device set at its first query, so each G gets its own."""
@@ -146,4 +170,4 @@ def run_storm():
 if __name__ == "__main__":
     emit(devices_visible=n_vis, devices_tested=devs, device=sb.device_info(0))
     for w in (args or ["c3"]):
-        {"c3": run_c3, "grid": run_grid, "storm": run_storm}[w]()
+        {"c3": run_c3, "grid": run_grid, "storm": run_storm, "small": run_small}[w]()

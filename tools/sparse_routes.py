@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """STORM_t whole-container query through every route on one container: row-group stream kernel, flat probe kernel, block merge/probe
 kernel, densified rows + tensor kernel, and what AUTO picks.  JSON lines (run on the GPU box); the timings are what
-the route cost model in sparse.cu (choose_dense_route) is fitted to.
+the route cost model in sparse.cu (choose_route) is fitted to.
 
     python tools/sparse_routes.py [rows:bits:draws[:n_heavy:heavy_draws] ...]
 
