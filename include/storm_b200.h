@@ -55,7 +55,7 @@ int  STORM_b200_set_default_kernel(int kernel);
 
 /* ---- devices ---------------------------------------------------------------
  *
- * Queries behind storm.h run on a SET of devices (one process, one host thread): every device holds all
+ * Queries behind storm.h run on a SET of devices (one process, one calling thread): every device holds all
  * rows, device g of G computes shard g of the tile raster, the host adds G totals.  Rows reach the devices in
  * bands -- 1/G of a band over each device's own PCIe link, the other slices from the peers over NVLink -- and the
  * tiles of a band start as soon as it is complete on a device.  The set is read when a container first touches a
