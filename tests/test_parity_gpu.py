@@ -981,13 +981,16 @@ def test_multi_device_storm_t_queries_equal_single_device(sb, orc):
                 sb.set_device_list(())
 
 
-def test_two_host_threads_with_their_own_objects(sb, orc):
+@pytest.mark.parametrize("ids", [(), (0, 0)])
+def test_two_host_threads_with_their_own_objects(sb, orc, ids):
     """The reference's threading contract is one host thread per object (storm.c has no locks).  Two threads, each with
     its own containers and its own raw-buffer calls, run concurrently (ctypes releases the GIL) and get exact results:
     the process-wide pieces they share -- prefix cache, wave counters, staging ring, wrapper scratch arenas, FP4
-    self-test, per-thread tensor-map cache -- are locked or thread-local."""
+    self-test, per-thread tensor-map cache, and (on a device set: ids) the per-device worker threads -- are locked or
+    thread-local."""
     import threading
     M = 65536
+    sb.set_device_list(list(ids))
     jobs = []
     for t in range(2):
         rows = [orc.gen_row_positions(200 + t, i, [5, 150, 4000, 30000, 90][i % 5], M) for i in range(900 + 100 * t)]
@@ -1016,4 +1019,5 @@ def test_two_host_threads_with_their_own_objects(sb, orc):
         th.start()
     for th in threads:
         th.join()
+    sb.set_device_list(())
     assert not errors, errors
