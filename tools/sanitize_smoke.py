@@ -85,12 +85,16 @@ srows = [orc.gen_row_positions(55, i, draws[i % len(draws)], M) for i in range(1
 sexact = orc.wrapper_diag(O.positions_to_dense(srows, M))
 lrows = [orc.gen_row_positions(56, i, [0, 1, 3, 17, 64, 200, 1000][i % 7], M) for i in range(150)]
 lexact = orc.wrapper_diag(O.positions_to_dense(lrows, M))
-for route in ("sparse", "dense"):
+for route in ("sparse", "dense", "split"):
     prev = sb.set_storm_route(route)
     with sb.Storm() as s:
         for p in srows:
             s.add(p)
         check(f"storm_t mixed route={route}", s.pairw_intersect_cardinality(), sexact)
+        if route == "split":
+            check("storm_t split route shards", sum(s.pairw_shard(k, 3) for k in range(3)), sexact)
+            sb.set_storm_route(prev)
+            continue
     for flat in ("stream", "flat", "block"):
         was = sb.set_sparse_flat(flat)
         with sb.Storm() as s:
@@ -103,7 +107,7 @@ for route in ("sparse", "dense"):
 # STORM_t on replicas, banded dense route, rectangles through densified rows
 for ids in ((0, 0),):
     sb.set_device_list(ids)
-    for route in ("sparse", "dense"):
+    for route in ("sparse", "dense", "split"):
         prev = sb.set_storm_route(route)
         with sb.Storm() as s:
             for p in srows:
