@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -266,6 +267,26 @@ __global__ void __launch_bounds__(256) flatten_rows_kernel(const SparseView v, c
     }
 }
 
+// Range-major flat form of the light rows: flat row k = container row rows[k] (NULL: row k); the values of its blocks
+// [q * range_blocks, (q + 1) * range_blocks) go to pos[off[q * (n + 1) + k] ...].
+__global__ void __launch_bounds__(256) flatten_ranges_kernel(const SparseView v, const uint32_t* rows, uint32_t n, uint32_t range_blocks,
+                                                             const uint64_t* off, uint32_t* pos) {
+    const uint32_t k_row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k_row >= n) return;
+    const uint32_t row = rows ? rows[k_row] : k_row;
+    uint32_t cur = 0xFFFFFFFFu;
+    uint64_t o = 0;
+    for (uint32_t b = v.row_ptr[row]; b < v.row_ptr[row + 1]; ++b) {
+        const uint32_t len = v.blk_len[b], id = v.blk_id[b];      // (light rows hold no bitmap blocks)
+        const uint32_t q = id / range_blocks;
+        if (q != cur) { cur = q; o = off[(uint64_t)q * (n + 1) + k_row]; }
+        const uint32_t base = id << 16;
+        const uint16_t* src = v.lists + v.blk_off[b];
+        for (uint32_t k = lane; k < len; k += 32) pos[o + k] = base | src[k];
+        o += len;
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(SP_MAX_THREADS, 1) sparse_flat_kernel(const SparseJob job, const uint32_t bm_words) {
     extern __shared__ __align__(16) uint32_t s_bits[];            // bm_words: row i as a bitmap
@@ -502,6 +523,9 @@ struct StormState {
     // Split route (containers that hold heavy rows -- a bitmap block, or more values than a row group may -- among
     // light ones): the light rows' own flat form and row groups, and the list of heavy rows.
     uint32_t n_light = 0, n_heavy = 0; uint64_t light_nnz = 0;
+    uint32_t n_ranges = 1, range_blocks = 1;     // position ranges of the light mirror (whole blocks each)
+    bool light_mirror = false;                   // the arrays below exist (heavy rows, or more than one range)
+    std::vector<uint64_t> range_nnz;
     uint32_t *d_light_rows = nullptr, *d_heavy_rows = nullptr, *d_lgroup_start = nullptr, *d_lpos = nullptr;
     uint64_t* d_lpos_off = nullptr; bool lflat_valid = false;
     std::vector<uint32_t> h_lgroup_start;
@@ -521,7 +545,7 @@ void free_mirror(StormState* st) {
                     (void*)st->d_lpos, (void*)st->d_lpos_off})
         if (p) cudaFree(p);
     st->d_light_rows = st->d_heavy_rows = st->d_lgroup_start = st->d_lpos = nullptr; st->d_lpos_off = nullptr;
-    st->lflat_valid = false; st->h_lgroup_start.clear();
+    st->lflat_valid = false; st->h_lgroup_start.clear(); st->light_mirror = false;
     st->d_row_ptr = st->d_row_nnz = st->d_blk_id = st->d_blk_len = nullptr;
     st->d_blk_off = nullptr; st->d_lists = nullptr; st->d_words = nullptr;
     st->d_pos_off = nullptr; st->d_pos = nullptr; st->flat_valid = false;
@@ -553,8 +577,9 @@ int ensure_state(StormState* st) {
 struct HostMirror {
     std::vector<uint32_t> row_ptr, row_nnz, row_nnz_dev, blk_id, blk_len, group_start;
     std::vector<uint32_t> light_rows, heavy_rows, lgroup_start;       // split route (filled only if there are heavy rows)
-    std::vector<uint64_t> blk_off, words, pos_off, lpos_off;
+    std::vector<uint64_t> blk_off, words, pos_off, lpos_off, range_nnz;
     uint64_t light_nnz = 0;
+    uint32_t n_ranges = 1, range_blocks = 1;
     std::vector<uint16_t> lists;
     uint32_t max_blocks = 0, max_blk_id = 0, max_row_nnz = 0;
     uint64_t n_bitmap_blocks = 0, total_nnz = 0;
@@ -603,17 +628,46 @@ void build_host_mirror(const STORM_t* s, HostMirror* h) {
     // heavy rows: a bitmap block, or too many values for a row group of the stream kernel
     for (uint32_t r = 0; r < s->n_conts; ++r)
         if ((h->row_nnz_dev[r] & ROW_HAS_BITMAP) || h->row_nnz[r] > STREAM_ENTRIES) { h->row_nnz_dev[r] |= ROW_HEAVY; h->heavy_rows.push_back(r); }
-    if (!h->heavy_rows.empty()) {
-        std::vector<uint32_t> lnnz;
-        h->lpos_off.assign(1, 0);
-        for (uint32_t r = 0; r < s->n_conts; ++r)
-            if (!(h->row_nnz_dev[r] & ROW_HEAVY)) {
-                h->light_rows.push_back(r);
-                lnnz.push_back(h->row_nnz[r]);
-                h->lpos_off.push_back(h->lpos_off.back() + h->row_nnz[r]);
-            }
-        h->light_nnz = h->lpos_off.back();
-        stream_groups(lnnz.data(), lnnz.size(), &h->lgroup_start);
+    // The light rows' mirror for the stream kernel, cut into n_ranges position ranges (whole blocks) so that 32 rows fit
+    // the shared-memory table range by range whatever a row holds in total (stream_ranges).  Built when the container
+    // has heavy rows (split route) or needs more than one range; otherwise the plain flat form above serves.
+    const uint32_t span = h->max_blk_id + 1;
+    const uint64_t n_light = s->n_conts - h->heavy_rows.size();
+    uint64_t light_total = 0;
+    for (uint32_t r = 0; r < s->n_conts; ++r) if (!(h->row_nnz_dev[r] & ROW_HEAVY)) light_total += h->row_nnz[r];
+    h->light_nnz = light_total;
+    h->range_blocks = span;
+    h->n_ranges = n_light ? stream_ranges((double)light_total / (double)n_light, span, &h->range_blocks) : 1;
+    if (!h->heavy_rows.empty() || h->n_ranges > 1) {
+        const uint32_t P = h->n_ranges;
+        if (!h->heavy_rows.empty())
+            for (uint32_t r = 0; r < s->n_conts; ++r) if (!(h->row_nnz_dev[r] & ROW_HEAVY)) h->light_rows.push_back(r);
+        std::vector<uint32_t> cnt((size_t)n_light * P, 0);           // values of light row k in range q: cnt[k * P + q]
+        uint64_t k = 0;
+        for (uint32_t r = 0; r < s->n_conts; ++r) {
+            if (h->row_nnz_dev[r] & ROW_HEAVY) continue;
+            for (uint32_t b = h->row_ptr[r]; b < h->row_ptr[r + 1]; ++b) cnt[k * P + h->blk_id[b] / h->range_blocks] += h->blk_len[b];
+            ++k;
+        }
+        // range-major CSR: range q's offsets are lpos_off[q * (n_light + 1) ...], absolute into one position array
+        h->lpos_off.assign((size_t)P * (n_light + 1), 0);
+        h->range_nnz.assign(P, 0);
+        uint64_t at = 0;
+        for (uint32_t q = 0; q < P; ++q) {
+            for (uint64_t i = 0; i < n_light; ++i) { h->lpos_off[q * (n_light + 1) + i] = at; at += cnt[i * P + q]; h->range_nnz[q] += cnt[i * P + q]; }
+            h->lpos_off[q * (n_light + 1) + n_light] = at;
+        }
+        // row groups shared by every range: at most 32 rows, at most STREAM_ENTRIES values in any one range
+        std::vector<uint32_t>& gs = h->lgroup_start;
+        gs.assign(1, 0u);
+        std::vector<uint64_t> in_group(P, 0);
+        for (uint64_t i = 0; i < n_light; ++i) {
+            bool cut = i > gs.back() && i - gs.back() == STREAM_GROUP;
+            for (uint32_t q = 0; q < P && !cut; ++q) cut = i > gs.back() && in_group[q] + cnt[i * P + q] > STREAM_ENTRIES;
+            if (cut) { gs.push_back((uint32_t)i); std::fill(in_group.begin(), in_group.end(), 0); }
+            for (uint32_t q = 0; q < P; ++q) in_group[q] += cnt[i * P + q];
+        }
+        gs.push_back((uint32_t)n_light);
     }
 }
 
@@ -630,11 +684,14 @@ int upload_mirror(StormState* st, const HostMirror& h, uint32_t n_conts) {
         (rc = upload(&st->d_words, h.words, st->stream)))
         return rc;
     st->n_heavy = (uint32_t)h.heavy_rows.size();
-    st->n_light = st->n_heavy ? (uint32_t)h.light_rows.size() : n_conts;
-    st->light_nnz = st->n_heavy ? h.light_nnz : h.total_nnz;
-    if (st->n_heavy) {
+    st->n_light = n_conts - st->n_heavy;
+    st->light_nnz = h.light_nnz;
+    st->n_ranges = h.n_ranges; st->range_blocks = h.range_blocks;
+    st->light_mirror = !h.lpos_off.empty();
+    if (st->light_mirror) {
         st->h_lgroup_start = h.lgroup_start;
-        if ((rc = upload(&st->d_light_rows, h.light_rows, st->stream)) || (rc = upload(&st->d_heavy_rows, h.heavy_rows, st->stream)) ||
+        st->range_nnz = h.range_nnz;
+        if ((st->n_heavy && ((rc = upload(&st->d_light_rows, h.light_rows, st->stream)) || (rc = upload(&st->d_heavy_rows, h.heavy_rows, st->stream)))) ||
             (rc = upload(&st->d_lgroup_start, h.lgroup_start, st->stream)) || (rc = upload(&st->d_lpos_off, h.lpos_off, st->stream)))
             return rc;
     }
@@ -730,7 +787,7 @@ int ensure_light_flat(StormState* st, bool* ok) {
         st->d_lpos = nullptr; *ok = false;
         return STORM_B200_OK;
     }
-    flatten_rows_kernel<<<(st->n_light + 7) / 8, 256, 0, st->stream>>>(view_of(st), st->d_light_rows, st->n_light, st->d_lpos_off, st->d_lpos);
+    flatten_ranges_kernel<<<(st->n_light + 7) / 8, 256, 0, st->stream>>>(view_of(st), st->d_light_rows, st->n_light, st->range_blocks, st->d_lpos_off, st->d_lpos);
     STORM_CUDA_TRY(cudaGetLastError());
     count_launch();
     st->lflat_valid = true;
@@ -792,15 +849,29 @@ bool stream_groups(const uint32_t* row_nnz, uint64_t n_rows, std::vector<uint32_
     return ok;
 }
 
+// Position ranges the light mirror is cut into: a group should hold 32 rows, i.e. a row at most STREAM_ENTRIES / 32 = 256
+// values per range (25 % head-room for uneven rows); ranges are whole blocks, so at most `span` of them.
+uint32_t stream_ranges(double avg_nnz, uint32_t span, uint32_t* range_blocks) {
+    span = std::max(1u, span);
+    const double need = avg_nnz * (double)STREAM_GROUP / (double)STREAM_ENTRIES * 1.25;
+    const uint32_t p = std::min(span, need <= 1.0 ? 1u : (uint32_t)std::ceil(need));
+    const uint32_t rb = (span + p - 1) / p;                                  // blocks per range
+    if (range_blocks) *range_blocks = rb;
+    return (span + rb - 1) / rb;
+}
+
 // Seconds the stream kernel needs for `pairs` pairs of rows holding avg_nnz values: one probe per partner position
-// and GROUP of rows i (a group holds min(32, 8192 / values per row) rows); a probe is one filter lookup plus, for the
-// hits and the filter's false positives, a walk through the table, both growing with the table's load.  Fitted to
-// 10 000 x 524 288 at 5 / 104 / 300 / 524 / 1 000 values per row (0.03 / 0.22 / 1.19 / 3.46 / 12.4 ms) and
-// 3 000 x 1 048 576 at 1 000 (1.24 ms), profiles/r01_sparse_routes_v4.jsonl.
-double stream_seconds(double pairs, double avg_nnz) {
-    const double group = std::min(32.0, std::max(1.0, std::floor((double)STREAM_ENTRIES / std::max(1.0, avg_nnz))));
-    const double load = std::min(0.5, group * avg_nnz / (double)STREAM_CAP);
-    return 1.5e-5 + pairs * avg_nnz / group * (1.1e-12 + 1.8e-12 * load);
+// and GROUP of rows i (a group holds min(32, 8192 / values per row and range) rows); a probe is one filter lookup plus,
+// for the hits and the filter's false positives, a walk through the table, both growing with the table's load.  Fitted to
+// 10 000 x 524 288 at 5 / 104 / 300 / 524 / 1 000 / 1 500 / 2 097 values per row (0.03 / 0.22 / 0.65 / 1.35 / 3.58 / 4.12 /
+// 7.63 ms with 1 / 1 / 2 / 3 / 4 / 8 / 8 position ranges) and 3 000 x 1 048 576 at 1 000 (0.42 ms),
+// profiles/r02_sparse_routes_ranges.jsonl: 1.06 ps per probe on a nearly empty table, 2.3 ps at load 1/2; with `ranges`
+// position ranges the same probes run against tables that hold 1 / ranges of each row, one launch per range.
+double stream_seconds(double pairs, double avg_nnz, uint32_t ranges) {
+    const double per_range = std::max(1.0, avg_nnz / (double)std::max(1u, ranges));
+    const double group = std::min(32.0, std::max(1.0, std::floor((double)STREAM_ENTRIES / per_range)));
+    const double load = std::min(0.5, group * per_range / (double)STREAM_CAP);
+    return 1.5e-5 + 4e-6 * (double)(std::max(1u, ranges) - 1u) + pairs * avg_nnz / group * (1.06e-12 + 4.9e-12 * load * load);
 }
 
 // Totals of rows [i0, i1) (flat form a_*, row groups h/d_group_start) against rows [j0, j1) (flat form b_*).
@@ -880,18 +951,20 @@ void storm_route_model(uint64_t n_rows, uint64_t W, double avg_nnz, double avg_b
     const double dense_rate = fp4 ? 6.0e13 : 3.5e13;
     *dense_s = pairs * (double)W / dense_rate + 3e-5 + (dense_resident ? 0.0 : (double)n_rows * (double)W * 8.0 / 2e12);
     *sparse_s = pairs * 1e-9 * (0.08 + 0.16 * avg_blocks + 0.0003 * avg_nnz) + 1e-5;             // block merge/probe kernel
-    if (stream_applies) *sparse_s = std::min(*sparse_s, stream_seconds(pairs, avg_nnz));          // row-group stream kernel
+    if (stream_applies)                                                                           // row-group stream kernel
+        *sparse_s = std::min(*sparse_s, stream_seconds(pairs, avg_nnz, stream_ranges(avg_nnz, (uint32_t)((W + BLOCK_WORDS - 1) / BLOCK_WORDS), nullptr)));
 }
 
 // Split route: the light rows among themselves through the stream kernel, every pair with a heavy row through the
 // block merge/probe kernel (rows i = the heavy rows).  Heavy x heavy pairs meet in bitmap blocks: 8 KiB per shared
 // block from L2, ~2 ns.
-double split_seconds(uint64_t n_rows, uint64_t n_heavy, double light_nnz, double total_nnz, double max_blocks, double n_bitmap_blocks) {
+double split_seconds(uint64_t n_rows, uint64_t n_heavy, double light_nnz, double total_nnz, double max_blocks, double n_bitmap_blocks,
+                     uint32_t span) {
     const double nl = (double)(n_rows - n_heavy), nh = (double)n_heavy;
     const double hh_pairs = 0.5 * nh * (nh - 1.0), h_pairs = nh * nl + hh_pairs;
     double t = 2e-5 + h_pairs * 1e-9 * (0.08 + 0.16 * max_blocks + 0.0003 * total_nnz / (double)n_rows);
     if (n_heavy) t += hh_pairs * (n_bitmap_blocks / nh) * 2e-9;
-    if (nl >= 2.0) t += stream_seconds(0.5 * nl * (nl - 1.0), light_nnz / nl);
+    if (nl >= 2.0) t += stream_seconds(0.5 * nl * (nl - 1.0), light_nnz / nl, stream_ranges(light_nnz / nl, span, nullptr));
     return t;
 }
 
@@ -915,7 +988,7 @@ int choose_route(const StormState* st, uint64_t n_rows) {
     int route = dense_applies && dense_s < sparse_s ? 2 : 1;
     if (split_applies) {
         const double split_s = split_seconds(n_rows, st->n_heavy, (double)st->light_nnz, (double)st->total_nnz, (double)st->max_blocks,
-                                             (double)st->n_bitmap_blocks);
+                                             (double)st->n_bitmap_blocks, st->max_blk_id + 1);
         if (split_s < (route == 2 ? dense_s : sparse_s)) route = 4;
     }
     return route;
@@ -1035,14 +1108,21 @@ int storm_query_on(StormState* st, uint32_t n_conts, int route, uint32_t shard, 
                               reinterpret_cast<uint64_t*>(st->d_total), st->stream);
     }
     int rc = STORM_B200_OK;
-    if (route == 4) {
+    // The light rows through the stream kernel, range by range of the light mirror (one range and no heavy rows: the
+    // plain flat form below); then, on the split route, every pair with a heavy row through the block kernel.
+    const bool ranged = route == 4 || (st->light_mirror && st->n_heavy == 0 && g_sparse_flat && g_sparse_stream);
+    if (ranged) {
         bool ok = false;
         if ((rc = ensure_light_flat(st, &ok))) return rc;
         if (ok) {
-            st->last_route = 4;
-            if ((rc = launch_sparse_stream(st->d_lpos_off, st->d_lpos, st->h_lgroup_start, st->d_lgroup_start, st->d_lpos_off, st->d_lpos,
-                                           st->light_nnz, 0, st->n_light, 0, st->n_light, 1, shard, n_shards, st->d_total, st->stream)))
-                return rc;
+            st->last_route = route == 4 ? 4 : 1;
+            const uint64_t stride = (uint64_t)st->n_light + 1;
+            for (uint32_t q = 0; q < st->n_ranges; ++q)
+                if ((rc = launch_sparse_stream(st->d_lpos_off + q * stride, st->d_lpos, st->h_lgroup_start, st->d_lgroup_start,
+                                               st->d_lpos_off + q * stride, st->d_lpos, st->range_nnz[q], 0, st->n_light, 0, st->n_light, 1,
+                                               shard, n_shards, st->d_total, st->stream)))
+                    return rc;
+            if (route != 4) return STORM_B200_OK;
             SparseJob job{};
             job.A = job.B = view_of(st);
             job.i_list = st->d_heavy_rows;
@@ -1384,7 +1464,7 @@ int STORM_b200_storm_route_model(uint64_t n_rows, uint32_t n_words, double avg_n
 double STORM_b200_storm_split_model(uint64_t n_rows, uint64_t n_heavy, double light_nnz, double total_nnz, double max_blocks,
                                     double n_bitmap_blocks) {
     if (n_rows < 2 || n_heavy > n_rows) return -1.0;
-    return split_seconds(n_rows, n_heavy, light_nnz, total_nnz, max_blocks, n_bitmap_blocks);
+    return split_seconds(n_rows, n_heavy, light_nnz, total_nnz, max_blocks, n_bitmap_blocks, (uint32_t)std::max(1.0, max_blocks));
 }
 
 int STORM_b200_set_sparse_flat(int mode) {

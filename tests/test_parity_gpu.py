@@ -358,6 +358,34 @@ def test_storm_t_split_route(sb, orc, M):
         sb.set_storm_route(prev)
 
 
+def test_storm_t_stream_kernel_position_ranges(sb, orc):
+    """Rows of a few hundred to a few thousand values: the light mirror is cut into position ranges (whole blocks) so that
+    32 rows fit the stream kernel's table range by range.  Even rows, rows whose values sit in ONE block (a group then
+    holds few rows), empty rows and rows that only touch the last range; totals, shards, mutation."""
+    M = 16 * 65536
+    rng = np.random.default_rng(5)
+    rows = [orc.gen_row_positions(131, i, [900, 2500, 40, 1500, 0, 3000][i % 6], M) for i in range(400)]
+    for r in range(7, 400, 13):                                   # all values inside block 3 (3 800 draws: below the bitmap limit)
+        rows[r] = (3 * 65536 + np.unique(rng.integers(0, 65536, 3800))).astype(np.uint32)
+    for r in range(11, 400, 17):                                  # only the last range
+        rows[r] = (15 * 65536 + np.unique(rng.integers(0, 65536, 700))).astype(np.uint32)
+    vals = O.positions_to_dense(rows, M)
+    exact = orc.wrapper_diag(vals)
+    prev = sb.set_storm_route("sparse")
+    try:
+        with sb.Storm() as s:
+            for p in rows:
+                s.add(p)
+            assert s.pairw_intersect_cardinality() == exact
+            assert s.last_route() == "sparse"
+            assert sum(s.pairw_shard(k, 7) for k in range(7)) == exact
+            assert (s.pairw_rect(0, 400, 0, 400) == orc.rect_counts(vals, 0, 400, 0, 400)).all()   # (row-major flat form, untouched)
+            s.add(rows[7])
+            assert s.pairw_intersect_cardinality() == orc.wrapper_diag(np.concatenate([vals, vals[7:8]]))
+    finally:
+        sb.set_storm_route(prev)
+
+
 @pytest.mark.parametrize("M", [2 * 65536, 1048576, 20 * 65536, 21 * 65536 + 5])
 def test_storm_t_flat_probe_kernel_equals_block_kernel(sb, orc, M):
     """Sparse route on containers without bitmap blocks: the row-group stream kernel (totals), the flat probe kernel
