@@ -59,7 +59,7 @@ int launch_gather_rows(uint64_t* dst, const uint64_t* src, uint64_t stride, cons
 // stream_seconds is the fitted cost model the route decisions use.
 bool stream_groups(const uint32_t* row_nnz, uint64_t n_rows, std::vector<uint32_t>* group_start);
 double stream_seconds(double pairs, double avg_nnz, uint32_t ranges = 1);
-uint32_t stream_ranges(double avg_nnz, uint32_t span, uint32_t* range_blocks);
+uint32_t stream_ranges(double avg_nnz, uint32_t span, uint32_t* range_bits);
 int launch_sparse_stream(const uint64_t* a_off, const uint32_t* a_pos, const std::vector<uint32_t>& h_group_start,
                          const uint32_t* d_group_start, const uint64_t* b_off, const uint32_t* b_pos, uint64_t b_total_nnz,
                          uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1, int strict_upper,

@@ -267,23 +267,34 @@ __global__ void __launch_bounds__(256) flatten_rows_kernel(const SparseView v, c
     }
 }
 
-// Range-major flat form of the light rows: flat row k = container row rows[k] (NULL: row k); the values of its blocks
-// [q * range_blocks, (q + 1) * range_blocks) go to pos[off[q * (n + 1) + k] ...].
-__global__ void __launch_bounds__(256) flatten_ranges_kernel(const SparseView v, const uint32_t* rows, uint32_t n, uint32_t range_blocks,
-                                                             const uint64_t* off, uint32_t* pos) {
+// Range-major flat form of the light rows: flat row k = container row rows[k] (NULL: row k); its values at positions
+// [q * range_bits, (q + 1) * range_bits) go to pos[off[q * (n + 1) + k] ...], in order.  A row's values are ascending, so
+// range q's are the contiguous run that starts after the S_q values of the earlier ranges: lane q of the row's warp
+// keeps off[q][k] - S_q (at most 32 ranges) and value number idx of the row lands at that + idx.
+constexpr uint32_t STREAM_MAX_RANGES = 32;
+__global__ void __launch_bounds__(256) flatten_ranges_kernel(const SparseView v, const uint32_t* rows, uint32_t n, uint32_t n_ranges,
+                                                             uint32_t range_bits, const uint64_t* off, uint32_t* pos) {
     const uint32_t k_row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k_row >= n) return;
     const uint32_t row = rows ? rows[k_row] : k_row;
-    uint32_t cur = 0xFFFFFFFFu;
-    uint64_t o = 0;
+    uint64_t o = 0, c = 0;
+    if (lane < n_ranges) { o = off[(uint64_t)lane * (n + 1) + k_row]; c = off[(uint64_t)lane * (n + 1) + k_row + 1] - o; }
+    uint64_t incl = c;                                             // inclusive scan of the per-range counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
+    const uint64_t base_q = o - (incl - c);                        // off[q][k] - S_q
+    uint64_t idx = 0;
     for (uint32_t b = v.row_ptr[row]; b < v.row_ptr[row + 1]; ++b) {
-        const uint32_t len = v.blk_len[b], id = v.blk_id[b];      // (light rows hold no bitmap blocks)
-        const uint32_t q = id / range_blocks;
-        if (q != cur) { cur = q; o = off[(uint64_t)q * (n + 1) + k_row]; }
-        const uint32_t base = id << 16;
+        const uint32_t len = v.blk_len[b];                         // (light rows hold no bitmap blocks)
+        const uint32_t hi = v.blk_id[b] << 16;
         const uint16_t* src = v.lists + v.blk_off[b];
-        for (uint32_t k = lane; k < len; k += 32) pos[o + k] = base | src[k];
-        o += len;
+        for (uint32_t k0 = 0; k0 < len; k0 += 32) {                // (warp-uniform trip count: the shuffle below needs every lane)
+            const uint32_t k = k0 + lane;
+            const uint32_t p = hi | (k < len ? src[k] : 0u);
+            const uint64_t dst = __shfl_sync(0xffffffffu, base_q, (int)min(p / range_bits, n_ranges - 1u)) + idx + k;
+            if (k < len) pos[dst] = p;
+        }
+        idx += len;
     }
 }
 
@@ -523,7 +534,7 @@ struct StormState {
     // Split route (containers that hold heavy rows -- a bitmap block, or more values than a row group may -- among
     // light ones): the light rows' own flat form and row groups, and the list of heavy rows.
     uint32_t n_light = 0, n_heavy = 0; uint64_t light_nnz = 0;
-    uint32_t n_ranges = 1, range_blocks = 1;     // position ranges of the light mirror (whole blocks each)
+    uint32_t n_ranges = 1, range_bits = 0;       // position ranges of the light mirror (range q = positions [q, q + 1) * range_bits)
     bool light_mirror = false;                   // the arrays below exist (heavy rows, or more than one range)
     std::vector<uint64_t> range_nnz;
     uint32_t *d_light_rows = nullptr, *d_heavy_rows = nullptr, *d_lgroup_start = nullptr, *d_lpos = nullptr;
@@ -579,7 +590,7 @@ struct HostMirror {
     std::vector<uint32_t> light_rows, heavy_rows, lgroup_start;       // split route (filled only if there are heavy rows)
     std::vector<uint64_t> blk_off, words, pos_off, lpos_off, range_nnz;
     uint64_t light_nnz = 0;
-    uint32_t n_ranges = 1, range_blocks = 1;
+    uint32_t n_ranges = 1, range_bits = 0;
     std::vector<uint16_t> lists;
     uint32_t max_blocks = 0, max_blk_id = 0, max_row_nnz = 0;
     uint64_t n_bitmap_blocks = 0, total_nnz = 0;
@@ -628,16 +639,15 @@ void build_host_mirror(const STORM_t* s, HostMirror* h) {
     // heavy rows: a bitmap block, or too many values for a row group of the stream kernel
     for (uint32_t r = 0; r < s->n_conts; ++r)
         if ((h->row_nnz_dev[r] & ROW_HAS_BITMAP) || h->row_nnz[r] > STREAM_ENTRIES) { h->row_nnz_dev[r] |= ROW_HEAVY; h->heavy_rows.push_back(r); }
-    // The light rows' mirror for the stream kernel, cut into n_ranges position ranges (whole blocks) so that 32 rows fit
-    // the shared-memory table range by range whatever a row holds in total (stream_ranges).  Built when the container
-    // has heavy rows (split route) or needs more than one range; otherwise the plain flat form above serves.
+    // The light rows' mirror for the stream kernel, cut into n_ranges position ranges so that 32 rows fit the
+    // shared-memory table range by range, at a low load, whatever a row holds in total (stream_ranges).  Built when the
+    // container has heavy rows (split route) or needs more than one range; otherwise the plain flat form above serves.
     const uint32_t span = h->max_blk_id + 1;
     const uint64_t n_light = s->n_conts - h->heavy_rows.size();
     uint64_t light_total = 0;
     for (uint32_t r = 0; r < s->n_conts; ++r) if (!(h->row_nnz_dev[r] & ROW_HEAVY)) light_total += h->row_nnz[r];
     h->light_nnz = light_total;
-    h->range_blocks = span;
-    h->n_ranges = n_light ? stream_ranges((double)light_total / (double)n_light, span, &h->range_blocks) : 1;
+    h->n_ranges = n_light ? stream_ranges((double)light_total / (double)n_light, span, &h->range_bits) : 1;
     if (!h->heavy_rows.empty() || h->n_ranges > 1) {
         const uint32_t P = h->n_ranges;
         if (!h->heavy_rows.empty())
@@ -646,7 +656,14 @@ void build_host_mirror(const STORM_t* s, HostMirror* h) {
         uint64_t k = 0;
         for (uint32_t r = 0; r < s->n_conts; ++r) {
             if (h->row_nnz_dev[r] & ROW_HEAVY) continue;
-            for (uint32_t b = h->row_ptr[r]; b < h->row_ptr[r + 1]; ++b) cnt[k * P + h->blk_id[b] / h->range_blocks] += h->blk_len[b];
+            for (uint32_t b = h->row_ptr[r]; b < h->row_ptr[r + 1]; ++b) {
+                const uint64_t lo = (uint64_t)h->blk_id[b] << 16;
+                const uint16_t* list = h->lists.data() + h->blk_off[b];
+                const uint32_t len = h->blk_len[b];
+                const uint64_t q0 = std::min<uint64_t>(lo / h->range_bits, P - 1), q1 = std::min<uint64_t>((lo + 65535) / h->range_bits, P - 1);
+                if (q0 == q1) { cnt[k * P + q0] += len; continue; }
+                for (uint32_t e = 0; e < len; ++e) ++cnt[k * P + std::min<uint64_t>((lo + list[e]) / h->range_bits, P - 1)];
+            }
             ++k;
         }
         // range-major CSR: range q's offsets are lpos_off[q * (n_light + 1) ...], absolute into one position array
@@ -686,7 +703,7 @@ int upload_mirror(StormState* st, const HostMirror& h, uint32_t n_conts) {
     st->n_heavy = (uint32_t)h.heavy_rows.size();
     st->n_light = n_conts - st->n_heavy;
     st->light_nnz = h.light_nnz;
-    st->n_ranges = h.n_ranges; st->range_blocks = h.range_blocks;
+    st->n_ranges = h.n_ranges; st->range_bits = h.range_bits;
     st->light_mirror = !h.lpos_off.empty();
     if (st->light_mirror) {
         st->h_lgroup_start = h.lgroup_start;
@@ -787,7 +804,7 @@ int ensure_light_flat(StormState* st, bool* ok) {
         st->d_lpos = nullptr; *ok = false;
         return STORM_B200_OK;
     }
-    flatten_ranges_kernel<<<(st->n_light + 7) / 8, 256, 0, st->stream>>>(view_of(st), st->d_light_rows, st->n_light, st->range_blocks, st->d_lpos_off, st->d_lpos);
+    flatten_ranges_kernel<<<(st->n_light + 7) / 8, 256, 0, st->stream>>>(view_of(st), st->d_light_rows, st->n_light, st->n_ranges, st->range_bits, st->d_lpos_off, st->d_lpos);
     STORM_CUDA_TRY(cudaGetLastError());
     count_launch();
     st->lflat_valid = true;
@@ -849,23 +866,25 @@ bool stream_groups(const uint32_t* row_nnz, uint64_t n_rows, std::vector<uint32_
     return ok;
 }
 
-// Position ranges the light mirror is cut into: a group should hold 32 rows, i.e. a row at most STREAM_ENTRIES / 32 = 256
-// values per range (25 % head-room for uneven rows); ranges are whole blocks, so at most `span` of them.
-uint32_t stream_ranges(double avg_nnz, uint32_t span, uint32_t* range_blocks) {
-    span = std::max(1u, span);
-    const double need = avg_nnz * (double)STREAM_GROUP / (double)STREAM_ENTRIES * 1.25;
-    const uint32_t p = std::min(span, need <= 1.0 ? 1u : (uint32_t)std::ceil(need));
-    const uint32_t rb = (span + p - 1) / p;                                  // blocks per range
-    if (range_blocks) *range_blocks = rb;
-    return (span + rb - 1) / rb;
+// Position ranges the light mirror is cut into: a group should hold 32 rows at a table load near 1/4, i.e. a row about
+// 128 values per range; at most 32 ranges (one lane each in flatten_ranges_kernel).  Ranges are equal spans of
+// `range_bits` positions and need not respect block boundaries.
+uint32_t stream_ranges(double avg_nnz, uint32_t span, uint32_t* range_bits) {
+    const uint64_t bits = (uint64_t)std::max(1u, span) << 16;
+    const double need = avg_nnz / 128.0;
+    const uint32_t p = need <= 1.0 ? 1u : (uint32_t)std::min(32.0, std::ceil(need));
+    const uint64_t rb = (bits + p - 1) / p;
+    if (range_bits) *range_bits = (uint32_t)std::min<uint64_t>(rb, 0xFFFFFFFFull);
+    return (uint32_t)((bits + rb - 1) / rb);
 }
 
 // Seconds the stream kernel needs for `pairs` pairs of rows holding avg_nnz values: one probe per partner position
 // and GROUP of rows i (a group holds min(32, 8192 / values per row and range) rows); a probe is one filter lookup plus,
 // for the hits and the filter's false positives, a walk through the table, both growing with the table's load.  Fitted to
-// 10 000 x 524 288 at 5 / 104 / 300 / 524 / 1 000 / 1 500 / 2 097 values per row (0.03 / 0.22 / 0.65 / 1.35 / 3.58 / 4.12 /
-// 7.63 ms with 1 / 1 / 2 / 3 / 4 / 8 / 8 position ranges) and 3 000 x 1 048 576 at 1 000 (0.42 ms),
-// profiles/r02_sparse_routes_ranges.jsonl: 1.06 ps per probe on a nearly empty table, 2.3 ps at load 1/2; with `ranges`
+// 10 000 x 524 288 at 5 / 104 / 300 / 524 / 1 000 / 1 500 / 2 097 values per row on whole-block ranges (0.03 / 0.22 / 0.65 /
+// 1.35 / 3.58 / 4.12 / 7.63 ms with 1 / 1 / 2 / 3 / 4 / 8 / 8 position ranges, profiles/r02_sparse_routes_ranges.jsonl): 1.06 ps
+// per probe on a nearly empty table, 2.3 ps at load 1/2; with ranges of ~128 values per row it predicts 0.61 / 1.07 / 2.16 /
+// 3.23 / 4.48 / 6.44 ms for 300 ... 3 000 values per row against 0.62 / 1.20 / 2.27 / 3.18 / 4.56 / 6.60 measured (_v2).  With `ranges`
 // position ranges the same probes run against tables that hold 1 / ranges of each row, one launch per range.
 double stream_seconds(double pairs, double avg_nnz, uint32_t ranges) {
     const double per_range = std::max(1.0, avg_nnz / (double)std::max(1u, ranges));
