@@ -2,7 +2,7 @@
 // upload + tile-range pipeline that turns a host matrix into per-device partial totals.
 //
 // The north star shards the N x N upper triangle over the GPUs of one box BEHIND storm.h: one process, one
-// host thread, G devices.  Every device holds all rows; device g owns shard g of the
+// calling thread, G devices (the library issues the per-device driver calls from its own worker threads).  Every device holds all rows; device g owns shard g of the
 // tile raster; the host adds G uint64 totals.  A host matrix reaches the devices in row bands: each device
 // uploads 1/G of a band over its own PCIe link and pulls the other slices from its peers over NVLink
 // (cudaMemcpyPeerAsync on the copy engines), and because the raster is monotone in the largest row a tile

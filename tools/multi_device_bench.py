@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Multi-GPU behind the C ABI: one process, one host thread, G devices (run on a multi-GPU box: `gpurun --gpus 8`).
+"""Multi-GPU behind the C ABI: one process, one calling thread, G devices (run on a multi-GPU box: `gpurun --gpus 8`).
 
     python tools/multi_device_bench.py c3 [grid] [--devices 1,2,4,8]        (JSON lines on stdout)
 
