@@ -353,6 +353,7 @@ uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uin
     { DeviceGuard guard(prim->ctx.device); cudaEventRecord(prim->ev[1], prim->ctx.stream); }
 
     int rc = STORM_B200_OK;
+    uint64_t fused = RESIDENT_TOTAL_NONE;                                 // set by banded_triangle if it has read the totals back itself
     bool hybrid = false, stream = false;
     if (mode == QUERY_LIST) {
         build_list_meta(c, st);
@@ -382,7 +383,7 @@ uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uin
         // every pair through the tile kernel: rows not yet on the devices go up band by band (1/G of a band per
         // PCIe link, the rest from the peers) while the tiles of the bands already complete are being computed
         rc = banded_triangle(ctxs.data(), arenas.data(), G, st->stride, mirror_of(c, st), st->uploaded_rows, c->n_data,
-                             c->n_bitmaps_vector, shard, n_shards, kernel);
+                             c->n_bitmaps_vector, shard, n_shards, kernel, &fused);
         if (!rc) st->uploaded_rows = c->n_data;
     } else {
         if (!stream && (upload_pending(c, st, c->n_data))) return (uint64_t)-1;          // the probe kernel reads the bitmaps
@@ -422,8 +423,9 @@ uint64_t contig_query(STORM_contiguous_t* c, QueryMode mode, uint32_t shard, uin
     }
     if (rc) return (uint64_t)-1;
     { DeviceGuard guard(prim->ctx.device); cudaEventRecord(prim->ev[2], prim->ctx.stream); }
-    const uint64_t total = collect_totals(ctxs.data(), G, "query");
+    const uint64_t total = fused != RESIDENT_TOTAL_NONE ? fused : collect_totals(ctxs.data(), G, "query");
     if (total == (uint64_t)-1) return total;
+    if (fused != RESIDENT_TOTAL_NONE) { DeviceGuard guard(prim->ctx.device); cudaEventSynchronize(prim->ev[2]); }
     float up = 0, kn = 0;
     cudaEventElapsedTime(&up, prim->ev[0], prim->ev[1]);
     cudaEventElapsedTime(&kn, prim->ev[1], prim->ev[2]);
@@ -1143,7 +1145,9 @@ uint64_t STORM_b200_pairw_devices(const uint64_t* const* d_rows, const int* devi
         if (check_rows(d_rows[g], row_stride_words, n_words)) return (uint64_t)-1;
         if (ctxs[g]->zero_total()) return (uint64_t)-1;
     }
-    if (banded_triangle(ctxs.data(), arenas.data(), n_devices, row_stride_words, HostRows{}, n_rows, n_rows, n_words, 0, 1, kernel)) return (uint64_t)-1;
+    uint64_t fused = RESIDENT_TOTAL_NONE;
+    if (banded_triangle(ctxs.data(), arenas.data(), n_devices, row_stride_words, HostRows{}, n_rows, n_rows, n_words, 0, 1, kernel, &fused)) return (uint64_t)-1;
+    if (fused != RESIDENT_TOTAL_NONE) return fused;
     return collect_totals(ctxs.data(), n_devices, "STORM_b200_pairw_devices");
 }
 

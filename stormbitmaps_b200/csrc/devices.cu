@@ -316,8 +316,11 @@ int upload_rows(DevCtx* dc, uint64_t* arena, uint64_t stride, const HostRows& sr
     return STORM_B200_OK;
 }
 
+static int collect_one(DevCtx* d, const char* what);
+
 int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_t stride, const HostRows& src,
-                    uint64_t resident, uint64_t n_rows, uint32_t n_words, uint32_t shard, uint32_t n_shards, int kernel) {
+                    uint64_t resident, uint64_t n_rows, uint32_t n_words, uint32_t shard, uint32_t n_shards, int kernel,
+                    uint64_t* resident_total) {
     if (G < 1 || n_shards == 0 || shard >= n_shards) { set_error("shard %u of %u on %d devices", shard, n_shards, G); return STORM_B200_EINVAL; }
     if (n_rows < 2) return STORM_B200_OK;
     // one kernel for every device (the tile shape defines the raster the shards are ranges of)
@@ -347,6 +350,15 @@ int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_
     // tiles of the raster groups whose rows are all resident already: one launch per device, no waiting
     if (resident > n_rows) resident = n_rows;
     const uint64_t g_res = resident >= n_rows ? n_groups : resident / group_rows;
+    if (g_res == n_groups && resident_total && G > 1) {
+        // everything is resident: launch and read-back in ONE dispatch to the per-device threads
+        int rc = for_each_device(G, [&](int g) -> int { int r = launch(g, 0, prefix[g_res]); return r ? r : collect_one(devs[g], "query"); });
+        if (rc) return rc;
+        uint64_t total = 0;
+        for (int g = 0; g < G; ++g) total += *devs[g]->h_total;
+        *resident_total = total;
+        return STORM_B200_OK;
+    }
     { int rc = for_each_device(G, [&](int g) { return launch(g, 0, prefix[g_res]); }); if (rc) return rc; }
     if (g_res == n_groups) return STORM_B200_OK;
 
@@ -387,23 +399,25 @@ int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_
     return STORM_B200_OK;
 }
 
+// One device's part of collect_totals: read the total back, re-zero it for the next query while the host still waits,
+// and wait for both streams (the copy stream too: a peer may still be pulling slices out of this device's arena, and
+// the caller may reuse it).
+static int collect_one(DevCtx* d, const char* what) {
+    DeviceGuard guard(d->device);
+    const cudaError_t e0 = cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream);
+    d->total_zero = cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), d->stream) == cudaSuccess;
+    const cudaError_t e1 = cudaStreamSynchronize(d->stream), e2 = cudaStreamSynchronize(d->copy_stream);
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
+        set_error("%s failed on device %d: %s", what, d->device, cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2));
+        cudaGetLastError();
+        return STORM_B200_ECUDA;
+    }
+    return STORM_B200_OK;
+}
+
 uint64_t collect_totals(DevCtx* const* devs, int G, const char* what) {
-    // per device (each from its own host thread, for_each_device): read the total back, re-zero it for the next query
-    // while the host still waits, and wait for both streams (the copy stream too: a peer may still be pulling slices
-    // out of this device's arena, and the caller may reuse it)
-    const int rc = for_each_device(G, [&](int g) -> int {
-        DevCtx* d = devs[g];
-        DeviceGuard guard(d->device);
-        const cudaError_t e0 = cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream);
-        d->total_zero = cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), d->stream) == cudaSuccess;
-        const cudaError_t e1 = cudaStreamSynchronize(d->stream), e2 = cudaStreamSynchronize(d->copy_stream);
-        if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
-            set_error("%s failed on device %d: %s", what, d->device, cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2));
-            cudaGetLastError();
-            return STORM_B200_ECUDA;
-        }
-        return STORM_B200_OK;
-    });
+    // (each device from its own host thread, for_each_device)
+    const int rc = for_each_device(G, [&](int g) -> int { return collect_one(devs[g], what); });
     if (rc) return (uint64_t)-1;
     uint64_t total = 0;
     for (int g = 0; g < G; ++g) total += *devs[g]->h_total;

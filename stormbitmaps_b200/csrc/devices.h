@@ -78,9 +78,14 @@ int upload_rows(DevCtx* dc, uint64_t* arena, uint64_t stride, const HostRows& sr
 // Upper-triangle total of a host matrix over G devices.  Rows [0, resident) are already on (or on their way to, on
 // copy_stream) every device; the rest is uploaded band by band as described above, and device g computes shard
 // (shard * G + g) of (n_shards * G) of the tile raster into its own d_total (zeroed by the caller on `stream`).
-// Everything is asynchronous: the caller reads the G totals back and adds them.
+// Everything is asynchronous: the caller reads the G totals back and adds them (collect_totals).  One exception, for
+// short queries on several devices: if `resident_total` is given (preset to RESIDENT_TOTAL_NONE) and every row is
+// resident already, launch AND read-back go out in one dispatch to the per-device threads and the sum is stored there
+// -- the caller then skips collect_totals.
+constexpr uint64_t RESIDENT_TOTAL_NONE = ~0ull - 7;
 int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_t stride, const HostRows& src,
-                    uint64_t resident, uint64_t n_rows, uint32_t n_words, uint32_t shard, uint32_t n_shards, int kernel);
+                    uint64_t resident, uint64_t n_rows, uint32_t n_words, uint32_t shard, uint32_t n_shards, int kernel,
+                    uint64_t* resident_total = nullptr);
 
 // d_total of every device -> host, summed.  Returns UINT64_MAX (and sets the error) if any device failed.
 uint64_t collect_totals(DevCtx* const* devs, int G, const char* what);
