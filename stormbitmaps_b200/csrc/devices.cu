@@ -350,8 +350,9 @@ int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_
     // tiles of the raster groups whose rows are all resident already: one launch per device, no waiting
     if (resident > n_rows) resident = n_rows;
     const uint64_t g_res = resident >= n_rows ? n_groups : resident / group_rows;
-    if (g_res == n_groups && resident_total && G > 1) {
-        // everything is resident: launch and read-back in ONE dispatch to the per-device threads
+    if (g_res == n_groups && resident_total && G > 1 && g_device_threads.load(std::memory_order_relaxed)) {
+        // everything is resident: launch and read-back in ONE dispatch to the per-device threads (only with the threads:
+        // issued from one thread the read-back of device g would wait for its kernel before device g + 1 is launched)
         int rc = for_each_device(G, [&](int g) -> int { int r = launch(g, 0, prefix[g_res]); return r ? r : collect_one(devs[g], "query"); });
         if (rc) return rc;
         uint64_t total = 0;
