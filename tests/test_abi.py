@@ -118,6 +118,8 @@ def test_host_side_conventions_without_gpu(lib):
     assert c.add([5, 5, 9, 10]) == 4                       # returns n_values, duplicates collapse
     with pytest.raises(sb.StormError):
         c.add([65536])                                     # out of range is rejected, not written
+    with pytest.raises(sb.StormError, match="vector_length"):
+        c.add([7, 300, 64000, 70000, 12])                  # ... also after in-range values: the half-written row is undone
     # public fields are populated like the reference's
     class Contig(C.Structure):
         _fields_ = [("data", C.POINTER(C.c_uint64)), ("scalar", u32p), ("n_scalar", u32p), ("bitmaps", C.c_void_p),
@@ -129,6 +131,10 @@ def test_host_side_conventions_without_gpu(lib):
     assert s.data[0] == (1 << 1) | (1 << 5) | (1 << 9) and s.data[1024] == (1 << 5) | (1 << 9) | (1 << 10)
     assert [s.n_scalar[0], s.n_scalar[1]] == [3, 3] and s.tot_scalar == 6
     assert [s.scalar[i] for i in range(6)] == [1, 5, 9, 5, 9, 10]
+    assert all(s.data[2 * 1024 + w] == 0 for w in range(1024))               # nothing left behind by the rejected rows
+    assert c.add([64000, 3, 3]) == 3                       # unsorted input is accepted like the reference's (storm.c:1103-1115)
+    assert s.n_data == 3 and s.data[2 * 1024] == 1 << 3 and s.data[2 * 1024 + 1000] == 1 << (64000 - 64000 // 64 * 64)
+    assert s.n_scalar[2] == 2
     fn = C.CFUNCTYPE(C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t)(s.intsec_func)
     a = (C.c_uint64 * 2)(0b1011, 1 << 63)
     b = (C.c_uint64 * 2)(0b0110, 1 << 63)
