@@ -707,23 +707,42 @@ int STORM_contig_add(STORM_contiguous_t* c, const uint32_t* values, const uint32
     if (grow_host_rows(c, c->n_data + 1)) return -3;
     if (c->scalar == nullptr && grow_host_scalar(c, st, 1)) return -3;    // reference allocates it on first add (:1037-1041)
 
-    // :1103-1115, one pass: the bound check the reference lacks (it writes out of bounds) is a never-taken branch in
-    // front of the reference's own read-modify-write -- measured against a separate validation pass plus a
-    // register-accumulated word (branchy or branchless): 1.8 against 3.7-4.1 ns per position on the build host.
-    // A position out of range undoes the row (rows are append-only: it was all zero) and adds nothing.
+    // :1103-1115, one pass.  The bound check the reference lacks (it writes out of bounds) is a never-taken branch; a
+    // position out of range undoes the row (rows are append-only: it was all zero) and adds nothing.  The reference's
+    // read-modify-write of memory per bit is a dependency chain through store forwarding (~5 cycles per bit of the same
+    // word: a third of the bits set means ~20 links per word), so while the positions ascend -- what every caller passes
+    // -- the bits of the current word are kept in a register, masked away without a branch when the word changes, and
+    // simply stored every time: the last store of a word holds all its bits.  The first descending position hands the
+    // rest of the row to the read-modify-write loop.
     uint64_t* row = c->data + c->n_data * c->n_bitmaps_vector;
     const uint64_t limit = c->vector_length;
-    uint32_t dups = 0, prev = ~values[0];
-    for (uint32_t i = 0; i < n_values; ++i) {
-        const uint32_t v = values[i];
-        if (v >= limit) {
-            memset(row, 0, (size_t)c->n_bitmaps_vector * sizeof(uint64_t));
-            set_error("position %u >= vector_length %llu", v, (unsigned long long)c->vector_length);
-            return -3;
+    uint32_t dups = 0, last = 0, i = 0;
+    bool reject = false;
+    {
+        uint64_t word = ~0ull, bits = 0;
+        for (; i < n_values; ++i) {
+            const uint32_t v = values[i];
+            if (v >= limit) { reject = true; break; }
+            if (v < last) break;
+            dups += (uint32_t)(i != 0) & (uint32_t)(v == last);           // adjacent duplicates are skipped (:1106-1108)
+            last = v;
+            const uint64_t w = v >> 6;
+            bits = (bits & (0 - (uint64_t)(w == word))) | (1ull << (v & 63));
+            word = w;
+            row[w] = bits;
         }
-        dups += (v == prev);                                              // adjacent duplicates are skipped (:1106-1108)
-        prev = v;
+    }
+    for (; i < n_values && !reject; ++i) {
+        const uint32_t v = values[i];
+        if (v >= limit) { reject = true; break; }
+        dups += (uint32_t)(v == last);
+        last = v;
         row[v >> 6] |= 1ull << (v & 63);
+    }
+    if (reject) {
+        memset(row, 0, (size_t)c->n_bitmaps_vector * sizeof(uint64_t));
+        set_error("position %u >= vector_length %llu", values[i], (unsigned long long)c->vector_length);
+        return -3;
     }
     const uint32_t used = n_values - dups;
     if (st->pos_off.size() <= c->n_data) st->pos_off.resize(std::max<size_t>(c->n_data + 1, st->pos_off.size() * 2));
