@@ -268,33 +268,35 @@ __global__ void __launch_bounds__(256) flatten_rows_kernel(const SparseView v, c
 }
 
 // Range-major flat form of the light rows: flat row k = container row rows[k] (NULL: row k); its values at positions
-// [q * range_bits, (q + 1) * range_bits) go to pos[off[q * (n + 1) + k] ...], in order.  A row's values are ascending, so
-// range q's are the contiguous run that starts after the S_q values of the earlier ranges: lane q of the row's warp
-// keeps off[q][k] - S_q (at most 32 ranges) and value number idx of the row lands at that + idx.
+// [q * range_bits, (q + 1) * range_bits) go to pos[off[q * (n + 1) + k] ...].  Lane q of the row's warp owns range q (at
+// most 32 ranges): it holds where the range's part of this row starts and how many values it has received.  The 32
+// values a warp reads at a time are dealt out range by range (usually one or two distinct ranges: the lists ascend),
+// but nothing here relies on their order -- a list block built from unsorted input lands in the right ranges too.
 constexpr uint32_t STREAM_MAX_RANGES = 32;
 __global__ void __launch_bounds__(256) flatten_ranges_kernel(const SparseView v, const uint32_t* rows, uint32_t n, uint32_t n_ranges,
                                                              uint32_t range_bits, const uint64_t* off, uint32_t* pos) {
     const uint32_t k_row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k_row >= n) return;
     const uint32_t row = rows ? rows[k_row] : k_row;
-    uint64_t o = 0, c = 0;
-    if (lane < n_ranges) { o = off[(uint64_t)lane * (n + 1) + k_row]; c = off[(uint64_t)lane * (n + 1) + k_row + 1] - o; }
-    uint64_t incl = c;                                             // inclusive scan of the per-range counts
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
-    const uint64_t base_q = o - (incl - c);                        // off[q][k] - S_q
-    uint64_t idx = 0;
+    uint64_t cursor = lane < n_ranges ? off[(uint64_t)lane * (n + 1) + k_row] : 0;     // next free slot of range `lane`
     for (uint32_t b = v.row_ptr[row]; b < v.row_ptr[row + 1]; ++b) {
         const uint32_t len = v.blk_len[b];                         // (light rows hold no bitmap blocks)
         const uint32_t hi = v.blk_id[b] << 16;
         const uint16_t* src = v.lists + v.blk_off[b];
-        for (uint32_t k0 = 0; k0 < len; k0 += 32) {                // (warp-uniform trip count: the shuffle below needs every lane)
-            const uint32_t k = k0 + lane;
-            const uint32_t p = hi | (k < len ? src[k] : 0u);
-            const uint64_t dst = __shfl_sync(0xffffffffu, base_q, (int)min(p / range_bits, n_ranges - 1u)) + idx + k;
-            if (k < len) pos[dst] = p;
+        for (uint32_t k0 = 0; k0 < len; k0 += 32) {                // (warp-uniform trip count)
+            const bool valid = k0 + lane < len;
+            const uint32_t p = hi | (valid ? src[k0 + lane] : 0u);
+            const uint32_t q = min(p / range_bits, n_ranges - 1u);
+            uint32_t todo = __ballot_sync(0xffffffffu, valid);
+            while (todo) {                                         // one round per distinct range among the 32 values
+                const uint32_t ql = __shfl_sync(0xffffffffu, q, __ffs(todo) - 1);
+                const uint32_t m = __ballot_sync(0xffffffffu, valid && q == ql);
+                const uint64_t at = __shfl_sync(0xffffffffu, cursor, (int)ql);
+                if (valid && q == ql) pos[at + __popc(m & ((1u << lane) - 1u))] = p;
+                if (lane == ql) cursor += __popc(m);
+                todo &= ~m;
+            }
         }
-        idx += len;
     }
 }
 
