@@ -642,15 +642,21 @@ void build_host_mirror(const STORM_t* s, HostMirror* h) {
     for (uint32_t r = 0; r < s->n_conts; ++r)
         if ((h->row_nnz_dev[r] & ROW_HAS_BITMAP) || h->row_nnz[r] > STREAM_ENTRIES) { h->row_nnz_dev[r] |= ROW_HEAVY; h->heavy_rows.push_back(r); }
     // The light rows' mirror for the stream kernel, cut into n_ranges position ranges so that 32 rows fit the
-    // shared-memory table range by range, at a low load, whatever a row holds in total (stream_ranges).  Built when the
-    // container has heavy rows (split route) or needs more than one range; otherwise the plain flat form above serves.
+    // shared-memory table range by range, at a low load, whatever a row holds in total (stream_ranges).  Here only its
+    // shape is fixed (the route model needs it); the arrays are built by build_light_arrays when a route reads them.
     const uint32_t span = h->max_blk_id + 1;
     const uint64_t n_light = s->n_conts - h->heavy_rows.size();
     uint64_t light_total = 0;
     for (uint32_t r = 0; r < s->n_conts; ++r) if (!(h->row_nnz_dev[r] & ROW_HEAVY)) light_total += h->row_nnz[r];
     h->light_nnz = light_total;
     h->n_ranges = n_light ? stream_ranges((double)light_total / (double)n_light, span, &h->range_bits) : 1;
-    if (!h->heavy_rows.empty() || h->n_ranges > 1) {
+}
+
+// The light mirror's arrays (range-major offsets, row groups, the list of light rows): built only when the route a
+// query takes reads them -- a container the cost model densifies never pays for them.
+void build_light_arrays(const STORM_t* s, HostMirror* h) {
+    const uint64_t n_light = s->n_conts - h->heavy_rows.size();
+    {
         const uint32_t P = h->n_ranges;
         if (!h->heavy_rows.empty())
             for (uint32_t r = 0; r < s->n_conts; ++r) if (!(h->row_nnz_dev[r] & ROW_HEAVY)) h->light_rows.push_back(r);
@@ -690,6 +696,18 @@ void build_host_mirror(const STORM_t* s, HostMirror* h) {
     }
 }
 
+// One replica's copy of the light mirror's arrays (its positions are flattened on the device on first use).
+int upload_light(StormState* st, const HostMirror& h) {
+    int rc = STORM_B200_OK;
+    st->h_lgroup_start = h.lgroup_start;
+    st->range_nnz = h.range_nnz;
+    if ((!h.light_rows.empty() && (rc = upload(&st->d_light_rows, h.light_rows, st->stream))) ||
+        (rc = upload(&st->d_lgroup_start, h.lgroup_start, st->stream)) || (rc = upload(&st->d_lpos_off, h.lpos_off, st->stream)))
+        return rc;
+    st->light_mirror = true;
+    return STORM_B200_OK;
+}
+
 // One replica's copy of the mirror (on the current device = the replica's).
 int upload_mirror(StormState* st, const HostMirror& h, uint32_t n_conts) {
     int rc = ensure_state(st);
@@ -706,14 +724,8 @@ int upload_mirror(StormState* st, const HostMirror& h, uint32_t n_conts) {
     st->n_light = n_conts - st->n_heavy;
     st->light_nnz = h.light_nnz;
     st->n_ranges = h.n_ranges; st->range_bits = h.range_bits;
-    st->light_mirror = !h.lpos_off.empty();
-    if (st->light_mirror) {
-        st->h_lgroup_start = h.lgroup_start;
-        st->range_nnz = h.range_nnz;
-        if ((st->n_heavy && ((rc = upload(&st->d_light_rows, h.light_rows, st->stream)) || (rc = upload(&st->d_heavy_rows, h.heavy_rows, st->stream)))) ||
-            (rc = upload(&st->d_lgroup_start, h.lgroup_start, st->stream)) || (rc = upload(&st->d_lpos_off, h.lpos_off, st->stream)))
-            return rc;
-    }
+    if (st->n_heavy && (rc = upload(&st->d_heavy_rows, h.heavy_rows, st->stream))) return rc;
+    if (!h.lpos_off.empty() && (rc = upload_light(st, h))) return rc;
     STORM_CUDA_TRY(cudaStreamSynchronize(st->stream));              // (the host vectors may die after this)
     st->n_rows = n_conts;
     st->max_blocks = h.max_blocks;
@@ -749,6 +761,9 @@ int resolve_replicas(StormState* st) {
 
 // Flatten the host containers and bring every replica up to date (whole-container rebuild on change).
 // `all` = false: this state only (rectangles, XY^T).
+int choose_route(const StormState* st, uint64_t n_rows);
+bool route_reads_light(int route, const StormState* st);
+
 int sync_mirror(const STORM_t* s, StormState* st, bool all = false) {
     if (all) { int rc = resolve_replicas(st); if (rc) return rc; }
     std::vector<StormState*> targets{st};
@@ -758,11 +773,38 @@ int sync_mirror(const STORM_t* s, StormState* st, bool all = false) {
     if (!need) return STORM_B200_OK;
     HostMirror h;
     build_host_mirror(s, &h);
+    if (all && s->n_conts >= 2) {                                        // whole-container queries: will the route read the light mirror?
+        StormState probe;                                                // (the statistics choose_route looks at, nothing else)
+        probe.n_heavy = (uint32_t)h.heavy_rows.size(); probe.n_light = s->n_conts - probe.n_heavy; probe.light_nnz = h.light_nnz;
+        probe.n_ranges = h.n_ranges; probe.max_blk_id = h.max_blk_id; probe.max_blocks = h.max_blocks; probe.max_row_nnz = h.max_row_nnz;
+        probe.total_nnz = h.total_nnz; probe.total_blocks = h.blk_id.size(); probe.n_bitmap_blocks = h.n_bitmap_blocks;
+        if (route_reads_light(choose_route(&probe, s->n_conts), &probe)) build_light_arrays(s, &h);
+    }
     for (StormState* t : targets) {
         if (!(t->dirty || !t->d_total || t->n_rows != s->n_conts)) continue;
         DeviceGuard guard(t->device);
         int rc = upload_mirror(t, h, s->n_conts);
         if (rc) return rc;
+    }
+    return STORM_B200_OK;
+}
+
+// The light mirror's arrays after the fact (a route knob changed since the mirror was built): every replica that lacks them.
+int sync_light(const STORM_t* s, StormState* st) {
+    std::vector<StormState*> targets{st};
+    targets.insert(targets.end(), st->replicas.begin(), st->replicas.end());
+    bool need = false;
+    for (StormState* t : targets) need = need || !t->light_mirror;
+    if (!need) return STORM_B200_OK;
+    HostMirror h;
+    build_host_mirror(s, &h);
+    build_light_arrays(s, &h);
+    for (StormState* t : targets) {
+        if (t->light_mirror) continue;
+        DeviceGuard guard(t->device);
+        int rc = upload_light(t, h);
+        if (rc) return rc;
+        STORM_CUDA_TRY(cudaStreamSynchronize(t->stream));               // (the host vectors die at scope exit)
     }
     return STORM_B200_OK;
 }
@@ -1015,6 +1057,14 @@ int choose_route(const StormState* st, uint64_t n_rows) {
     return route;
 }
 
+// Whole-container totals on the sparse side read the light mirror when the container has heavy rows (split route) or its
+// rows need more than one position range; with one range and no heavy rows the plain flat form serves.
+bool route_reads_light(int route, const StormState* st) {
+    if (route == 4) return true;
+    return route == 1 && st->n_heavy == 0 && st->n_ranges > 1 && g_sparse_flat && g_sparse_stream &&
+           st->n_bitmap_blocks == 0 && st->max_row_nnz <= STREAM_ENTRIES;
+}
+
 // Does the dense form of the rows fit on this device (keeping 20 % of the free memory)?
 bool dense_fits(const StormState* st, uint64_t n_rows) {
     const uint64_t W = ((uint64_t)st->max_blk_id + 1) * BLOCK_WORDS;
@@ -1131,7 +1181,7 @@ int storm_query_on(StormState* st, uint32_t n_conts, int route, uint32_t shard, 
     int rc = STORM_B200_OK;
     // The light rows through the stream kernel, range by range of the light mirror (one range and no heavy rows: the
     // plain flat form below); then, on the split route, every pair with a heavy row through the block kernel.
-    const bool ranged = route == 4 || (st->light_mirror && st->n_heavy == 0 && g_sparse_flat && g_sparse_stream);
+    const bool ranged = st->light_mirror && route_reads_light(route, st);
     if (ranged) {
         bool ok = false;
         if ((rc = ensure_light_flat(st, &ok))) return rc;
@@ -1181,6 +1231,7 @@ uint64_t storm_query(STORM_t* s, uint32_t shard, uint32_t n_shards) {
     reps.insert(reps.end(), st->replicas.begin(), st->replicas.end());
     const uint32_t G = (uint32_t)reps.size();
     const int route = choose_route(st, s->n_conts);
+    if (route_reads_light(route, st) && sync_light(s, st)) return (uint64_t)-1;
     // one host thread per replica (devices.h: for_each_device): launch its share, read its total back, wait
     const int rc = for_each_device((int)G, [&](int g) -> int {
         StormState* r = reps[g];
