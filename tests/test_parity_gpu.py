@@ -371,11 +371,14 @@ def test_storm_t_stream_kernel_position_ranges(sb, orc):
         rows[r] = (15 * 65536 + np.unique(rng.integers(0, 65536, 700))).astype(np.uint32)
     vals = O.positions_to_dense(rows, M)
     exact = orc.wrapper_diag(vals)
-    prev = sb.set_storm_route("sparse")
+    prev = sb.set_storm_route("dense")
     try:
         with sb.Storm() as s:
             for p in rows:
                 s.add(p)
+            assert s.pairw_intersect_cardinality() == exact           # mirror built for the densified route: no light arrays yet
+            assert s.last_route() == "dense"
+            sb.set_storm_route("sparse")                              # ... they are added when a route first reads them
             assert s.pairw_intersect_cardinality() == exact
             assert s.last_route() == "sparse"
             assert sum(s.pairw_shard(k, 7) for k in range(7)) == exact
