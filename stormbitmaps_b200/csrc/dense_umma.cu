@@ -1163,11 +1163,14 @@ extern "C" int STORM_b200_set_umma_chain(int on) {
 // Development / measurement knob: bit 0 = hardware-suspended mbarrier waits, bit 1 = scaled expansion.
 // Returns the previous value.
 extern "C" int STORM_b200_set_umma_variant(int variant) {
+    const int hints = storm::g_umma_l2_hints.load();
     const int prev = storm::g_umma_variant.load() | (storm::g_umma_fp4_wide.load() ? 8 : 0) | (storm::g_umma_out_tma.load() ? 16 : 0) |
-                     (storm::g_umma_l2_hints.load() ? 32 : 0);
+                     (hints ? 32 : 0);
     if (variant >= 0 && variant <= 63) {
         storm::g_umma_variant.store(variant & 3); storm::g_umma_fp4_wide.store((variant >> 3) & 1); storm::g_umma_out_tma.store((variant >> 4) & 1);
-        storm::g_umma_l2_hints.store((variant >> 5) & 1);   // (STORM_b200_set_umma_l2_hints picks between its two forms)
+        // bit 5 switches the hints on or off; which of the two forms is STORM_b200_set_umma_l2_hints' business (a caller
+        // that restores a previous value must not turn mode 2 into mode 1)
+        storm::g_umma_l2_hints.store(((variant >> 5) & 1) ? (hints ? hints : 2) : 0);
     }
     return prev;
 }
