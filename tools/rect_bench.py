@@ -12,7 +12,7 @@ import stormbitmaps_b200 as sb
 L = sb.load()
 from stormbitmaps_b200 import _lib
 
-variants = [None]                                 # --variants=51,115: STORM_b200_set_umma_variant values to time the counts with
+variants = [None]                                 # --variants=51,35: STORM_b200_set_umma_variant values to time the counts with (35 = without the TMA-store drain)
 for a in list(sys.argv[1:]):
     if a.startswith("--variants="):
         variants = [int(x) for x in a.split("=")[1].split(",")]
