@@ -196,6 +196,7 @@ int DevCtx::init(int dev) {
     DeviceGuard guard(dev);
     STORM_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     STORM_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    STORM_CUDA_TRY(cudaStreamCreateWithFlags(&pull_stream, cudaStreamNonBlocking));
     STORM_CUDA_TRY(cudaMalloc(&d_total, sizeof(unsigned long long)));
     STORM_CUDA_TRY(cudaMallocHost(&h_total, sizeof(unsigned long long)));
     for (cudaEvent_t& e : slice_ready) STORM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -218,6 +219,7 @@ void DevCtx::destroy() {
     if (device < 0) return;
     DeviceGuard guard(device);
     if (copy_stream) cudaStreamSynchronize(copy_stream);
+    if (pull_stream) cudaStreamSynchronize(pull_stream);
     if (stream) cudaStreamSynchronize(stream);
     {
         std::lock_guard<std::mutex> lock(g_stage.mu);
@@ -231,7 +233,8 @@ void DevCtx::destroy() {
     if (h_total) cudaFreeHost(h_total);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    mark = nullptr; d_total = nullptr; h_total = nullptr; stream = nullptr; copy_stream = nullptr;
+    if (pull_stream) cudaStreamDestroy(pull_stream);
+    mark = nullptr; d_total = nullptr; h_total = nullptr; stream = nullptr; copy_stream = nullptr; pull_stream = nullptr;
     device = -1;
 }
 
@@ -379,21 +382,28 @@ int banded_triangle(DevCtx* const* devs, uint64_t* const* arenas, int G, uint64_
             if (G > 1) { DeviceGuard guard(devs[g]->device); STORM_CUDA_TRY(cudaEventRecord(devs[g]->slice_ready[band], devs[g]->copy_stream)); }
         }
         for (int g = 0; g < G; ++g) {
-            DeviceGuard guard(devs[g]->device);
+            // The peer pulls of a band run on their own stream: NVLink moves band k's slices while PCIe already carries
+            // band k + 1's (on one stream the upload of the next band waited for the pulls of this one).  The pull
+            // stream first waits for this device's own slice -- everything queued on the copy stream before it, arena
+            // zeroing included, is then done -- so that nothing can overwrite a pulled slice.
+            DevCtx* d = devs[g];
+            DeviceGuard guard(d->device);
+            cudaStream_t ps = G > 1 ? d->pull_stream : d->copy_stream;
+            if (G > 1) STORM_CUDA_TRY(cudaStreamWaitEvent(ps, d->slice_ready[band], 0));
             for (int o = 1; o < G; ++o) {                                 // pull the other slices, nearest neighbour first (spreads the NVLink load)
                 const int p = (g + o) % G;
                 if (cut[p + 1] <= cut[p]) continue;
-                STORM_CUDA_TRY(cudaStreamWaitEvent(devs[g]->copy_stream, devs[p]->slice_ready[band], 0));
+                STORM_CUDA_TRY(cudaStreamWaitEvent(ps, devs[p]->slice_ready[band], 0));
                 uint64_t* dst = arenas[g] + cut[p] * stride;
                 const uint64_t* from = arenas[p] + cut[p] * stride;
                 const size_t bytes = (cut[p + 1] - cut[p]) * stride * 8;
-                if (devs[p]->device == devs[g]->device)
-                    STORM_CUDA_TRY(cudaMemcpyAsync(dst, from, bytes, cudaMemcpyDeviceToDevice, devs[g]->copy_stream));
+                if (devs[p]->device == d->device)
+                    STORM_CUDA_TRY(cudaMemcpyAsync(dst, from, bytes, cudaMemcpyDeviceToDevice, ps));
                 else
-                    STORM_CUDA_TRY(cudaMemcpyPeerAsync(dst, devs[g]->device, from, devs[p]->device, bytes, devs[g]->copy_stream));
+                    STORM_CUDA_TRY(cudaMemcpyPeerAsync(dst, d->device, from, devs[p]->device, bytes, ps));
             }
-            STORM_CUDA_TRY(cudaEventRecord(devs[g]->band_ready[band], devs[g]->copy_stream));
-            STORM_CUDA_TRY(cudaStreamWaitEvent(devs[g]->stream, devs[g]->band_ready[band], 0));
+            STORM_CUDA_TRY(cudaEventRecord(d->band_ready[band], ps));
+            STORM_CUDA_TRY(cudaStreamWaitEvent(d->stream, d->band_ready[band], 0));
         }
         { int rc = for_each_device(G, [&](int g) { return launch(g, prefix[g0], prefix[g1]); }); if (rc) return rc; }
     }
@@ -407,9 +417,9 @@ static int collect_one(DevCtx* d, const char* what) {
     DeviceGuard guard(d->device);
     const cudaError_t e0 = cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream);
     d->total_zero = cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), d->stream) == cudaSuccess;
-    const cudaError_t e1 = cudaStreamSynchronize(d->stream), e2 = cudaStreamSynchronize(d->copy_stream);
-    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) {
-        set_error("%s failed on device %d: %s", what, d->device, cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2));
+    const cudaError_t e1 = cudaStreamSynchronize(d->stream), e2 = cudaStreamSynchronize(d->copy_stream), e3 = cudaStreamSynchronize(d->pull_stream);
+    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        set_error("%s failed on device %d: %s", what, d->device, cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
         cudaGetLastError();
         return STORM_B200_ECUDA;
     }

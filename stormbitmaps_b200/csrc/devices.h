@@ -37,11 +37,12 @@ struct DeviceGuard {
 struct DevCtx {
     int device = -1;
     cudaStream_t stream = nullptr;                   // kernels
-    cudaStream_t copy_stream = nullptr;              // uploads and peer pulls run ahead of the kernels here
+    cudaStream_t copy_stream = nullptr;              // uploads (host -> this device) run ahead of the kernels here
+    cudaStream_t pull_stream = nullptr;              // peer pulls of a band (NVLink), so that they overlap the next band's upload (PCIe)
     unsigned long long* d_total = nullptr;
     unsigned long long* h_total = nullptr;           // pinned
     cudaEvent_t slice_ready[MAX_BANDS] = {};         // copy_stream: this device's own slice of band k is uploaded
-    cudaEvent_t band_ready[MAX_BANDS] = {};          // copy_stream: every row of band k is on this device
+    cudaEvent_t band_ready[MAX_BANDS] = {};          // pull_stream: every row of band k is on this device
     cudaEvent_t stage_done[STAGE_SLOTS] = {};        // copy_stream: the H2D out of staging slot s has finished
     cudaEvent_t mark = nullptr;                      // scratch event (stream <-> copy_stream ordering)
     bool total_zero = false;                         // d_total was zeroed on `stream` after the last read-back
