@@ -76,6 +76,9 @@ int STORM_b200_get_devices(int* ids, int cap);
  * query take the others -- which is what lets 0.3 ms queries scale over 8 devices.  0 = issue everything from the
  * calling thread.  Returns the previous value. */
 int STORM_b200_set_device_threads(int on);
+/* Test hook for that pool (no device needed): n jobs, job `fail_at` (if >= 0) fails on purpose; returns the pool's return
+ * code (the failing job's, with its message as the caller's last error) or -100 if a job did not run exactly once. */
+int STORM_b200_selftest_device_threads(int n, int fail_at);
 
 /* ---- dense path on device-resident rows ----------------------------------
  *

@@ -126,6 +126,7 @@ SIGNATURES = {
     "STORM_b200_set_device_list": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "STORM_b200_get_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "STORM_b200_set_device_threads": (C.c_int, [C.c_int]),
+    "STORM_b200_selftest_device_threads": (C.c_int, [C.c_int, C.c_int]),
     "STORM_b200_contig_device_count": (C.c_int, [C.c_void_p]),
     "STORM_b200_contig_add_dense": (C.c_int, [C.c_void_p, u64p, C.c_uint64, C.c_uint64]),
     "STORM_b200_contig_rehome": (C.c_int, [C.c_void_p]),

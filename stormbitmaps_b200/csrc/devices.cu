@@ -140,11 +140,17 @@ public:
     int run(int n, const std::function<int(int)>& fn) {
         if (n <= 1) return n == 1 ? fn(0) : STORM_B200_OK;
         std::lock_guard<std::mutex> lock(run_mu_);
-        while ((int)workers_.size() < n - 1) {
-            std::unique_ptr<Worker> w(new Worker());
-            Worker* raw = w.get();
-            raw->th = std::thread(loop, raw);
-            workers_.push_back(std::move(w));
+        try {
+            while ((int)workers_.size() < n - 1) {
+                std::unique_ptr<Worker> w(new Worker());
+                Worker* raw = w.get();
+                raw->th = std::thread(loop, raw);
+                workers_.push_back(std::move(w));
+            }
+        } catch (...) {                              // no thread to be had: the caller issues everything itself
+            int rc = STORM_B200_OK;
+            for (int g = 0; g < n; ++g) { const int r = fn(g); if (r && !rc) rc = r; }
+            return rc;
         }
         for (int k = 1; k < n; ++k) {
             Worker* w = workers_[k - 1].get();
@@ -468,6 +474,20 @@ int STORM_b200_set_device_list(const int* ids, int n) {
 // 1 (default): the per-device calls of a multi-device query go out from one host thread per device; 0: from the
 // calling thread alone.  Returns the previous value.
 int STORM_b200_set_device_threads(int on) { return g_device_threads.exchange(on != 0); }
+
+// Test hook (no device needed): n jobs through the per-device thread pool; job k records that it ran, job `fail_at`
+// (if >= 0) fails with a message.  Returns the pool's return code, or -100 if a job did not run exactly once.
+int STORM_b200_selftest_device_threads(int n, int fail_at) {
+    if (n < 0 || n > 64) return STORM_B200_EINVAL;
+    std::vector<int> ran(n > 0 ? n : 1, 0);
+    const int rc = for_each_device(n, [&](int k) -> int {
+        ++ran[k];
+        if (k == fail_at) { set_error("job %d failed on purpose", k); return STORM_B200_EINVAL; }
+        return STORM_B200_OK;
+    });
+    for (int k = 0; k < n; ++k) if (ran[k] != 1) return -100;
+    return rc;
+}
 
 // The devices a query made now would use: fills ids[0 .. min(cap, count)) and returns the count (negative on error).
 int STORM_b200_get_devices(int* ids, int cap) {

@@ -255,6 +255,42 @@ def test_split_route_model(lib):
     assert sb.storm_split_model(1, 0, 0, 0, 1, 0) < 0
 
 
+def test_per_device_thread_pool_without_a_device(lib):
+    """The pool that issues the per-device calls of a multi-device query (devices.cu: DevicePool), driven through its
+    test hook on the CPU: every job runs exactly once for 1 .. 9 "devices", thousands of dispatches back to back
+    (workers polling) and after pauses (workers asleep), from two caller threads at once; a failing job's code and
+    message reach the caller; with the threads off the same jobs run on the caller."""
+    import threading, time
+    import stormbitmaps_b200 as sb
+    for n in range(0, 10):
+        assert lib.STORM_b200_selftest_device_threads(n, -1) == 0, n
+    for k in range(3000):
+        assert lib.STORM_b200_selftest_device_threads(2 + k % 7, -1) == 0
+        if k % 1000 == 999:
+            time.sleep(0.02)
+    assert lib.STORM_b200_selftest_device_threads(8, 5) == -1
+    assert "job 5 failed on purpose" in sb.last_error()
+    assert lib.STORM_b200_selftest_device_threads(8, 0) == -1 and "job 0 failed" in sb.last_error()
+    bad = []
+
+    def hammer():
+        for k in range(2000):
+            if lib.STORM_b200_selftest_device_threads(3 + k % 5, -1) != 0:
+                bad.append(k)
+    ts = [threading.Thread(target=hammer) for _ in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not bad
+    assert sb.set_device_threads(False) is True
+    try:
+        assert lib.STORM_b200_selftest_device_threads(8, -1) == 0
+        assert lib.STORM_b200_selftest_device_threads(8, 2) == -1 and "job 2 failed" in sb.last_error()
+    finally:
+        sb.set_device_threads(True)
+
+
 def test_header_declares_every_reference_prototype():
     """Drop-in means every function the reference's storm.h declares is declared (and exported) here.  The name list
     is a committed fixture (minted with: grep -oE '\\bSTORM_[a-zA-Z0-9_]+ *\\(' /root/reference/storm.h | tr -d ' (' | sort -u, minus the STORM_ALIGN macro);
