@@ -916,7 +916,8 @@ bool stream_groups(const uint32_t* row_nnz, uint64_t n_rows, std::vector<uint32_
 uint32_t stream_ranges(double avg_nnz, uint32_t span, uint32_t* range_bits) {
     const uint64_t bits = (uint64_t)std::max(1u, span) << 16;
     const double need = avg_nnz / 128.0;
-    const uint32_t p = need <= 1.0 ? 1u : (uint32_t)std::min(32.0, std::ceil(need));
+    static_assert(STREAM_MAX_RANGES <= 32, "flatten_ranges_kernel keeps one range per lane");
+    const uint32_t p = need <= 1.0 ? 1u : (uint32_t)std::min((double)STREAM_MAX_RANGES, std::ceil(need));
     const uint64_t rb = (bits + p - 1) / p;
     if (range_bits) *range_bits = (uint32_t)std::min<uint64_t>(rb, 0xFFFFFFFFull);
     return (uint32_t)((bits + rb - 1) / rb);

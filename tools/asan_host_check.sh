@@ -32,4 +32,4 @@ open(p, "w").write(s)
 P
 cd "$work/repo"
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0 \
-  python -m pytest tests/test_abi.py -x -q -k "host or builder or loudly or exported" 2>&1 | tail -n 3
+  python -m pytest tests/test_abi.py -x -q -k "host or builder or loudly or exported or thread_pool" 2>&1 | tail -n 3
